@@ -1,0 +1,164 @@
+/*
+ * lsm_b200.h - C ABI of the B200-native batched simulator for the per-step hot path of
+ * Layered-Safe-MARL's `navigation_graph_safe` environment.
+ *
+ * Plain pointers and sizes only (no torch / ATen types). Every pointer inside lsm_buffers and
+ * lsm_grid_desc is a DEVICE pointer; the caller (the Python B200GraphVecEnv, or any other host)
+ * owns the memory. All launches go to the cudaStream_t passed as `stream` (void*; NULL = default).
+ * No entry point synchronises the device.
+ *
+ * Every function returns 0 on success, a non-zero code otherwise, and then lsm_last_error()
+ * describes the failure (thread-local string).
+ *
+ * What each entry point replaces in the reference (paths relative to the reference root):
+ *   lsm_step     GraphSubprocVecEnv.step_async/step_wait  onpolicy/envs/env_wrappers.py:983-996
+ *                + graphworker 'step' incl. auto-reset     onpolicy/envs/env_wrappers.py:851-875
+ *                + MultiAgentGraphEnv.step                 multiagent/environment.py:963-1042
+ *                + World.step / apply_safety_filter        multiagent/core.py:593-709
+ *                + both safety handles                     multiagent/safety_filter.py:203-433
+ *                + reward / goal / observation / graph     multiagent/custom_scenarios/navigation_graph_safe.py:576-994
+ *   lsm_reset    GraphSubprocVecEnv.reset                  onpolicy/envs/env_wrappers.py:998-1005
+ *                + MultiAgentGraphEnv.reset                multiagent/environment.py:1046-1074
+ *                + reset_world / update_curriculum / random_scenario
+ *                                                          navigation_graph_safe.py:264-366,1199-1367
+ *   lsm_observe  the observation half of reset (used after lsm set_state style injection)
+ *   lsm_set_value_grid / lsm_set_ttr_grid
+ *                HjDataHandle.__init__                     multiagent/safety_filter.py:154-168
+ *                TTR grid loading in make_world            navigation_graph_safe.py:128-138
+ *   lsm_create   Scenario.make_world (constants only)      navigation_graph_safe.py:58-262
+ */
+#ifndef LSM_B200_H
+#define LSM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LSM_ABI_VERSION 1
+
+enum { LSM_DYN_DOUBLE_INTEGRATOR = 0, LSM_DYN_AIRTAXI = 1 };
+
+/* switches of multiagent/config.py:RewardBinaryConfig plus the make_world arguments that gate code */
+enum {
+    LSM_FLAG_SAFETY_VIOLATION = 1 << 0,
+    LSM_FLAG_HJ_VALUE = 1 << 1,
+    LSM_FLAG_POTENTIAL_CONFLICT = 1 << 2,
+    LSM_FLAG_SEPARATION_DISTANCE_CURRICULUM = 1 << 3,
+    LSM_FLAG_INITIAL_PHASE_USE_SAFETY_FILTER = 1 << 4,
+    LSM_FLAG_DIFF_FROM_FILTERED_ACTION = 1 << 5,
+    LSM_FLAG_USE_SAFETY_FILTER = 1 << 6,   /* the --use_safety_filter argument */
+    LSM_FLAG_SHARED_REWARD = 1 << 7,       /* --collaborative */
+    LSM_FLAG_USE_MASKING = 1 << 8          /* --use_masking (required, reference quirk Q9) */
+};
+
+/* state layout: agent_f64[field][env][agent], agent_i32[field][env][agent],
+ * landmarks[field][env][order*N + agent], env_f64[field][env], env_i32[field][env] */
+enum {
+    LSM_AF_X = 0, LSM_AF_Y, LSM_AF_S2 /* vx | theta */, LSM_AF_S3 /* vy | speed */,
+    LSM_AF_P_DIST, LSM_AF_STATE_TIME, LSM_AF_MIN_REL_DIST, LSM_AF_GOAL_MIN_TIME,
+    LSM_AF_TIMES_REQ_A, LSM_AF_TIMES_REQ_B, LSM_AF_DISTS_GOAL_A, LSM_AF_DISTS_GOAL_B,
+    LSM_AF_DIST_LEFT, LSM_AF_EP_TRAVEL_DIST, LSM_AF_EP_MIN_DIST, LSM_AF_ACTION_DIFF,
+    LSM_AF_COUNT
+};
+enum {
+    LSM_AI_REACHED = 0, LSM_AI_DONE, LSM_AI_SAFETY_FILTERED, LSM_AI_DECONFLICT_IDX,
+    LSM_AI_NUM_COLLISIONS, LSM_AI_EP_TRAVEL_LEN, LSM_AI_EP_CONFLICT, LSM_AI_EP_MULTI,
+    LSM_AI_EP_DONE, LSM_AI_COUNT
+};
+enum { LSM_LF_X = 0, LSM_LF_Y, LSM_LF_HEADING, LSM_LF_SPEED, LSM_LF_SIN, LSM_LF_COS, LSM_LF_COUNT };
+enum { LSM_EF_CURRICULUM_RATIO = 0, LSM_EF_COUNT };
+enum { LSM_EI_CURRENT_STEP = 0, LSM_EI_RESET_COUNT, LSM_EI_PARITY, LSM_EI_JUST_RESET, LSM_EI_COUNT };
+enum {
+    LSM_EP_TRAVEL_TIME_MEAN = 0, LSM_EP_TRAVEL_DISTANCE_MEAN, LSM_EP_DONE_PERCENTAGE,
+    LSM_EP_NUM_REACHED_GOAL_MEAN, LSM_EP_CONFLICT_PERCENTAGE, LSM_EP_MIN_DISTANCE_MEAN,
+    LSM_EP_MIN_DISTANCE_MIN, LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE, LSM_EP_COUNT
+};
+
+#define LSM_MAX_AGENTS 32
+#define LSM_MAX_LANDMARKS 128
+#define LSM_NUM_ACTIONS 25
+
+typedef struct lsm_config {
+    int32_t dynamics, num_agents, num_landmarks /* per agent */, episode_length;
+    int32_t num_total_episode, num_internal_step;
+    uint32_t flags;
+    int32_t _pad;
+    double world_size;
+    double dt, coordination_range, dist_thresh, heading_thresh, speed_thresh;
+    double goal_speed_min, goal_speed_max, separation_distance_target;
+    double engagement_distance_ref, engagement_ref_separation, cbf_rate, agent_max_speed;
+    double goal_rew, safety_violation_rew, hj_value_rew, potential_conflict_rew;
+    double diff_from_filtered_action_rew, min_reward, max_reward;
+    double act_tab0[5], act_tab1[5];   /* np.linspace tables of environment.py:387-410 */
+} lsm_config;
+
+typedef struct lsm_grid_desc {
+    int32_t ndim;
+    int32_t shape[5];
+    int32_t periodic[5];
+    int32_t _pad;
+    double lo[5], hi[5];
+    double separation_distance;   /* separation distance the values encode */
+    double ttr_max;
+    const float *values;          /* DEVICE [prod(shape)], C order */
+    const float *grads;           /* DEVICE [prod(shape)][ndim], or NULL */
+} lsm_grid_desc;
+
+typedef struct lsm_buffers {
+    int64_t num_envs;
+    int64_t env_id_base;          /* global index of env 0 of this shard (keys the reset RNG stream) */
+    double *agent_f64;            /* [LSM_AF_COUNT][num_envs][N] */
+    int32_t *agent_i32;           /* [LSM_AI_COUNT][num_envs][N] */
+    double *landmarks;            /* [LSM_LF_COUNT][num_envs][N*L] */
+    double *env_f64;              /* [LSM_EF_COUNT][num_envs] */
+    int32_t *env_i32;             /* [LSM_EI_COUNT][num_envs] */
+    /* outputs */
+    float *obs;                   /* [num_envs][N][D]       D = 7 (DI) | 6 (airtaxi) */
+    float *node_obs;              /* [num_envs][N][E][F]    F = 10 (DI) | 11 (airtaxi), E = N(1+L) */
+    float *adj;                   /* [num_envs][N][E][E] */
+    float *reward;                /* [num_envs][N] */
+    uint8_t *done;                /* [num_envs][N] */
+    double *safe_action;          /* [num_envs][N][2]  control applied in the last internal step */
+    double *ep_info;              /* [num_envs][LSM_EP_COUNT]  summary written when an env resets */
+    float *reward_individual;     /* [num_envs][N] or NULL: pre-sum reward when LSM_FLAG_SHARED_REWARD */
+} lsm_buffers;
+
+typedef struct lsm_launch_info {
+    int32_t grid_blocks, block_threads, warps_per_block, envs_per_warp;
+    int32_t smem_bytes_per_block, regs_per_thread, blocks_per_sm, sm_count;
+} lsm_launch_info;
+
+typedef struct lsm_handle lsm_handle;
+
+int lsm_abi_version(void);
+const char *lsm_last_error(void);
+
+int lsm_create(const lsm_config *cfg, lsm_handle **out);
+int lsm_destroy(lsm_handle *h);
+int lsm_set_value_grid(lsm_handle *h, const lsm_grid_desc *g);
+int lsm_set_ttr_grid(lsm_handle *h, const lsm_grid_desc *g);
+int lsm_bind_buffers(lsm_handle *h, const lsm_buffers *b);
+int lsm_get_launch_info(lsm_handle *h, lsm_launch_info *out);
+
+/* One env.step for every env (exactly one of action_idx / action_onehot non-NULL):
+ *   action_idx    DEVICE int32 [num_envs][N] in [0,25)
+ *   action_onehot DEVICE float [num_envs][N][25]; argmax (first maximum) is taken on device
+ * episode is the `num_current_episode` the runner passes to envs.step; auto_reset != 0 reproduces
+ * graphworker (reset an env whose agents are all done, keep the step's rewards/dones). */
+int lsm_step(lsm_handle *h, const int32_t *action_idx, const float *action_onehot, int64_t episode,
+             uint64_t seed, int auto_reset, void *stream);
+
+/* env.reset(episode) for every env with env_mask[e] != 0 (DEVICE uint8, NULL = all). sample != 0
+ * draws a new random scenario on device; sample == 0 keeps the injected agents / landmarks. */
+int lsm_reset(lsm_handle *h, const uint8_t *env_mask, int64_t episode, uint64_t seed, int sample,
+              void *stream);
+
+/* Re-emit obs / node_obs / adj from the bound state without stepping. */
+int lsm_observe(lsm_handle *h, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,9 @@
+"""B200-native batched simulator for the per-step hot path of Layered-Safe-MARL's
+`navigation_graph_safe` environment. The compute path is the sm_100a library
+`liblsm_b200.so` behind include/lsm_b200.h; there is no CPU fallback."""
+from .config import (AirTaxiConfig, DoubleIntegratorConfig, RewardBinaryConfig, RewardWeightConfig,
+                     ScenarioParams, scenario_params_from_args)
+from .vec_env import B200GraphVecEnv
+
+__all__ = ['AirTaxiConfig', 'DoubleIntegratorConfig', 'RewardBinaryConfig', 'RewardWeightConfig',
+           'ScenarioParams', 'scenario_params_from_args', 'B200GraphVecEnv']

@@ -1,0 +1,37 @@
+"""Build the sm_100a shared library in-tree (nvcc cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, 'csrc')
+LIB_PATH = os.path.join(HERE, 'liblsm_b200.so')
+SOURCES = [os.path.join(CSRC, 'lsm_kernels.cu'), os.path.join(CSRC, 'lsm_capi.cu')]
+DEPS = SOURCES + [os.path.join(CSRC, 'lsm_device.cuh'), os.path.join(CSRC, 'lsm_host.h'),
+                  os.path.join(os.path.dirname(HERE), 'include', 'lsm_b200.h')]
+
+NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
+              # no FMA contraction: float64 intermediates must round like the reference's numpy arithmetic
+              '-fmad=false',
+              '-Xcompiler', '-fPIC', '-shared']
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(p) > t for p in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = os.environ.get('NVCC', 'nvcc')
+    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + proc.stdout)
+    if verbose:
+        print(proc.stdout)
+    return LIB_PATH

@@ -1,0 +1,268 @@
+// lsm_capi.cu - the extern "C" boundary declared in include/lsm_b200.h.
+// Host-only logic: validation, shared-memory layout, lookup tables, launch geometry.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lsm_host.h"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char* what) {
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return 100 + (int)e;
+}
+
+int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
+int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+}  // namespace
+
+struct lsm_handle {
+    lsm::KParams kp;
+    bool have_buffers = false;
+    int device = 0;
+    int sm_count = 0;
+    int grid_cap = 0;           // sm_count * blocks_per_sm
+    int warps_per_block = 0;
+    int block_threads = 0;
+    int smem_per_block = 0;
+    int regs = 0;
+    int blocks_per_sm = 0;
+    uint16_t* d_pair_tab = nullptr;
+    uint32_t* d_sel_tab = nullptr;
+    size_t persist_bytes = 0;
+    size_t max_window = 0;
+};
+
+extern "C" {
+
+int lsm_abi_version(void) { return LSM_ABI_VERSION; }
+const char* lsm_last_error(void) { return g_err.c_str(); }
+
+int lsm_create(const lsm_config* cfg, lsm_handle** out) {
+    if (cfg == nullptr || out == nullptr) return fail(1, "lsm_create: null argument");
+    *out = nullptr;
+    const int N = cfg->num_agents, L = cfg->num_landmarks;
+    if (cfg->dynamics != LSM_DYN_DOUBLE_INTEGRATOR && cfg->dynamics != LSM_DYN_AIRTAXI)
+        return fail(2, "lsm_create: dynamics must be 0 (double_integrator) or 1 (airtaxi)");
+    if (N < 1 || N > LSM_MAX_AGENTS) return fail(2, "lsm_create: num_agents must be in [1, 32]");
+    if (L < 2) return fail(2, "lsm_create: num_landmarks (per agent) must be >= 2 (reference asserts len(goal_position) > 1)");
+    if (N * L > LSM_MAX_LANDMARKS) return fail(2, "lsm_create: num_agents*num_landmarks must be <= 128 (np.int8 landmark index, Q8)");
+    if (!(cfg->flags & LSM_FLAG_USE_MASKING)) return fail(2, "lsm_create: use_masking=False is not supported (reference raises, Q9)");
+    if (cfg->num_internal_step < 1) return fail(2, "lsm_create: num_internal_step must be >= 1");
+    if (cfg->num_total_episode < 1) return fail(2, "lsm_create: num_total_episode must be >= 1");
+    if (cfg->episode_length < 1) return fail(2, "lsm_create: episode_length must be >= 1");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(3, "lsm_create: no CUDA device - this library has no CPU fallback");
+    lsm_handle* h = new lsm_handle();
+    std::memset(&h->kp, 0, sizeof(h->kp));
+    e = cudaGetDevice(&h->device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDevice"); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, h->device);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDeviceProperties"); }
+    h->sm_count = prop.multiProcessorCount;
+    h->max_window = (size_t)prop.accessPolicyMaxWindowSize;
+    if (prop.persistingL2CacheMaxSize > 0) {
+        size_t want = (size_t)prop.persistingL2CacheMaxSize;
+        if (want > ((size_t)32 << 20)) want = (size_t)32 << 20;
+        cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);   // best effort
+        cudaGetLastError();
+    }
+
+    lsm::KParams& kp = h->kp;
+    kp.c = *cfg;
+    const int M = N * L, E = N + M;
+    kp.N = N; kp.L = L; kp.M = M; kp.E = E;
+    kp.D = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
+    kp.F = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
+    kp.G = next_pow2(N);
+    kp.EPW = 32 / kp.G;
+    kp.W = (E + 31) / 32;
+    kp.adj_vec = (E % 4 == 0) ? 4 : 1;
+    for (int k = 0; k < 5; ++k) {
+        const double stair = (double)k / 4.0;
+        const double phase = stair * 0.5 * lsm::kPi;
+        kp.sep_ratio_tab[k] = 1.0 - std::cos(phase);
+    }
+    // shared-memory layout of one environment
+    lsm::SmemLayout& sl = kp.sl;
+    int off = 0;
+    auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
+    const int dN = 8 * N, dM = 8 * M, iN = 4 * N;
+    sl.ax = take(dN, 8); sl.ay = take(dN, 8); sl.as2 = take(dN, 8); sl.as3 = take(dN, 8);
+    sl.vpre_x = take(dN, 8); sl.vpre_y = take(dN, 8); sl.vpost_x = take(dN, 8); sl.vpost_y = take(dN, 8);
+    sl.spd_post = take(dN, 8); sl.sth = take(dN, 8); sl.cth = take(dN, 8);
+    sl.rawx = take(dN, 8); sl.rawy = take(dN, 8);
+    sl.lx = take(dM, 8); sl.ly = take(dM, 8); sl.lh = take(dM, 8); sl.lsp = take(dM, 8);
+    sl.lsin = take(dM, 8); sl.lcos = take(dM, 8);
+    sl.daa = take(8 * N * N, 8);
+    sl.dthr = take(4 * E * E, 16);
+    sl.goal_pre = take(iN, 4); sl.goal_post = take(iN, 4); sl.reached_pre = take(iN, 4); sl.reached_post = take(iN, 4);
+    sl.done_pre = take(iN, 4); sl.done_post = take(iN, 4);
+    sl.disc_pre = take(4 * kp.W, 4); sl.disc_post = take(4 * kp.W, 4);
+    sl.keepm = take(4 * N * kp.W, 4);
+    sl.bytes_per_env = align_up(off, 16);
+    kp.smem_per_warp = sl.bytes_per_env * kp.EPW;
+
+    // launch geometry: as many warps per block as fit ~100 KB so that two blocks share an SM
+    int wpb = (100 * 1024) / kp.smem_per_warp;
+    if (wpb > 8) wpb = 8;
+    if (wpb < 1) wpb = 1;
+    h->warps_per_block = wpb;
+    h->block_threads = 32 * wpb;
+    h->smem_per_block = kp.smem_per_warp * wpb;
+    if ((size_t)h->smem_per_block > (size_t)prop.sharedMemPerBlockOptin) {
+        delete h;
+        return fail(4, "lsm_create: one environment group does not fit in shared memory");
+    }
+    e = lsm::fused_kernel_prepare(cfg->dynamics, h->smem_per_block, h->block_threads, &h->regs, &h->blocks_per_sm);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "fused_kernel_prepare"); }
+    if (h->blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: kernel does not fit on an SM"); }
+    h->grid_cap = h->sm_count * h->blocks_per_sm;
+
+    // lookup tables
+    std::vector<uint16_t> pairs;
+    pairs.reserve((size_t)E * (E - 1));
+    for (int a = 0; a < E; ++a) for (int b = a + 1; b < E; ++b) { pairs.push_back((uint16_t)a); pairs.push_back((uint16_t)b); }
+    kp.num_pairs = (int)(pairs.size() / 2);
+    std::vector<uint32_t> sel((size_t)N * kp.W, 0u);
+    for (int i = 0; i < N; ++i) for (int ent = 0; ent < E; ++ent) {
+        const int owner = ent < N ? ent : (ent - N) % N;
+        if (owner <= i) sel[(size_t)i * kp.W + (ent >> 5)] |= 1u << (ent & 31);
+    }
+    e = cudaMalloc(&h->d_pair_tab, pairs.size() * sizeof(uint16_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_pair_tab, pairs.data(), pairs.size() * sizeof(uint16_t), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_sel_tab, sel.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_sel_tab, sel.data(), sel.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { lsm_destroy(h); return cuda_fail(e, "table upload"); }
+    kp.pair_tab = h->d_pair_tab; kp.sel_tab = h->d_sel_tab;
+    // cos/sin(phi_k) of utils.py:291 (np.linspace(0, 2pi, 50, endpoint=False)), host libm
+    double ctab[lsm::kMagSegments], stab[lsm::kMagSegments];
+    const double step = (2.0 * lsm::kPi - 0.0) / (double)lsm::kMagSegments;
+    for (int k = 0; k < lsm::kMagSegments; ++k) {
+        const double phi = (double)k * step + 0.0;
+        ctab[k] = std::cos(phi); stab[k] = std::sin(phi);
+    }
+    e = lsm::upload_magnetic_tables(ctab, stab);
+    if (e != cudaSuccess) { lsm_destroy(h); return cuda_fail(e, "upload_magnetic_tables"); }
+    *out = h;
+    return 0;
+}
+
+int lsm_destroy(lsm_handle* h) {
+    if (h == nullptr) return 0;
+    if (h->d_pair_tab) cudaFree(h->d_pair_tab);
+    if (h->d_sel_tab) cudaFree(h->d_sel_tab);
+    delete h;
+    return 0;
+}
+
+static int fill_grid(const lsm_grid_desc* g, lsm::GridDev* d, int want_ndim, bool need_grads, const char* who) {
+    if (g == nullptr || g->values == nullptr) return fail(1, std::string(who) + ": null grid");
+    if (g->ndim != want_ndim) return fail(2, std::string(who) + ": wrong grid dimensionality");
+    if (need_grads && g->grads == nullptr) return fail(2, std::string(who) + ": gradient array required");
+    std::memset(d, 0, sizeof(*d));
+    d->ndim = g->ndim;
+    for (int k = 0; k < g->ndim; ++k) {
+        if (g->shape[k] < 2) return fail(2, std::string(who) + ": every grid dimension needs >= 2 nodes");
+        d->shape[k] = g->shape[k]; d->periodic[k] = g->periodic[k] ? 1 : 0; d->lo[k] = g->lo[k];
+        const double n = (double)g->shape[k];
+        d->spacing[k] = g->periodic[k] ? (g->hi[k] - g->lo[k]) / n : (g->hi[k] - g->lo[k]) / (n - 1.0);
+    }
+    d->separation_distance = g->separation_distance; d->ttr_max = g->ttr_max;
+    d->values = g->values; d->grads = g->grads;
+    return 0;
+}
+
+int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
+    if (h == nullptr) return fail(1, "lsm_set_value_grid: null handle");
+    const int want = h->kp.c.dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    int rc = fill_grid(g, &h->kp.vg, want, true, "lsm_set_value_grid");
+    if (rc) return rc;
+    h->kp.has_vg = 1;
+    size_t cells = 1;
+    for (int k = 0; k < g->ndim; ++k) cells *= (size_t)g->shape[k];
+    h->persist_bytes = cells * sizeof(float);
+    if (h->persist_bytes > h->max_window) h->persist_bytes = h->max_window;
+    return 0;
+}
+
+int lsm_set_ttr_grid(lsm_handle* h, const lsm_grid_desc* g) {
+    if (h == nullptr) return fail(1, "lsm_set_ttr_grid: null handle");
+    int rc = fill_grid(g, &h->kp.tg, 4, false, "lsm_set_ttr_grid");
+    if (rc) return rc;
+    h->kp.has_tg = 1;
+    return 0;
+}
+
+int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
+    if (h == nullptr || b == nullptr) return fail(1, "lsm_bind_buffers: null argument");
+    if (b->num_envs < 1) return fail(2, "lsm_bind_buffers: num_envs must be >= 1");
+    const void* ptrs[] = { b->agent_f64, b->agent_i32, b->landmarks, b->env_f64, b->env_i32, b->obs, b->node_obs,
+                           b->adj, b->reward, b->done, b->safe_action, b->ep_info };
+    for (const void* p : ptrs) if (p == nullptr) return fail(2, "lsm_bind_buffers: every buffer pointer must be non-null");
+    if (((uintptr_t)b->adj & 15u) || ((uintptr_t)b->node_obs & 15u))
+        return fail(2, "lsm_bind_buffers: adj and node_obs must be 16-byte aligned");
+    h->kp.b = *b;
+    h->have_buffers = true;
+    return 0;
+}
+
+int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
+    if (h == nullptr || out == nullptr) return fail(1, "lsm_get_launch_info: null argument");
+    const long long ngroups = h->have_buffers ? (h->kp.b.num_envs + h->kp.EPW - 1) / h->kp.EPW : 0;
+    long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
+    if (blocks > h->grid_cap) blocks = h->grid_cap;
+    out->grid_blocks = (int32_t)blocks; out->block_threads = h->block_threads; out->warps_per_block = h->warps_per_block;
+    out->envs_per_warp = h->kp.EPW; out->smem_bytes_per_block = h->smem_per_block; out->regs_per_thread = h->regs;
+    out->blocks_per_sm = h->blocks_per_sm; out->sm_count = h->sm_count;
+    return 0;
+}
+
+static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, const float* action_onehot,
+                  const uint8_t* env_mask, int64_t episode, uint64_t seed, void* stream, const char* who) {
+    if (h == nullptr) return fail(1, std::string(who) + ": null handle");
+    if (!h->have_buffers) return fail(5, std::string(who) + ": lsm_bind_buffers has not been called");
+    const lsm_config& c = h->kp.c;
+    const bool needs_vg = (c.flags & (LSM_FLAG_USE_SAFETY_FILTER | LSM_FLAG_HJ_VALUE)) != 0;
+    if (needs_vg && !h->kp.has_vg) return fail(5, std::string(who) + ": safety filter / HJ_VALUE enabled but no value grid set");
+    if (c.dynamics == LSM_DYN_AIRTAXI && !h->kp.has_tg) return fail(5, std::string(who) + ": airtaxi needs a TTR grid");
+    lsm::KParams kp = h->kp;
+    kp.mode = mode; kp.flag = flag; kp.action_idx = action_idx; kp.action_onehot = action_onehot;
+    kp.env_mask = env_mask; kp.episode = (long long)episode; kp.seed = (unsigned long long)seed;
+    const long long ngroups = (kp.b.num_envs + kp.EPW - 1) / kp.EPW;
+    long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
+    if (blocks > h->grid_cap) blocks = h->grid_cap;
+    const void* persist = (mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
+    cudaError_t e = lsm::fused_kernel_launch(kp, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
+                                             persist, h->persist_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, who);
+    return 0;
+}
+
+int lsm_step(lsm_handle* h, const int32_t* action_idx, const float* action_onehot, int64_t episode, uint64_t seed,
+             int auto_reset, void* stream) {
+    if ((action_idx == nullptr) == (action_onehot == nullptr))
+        return fail(2, "lsm_step: pass exactly one of action_idx / action_onehot");
+    return launch(h, lsm::MODE_STEP, auto_reset ? 1 : 0, action_idx, action_onehot, nullptr, episode, seed, stream, "lsm_step");
+}
+
+int lsm_reset(lsm_handle* h, const uint8_t* env_mask, int64_t episode, uint64_t seed, int sample, void* stream) {
+    return launch(h, lsm::MODE_RESET, sample ? 1 : 0, nullptr, nullptr, env_mask, episode, seed, stream, "lsm_reset");
+}
+
+int lsm_observe(lsm_handle* h, void* stream) {
+    return launch(h, lsm::MODE_OBSERVE, 0, nullptr, nullptr, nullptr, 0, 0, stream, "lsm_observe");
+}
+
+}  // extern "C"

@@ -1,0 +1,361 @@
+"""B200GraphVecEnv - device-resident drop-in for the reference's vectorised graph environment.
+
+Mirrors `GraphSubprocVecEnv` (reference onpolicy/envs/env_wrappers.py:951-1028) over
+`GraphMPEEnv(args)` (multiagent/MPE_env.py:56-84): same constructor inputs (the argparse Namespace
+`make_world` reads), same attributes (spaces), same `reset` / `step` / `step_async` / `step_wait`
+signatures and return tuples
+
+    reset(num_current_episode) -> (obs, agent_id, node_obs, adj, infos)
+    step(actions, num_current_episode) -> (obs, agent_id, node_obs, adj, rewards, dones, infos)
+
+for `num_envs` environments that live on one GPU. All arithmetic happens in the hand-written
+sm_100a kernel behind the C ABI of include/lsm_b200.h; torch only provides device memory and the
+CUDA stream. There is no CPU fallback.
+
+Returned arrays are float32 CUDA tensors that alias the environment's output buffers: they stay
+valid until the next `step`/`reset` (pass `copy=True` to get private clones, or `numpy_outputs=True`
+to get host numpy arrays like the reference returns).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import layout as LY
+from .config import (DYN_DOUBLE_INTEGRATOR, FLAG_SHARED_REWARD, FLAG_USE_SAFETY_FILTER, FLAG_HJ_VALUE,
+                     RewardBinaryConfig, RewardWeightConfig, ScenarioParams, scenario_params_from_args)
+from .hj_grid import HjGrid, synthetic_airtaxi_grid, synthetic_di_grid, synthetic_ttr_grid
+from .infos import LazyInfos
+from .spaces import Box, Discrete
+
+
+def action_tables(dynamics: int):
+    """np.linspace tables of MultiAgentBaseEnv._set_action (reference multiagent/environment.py:387-410)."""
+    if dynamics == DYN_DOUBLE_INTEGRATOR:
+        return np.linspace(-0.5, 0.5, 5), np.linspace(-0.5, 0.5, 5)
+    return np.linspace(-0.1, 0.1, 5), np.linspace(-0.001, 0.002, 5)
+
+
+def make_config_struct(p: ScenarioParams) -> _lib.LsmConfig:
+    c = _lib.LsmConfig()
+    for name, _ in _lib.LsmConfig._fields_:
+        if name in ('_pad', 'act_tab0', 'act_tab1'):
+            continue
+        setattr(c, name, getattr(p, name))
+    t0, t1 = action_tables(p.dynamics)
+    c.act_tab0 = (C.c_double * 5)(*[float(v) for v in t0])
+    c.act_tab1 = (C.c_double * 5)(*[float(v) for v in t1])
+    return c
+
+
+class _DeviceGrid:
+    """An HjGrid uploaded to the GPU + its C descriptor."""
+
+    def __init__(self, grid: HjGrid, device):
+        self.values = torch.from_numpy(np.ascontiguousarray(grid.values, dtype=np.float32)).to(device)
+        self.grads = None
+        if grid.grads is not None:
+            self.grads = torch.from_numpy(np.ascontiguousarray(grid.grads, dtype=np.float32)).to(device)
+        d = _lib.LsmGridDesc()
+        d.ndim = grid.ndim
+        for k in range(grid.ndim):
+            d.shape[k] = int(grid.shape[k])
+            d.periodic[k] = int(bool(grid.periodic[k]))
+            d.lo[k] = float(grid.lo[k])
+            d.hi[k] = float(grid.hi[k])
+        d.separation_distance = float(grid.separation_distance)
+        d.ttr_max = float(grid.ttr_max)
+        d.values = self.values.data_ptr()
+        d.grads = self.grads.data_ptr() if self.grads is not None else None
+        self.desc = d
+
+
+class B200GraphVecEnv:
+    def __init__(self, args, num_envs: Optional[int] = None, device='cuda:0', seed: int = 0,
+                 value_grid: Optional[HjGrid] = None, ttr_grid: Optional[HjGrid] = None,
+                 binary_cfg=RewardBinaryConfig, weight_cfg=RewardWeightConfig, env_id_base: int = 0,
+                 numpy_outputs: bool = False, auto_reset: bool = True):
+        if not torch.cuda.is_available():
+            raise RuntimeError("B200GraphVecEnv needs a CUDA device; there is no CPU fallback")
+        self.lib = _lib.load()   # raises if the sm_100a library is missing
+        self.device = torch.device(device)
+        torch.cuda.set_device(self.device)
+        self.params = scenario_params_from_args(args, binary_cfg=binary_cfg, weight_cfg=weight_cfg)
+        p = self.params
+        self.num_envs = int(num_envs if num_envs is not None else args.n_rollout_threads)
+        self.n = self.num_envs
+        self.num_agents = self.N = p.num_agents
+        self.L = p.num_landmarks
+        self.M = self.N * self.L
+        self.E = self.N + self.M
+        self.D = p.obs_dim
+        self.F = p.node_feat_dim
+        self.seed = int(seed)
+        self.env_id_base = int(env_id_base)
+        self.numpy_outputs = bool(numpy_outputs)
+        self.auto_reset = bool(auto_reset)
+        self._step_id = 0
+
+        # --- spaces (environment.py:85-204, 928-960); only .shape / .n / class name are read by callers
+        N, E = self.N, self.E
+        self.action_space = [Discrete(LY.NUM_ACTIONS) for _ in range(N)]
+        self.observation_space = [Box(-np.inf, np.inf, (self.D,)) for _ in range(N)]
+        self.share_observation_space = [Box(-np.inf, np.inf, (self.D * N,)) for _ in range(N)]
+        self.node_observation_space = [Box(-np.inf, np.inf, (E, self.F)) for _ in range(N)]
+        self.adj_observation_space = [Box(-np.inf, np.inf, (E, E)) for _ in range(N)]
+        self.edge_observation_space = [Box(-np.inf, np.inf, (1,)) for _ in range(N)]
+        self.agent_id_observation_space = [Box(-np.inf, np.inf, (1,)) for _ in range(N)]
+        self.share_agent_id_observation_space = [Box(-np.inf, np.inf, (N,)) for _ in range(N)]
+
+        # --- handle
+        cfg = make_config_struct(p)
+        self._cfg = cfg
+        self._h = C.c_void_p()
+        _lib.check(self.lib.lsm_create(C.byref(cfg), C.byref(self._h)), 'lsm_create')
+
+        # --- grids (HjDataHandle / TTR loading); synthetic when none is given
+        needs_vg = bool(p.flags & (FLAG_USE_SAFETY_FILTER | FLAG_HJ_VALUE))
+        self.value_grid = None
+        self.ttr_grid = None
+        if needs_vg:
+            if value_grid is None:
+                value_grid = synthetic_di_grid() if p.dynamics == DYN_DOUBLE_INTEGRATOR else synthetic_airtaxi_grid()
+            self.value_grid = _DeviceGrid(value_grid, self.device)
+            _lib.check(self.lib.lsm_set_value_grid(self._h, C.byref(self.value_grid.desc)), 'lsm_set_value_grid')
+        if p.dynamics != DYN_DOUBLE_INTEGRATOR:
+            if ttr_grid is None:
+                ttr_grid = synthetic_ttr_grid()
+            self.ttr_grid = _DeviceGrid(ttr_grid, self.device)
+            _lib.check(self.lib.lsm_set_ttr_grid(self._h, C.byref(self.ttr_grid.desc)), 'lsm_set_ttr_grid')
+
+        # --- state + output buffers in HBM
+        n, M = self.n, self.M
+        dev = self.device
+        f64, i32, f32 = torch.float64, torch.int32, torch.float32
+        self.agent_f64 = torch.zeros((LY.AF_COUNT, n, N), dtype=f64, device=dev)
+        for k in (LY.AF_EP_MIN_DIST, LY.AF_MIN_REL_DIST, LY.AF_GOAL_MIN_TIME):
+            self.agent_f64[k].fill_(float('inf'))
+        for k in (LY.AF_TIMES_REQ_A, LY.AF_TIMES_REQ_B, LY.AF_DISTS_GOAL_A, LY.AF_DISTS_GOAL_B, LY.AF_DIST_LEFT):
+            self.agent_f64[k].fill_(-1.0)
+        self.agent_i32 = torch.zeros((LY.AI_COUNT, n, N), dtype=i32, device=dev)
+        self.agent_i32[LY.AI_DECONFLICT_IDX].fill_(-1)
+        self.landmarks = torch.zeros((LY.LF_COUNT, n, M), dtype=f64, device=dev)
+        self.env_f64 = torch.zeros((LY.EF_COUNT, n), dtype=f64, device=dev)
+        self.env_i32 = torch.zeros((LY.EI_COUNT, n), dtype=i32, device=dev)
+        self.obs = torch.zeros((n, N, self.D), dtype=f32, device=dev)
+        self.node_obs = torch.zeros((n, N, E, self.F), dtype=f32, device=dev)
+        self.adj = torch.zeros((n, N, E, E), dtype=f32, device=dev)
+        self.reward = torch.zeros((n, N), dtype=f32, device=dev)
+        self.done = torch.zeros((n, N), dtype=torch.uint8, device=dev)
+        self.safe_action = torch.zeros((n, N, 2), dtype=f64, device=dev)
+        self.ep_info = torch.zeros((n, LY.EP_COUNT), dtype=f64, device=dev)
+        self.reward_individual = None
+        if p.flags & FLAG_SHARED_REWARD:
+            self.reward_individual = torch.zeros((n, N), dtype=f32, device=dev)
+        # agent ids are constant (scenario.get_id -> global_id == agent index)
+        self.agent_id = torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1).expand(n, N, 1).contiguous()
+        self._agent_id_np = None
+        b = _lib.LsmBuffers()
+        b.num_envs = n
+        b.env_id_base = self.env_id_base
+        for name in ('agent_f64', 'agent_i32', 'landmarks', 'env_f64', 'env_i32', 'obs', 'node_obs', 'adj',
+                     'reward', 'done', 'safe_action', 'ep_info'):
+            setattr(b, name, getattr(self, name).data_ptr())
+        b.reward_individual = self.reward_individual.data_ptr() if self.reward_individual is not None else None
+        self._buffers = b
+        _lib.check(self.lib.lsm_bind_buffers(self._h, C.byref(b)), 'lsm_bind_buffers')
+        # pinned staging for host-side callers (the unmodified runner hands numpy one-hot actions)
+        self._act_pinned = None
+        self._act_dev = None
+        self._pending_actions = None
+        self._pending_episode = None
+        self.closed = False
+
+    # ------------------------------------------------------------------------------------------
+    def launch_info(self) -> dict:
+        li = _lib.LsmLaunchInfo()
+        _lib.check(self.lib.lsm_get_launch_info(self._h, C.byref(li)), 'lsm_get_launch_info')
+        return {k: int(getattr(li, k)) for k, _ in _lib.LsmLaunchInfo._fields_}
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _stage_actions(self, actions):
+        """-> (idx_ptr, onehot_ptr). Accepts (n,N) integer indices or (n,N,25) one-hot, torch or numpy."""
+        n, N = self.n, self.N
+        if isinstance(actions, np.ndarray) or not torch.is_tensor(actions):
+            a = np.asarray(actions)
+            if a.ndim == 3:
+                a = np.ascontiguousarray(a, dtype=np.float32)
+            else:
+                a = np.ascontiguousarray(a, dtype=np.int32)
+            if self._act_pinned is None or self._act_pinned.shape != a.shape or \
+                    self._act_pinned.numpy().dtype != a.dtype:
+                self._act_pinned = torch.from_numpy(a.copy()).pin_memory()
+                self._act_dev = torch.empty_like(self._act_pinned, device=self.device)
+            self._act_pinned.numpy()[...] = a
+            self._act_dev.copy_(self._act_pinned, non_blocking=True)
+            t = self._act_dev
+        else:
+            t = actions
+            if t.device != self.device:
+                t = t.to(self.device, non_blocking=True)
+            if t.dim() == 3:
+                if t.dtype != torch.float32:
+                    t = t.to(torch.float32)
+            elif t.dtype != torch.int32:
+                t = t.to(torch.int32)
+            t = t.contiguous()
+        self._act_keepalive = t
+        if t.dim() == 3:
+            assert tuple(t.shape) == (n, N, LY.NUM_ACTIONS), f"one-hot actions must be {(n, N, LY.NUM_ACTIONS)}"
+            return None, C.c_void_p(t.data_ptr())
+        assert tuple(t.shape) == (n, N), f"action indices must be {(n, N)}"
+        return C.c_void_p(t.data_ptr()), None
+
+    def _outputs(self, with_step: bool, copy: bool):
+        outs = [self.obs, self.agent_id, self.node_obs, self.adj]
+        if with_step:
+            outs += [self.reward, self.done.view(torch.bool)]
+        if self.numpy_outputs:
+            # host copies like the reference returns (float64 there; float32 here - every consumer casts)
+            return [t.cpu().numpy() for t in outs]
+        if copy:
+            return [t.clone() for t in outs]
+        return outs
+
+    # ------------------------------------------------------------------------------------------
+    def reset(self, num_current_episode: int = 0, copy: bool = False):
+        """GraphSubprocVecEnv.reset (env_wrappers.py:998-1005): every env draws a new scenario."""
+        self._step_id += 1
+        _lib.check(self.lib.lsm_reset(self._h, None, int(num_current_episode), self.seed, 1, self._stream()),
+                   'lsm_reset')
+        obs, agent_id, node_obs, adj = self._outputs(False, copy)
+        infos = LazyInfos(self, self._step_id, reset_only=True)
+        return obs, agent_id, node_obs, adj, infos
+
+    def reset_from_state(self, num_current_episode: int = 0):
+        """reset bookkeeping + observation for the currently injected agents / landmarks (no sampling)."""
+        self._step_id += 1
+        _lib.check(self.lib.lsm_reset(self._h, None, int(num_current_episode), self.seed, 0, self._stream()),
+                   'lsm_reset')
+        return self._outputs(False, False)
+
+    def observe(self):
+        """Re-emit obs / node_obs / adj from the current state (after set_state)."""
+        _lib.check(self.lib.lsm_observe(self._h, self._stream()), 'lsm_observe')
+        return self._outputs(False, False)
+
+    def step_async(self, actions, num_current_episode=None):
+        self._pending_actions = actions
+        self._pending_episode = num_current_episode
+
+    def step_wait(self, copy: bool = False):
+        actions, episode = self._pending_actions, self._pending_episode
+        self._pending_actions = None
+        idx_ptr, onehot_ptr = self._stage_actions(actions)
+        self._step_id += 1
+        ep = 0 if episode is None else int(episode)
+        _lib.check(self.lib.lsm_step(self._h, idx_ptr, onehot_ptr, ep, self.seed, int(self.auto_reset),
+                                     self._stream()), 'lsm_step')
+        obs, agent_id, node_obs, adj, rewards, dones = self._outputs(True, copy)
+        infos = LazyInfos(self, self._step_id, reset_only=False)
+        return obs, agent_id, node_obs, adj, rewards, dones, infos
+
+    def step(self, actions, num_current_episode=None, copy: bool = False):
+        """ShareVecEnv.step (env_wrappers.py:103-110)."""
+        self.step_async(actions, num_current_episode)
+        return self.step_wait(copy=copy)
+
+    def close(self):
+        if not self.closed and self._h:
+            self.lib.lsm_destroy(self._h)
+            self._h = C.c_void_p()
+        self.closed = True
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------------------------------
+    # named-state interchange (checkpoint / parity injection); leading axis = env
+    def set_state(self, s: dict):
+        dev = self.device
+
+        def t(v, dtype):
+            return torch.as_tensor(np.asarray(v), dtype=dtype, device=dev)
+
+        f, i = self.agent_f64, self.agent_i32
+        v = t(s['agent_values'], torch.float64)
+        f[LY.AF_X].copy_(v[..., 0]); f[LY.AF_Y].copy_(v[..., 1]); f[LY.AF_S2].copy_(v[..., 2]); f[LY.AF_S3].copy_(v[..., 3])
+        f[LY.AF_P_DIST].copy_(t(s['p_dist'], torch.float64)); f[LY.AF_STATE_TIME].copy_(t(s['state_time'], torch.float64))
+        f[LY.AF_MIN_REL_DIST].copy_(t(s['min_relative_distance'], torch.float64))
+        f[LY.AF_GOAL_MIN_TIME].copy_(t(s['goal_min_time'], torch.float64))
+        tr = t(s['times_required'], torch.float64); dg = t(s['dists_to_goal'], torch.float64)
+        f[LY.AF_TIMES_REQ_A].copy_(tr); f[LY.AF_TIMES_REQ_B].copy_(tr)
+        f[LY.AF_DISTS_GOAL_A].copy_(dg); f[LY.AF_DISTS_GOAL_B].copy_(dg)
+        f[LY.AF_DIST_LEFT].copy_(t(s['dist_left_to_goal'], torch.float64))
+        f[LY.AF_EP_TRAVEL_DIST].copy_(t(s['ep_travel_distance'], torch.float64))
+        f[LY.AF_EP_MIN_DIST].copy_(t(s['ep_min_distance'], torch.float64))
+        f[LY.AF_ACTION_DIFF].copy_(t(s['action_diff'], torch.float64))
+        i[LY.AI_REACHED].copy_(t(s['reached_goal'], torch.int32)); i[LY.AI_DONE].copy_(t(s['done'], torch.int32))
+        i[LY.AI_SAFETY_FILTERED].copy_(t(s['safety_filtered'], torch.int32))
+        i[LY.AI_DECONFLICT_IDX].copy_(t(s['deconflicting_agent_index'], torch.int32))
+        i[LY.AI_NUM_COLLISIONS].copy_(t(s['num_agent_collisions'], torch.int32))
+        i[LY.AI_EP_TRAVEL_LEN].copy_(t(s['ep_travel_length'], torch.int32))
+        i[LY.AI_EP_CONFLICT].copy_(t(s['ep_conflict'], torch.int32))
+        i[LY.AI_EP_MULTI].copy_(t(s['ep_multi_engagement'], torch.int32))
+        i[LY.AI_EP_DONE].copy_(t(s['ep_done'], torch.int32))
+        lp = t(s['landmark_pos'], torch.float64); lh = t(s['landmark_heading'], torch.float64)
+        lm = self.landmarks
+        lm[LY.LF_X].copy_(lp[..., 0]); lm[LY.LF_Y].copy_(lp[..., 1]); lm[LY.LF_HEADING].copy_(lh)
+        lm[LY.LF_SPEED].copy_(t(s['landmark_speed'], torch.float64))
+        # sin / cos of the landmark headings are tabulated on the HOST (libm), like after a host-side load
+        lh_np = np.asarray(s['landmark_heading'], dtype=np.float64)
+        lm[LY.LF_SIN].copy_(t(np.sin(lh_np), torch.float64)); lm[LY.LF_COS].copy_(t(np.cos(lh_np), torch.float64))
+        self.env_f64[LY.EF_CURRICULUM_RATIO].copy_(t(s['curriculum_ratio'], torch.float64))
+        self.env_i32[LY.EI_CURRENT_STEP].copy_(t(s['current_step'], torch.int32))
+
+    def get_state(self) -> dict:
+        f = self.agent_f64.cpu().numpy(); i = self.agent_i32.cpu().numpy()
+        lm = self.landmarks.cpu().numpy()
+        ei = self.env_i32.cpu().numpy(); ef = self.env_f64.cpu().numpy()
+        par = ei[LY.EI_PARITY][:, None].astype(bool)
+        s = {}
+        s['agent_values'] = np.stack([f[LY.AF_X], f[LY.AF_Y], f[LY.AF_S2], f[LY.AF_S3]], axis=-1)
+        s['p_dist'] = f[LY.AF_P_DIST]; s['state_time'] = f[LY.AF_STATE_TIME]
+        s['min_relative_distance'] = f[LY.AF_MIN_REL_DIST]; s['goal_min_time'] = f[LY.AF_GOAL_MIN_TIME]
+        s['times_required'] = np.where(par, f[LY.AF_TIMES_REQ_B], f[LY.AF_TIMES_REQ_A])
+        s['dists_to_goal'] = np.where(par, f[LY.AF_DISTS_GOAL_B], f[LY.AF_DISTS_GOAL_A])
+        s['dist_left_to_goal'] = f[LY.AF_DIST_LEFT]
+        s['ep_travel_distance'] = f[LY.AF_EP_TRAVEL_DIST]; s['ep_min_distance'] = f[LY.AF_EP_MIN_DIST]
+        s['action_diff'] = f[LY.AF_ACTION_DIFF]
+        s['reached_goal'] = i[LY.AI_REACHED]; s['done'] = i[LY.AI_DONE].astype(bool)
+        s['safety_filtered'] = i[LY.AI_SAFETY_FILTERED].astype(bool)
+        s['deconflicting_agent_index'] = i[LY.AI_DECONFLICT_IDX]
+        s['num_agent_collisions'] = i[LY.AI_NUM_COLLISIONS].astype(np.float64)
+        s['ep_travel_length'] = i[LY.AI_EP_TRAVEL_LEN].astype(np.float64)
+        s['ep_conflict'] = i[LY.AI_EP_CONFLICT].astype(np.float64)
+        s['ep_multi_engagement'] = i[LY.AI_EP_MULTI].astype(np.float64)
+        s['ep_done'] = i[LY.AI_EP_DONE].astype(np.float64)
+        s['landmark_pos'] = np.stack([lm[LY.LF_X], lm[LY.LF_Y]], axis=-1)
+        s['landmark_heading'] = lm[LY.LF_HEADING]; s['landmark_speed'] = lm[LY.LF_SPEED]
+        s['curriculum_ratio'] = ef[LY.EF_CURRICULUM_RATIO]; s['current_step'] = ei[LY.EI_CURRENT_STEP]
+        return s
+
+    # ------------------------------------------------------------------------------------------
+    def episode_stats(self, reduce_group=None) -> dict:
+        """Mean of the last reported episode summaries over the envs of this shard; with
+        `reduce_group` (torch.distributed) the mean over all shards (NCCL all_reduce of 9 floats)."""
+        s = torch.cat([self.ep_info.sum(dim=0), torch.tensor([float(self.n)], dtype=torch.float64, device=self.device)])
+        if reduce_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=reduce_group if reduce_group is not True else None)
+        vals = (s[:-1] / s[-1]).cpu().numpy()
+        return {k: float(vals[j]) for j, k in enumerate(LY.EP_INFO_KEYS)}

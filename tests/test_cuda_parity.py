@@ -1,0 +1,187 @@
+"""GPU: the CUDA environment (through the C ABI) against (1) the golden rollouts of the unmodified
+reference and (2) the C oracle on batches of seeded environments.
+
+Bar: adjacency pattern, done flags, goal counters, filter masks, deconflicting indices, collision and
+episode counters bit-exact; continuous values within 1e-5 relative (tests/_golden.RTOL)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+import _golden as G
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'oracle'))
+
+pytestmark = pytest.mark.gpu
+
+CASES = G.golden_names()
+
+
+class CudaAdapter:
+    """Gives the CUDA env the attribute surface the shared check_step helper expects."""
+
+    def __init__(self, args, flags, n=1, seed=0, auto_reset=False):
+        import torch
+        from layered_safe_marl_b200 import B200GraphVecEnv
+        self.torch = torch
+        self.env = B200GraphVecEnv(args, num_envs=n, seed=seed, binary_cfg=flags, auto_reset=auto_reset)
+
+    def set_state(self, s):
+        self.env.set_state(s)
+
+    def get_state(self):
+        return self.env.get_state()
+
+    def step(self, actions, episode=0):
+        self.env.step(self.torch.as_tensor(np.asarray(actions), dtype=self.torch.int32, device=self.env.device), episode)
+        self.torch.cuda.synchronize()
+
+    def observe(self):
+        self.env.observe()
+        self.torch.cuda.synchronize()
+
+    def reset_from_state(self, episode):
+        self.env.reset_from_state(episode)
+        self.torch.cuda.synchronize()
+
+    @property
+    def obs(self): return self.env.obs.cpu().numpy()
+    @property
+    def node_obs(self): return self.env.node_obs.cpu().numpy()
+    @property
+    def adj(self): return self.env.adj.cpu().numpy()
+    @property
+    def reward(self): return self.env.reward.cpu().numpy()
+    @property
+    def done(self): return self.env.done.cpu().numpy()
+    @property
+    def ep_info(self): return self.env.ep_info.cpu().numpy()
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_golden_reset_observation(name):
+    z, meta, args, flags, params = G.load_case(name)
+    env = CudaAdapter(args, flags)
+    env.set_state(G.state0(z))
+    env.observe()
+    G.assert_close(env.obs[0], z['obs0'], 'obs0')
+    G.assert_close(env.node_obs[0], z['node_obs0'], 'node_obs0')
+    G.assert_same_mask(env.adj[0] != 0, z['adj0'] != 0, 'adj0 pattern')
+    G.assert_close(env.adj[0], z['adj0'], 'adj0')
+
+
+@pytest.mark.parametrize('name', CASES)
+def test_golden_rollout(name):
+    from test_oracle_golden import rollout_with_tie_policy
+    z, meta, args, flags, params = G.load_case(name)
+    env, ties = rollout_with_tie_policy(lambda: CudaAdapter(args, flags), z, meta, name,
+                                        lambda e, a: e.step(a, episode=meta['episode']))
+    if ties:
+        print(f"{name}: roundoff ties at {ties}")
+    else:
+        env.reset_from_state(meta['episode'])
+        G.assert_close(env.ep_info[0], z['ep_info'], f'{name} ep_info')
+
+
+def _compare_with_oracle(args, flags, n, T, episode, seed, auto_reset, max_bad_env_fraction=0.0):
+    """Same Philox-seeded resets and the same actions through the CUDA env and the C oracle."""
+    import torch
+    import oracle_env as O
+    from layered_safe_marl_b200 import config as cfg
+    params = cfg.scenario_params_from_args(args, binary_cfg=flags)
+    vg, tg = G.value_grid_for(params)
+    ora = O.OracleEnv(params.asdict(), n, value_grid=vg, ttr_grid=tg, seed=seed, nthreads=8)
+    cu = CudaAdapter(args, flags, n=n, seed=seed, auto_reset=auto_reset)
+    ora.reset(episode=episode, sample=True)
+    cu.env.reset(episode)
+    torch.cuda.synchronize()
+    rng = np.random.default_rng(seed + 7)
+    bad_envs = np.zeros(n, dtype=bool)
+
+    def compare(tag):
+        so, sc = ora.get_state(), cu.get_state()
+        ok = ~bad_envs
+        for k in ('reached_goal', 'done', 'safety_filtered', 'deconflicting_agent_index', 'num_agent_collisions',
+                  'ep_travel_length', 'ep_conflict', 'ep_multi_engagement', 'ep_done', 'current_step'):
+            a, b = np.asarray(so[k]), np.asarray(sc[k])
+            diff = (a != b).reshape(n, -1).any(axis=1)
+            bad_envs[:] |= diff
+        a, b = ora.adj != 0, cu.adj != 0
+        bad_envs[:] |= (a != b).reshape(n, -1).any(axis=1)
+        bad_envs[:] |= (ora.done != cu.done).reshape(n, -1).any(axis=1)
+        ok = ~bad_envs
+        if ok.any():
+            for k in ('agent_values', 'p_dist', 'min_relative_distance', 'times_required', 'dists_to_goal',
+                      'dist_left_to_goal', 'ep_travel_distance', 'ep_min_distance', 'action_diff',
+                      'landmark_pos', 'landmark_heading', 'landmark_speed', 'curriculum_ratio'):
+                G.assert_close(np.asarray(sc[k])[ok], np.asarray(so[k])[ok], f'{tag} {k}')
+            G.assert_close(cu.obs[ok], ora.obs[ok], f'{tag} obs')
+            G.assert_close(cu.node_obs[ok], ora.node_obs[ok], f'{tag} node_obs')
+            G.assert_close(cu.adj[ok], ora.adj[ok], f'{tag} adj')
+            G.assert_close(cu.reward[ok], ora.reward[ok], f'{tag} reward')
+
+    compare('reset')
+    assert not bad_envs.any(), "reset state differs between CUDA and oracle"
+    for t in range(T):
+        a = rng.integers(0, 25, (n, params.num_agents)).astype(np.int32)
+        ora.step(a, episode=episode, auto_reset=auto_reset)
+        cu.step(a, episode=episode)
+        compare(f't={t}')
+        G.assert_close(cu.ep_info[~bad_envs], ora.ep_info[~bad_envs], f't={t} ep_info')
+    frac = bad_envs.mean()
+    assert frac <= max_bad_env_fraction, f"{bad_envs.sum()} of {n} envs diverged in a discrete output ({frac:.2e})"
+    return ora, cu
+
+
+def test_oracle_batch_di_filter():
+    """BASELINE config 2 shape (DI, 8 agents, filter on) on 512 seeded envs, 25 steps."""
+    args = G.default_args(num_agents=8, use_safety_filter=True, episode_length=250, world_size=4)
+    _compare_with_oracle(args, G.BinaryFlags({}), n=512, T=25, episode=6249, seed=11, auto_reset=True)
+
+
+def test_oracle_batch_di_nofilter_autoreset():
+    """Config 1 shape with short episodes so that device-side auto-reset (Philox sampler) is exercised."""
+    args = G.default_args(num_agents=3, use_safety_filter=False, episode_length=6, world_size=4)
+    _compare_with_oracle(args, G.BinaryFlags({}), n=257, T=20, episode=0, seed=5, auto_reset=True)
+
+
+def test_oracle_batch_di_allflags():
+    args = G.default_args(num_agents=5, use_safety_filter=True, episode_length=10, world_size=2, collaborative=True)
+    flags = G.BinaryFlags(dict(SAFETY_VIOLATION=True, HJ_VALUE=True, POTENTIAL_CONFLICT=True,
+                               SEPARATION_DISTANCE_CURRICULUM=True, INITIAL_PHASE_USE_SAFETY_FILTER=True,
+                               DIFF_FROM_FILTERED_ACTION=True))
+    _compare_with_oracle(args, flags, n=300, T=25, episode=3500, seed=3, auto_reset=True, max_bad_env_fraction=0.01)
+
+
+def test_oracle_batch_airtaxi_filter_pc():
+    """BASELINE config 3 shape (airtaxi, 10 agents, POTENTIAL_CONFLICT, filter on), obstacle-free."""
+    args = G.default_args(dynamics_type='airtaxi', num_agents=10, use_safety_filter=True, episode_length=350, world_size=6)
+    _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=True)), n=256, T=25, episode=6249, seed=2,
+                         auto_reset=True, max_bad_env_fraction=0.01)
+
+
+def test_oracle_batch_dense32():
+    """BASELINE config 4 shape (32 agents, E=96) on a few envs."""
+    args = G.default_args(num_agents=32, use_safety_filter=True, episode_length=250, world_size=4)
+    _compare_with_oracle(args, G.BinaryFlags({}), n=24, T=6, episode=6249, seed=9, auto_reset=True)
+
+
+def test_onehot_actions_and_numpy_outputs():
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    args = G.default_args(num_agents=4, use_safety_filter=False, episode_length=25)
+    e1 = B200GraphVecEnv(args, num_envs=33, seed=1)
+    e2 = B200GraphVecEnv(args, num_envs=33, seed=1, numpy_outputs=True)
+    e1.reset(0); e2.reset(0)
+    rng = np.random.default_rng(0)
+    for _ in range(5):
+        idx = rng.integers(0, 25, (33, 4))
+        onehot = np.eye(25)[idx]            # what GMPERunner.collect builds (graph_mpe_runner.py:431-433)
+        o1 = e1.step(torch.as_tensor(idx, device=e1.device))
+        o2 = e2.step(onehot)
+        assert isinstance(o2[0], np.ndarray) and o2[0].dtype == np.float32
+        for a, b in zip(o1[:6], o2[:6]):
+            np.testing.assert_array_equal(a.cpu().numpy(), b)
+    infos = o2[6]
+    assert len(infos) == 33 and len(infos[0]) >= 4 and 'Safety filtered' in infos[0][0]
