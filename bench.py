@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the fused step kernel on BASELINE.json's headline configuration.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|cfg3|cfg4|cfg1]
+
+A "step" is one `env.step` of every environment of the shard (BASELINE configs[1]: double
+integrator, 8 agents, 2 landmarks per agent, HJ safety filter on with the synthetic value grid,
+4096 environments per GPU). Prints ONE JSON line (rank 0).
+
+  value     agent-steps/s, whole job, actions already resident in HBM, CUDA-event timed per step with
+            an L2 flush between timed steps; max over ranks.
+  e2e       the same metric through the public API the reference's runner calls
+            (B200GraphVecEnv.step with HOST one-hot actions in pinned memory, every returned array
+            copied back to pinned host memory) - host<->device copies inside the timed region.
+  roofline  algorithmic bytes per launch / mean kernel time vs the measured HBM copy peak.
+  cpu_baseline   the C oracle (a port of the reference's Python path) on this box's host cores, bounded sample.
+
+`--impl reference` times the CPU oracle port alone (the reference itself is Python and does not exist
+on the GPU box); rank 0 only.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+sys.path.insert(0, os.path.join(REPO, 'tests'))
+
+import numpy as np  # noqa: E402
+
+METRIC = "agent-steps/sec (graph obs + HJ filter on)"
+UNIT = "agent-steps/s"
+
+WORKLOADS = {
+    # name: (args overrides, RewardBinaryConfig switches, envs per GPU, episode index)
+    'cfg2': (dict(dynamics_type='double_integrator', num_agents=8, num_landmarks=2, use_safety_filter=True,
+                  world_size=4, episode_length=250), {}, 4096, 6249),
+    'cfg3': (dict(dynamics_type='airtaxi', num_agents=10, num_landmarks=2, use_safety_filter=True,
+                  world_size=6, episode_length=350), dict(POTENTIAL_CONFLICT=True), 16384, 6249),
+    'cfg4': (dict(dynamics_type='double_integrator', num_agents=32, num_landmarks=2, use_safety_filter=True,
+                  world_size=4, episode_length=250), {}, 8192, 6249),
+    'cfg1': (dict(dynamics_type='double_integrator', num_agents=3, num_landmarks=2, use_safety_filter=False,
+                  world_size=4, episode_length=25), {}, 4096, 0),
+}
+WORKLOAD_DESC = {
+    'cfg2': "BASELINE configs[1]: double integrator (crazyflie) 8 agents, HJ safety filter on (synthetic value grid "
+            "41x41x21x21), 4096 parallel envs per B200",
+    'cfg3': "BASELINE configs[2] (obstacle-free): airtaxi 10 agents, POTENTIAL_CONFLICT reward, filter on, 16384 envs per B200",
+    'cfg4': "BASELINE configs[3]: dense 32 agents, 8192 envs per B200",
+    'cfg1': "BASELINE configs[0] shape: double integrator 3 agents, filter off, 4096 envs per B200",
+}
+
+
+def algorithmic_bytes_per_env_step(N, L, D, F):
+    """fp32 outputs + fp64 state read/write + flags + action index."""
+    E = N * (1 + L)
+    return 4 * N * (E * F + E * E + D + 2) + 77 * N
+
+
+def measured_peak():
+    p = os.path.join(REPO, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        try:
+            with open(p) as f:
+                return float(json.load(f)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+        except Exception:
+            pass
+    return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    QUERY = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+             'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.QUERY}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.gpu_index)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ''
+        sm, smax, reasons = [], [], set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(',')]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_args(workload):
+    import _golden as G
+    kw, flags, n_envs, episode = WORKLOADS[workload]
+    return G.default_args(**kw), G.BinaryFlags(flags), n_envs, episode
+
+
+def oracle_throughput(workload, n_envs, steps, warmup, nthreads, seed=0):
+    """Time the C oracle port (reference algorithm on CPU) on a bounded sample."""
+    import _golden as G
+    sys.path.insert(0, os.path.join(REPO, 'oracle'))
+    import oracle_env as O
+    from layered_safe_marl_b200 import config as cfg
+    args, flags, _, episode = build_args(workload)
+    params = cfg.scenario_params_from_args(args, binary_cfg=flags)
+    vg, tg = G.value_grid_for(params)
+    env = O.OracleEnv(params.asdict(), n_envs, value_grid=vg, ttr_grid=tg, seed=seed, nthreads=nthreads)
+    env.reset(episode=episode, sample=True)
+    rng = np.random.default_rng(1234)
+    acts = rng.integers(0, 25, (warmup + steps, n_envs, params.num_agents)).astype(np.int32)
+    for t in range(warmup):
+        env.step(acts[t], episode=episode, auto_reset=True)
+    t0 = time.perf_counter()
+    for t in range(warmup, warmup + steps):
+        env.step(acts[t], episode=episode, auto_reset=True)
+    dt = time.perf_counter() - t0
+    return n_envs * params.num_agents * steps / dt, dt, params
+
+
+def run_reference(a):
+    """`--impl reference`: the CPU oracle port with every host thread; rank 0 only."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    n_sample = 1024
+    val, dt, params = oracle_throughput(a.workload, n_sample, a.steps, a.warmup, cores)
+    sample = f"{n_sample} envs x {a.steps} steps of {a.workload} on {cores} host threads (C oracle port of the reference's Python path)"
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+            "warmup": a.warmup, "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[a.workload], "sample_envs": n_sample},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+    from layered_safe_marl_b200 import B200GraphVecEnv
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    device = torch.device(f'cuda:{local_rank}')
+    torch.cuda.set_device(device)
+
+    args, flags, n_envs, episode = build_args(a.workload)
+    if a.envs:
+        n_envs = a.envs
+    env = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=1234, binary_cfg=flags,
+                          env_id_base=rank * n_envs)
+    N, L, D, F = env.N, env.L, env.D, env.F
+    K, W = a.steps, a.warmup
+    gen = torch.Generator(device=device); gen.manual_seed(1234 + rank)
+    actions = torch.randint(0, 25, (W + K, n_envs, N), generator=gen, device=device, dtype=torch.int32)
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # 256 MiB > 126 MB L2
+
+    env.reset(episode)
+    for t in range(W):
+        env.step(actions[t], episode)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    for t in range(K):
+        flush.fill_(0.0)                      # L2 flush between timed iterations (not timed)
+        starts[t].record()
+        env.step(actions[W + t], episode)     # ONE launch of lsm_fused_kernel
+        stops[t].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
+    total_ms = float(step_ms.sum())
+    # back-to-back (no flush) timing for reference
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(K):
+        env.step(actions[W + t], episode)
+    e1.record()
+    torch.cuda.synchronize()
+    noflush_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        tt = torch.tensor([total_ms, noflush_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, noflush_ms = float(tt[0]), float(tt[1])
+        stats = env.episode_stats(reduce_group=True)   # the only collective of this path: episode statistics
+    else:
+        stats = env.episode_stats()
+    total_envs = n_envs * world
+    value = total_envs * N * K / (total_ms / 1000.0)
+
+    # ---- e2e: host one-hot actions in, every returned array back to pinned host memory --------------
+    Ke = max(3, min(K, a.e2e_steps))
+    env_h = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=4321, binary_cfg=flags,
+                            env_id_base=rank * n_envs, numpy_outputs=True)
+    env_h.reset(episode)
+    rng = np.random.default_rng(99 + rank)
+    onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + 2, n_envs, N))]).pin_memory()
+    for t in range(2):
+        env_h.step(onehot_host[t].numpy(), episode)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s0.record()
+    chk = 0.0
+    for t in range(Ke):
+        out = env_h.step(onehot_host[2 + t].numpy(), episode)
+        chk += float(out[4][0, 0])            # touch the host result
+    s1.record()
+    torch.cuda.synchronize()
+    e2e_ms = s0.elapsed_time(s1)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt[0])
+    e2e_value = total_envs * N * Ke / (e2e_ms / 1000.0)
+    h2d = n_envs * N * 25 * 4
+    d2h = n_envs * (N * D * 4 + N * 4 + N * env.E * F * 4 + N * env.E * env.E * 4 + N * 4 + N)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant (only) kernel -------------------------------------------------
+    peak, peak_src = measured_peak()
+    bytes_per_launch = algorithmic_bytes_per_env_step(N, L, D, F) * n_envs
+    mean_kernel_s = float(step_ms.mean()) / 1000.0
+    achieved = bytes_per_launch / mean_kernel_s / 1e9
+    traffic = None
+    tp = os.path.join(REPO, 'profiles', 'traffic_r01.json')
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                traffic = json.load(f).get(a.workload)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel": "lsm_fused_kernel",
+                "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": float(step_ms.mean()),
+                "median_launch_ms": float(np.median(step_ms))}
+
+    # ---- CPU baseline (bounded sample) ----------------------------------------------------------
+    cpu = None
+    if not a.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        n_s = 512
+        probe, dtp, _ = oracle_throughput(a.workload, n_s, 3, 1, cores)
+        steps_s = int(max(5, min(400, 12.0 / max(dtp / 3, 1e-6))))
+        val, dts, _ = oracle_throughput(a.workload, n_s, steps_s, 2, cores)
+        cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"{n_s} envs x {steps_s} steps of {a.workload} ({dts:.1f} s) with the C oracle port of the "
+                         f"reference's Python path on {cores} host threads; the Python reference itself measured "
+                         f"1.0e3 agent-steps/s on 8 cores (BASELINE.md)"}
+
+    li = env.launch_info()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD_DESC[a.workload], "envs_per_gpu": n_envs, "num_agents": N,
+                       "landmarks_per_agent": L, "entities": env.E, "value_grid": "synthetic (shape assumed)",
+                       "l2": "256 MiB flush between timed steps", "parallelism": f"env-shard x{world}",
+                       "launch": li},
+            "ms_per_step_back_to_back": noflush_ms / K,
+            "value_back_to_back": total_envs * N * K / (noflush_ms / 1000.0),
+            "wall_s_timed_loop": t_wall,
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": Ke, "ms_per_step": e2e_ms / Ke,
+                    "api": "B200GraphVecEnv.step(host one-hot float32 actions) -> host numpy obs/agent_id/node_obs/adj/rewards/dones"},
+            "gpu_launches": K,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "episode_stats": stats}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=200)
+    ap.add_argument('--warmup', type=int, default=20)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload’s)')
+    ap.add_argument('--e2e-steps', type=int, default=20)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    a = ap.parse_args()
+    if a.warmup < 3:
+        a.warmup = 3
+    if a.impl == 'reference':
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == '__main__':
+    main()

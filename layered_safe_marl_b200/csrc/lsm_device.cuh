@@ -79,7 +79,8 @@ __device__ __forceinline__ double norm2(double a, double b) { return sqrt(a * a 
 __device__ __forceinline__ double f32r(double v) { return (double)(float)v; }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10, identical stream to oracle/lsm_oracle.c so that device resets are checkable
+// Philox4x32-10 (Salmon et al. 2011): counter based, keyed by (seed, env, reset_count), so a device
+// reset can be replayed exactly by an independent CPU implementation of the same generator
 // ---------------------------------------------------------------------------------------------
 struct Rng {
     uint32_t k0, k1, env, reset_count, block;

@@ -173,6 +173,7 @@ class B200GraphVecEnv:
         self._act_dev = None
         self._pending_actions = None
         self._pending_episode = None
+        self._host_out = None
         self.closed = False
 
     # ------------------------------------------------------------------------------------------
@@ -222,8 +223,26 @@ class B200GraphVecEnv:
         if with_step:
             outs += [self.reward, self.done.view(torch.bool)]
         if self.numpy_outputs:
-            # host copies like the reference returns (float64 there; float32 here - every consumer casts)
-            return [t.cpu().numpy() for t in outs]
+            # host arrays like the reference returns (float64 there; float32 here - every consumer casts).
+            # Staged through pinned buffers that are reused every step: valid until the next step/reset.
+            if self._host_out is None:
+                self._host_out = {}
+            res = []
+            for t in outs:
+                key = t.data_ptr()
+                if t is self.agent_id:
+                    if self._agent_id_np is None:
+                        self._agent_id_np = t.cpu().numpy()
+                    res.append(self._agent_id_np)
+                    continue
+                hb = self._host_out.get(key)
+                if hb is None:
+                    hb = torch.empty(t.shape, dtype=t.dtype, device='cpu').pin_memory()
+                    self._host_out[key] = hb
+                hb.copy_(t, non_blocking=True)
+                res.append(hb)
+            torch.cuda.current_stream(self.device).synchronize()
+            return [r if isinstance(r, np.ndarray) else r.numpy() for r in res]
         if copy:
             return [t.clone() for t in outs]
         return outs
@@ -352,10 +371,10 @@ class B200GraphVecEnv:
     # ------------------------------------------------------------------------------------------
     def episode_stats(self, reduce_group=None) -> dict:
         """Mean of the last reported episode summaries over the envs of this shard; with
-        `reduce_group` (torch.distributed) the mean over all shards (NCCL all_reduce of 9 floats)."""
-        s = torch.cat([self.ep_info.sum(dim=0), torch.tensor([float(self.n)], dtype=torch.float64, device=self.device)])
-        if reduce_group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(s, op=dist.ReduceOp.SUM, group=reduce_group if reduce_group is not True else None)
-        vals = (s[:-1] / s[-1]).cpu().numpy()
-        return {k: float(vals[j]) for j, k in enumerate(LY.EP_INFO_KEYS)}
+        `reduce_group` (True = default group, or a torch.distributed group) the mean over all shards
+        (one NCCL all_reduce of 9 doubles - the only collective of this path)."""
+        from .sharding import allreduce_episode_stats
+        if reduce_group is None:
+            vals = self.ep_info.mean(dim=0).cpu().numpy()
+            return {k: float(vals[j]) for j, k in enumerate(LY.EP_INFO_KEYS)}
+        return allreduce_episode_stats(self.ep_info, None if reduce_group is True else reduce_group)
