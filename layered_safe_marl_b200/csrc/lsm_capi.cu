@@ -2,6 +2,7 @@
 // Host-only logic: validation, shared-memory layout, lookup tables, launch geometry.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -38,6 +39,11 @@ struct lsm_handle {
     uint32_t* d_sel_tab = nullptr;
     size_t persist_bytes = 0;
     size_t max_window = 0;
+    bool spec = false;          // compile-time specialised kernel available for (dynamics, N, L)
+    int bytes_per_env = 0;      // shared memory of one environment record
+    int epw_max = 1;            // 32 / G
+    int smem_optin = 0;
+    int forced_epw = 0;         // LSM_EPW environment override (experiments)
 };
 
 extern "C" {
@@ -87,6 +93,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     kp.F = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
     kp.G = next_pow2(N);
     kp.EPW = 32 / kp.G;
+    h->epw_max = kp.EPW;
     kp.W = (E + 31) / 32;
     kp.adj_vec = (E % 4 == 0) ? 4 : 1;
     for (int k = 0; k < 5; ++k) {
@@ -94,7 +101,15 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
         const double phase = stair * 0.5 * lsm::kPi;
         kp.sep_ratio_tab[k] = 1.0 - std::cos(phase);
     }
-    // shared-memory layout of one environment
+    // exact squared radius: d < R  <=>  d2 < r2_lt for d = sqrt_rn(d2)  (sqrt_rn is monotone)
+    {
+        const double R = cfg->coordination_range;
+        double t = R * R;
+        while (std::sqrt(t) >= R) t = std::nextafter(t, 0.0);
+        while (std::sqrt(t) < R) t = std::nextafter(t, INFINITY);
+        kp.r2_lt = t;
+    }
+    // shared-memory layout of one environment (generic kernel; the specialised kernels use a struct)
     lsm::SmemLayout& sl = kp.sl;
     int off = 0;
     auto take = [&](int bytes, int align) { off = align_up(off, align); int o = off; off += bytes; return o; };
@@ -112,28 +127,50 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.disc_pre = take(4 * kp.W, 4); sl.disc_post = take(4 * kp.W, 4);
     sl.keepm = take(4 * N * kp.W, 4);
     sl.bytes_per_env = align_up(off, 16);
-    kp.smem_per_warp = sl.bytes_per_env * kp.EPW;
+    h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    // launch geometry: as many warps per block as fit ~100 KB so that two blocks share an SM
-    int wpb = (100 * 1024) / kp.smem_per_warp;
-    if (wpb > 8) wpb = 8;
-    if (wpb < 1) wpb = 1;
-    h->warps_per_block = wpb;
-    h->block_threads = 32 * wpb;
-    h->smem_per_block = kp.smem_per_warp * wpb;
-    if ((size_t)h->smem_per_block > (size_t)prop.sharedMemPerBlockOptin) {
+    int spec_bytes = 0, spec_block = 0;
+    const char* force_generic = std::getenv("LSM_FORCE_GENERIC");
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &spec_bytes, &spec_block) &&
+              !(force_generic != nullptr && force_generic[0] == '1');
+    const char* fe = std::getenv("LSM_EPW");
+    h->forced_epw = fe ? std::atoi(fe) : 0;
+    if (h->spec) {
+        h->bytes_per_env = spec_bytes;
+        int wpb = spec_block / 32;
+        while (wpb > 1 && spec_bytes * wpb > h->smem_optin) --wpb;     // 32-agent records are ~60 KB each
+        h->warps_per_block = wpb;
+        h->block_threads = 32 * wpb;
+    } else {
+        h->bytes_per_env = sl.bytes_per_env;
+        // as many warps per block as fit ~100 KB so that two blocks share an SM
+        kp.smem_per_warp = sl.bytes_per_env * kp.EPW;
+        int wpb = (100 * 1024) / kp.smem_per_warp;
+        if (wpb > 8) wpb = 8;
+        if (wpb < 1) wpb = 1;
+        h->warps_per_block = wpb;
+        h->block_threads = 32 * wpb;
+    }
+    // provisional geometry (re-evaluated in lsm_bind_buffers once num_envs is known)
+    if (h->spec) kp.EPW = 1;
+    kp.smem_per_warp = h->bytes_per_env * kp.EPW;
+    h->smem_per_block = kp.smem_per_warp * h->warps_per_block;
+    if (h->smem_per_block > h->smem_optin) {
         delete h;
         return fail(4, "lsm_create: one environment group does not fit in shared memory");
     }
-    e = lsm::fused_kernel_prepare(cfg->dynamics, h->smem_per_block, h->block_threads, &h->regs, &h->blocks_per_sm);
-    if (e != cudaSuccess) { delete h; return cuda_fail(e, "fused_kernel_prepare"); }
+    e = lsm::kernel_prepare(cfg->dynamics, N, L, h->spec, h->smem_per_block, h->block_threads, &h->regs, &h->blocks_per_sm);
+    if (e != cudaSuccess) { delete h; return cuda_fail(e, "kernel_prepare"); }
     if (h->blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: kernel does not fit on an SM"); }
     h->grid_cap = h->sm_count * h->blocks_per_sm;
 
     // lookup tables
     std::vector<uint16_t> pairs;
     pairs.reserve((size_t)E * (E - 1));
-    for (int a = 0; a < E; ++a) for (int b = a + 1; b < E; ++b) { pairs.push_back((uint16_t)a); pairs.push_back((uint16_t)b); }
+    for (int a = 0; a < E; ++a) for (int b = a + 1; b < E; ++b) {
+        if (h->spec && b < N) continue;   // the specialised kernels take agent-agent distances from the float64 block
+        pairs.push_back((uint16_t)a); pairs.push_back((uint16_t)b);
+    }
     kp.num_pairs = (int)(pairs.size() / 2);
     std::vector<uint32_t> sel((size_t)N * kp.W, 0u);
     for (int i = 0; i < N; ++i) for (int ent = 0; ent < E; ++ent) {
@@ -215,6 +252,39 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
         return fail(2, "lsm_bind_buffers: adj and node_obs must be 16-byte aligned");
     h->kp.b = *b;
     h->have_buffers = true;
+    if (h->spec) {
+        // Envs per warp is a launch choice. If even the densest packing needs more than one wave the batch is
+        // throughput-bound: pack epw_max envs per warp (fewest instructions per env). Otherwise take the
+        // SMALLEST packing whose warps are all resident at once (most parallelism inside the single wave).
+        int best_epw = h->epw_max, best_bps = 0;
+        const lsm_config& c = h->kp.c;
+        for (int epw = 1; epw <= h->epw_max; epw *= 2) {
+            const int smem = h->bytes_per_env * epw * h->warps_per_block;
+            if (smem > h->smem_optin) break;
+            int regs = 0, bps = 0;
+            cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, smem, h->block_threads, &regs, &bps);
+            if (e != cudaSuccess) return cuda_fail(e, "kernel_prepare");
+            if (bps < 1) break;
+            const long long ngroups = (b->num_envs + epw - 1) / epw;
+            const long long capacity = (long long)h->sm_count * bps * h->warps_per_block;
+            if (h->forced_epw == epw || (h->forced_epw == 0 && ngroups <= capacity)) { best_epw = epw; best_bps = bps; break; }
+            if (epw == h->epw_max) { best_epw = epw; best_bps = bps; }
+        }
+        if (best_bps == 0) {
+            // nothing fits in one wave: densest packing that fits in shared memory
+            int epw = h->epw_max;
+            while (epw > 1 && h->bytes_per_env * epw * h->warps_per_block > h->smem_optin) epw /= 2;
+            best_epw = epw;
+        }
+        h->kp.EPW = best_epw;
+        h->kp.smem_per_warp = h->bytes_per_env * best_epw;
+        h->smem_per_block = h->kp.smem_per_warp * h->warps_per_block;
+        cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, h->smem_per_block, h->block_threads,
+                                            &h->regs, &h->blocks_per_sm);
+        if (e != cudaSuccess) return cuda_fail(e, "kernel_prepare");
+        if (h->blocks_per_sm < 1) return fail(4, "lsm_bind_buffers: kernel does not fit on an SM");
+        h->grid_cap = h->sm_count * h->blocks_per_sm;
+    }
     return 0;
 }
 
@@ -244,8 +314,8 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
     if (blocks > h->grid_cap) blocks = h->grid_cap;
     const void* persist = (mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
-    cudaError_t e = lsm::fused_kernel_launch(kp, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
-                                             persist, h->persist_bytes);
+    cudaError_t e = lsm::kernel_launch(kp, h->spec, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
+                                       persist, h->persist_bytes);
     if (e != cudaSuccess) return cuda_fail(e, who);
     return 0;
 }

@@ -70,6 +70,7 @@ struct KParams {
     const uint16_t* pair_tab;  // [num_pairs][2] entity pairs a < b
     int num_pairs;
     const uint32_t* sel_tab;   // [N][W] entities whose owner agent is <= i
+    double r2_lt;              // smallest double whose correctly rounded sqrt is >= coordination_range
 };
 
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }

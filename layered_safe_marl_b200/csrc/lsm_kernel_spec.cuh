@@ -1,0 +1,783 @@
+// lsm_kernel_spec.cuh - step kernel specialised at compile time on (dynamics, N agents, L landmarks
+// per agent): constant-size shared-memory records, unrolled loops, immediate-offset stores.
+//
+// Differences from the generic kernel (same arithmetic for every thresholded quantity):
+//   * envs per warp (EPW) is a LAUNCH choice (1 .. 32/G): small batches run one environment per warp
+//     so that the whole batch is resident in one wave; large batches pack 32/G environments per warp.
+//   * the HJ value lookups run pair-parallel: every (ego, other) pair of the warp's environments is
+//     one lane-task (N*N tasks per env), results go to shared memory, the agent lane then takes the
+//     first minimum in `other` order exactly like np.argmin.
+//   * agent-agent distances (needed in float64 for thresholds) are pair-parallel too; agent-landmark
+//     and landmark-landmark distances only feed the float32 adjacency, so they use d^2 in float64
+//     against an EXACT squared threshold (host-computed smallest double whose correctly rounded sqrt
+//     is >= R) and a correctly rounded float32 sqrt for the stored value.
+//   * node features read float32 per-entity tables (sin/cos/speed of headings converted once per env).
+#pragma once
+#include "lsm_step_common.cuh"
+
+namespace lsm {
+
+template <int DYN, int N, int L>
+struct __align__(16) EnvShared {
+    static constexpr int M = N * L;
+    static constexpr int E = N + M;
+    static constexpr int W = (E + 31) / 32;
+    // agent state after the dynamics (as2/as3 hold the PRE-update velocity / heading+speed)
+    double ax[N], ay[N], as2[N], as3[N];
+    double vpre_x[N], vpre_y[N], vpost_x[N], vpost_y[N];   // world-frame velocity before / after own goal update
+    double spd_post[N], sth[N], cth[N];                    // airtaxi: speed after update, sin/cos(theta)
+    double rawx[N], rawy[N];                               // decoded raw controls
+    double lx[M], ly[M], lh[M], lsp[M], lsin[M], lcos[M];
+    double daa[N * N];                                     // agent-agent distances (P1: pre-integration, P2: post)
+    double fval[N * N];                                    // HJ value of (ego i, other j); +inf = out of range
+    float dthr[E * E];                                     // radius-thresholded distance matrix
+    float lsinf[M], lcosf[M], lspf[M];                     // float32 landmark tables for node features
+    int goal_pre[N], goal_post[N], reached_pre[N], reached_post[N], done_pre[N], done_post[N];
+    unsigned disc_pre[W], disc_post[W], keepm[N * W];
+    double cur_sep;                                        // scenario.separation_distance of this env (curriculum)
+    int cur_filter;                                        // world.use_safety_filter of this env (curriculum, Q5)
+};
+
+template <int N> struct Pow2 { static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
+
+// HJ value of one (ego, other) pair: safety_filter.py:192-201, 345-354
+template <int DYN, class S>
+__device__ __forceinline__ double pair_value(const KParams& kp, const Curriculum& q, const S& s, int i, int j) {
+    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    double rel[ND]; bool inr;
+    relative_state<DYN>(s.ax[i], s.ay[i], s.as2[i], s.as3[i], s.ax[j], s.ay[j], s.as2[j], s.as3[j], rel);
+    return hj_value<DYN>(kp, q, rel, inr);   // +inf when out of range
+}
+
+#define SAFP(f) (kp.b.agent_f64 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
+#define SAIP(f) (kp.b.agent_i32 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
+#define SEFP(f) (kp.b.env_f64 + (size_t)(f) * (size_t)n + (size_t)env)
+#define SEIP(f) (kp.b.env_i32 + (size_t)(f) * (size_t)n + (size_t)env)
+
+template <int DYN, int N, int L>
+__device__ __forceinline__ void emit_obs_row(const EnvShared<DYN, N, L>& S, int ai, int g, double x, double y,
+                                             double s2, double s3, float* o) {
+    // navigation_graph_safe.py:855-875, utils.py:114-137
+    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+        o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(S.lx[g] - x); o[3] = (float)(S.ly[g] - y);
+        o[4] = (float)S.lsin[g]; o[5] = (float)S.lcos[g]; o[6] = (float)S.lsp[g];
+    } else {
+        double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
+        const double rh = S.lh[g] - s2;
+        o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
+        o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
+    }
+}
+
+template <int DYN, int N, int L, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_constant__ KParams kp) {
+    using ES = EnvShared<DYN, N, L>;
+    constexpr int M = ES::M, E = ES::E, W = ES::W, EE = E * E;
+    constexpr int G = Pow2<N>::value;
+    constexpr int Dobs = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
+    constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
+    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const lsm_config& c = kp.c;
+    const int lane = threadIdx.x & 31;
+    const int warp_in_block = threadIdx.x >> 5;
+    const int warps_per_block = blockDim.x >> 5;
+    const int EPW = kp.EPW;                       // launch choice, 1 .. 32/G
+    const long long n = kp.b.num_envs;
+    const int le = lane / G;
+    const int ai = lane - le * G;
+    ES* const Sw = reinterpret_cast<ES*>(smem_raw) + (size_t)warp_in_block * EPW;   // this warp's env records
+    const bool lane_has_env = le < EPW;
+    ES& S = Sw[lane_has_env ? le : 0];
+    const unsigned group_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((le * G) & 31));
+    const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
+    const long long ngroups = (n + EPW - 1) / EPW;
+
+    for (long long grp = (long long)blockIdx.x * warps_per_block + warp_in_block; grp < ngroups;
+         grp += (long long)gridDim.x * warps_per_block) {
+        const long long env0 = grp * EPW;
+        const long long env = env0 + le;
+        bool env_on = lane_has_env && env < n;
+        if (kp.mode == MODE_RESET && kp.env_mask != nullptr && env_on) env_on = kp.env_mask[env] != 0;
+        const bool agent_on = env_on && ai < N;
+        if (__ballot_sync(0xffffffffu, env_on) == 0u) continue;
+        const int nenv = (int)((n - env0) < (long long)EPW ? (n - env0) : (long long)EPW);   // envs of this group
+
+        // ---------------- P0: load ----------------
+        double x = 0, y = 0, s2 = 0, s3 = 0, p_dist = 0, state_time = 0, min_rel = INFINITY, goal_min_time = INFINITY;
+        double times_req = -1, dists_goal = -1, dist_left = -1, ep_travel_dist = 0, ep_min_dist = INFINITY, action_diff = 0;
+        int reached = 0, done = 0, safety_filtered = 0, deconflict = -1, ncoll = 0;
+        int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0;
+        int current_step = 0, reset_count = 0, parity = 0;
+        double ratio = 0.0;
+        if (env_on) {
+            current_step = *SEIP(LSM_EI_CURRENT_STEP); reset_count = *SEIP(LSM_EI_RESET_COUNT);
+            parity = *SEIP(LSM_EI_PARITY); ratio = *SEFP(LSM_EF_CURRICULUM_RATIO);
+        }
+        if (agent_on) {
+            x = *SAFP(LSM_AF_X); y = *SAFP(LSM_AF_Y); s2 = *SAFP(LSM_AF_S2); s3 = *SAFP(LSM_AF_S3);
+            p_dist = *SAFP(LSM_AF_P_DIST); state_time = *SAFP(LSM_AF_STATE_TIME);
+            min_rel = *SAFP(LSM_AF_MIN_REL_DIST); goal_min_time = *SAFP(LSM_AF_GOAL_MIN_TIME);
+            times_req = *SAFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A);
+            dists_goal = *SAFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A);
+            dist_left = *SAFP(LSM_AF_DIST_LEFT); ep_travel_dist = *SAFP(LSM_AF_EP_TRAVEL_DIST);
+            ep_min_dist = *SAFP(LSM_AF_EP_MIN_DIST); action_diff = *SAFP(LSM_AF_ACTION_DIFF);
+            reached = *SAIP(LSM_AI_REACHED); done = *SAIP(LSM_AI_DONE);
+            safety_filtered = *SAIP(LSM_AI_SAFETY_FILTERED); deconflict = *SAIP(LSM_AI_DECONFLICT_IDX);
+            ncoll = *SAIP(LSM_AI_NUM_COLLISIONS); ep_len = *SAIP(LSM_AI_EP_TRAVEL_LEN);
+            ep_conflict = *SAIP(LSM_AI_EP_CONFLICT); ep_multi = *SAIP(LSM_AI_EP_MULTI); ep_done = *SAIP(LSM_AI_EP_DONE);
+        }
+        // landmark tables of the group's environments: contiguous runs per field
+        {
+            const int total = nenv * M;
+#pragma unroll
+            for (int f = 0; f < LSM_LF_COUNT; ++f) {
+                const double* src = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)env0) * (size_t)M;
+                for (int idx = lane; idx < total; idx += 32) {
+                    const int el = idx / M, m = idx - el * M;
+                    const double v = src[idx];
+                    ES& T = Sw[el];
+                    if (f == 0) T.lx[m] = v; else if (f == 1) T.ly[m] = v; else if (f == 2) T.lh[m] = v;
+                    else if (f == 3) { T.lsp[m] = v; T.lspf[m] = (float)v; }
+                    else if (f == 4) { T.lsin[m] = v; T.lsinf[m] = (float)v; }
+                    else { T.lcos[m] = v; T.lcosf[m] = (float)v; }
+                }
+            }
+        }
+        Curriculum q = curriculum(kp, ratio);
+        if (agent_on) {
+            S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
+            S.done_pre[ai] = done; S.reached_pre[ai] = reached;
+            if (ai == 0) { S.cur_sep = q.sep; S.cur_filter = q.world_filter ? 1 : 0; }
+        }
+        __syncwarp();
+
+        bool all_done_env = false;
+        const unsigned any_filter = __ballot_sync(0xffffffffu, env_on && q.world_filter);
+
+        if (kp.mode == MODE_STEP) {
+            // ---------------- P1: action decode, safety filter, dynamics ----------------
+            current_step += 1;
+            double raw0 = 0.0, raw1 = 0.0;
+            if (agent_on) {
+                int idx;
+                if (kp.action_idx != nullptr) idx = kp.action_idx[(size_t)env * N + ai];
+                else {   // np.argmax over the one-hot row: first maximum
+                    const float* row = kp.action_onehot + ((size_t)env * N + ai) * LSM_NUM_ACTIONS;
+                    idx = 0; float best = row[0];
+                    for (int k = 1; k < LSM_NUM_ACTIONS; ++k) { const float v = row[k]; if (v > best) { best = v; idx = k; } }
+                }
+                const int i0 = idx / 5, i1 = idx - i0 * 5;
+                raw0 = c.act_tab0[i0]; raw1 = c.act_tab1[i1];
+                S.rawx[ai] = raw0; S.rawy[ai] = raw1;
+            }
+            __syncwarp();
+            double safe0 = raw0, safe1 = raw1;
+            for (int it = 0; it < c.num_internal_step; ++it) {
+                if (any_filter != 0u) {
+                    // (a) pair-parallel: distance and HJ value of every (ego, other) pair of the group
+                    for (int t = lane; t < nenv * N * N; t += 32) {
+                        const int el = t / (N * N), r = t - el * (N * N);
+                        const int i = r / N, j = r - i * N;
+                        ES& T = Sw[el];
+                        if (!T.cur_filter || i == j || T.done_pre[i] || T.done_pre[j]) continue;
+                        const double ddx = T.ax[j] - T.ax[i], ddy = T.ay[j] - T.ay[i];
+                        T.daa[r] = sqrt(ddx * ddx + ddy * ddy);
+                        Curriculum qe = q;
+                        qe.sep = T.cur_sep;          // the only curriculum scalar the HJ value depends on
+                        T.fval[r] = pair_value<DYN>(kp, qe, T, i, j);
+                    }
+                    __syncwarp();
+                }
+                if (agent_on && q.world_filter) {
+                    // (b) np.argmin over the others (first minimum, ascending agent index), then resolve
+                    int filt = 0, dec = -1;
+                    safe0 = raw0; safe1 = raw1;
+                    if (!done) {
+                        double best_d = 0.0, best_v = 0.0; int kd = -1, kv = -1;
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            if (j == ai || S.done_pre[j]) continue;
+                            const double dist = S.daa[ai * N + j], v = S.fval[ai * N + j];
+                            if (kd < 0 || dist < best_d) { kd = j; best_d = dist; }
+                            if (kv < 0 || v < best_v) { kv = j; best_v = v; }
+                        }
+                        if (kv >= 0) {
+                            dec = kv;
+                            const bool kv_in_range = !isinf(best_v);
+                            filter_resolve<DYN>(kp, best_d, best_v, kv_in_range, x, y, s2, s3, S.ax[kv], S.ay[kv], S.as2[kv],
+                                                S.as3[kv], raw0, raw1, S.rawx[kv], S.rawy[kv], safe0, safe1, filt);
+                        }
+                    }
+                    deconflict = dec; safety_filtered = filt;
+                }
+                __syncwarp();   // everyone has read the pre-integration states
+                if (agent_on) {
+                    const double d0 = raw0 - safe0, d1 = raw1 - safe1;
+                    action_diff = sqrt(d0 * d0 + d1 * d1);
+                    if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time);
+                    S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
+                }
+                __syncwarp();
+            }
+            // ---------------- P2: agent-agent distances (pair-parallel), goal / reward / done ----------------
+            for (int t = lane; t < nenv * N * N; t += 32) {
+                const int el = t / (N * N), r = t - el * (N * N);
+                const int i = r / N, j = r - i * N;
+                ES& T = Sw[el];
+                const double dx = T.ax[i] - T.ax[j], dy = T.ay[i] - T.ay[j];
+                T.daa[r] = sqrt(dx * dx + dy * dy);
+            }
+            __syncwarp();
+            int goal_pre = 0, goal_post = 0, reached_post = reached, done_post = done;
+            double rew = 0.0;
+            double vpx = 0, vpy = 0, vqx = 0, vqy = 0;
+            double theta = 0, speed = 0;
+            if (agent_on) {
+                // core.py:696-709
+                double m = INFINITY;
+                if (!done) {
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const double d = S.daa[ai * N + j];
+                        if (j != ai && !S.done_pre[j] && d < m) m = d;
+                    }
+                }
+                min_rel = m;
+                theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
+                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
+                else { const double ct = cos(s2), st = sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                goal_pre = goal_index(reached, ai, N, M);
+                const double gx = S.lx[goal_pre], gy = S.ly[goal_pre], gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
+                emit_obs_row<DYN, N, L>(S, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+                // reward_reach_goal: navigation_graph_safe.py:691-791
+                const double he = direction_alignment_error(theta, gh);
+                const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
+                const double se = fabs(speed - gs);
+                const double sen = clipd(se / q.speed_thresh, 0.0, 1.0);
+                double cra = ratio_sloped(ratio, 0.25, 0.75);
+                if (use_filter_arg) cra = 1.0;
+                const bool reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
+                if (reached_now) {
+                    const double spr = 1.0 - sen;
+                    const double pdx = gx - x, pdy = gy - y;
+                    double cte = pdx * sin(theta) - pdy * cos(theta);
+                    const double nrm = norm2(pdx, pdy);
+                    cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
+                    cte = clipd(cte, 0.0, 1.0);
+                    const double pr = hpr * spr * (1.0 - cte);
+                    double goal_rew;
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) goal_rew = c.goal_rew * pr;
+                    else goal_rew = c.goal_rew * (pr * cra + (1.0 - cra));
+                    if (!done) rew += goal_rew;
+                }
+                if (!done) {
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        if (!use_filter_arg) {   // utils.py:323-349
+                            const double cg = cos(gh), sg = sin(gh);
+                            double rpx, rpy, rvx, rvy;
+                            rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
+                            const double dist = norm2(rpx, rpy);
+                            const double ang = atan2(rpy, rpx);
+                            const double ang_range = kPi / 6;
+                            rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
+                            const double rh = magnetic_heading(rpx, rpy, 2.0 * q.dist_thresh);
+                            double ref_speed = pymax(gs, 0.1);
+                            const double dr = clipd(dist / 1.5, 0.0, 1.0);
+                            ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
+                            const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
+                            const double err = norm2(ex, ey);
+                            double pen;
+                            if (cos(ang) < cos(ang_range)) pen = err;
+                            else {
+                                const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
+                                pen = err * (1.0 - ar) + dist * ar;
+                            }
+                            double hap = 3.0 * pen;
+                            hap = clipd(1.0 - q.sloped, 0.0, 1.0) * hap;
+                            rew -= hap;
+                        }
+                        if (use_filter_arg) rew -= 1.0; else rew -= 1.0 * q.sloped;
+                    } else {
+                        double rpx, rpy;
+                        rotate_into(x - gx, y - gy, cos(gh), sin(gh), rpx, rpy);
+                        const double rs[4] = { rpx, rpy, theta - gh, speed };
+                        Stencil<4> st;
+                        stencil_setup<4>(kp.tg, rs, st);
+                        double ttr = st.valid ? stencil_value<4>(kp.tg, st) : NAN;
+                        if (isnan(ttr)) ttr = kp.tg.ttr_max;
+                        rew -= 0.04 * ttr;
+                        rew -= sen * cra;
+                    }
+                }
+                // update_reached_goal_and_done (+ freeze_agent): navigation_graph_safe.py:658-675, 1091-1099
+                if (reached_now && !done) reached_post = reached + 1;
+                done_post = done;
+                vqx = vpx; vqy = vpy;
+                double s2q = s2, s3q = s3;
+                if (reached_post >= L) {
+                    done_post = 1;
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { s2q = 0.0; s3q = 0.0; vqx = 0.0; vqy = 0.0; }
+                    else { s3q = 0.0; vqx = s3q * S.cth[ai]; vqy = s3q * S.sth[ai]; }
+                }
+                goal_post = goal_index(reached_post, ai, N, M);
+                S.vpre_x[ai] = vpx; S.vpre_y[ai] = vpy; S.vpost_x[ai] = vqx; S.vpost_y[ai] = vqy;
+                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3q;
+                S.goal_pre[ai] = goal_pre; S.goal_post[ai] = goal_post;
+                S.reached_post[ai] = reached_post; S.done_post[ai] = done_post;
+                // keep the PRE-update state in as2/as3 (the HJ_VALUE term of later agents reads an agent that
+                // is not done, whose pre and post states coincide); the lane's registers take the post state
+                s2 = s2q; s3 = s3q;
+            }
+            __syncwarp();
+            if (agent_on) {
+                if (c.flags & LSM_FLAG_SAFETY_VIOLATION) {         // navigation_graph_safe.py:793-798
+                    double r = 0.0;
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        if (a == ai) continue;
+                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
+                        if (S.daa[ai * N + a] < q.sep && !adone) r += q.conflict_rew;
+                    }
+                    rew += r;
+                }
+                if (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) {       // navigation_graph_safe.py:800-823
+                    int count = 0; double pen = 0.0;
+                    for (int a = 0; a < N; ++a) {
+                        if (a == ai) continue;
+                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
+                        const double rd = S.daa[ai * N + a];
+                        if (rd < q.eng && !adone) {
+                            const double rx = S.ax[a] - x, ry = S.ay[a] - y;
+                            const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
+                            const double dir = atan2(ry, rx);
+                            const double vax = a < ai ? S.vpost_x[a] : S.vpre_x[a];
+                            const double vay = a < ai ? S.vpost_y[a] : S.vpre_y[a];
+                            double change = cos(dir) * (vax - vpx) + sin(dir) * (vay - vpy);
+                            change = fabs(pymin(0.0, change));
+                            pen += change * closeness;
+                            count += 1;
+                        }
+                    }
+                    if (count > 1) rew += q.multi_rew * pen;
+                }
+                if ((c.flags & LSM_FLAG_DIFF_FROM_FILTERED_ACTION) && use_filter_arg) {   // :825-828
+                    if (!done) rew += q.diff_rew * action_diff;
+                }
+                if (c.flags & LSM_FLAG_HJ_VALUE) {                 // :830-837, core.py:459-468
+                    double r = 0.0;
+                    for (int a = 0; a < N; ++a) {
+                        if (a == ai) continue;
+                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
+                        if (adone) continue;
+                        const double v = pair_value<DYN>(kp, q, S, ai, a);   // as2/as3 hold the pre-update states
+                        const double cvp = fabs(pymin(v - 0.4, 0.0));
+                        r += q.cvalue_rew * cvp;
+                    }
+                    rew += r;
+                }
+                rew = clipd(rew, c.min_reward, c.max_reward);
+
+                // episode statistics: environment.py:1004-1022
+                if (!done_post) {
+                    ep_len += 1;
+                    ep_travel_dist += norm2(vqx, vqy) * c.dt;
+                    int cnt = 0; bool have = false; double mn = INFINITY;
+#pragma unroll
+                    for (int j = 0; j < N; ++j) {
+                        const int jdisc = j <= ai ? S.done_post[j] : S.done_pre[j];
+                        double d = jdisc ? 0.0 : S.daa[ai * N + j];
+                        d = (d < c.coordination_range && d > 0.0) ? d : 0.0;
+                        if (d != 0.0) { have = true; if (d < c.engagement_distance_ref) cnt++; if (d < mn) mn = d; }
+                    }
+                    if (have) {
+                        if (cnt > 1) ep_multi += 1;
+                        if (mn < c.separation_distance_target) ep_conflict += 1;
+                        if (mn < ep_min_dist) ep_min_dist = mn;
+                    }
+                }
+                if (done_post) ep_done = 1;
+                // info_callback state: navigation_graph_safe.py:386-413 (post-update goal and velocity)
+                {
+                    const double gx = S.lx[goal_post], gy = S.ly[goal_post];
+                    const double dx = x - gx, dy = y - gy;
+                    const double dist = sqrt(dx * dx + dy * dy);
+                    if (times_req == -1.0) {
+                        // a set times_required freezes all three fields, so the goal test is only needed here
+                        const double th2 = theta_of<DYN>(s2, s3), sp2 = speed_of<DYN>(s2, s3);
+                        const bool r2 = goal_reached<DYN>(x, y, th2, sp2, gx, gy, S.lh[goal_post], S.lsp[goal_post], q);
+                        if (r2) times_req = (double)current_step * c.dt;
+                        dists_goal = p_dist; dist_left = dist;
+                    }
+#pragma unroll
+                    for (int a = 0; a < N; ++a) {
+                        if (a == ai) continue;
+                        if (S.daa[ai * N + a] < 1.05 * (0.050 + 0.050)) ncoll += 1;
+                    }
+                }
+            }
+            if (agent_on && kp.b.reward_individual != nullptr) kp.b.reward_individual[(size_t)env * N + ai] = (float)rew;
+            if (c.flags & LSM_FLAG_SHARED_REWARD) {     // environment.py:1032-1037, sequential sum in agent order
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < N; ++k) s += __shfl_sync(0xffffffffu, rew, (le * G + k) & 31);
+                rew = s;
+            }
+            const bool done_out = done_post || (current_step >= c.episode_length);   // environment.py:260-268
+            const unsigned not_done = __ballot_sync(0xffffffffu, agent_on && !done_out);
+            all_done_env = env_on && ((not_done & group_mask) == 0u);
+            if (agent_on) {
+                kp.b.reward[(size_t)env * N + ai] = (float)rew;
+                kp.b.done[(size_t)env * N + ai] = (uint8_t)done_out;
+                reinterpret_cast<double2*>(kp.b.safe_action)[(size_t)env * N + ai] = make_double2(safe0, safe1);
+            }
+            reached = reached_post; done = done_post;
+            parity ^= 1;
+        } else {
+            if (agent_on) {
+                double vx, vy;
+                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
+                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                const int g = goal_index(reached, ai, N, M);
+                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
+                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
+                S.goal_pre[ai] = g; S.goal_post[ai] = g;
+                S.reached_post[ai] = reached; S.done_post[ai] = done;
+            }
+            __syncwarp();
+        }
+
+        // ---------------- P3: reset (graphworker auto-reset or explicit) ----------------
+        const bool do_reset = (kp.mode == MODE_STEP && kp.flag && all_done_env) || (kp.mode == MODE_RESET && env_on);
+        const bool sample = (kp.mode == MODE_STEP) ? true : (kp.flag != 0);
+        const unsigned reset_lanes = __ballot_sync(0xffffffffu, do_reset);
+        if (reset_lanes != 0u) {
+            double s_len = 0, s_dist = 0, s_done = 0, s_reached = 0, s_conf = 0, s_min = 0, s_multi = 0, mn = INFINITY;
+            const double len_i = ep_len == 0 ? 1.0 : (double)ep_len;
+            for (int k = 0; k < N; ++k) {
+                const int src = (le * G + k) & 31;
+                s_len += (double)__shfl_sync(0xffffffffu, ep_len, src);
+                s_dist += __shfl_sync(0xffffffffu, ep_travel_dist, src);
+                s_done += (double)__shfl_sync(0xffffffffu, ep_done, src);
+                s_reached += (double)__shfl_sync(0xffffffffu, reached, src);
+                s_conf += __shfl_sync(0xffffffffu, (double)ep_conflict / len_i, src);
+                s_multi += __shfl_sync(0xffffffffu, (double)ep_multi / len_i, src);
+                const double md = __shfl_sync(0xffffffffu, ep_min_dist, src);
+                s_min += md;
+                if (md < mn) mn = md;
+            }
+            if (do_reset && ai == 0) {
+                double* out = kp.b.ep_info + (size_t)env * LSM_EP_COUNT;
+                out[LSM_EP_TRAVEL_TIME_MEAN] = c.dt * (s_len / N);
+                out[LSM_EP_TRAVEL_DISTANCE_MEAN] = s_dist / N;
+                out[LSM_EP_DONE_PERCENTAGE] = s_done / N;
+                out[LSM_EP_NUM_REACHED_GOAL_MEAN] = s_reached / N;
+                out[LSM_EP_CONFLICT_PERCENTAGE] = s_conf / N;
+                const double mm = s_min / N;
+                out[LSM_EP_MIN_DISTANCE_MEAN] = isinf(mm) ? c.coordination_range : mm;
+                out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
+                out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
+            }
+            if (do_reset) {
+                current_step = 0;
+                ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
+                q = curriculum(kp, ratio);
+            }
+            if (do_reset && sample && ai == 0) {
+                // Scenario.random_scenario: navigation_graph_safe.py:1199-1367, utils.py:39-68
+                Rng r; r.init(kp.seed, (uint32_t)(kp.b.env_id_base + env), (uint32_t)reset_count);
+                const double ws = c.world_size;
+                double cra = ratio_sloped(ratio, 0.25, 0.75);
+                if (use_filter_arg) cra = 1.0;
+                for (int i = 0; i < N; ++i) {
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        S.ax[i] = r.uniform(-0.8 * ws, 0.8 * ws);
+                        S.ay[i] = r.uniform(-0.8 * ws, 0.8 * ws);
+                        S.as2[i] = 0.0; S.as3[i] = 0.0;
+                    } else {
+                        const double xmin = -0.5 * ws;
+                        const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
+                        const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
+                        S.ax[i] = r.uniform(xmin, xmax); S.ay[i] = ry;
+                        const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
+                        S.as2[i] = r.uniform(0.0, 2.0 * kPi);
+                        S.as3[i] = sp;
+                    }
+                }
+                for (int i = 0; i < N; ++i) {
+                    double xlo, xhi, ylo, yhi, min_d, max_d;
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        xlo = -0.5 * ws; xhi = 0.5 * ws; ylo = -0.5 * ws; yhi = 0.5 * ws;
+                        min_d = 0.25 * c.coordination_range; max_d = 0.75 * c.coordination_range;
+                    } else {
+                        const double yw = 0.1 * (1.0 - cra) + 0.5 * cra;
+                        xlo = 0.0; xhi = 0.75 * ws; ylo = -yw * ws; yhi = yw * ws;
+                        min_d = 0.5 * c.coordination_range; max_d = c.coordination_range;
+                    }
+                    for (int l = 0; l < L; ++l) {
+                        double gx = 0.0, gy = 0.0;
+                        if (l > 0) {
+                            for (int j = 0; j < 1000; ++j) {
+                                gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi);
+                                double dm = INFINITY;
+                                for (int k = 0; k < l; ++k) {
+                                    const double d = norm2(S.lx[k * N + i] - gx, S.ly[k * N + i] - gy);
+                                    if (d < dm) dm = d;
+                                }
+                                if (dm > min_d && dm < max_d) break;
+                            }
+                        } else { gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi); }
+                        S.lx[l * N + i] = gx; S.ly[l * N + i] = gy;
+                    }
+                    if (i > 0) for (int l = 0; l < L; ++l) if (r.uniform(0.0, 1.0) < 0.5) {
+                        S.lx[l * N + i] = S.lx[l * N + i - 1]; S.ly[l * N + i] = S.ly[l * N + i - 1];
+                    }
+                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+                        if (S.lx[i] > S.lx[N + i]) {
+                            const double tx = S.lx[i], ty = S.ly[i];
+                            S.lx[i] = S.lx[N + i]; S.ly[i] = S.ly[N + i]; S.lx[N + i] = tx; S.ly[N + i] = ty;
+                        }
+                    }
+                    for (int l = 0; l < L - 1; ++l)
+                        S.lh[l * N + i] = atan2(S.ly[(l + 1) * N + i] - S.ly[l * N + i], S.lx[(l + 1) * N + i] - S.lx[l * N + i]);
+                    const double last_heading = S.lh[(L - 2) * N + i];
+                    const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
+                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
+                    } else {
+                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
+                        const double var = r.uniform(0.0, 1.0);
+                        if (!(var < pymin(cr, 1.0 - 0.2))) {
+                            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
+                            S.lsp[(L - 1) * N + i] = c.goal_speed_min;
+                        }
+                    }
+                    for (int l = 0; l < L - 1; ++l) {
+                        const double pr = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? cr * 0.25 * kPi : cra * 0.1 * kPi;
+                        S.lh[l * N + i] += r.uniform(-pr, pr);
+                    }
+                    S.lh[(L - 1) * N + i] = last_heading;
+                    for (int l = 0; l < L; ++l) {
+                        const int m = l * N + i;
+                        S.lsin[m] = sin(S.lh[m]); S.lcos[m] = cos(S.lh[m]);
+                        S.lsinf[m] = (float)S.lsin[m]; S.lcosf[m] = (float)S.lcos[m]; S.lspf[m] = (float)S.lsp[m];
+                    }
+                }
+            }
+            __syncwarp();
+            if (do_reset && agent_on) {
+                if (sample) { x = S.ax[ai]; y = S.ay[ai]; s2 = S.as2[ai]; s3 = S.as3[ai]; }
+                done = 0; reached = 0;
+                p_dist = 0.0; state_time = 0.0;
+                goal_min_time = norm2(x - S.lx[ai], y - S.ly[ai]) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
+                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
+                ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
+                double vx, vy;
+                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
+                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
+                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
+                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
+                S.goal_pre[ai] = ai; S.goal_post[ai] = ai;
+                S.reached_pre[ai] = 0; S.reached_post[ai] = 0; S.done_pre[ai] = 0; S.done_post[ai] = 0;
+                emit_obs_row<DYN, N, L>(S, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+            }
+            if (do_reset && sample) reset_count += 1;
+            __syncwarp();
+            if (sample) {
+                for (int el = 0; el < nenv; ++el) {
+                    if (!((reset_lanes >> ((el * G) & 31)) & 1u)) continue;
+                    const ES& T = Sw[el];
+#pragma unroll
+                    for (int f = 0; f < LSM_LF_COUNT; ++f) {
+                        const double* srcp = f == 0 ? T.lx : f == 1 ? T.ly : f == 2 ? T.lh : f == 3 ? T.lsp : f == 4 ? T.lsin : T.lcos;
+                        double* dst = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)(env0 + el)) * (size_t)M;
+                        for (int m = lane; m < M; m += 32) dst[m] = srcp[m];
+                    }
+                }
+            }
+        } else if (kp.mode == MODE_OBSERVE && agent_on) {
+            emit_obs_row<DYN, N, L>(S, ai, S.goal_pre[ai], x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+        }
+
+        // ---------------- state write-back ----------------
+        if (kp.mode != MODE_OBSERVE) {
+            if (env_on && ai == 0) {
+                *SEIP(LSM_EI_CURRENT_STEP) = current_step; *SEIP(LSM_EI_RESET_COUNT) = reset_count;
+                *SEIP(LSM_EI_PARITY) = parity; *SEIP(LSM_EI_JUST_RESET) = do_reset ? 1 : 0;
+                *SEFP(LSM_EF_CURRICULUM_RATIO) = ratio;
+            }
+            if (agent_on) {
+                *SAFP(LSM_AF_X) = x; *SAFP(LSM_AF_Y) = y; *SAFP(LSM_AF_S2) = s2; *SAFP(LSM_AF_S3) = s3;
+                *SAFP(LSM_AF_P_DIST) = p_dist; *SAFP(LSM_AF_STATE_TIME) = state_time;
+                *SAFP(LSM_AF_MIN_REL_DIST) = min_rel; *SAFP(LSM_AF_GOAL_MIN_TIME) = goal_min_time;
+                *SAFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) = times_req;
+                *SAFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) = dists_goal;
+                if (do_reset) {
+                    *SAFP(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) = times_req;
+                    *SAFP(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) = dists_goal;
+                }
+                *SAFP(LSM_AF_DIST_LEFT) = dist_left; *SAFP(LSM_AF_EP_TRAVEL_DIST) = ep_travel_dist;
+                *SAFP(LSM_AF_EP_MIN_DIST) = ep_min_dist; *SAFP(LSM_AF_ACTION_DIFF) = action_diff;
+                *SAIP(LSM_AI_REACHED) = reached; *SAIP(LSM_AI_DONE) = done;
+                *SAIP(LSM_AI_SAFETY_FILTERED) = safety_filtered; *SAIP(LSM_AI_DECONFLICT_IDX) = deconflict;
+                *SAIP(LSM_AI_NUM_COLLISIONS) = ncoll; *SAIP(LSM_AI_EP_TRAVEL_LEN) = ep_len;
+                *SAIP(LSM_AI_EP_CONFLICT) = ep_conflict; *SAIP(LSM_AI_EP_MULTI) = ep_multi; *SAIP(LSM_AI_EP_DONE) = ep_done;
+            }
+        }
+        __syncwarp();
+
+        // ---------------- P4: graph observation ----------------
+        for (int el = 0; el < nenv; ++el) {
+            const long long ee = env0 + el;
+            if (kp.mode == MODE_RESET && kp.env_mask != nullptr && kp.env_mask[ee] == 0) continue;
+            ES& T = Sw[el];
+            // (a) thresholded distance matrix. Agent-agent block from the float64 distances of P2 (recomputed
+            //     when the env was just reset or nothing was stepped) ...
+            const bool fresh_positions = (kp.mode != MODE_STEP) || ((reset_lanes >> ((el * G) & 31)) & 1u);
+            for (int r = lane; r < N * N; r += 32) {
+                const int i = r / N, j = r - i * N;
+                const double d = fresh_positions ? norm2(T.ax[i] - T.ax[j], T.ay[i] - T.ay[j]) : T.daa[r];
+                T.dthr[i * E + j] = (d < c.coordination_range && d > 0.0) ? (float)d : 0.0f;
+            }
+            // ... agent-landmark and landmark-landmark pairs: d^2 in float64 vs the exact squared threshold
+            constexpr int NPAIR = N * M + M * (M - 1) / 2;
+            for (int p = lane; p < NPAIR; p += 32) {
+                const unsigned short pa = kp.pair_tab[2 * p], pb = kp.pair_tab[2 * p + 1];   // pa < pb, pb >= N
+                const double pax = pa < N ? T.ax[pa] : T.lx[pa - N], pay = pa < N ? T.ay[pa] : T.ly[pa - N];
+                const double dx = pax - T.lx[pb - N], dy = pay - T.ly[pb - N];
+                const double d2 = dx * dx + dy * dy;
+                const float v = (d2 < kp.r2_lt && d2 > 0.0) ? __fsqrt_rn((float)d2) : 0.0f;
+                T.dthr[pa * E + pb] = v; T.dthr[pb * E + pa] = v;
+            }
+            for (int e = N + lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
+            // (b) disconnected-entity bit masks before / after this step's goal updates (ballots)
+            unsigned any_change = 0u;
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const int e = w * 32 + lane;
+                bool dpre = false, dpost = false;
+                if (e < N) { dpre = T.done_pre[e] != 0; dpost = T.done_post[e] != 0; }
+                else if (e < E) {
+                    const int m = e - N, order = m / N, owner = m - order * N;
+                    dpre = T.reached_pre[owner] > order; dpost = T.reached_post[owner] > order;
+                }
+                const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
+                if (lane == 0) { T.disc_pre[w] = bpre; T.disc_post[w] = bpost; }
+                any_change |= (bpre ^ bpost);
+            }
+            __syncwarp();
+            for (int k = lane; k < N * W; k += 32) {
+                const int w = k % W;
+                const unsigned sel = kp.sel_tab[k];
+                T.keepm[k] = ~((T.disc_post[w] & sel) | (T.disc_pre[w] & ~sel));
+            }
+            __syncwarp();
+            // (c) node features: one lane per (observer, entity) row
+            {
+                float* nbase = kp.b.node_obs + (size_t)ee * (N * E * F);
+                for (int r = lane; r < N * E; r += 32) {
+                    const int i = r / E, e = r - i * E;
+                    float* o = nbase + r * F;
+                    const double xi = T.ax[i], yi = T.ay[i];
+                    const double vix = T.vpost_x[i], viy = T.vpost_y[i];
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        float f0, f1, f2, f3, f4, f5, f6, f7, f8, f9;
+                        if (e < N) {
+                            const bool post = e <= i;
+                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
+                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
+                            f0 = (float)(T.ax[e] - xi); f1 = (float)(T.ay[e] - yi);
+                            f2 = (float)(vex - vix); f3 = (float)(vey - viy);
+                            f4 = (float)(T.lx[g] - xi); f5 = (float)(T.ly[g] - yi);
+                            f6 = T.lsinf[g]; f7 = T.lcosf[g]; f8 = T.lspf[g]; f9 = 0.0f;
+                        } else {
+                            const int m = e - N;
+                            f0 = (float)(T.lx[m] - xi); f1 = (float)(T.ly[m] - yi);
+                            f2 = (float)(-vix); f3 = (float)(-viy); f4 = f0; f5 = f1;
+                            f6 = T.lsinf[m]; f7 = T.lcosf[m]; f8 = T.lspf[m]; f9 = 1.0f;
+                        }
+                        float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
+                        o2[0] = make_float2(f0, f1); o2[1] = make_float2(f2, f3); o2[2] = make_float2(f4, f5);
+                        o2[3] = make_float2(f6, f7); o2[4] = make_float2(f8, f9);
+                    } else {
+                        const double ci = T.cth[i], si = T.sth[i];
+                        if (e < N) {
+                            const bool post = e <= i;
+                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
+                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
+                            double rx, ry, gx, gy;
+                            rotate_into(T.ax[e] - xi, T.ay[e] - yi, ci, si, rx, ry);
+                            rotate_into(T.lx[g] - xi, T.ly[g] - yi, ci, si, gx, gy);
+                            const double ce = T.cth[e], se = T.sth[e];
+                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(vex - vix, vey - viy);
+                            o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
+                            o[5] = (float)gx; o[6] = (float)gy;
+                            o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
+                            o[9] = T.lspf[g]; o[10] = 0.0f;
+                        } else {
+                            const int m = e - N;
+                            double rx, ry;
+                            rotate_into(T.lx[m] - xi, T.ly[m] - yi, ci, si, rx, ry);
+                            const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
+                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
+                            o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
+                            o[9] = T.lspf[m]; o[10] = 1.0f;
+                        }
+                    }
+                }
+            }
+            // (d) adjacency
+            {
+                float* abase = kp.b.adj + (size_t)ee * (N * EE);
+                const unsigned any_disc = [&] { unsigned a = 0u; for (int w = 0; w < W; ++w) a |= T.disc_post[w]; return a; }();
+                if (E % 4 == 0) {
+                    constexpr int CPR = E / 4, CHUNKS = EE / 4;
+                    for (int ch = lane; ch < CHUNKS; ch += 32) {
+                        const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
+                        const float4 v = *reinterpret_cast<const float4*>(T.dthr + a * E + b4);
+                        float* dst = abase + a * E + b4;
+                        if (any_disc == 0u) {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), v);
+                        } else if (any_change == 0u) {
+                            // no goal update this step: every observer sees the same mask
+                            const bool ka = (T.keepm[a >> 5] >> (a & 31)) & 1u;
+                            const unsigned nib = ka ? ((T.keepm[b4 >> 5] >> (b4 & 31)) & 0xFu) : 0u;
+                            float4 o;
+                            o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
+                            o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
+#pragma unroll
+                            for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                        } else {
+#pragma unroll
+                            for (int i = 0; i < N; ++i) {
+                                const bool ka = (T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u;
+                                const unsigned nib = ka ? ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu) : 0u;
+                                float4 o;
+                                o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
+                                o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
+                                __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                            }
+                        }
+                    }
+                } else {
+                    for (int idx = lane; idx < EE; idx += 32) {
+                        const int a = idx / E, b2 = idx - a * E;
+                        const float v = T.dthr[idx];
+#pragma unroll
+                        for (int i = 0; i < N; ++i) {
+                            const bool keep = ((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
+                                              ((T.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u);
+                            __stcs(abase + i * EE + idx, keep ? v : 0.0f);
+                        }
+                    }
+                }
+            }
+            __syncwarp();
+        }
+        __syncwarp();
+    }
+}
+
+}  // namespace lsm

@@ -1,974 +1,62 @@
-// lsm_kernels.cu - the fused step / reset / observe kernel for sm_100a.
+// lsm_kernels.cu - translation unit of the step kernels for sm_100a.
 //
-// Work decomposition ("warp per env group"): a warp owns EPW = 32 / G consecutive environments,
-// G = next power of two >= N lanes per environment. Per-agent phases (action decode, HJ safety
-// filter, dynamics, goal / reward / done logic, episode statistics) run one lane per agent; the
-// graph observation (pairwise distances, radius-limited adjacency, node features) is built in the
-// warp's shared-memory slice and written with all 32 lanes. There is no block-level barrier:
-// warps only __syncwarp(), so one warp's stores overlap another warp's HJ-grid gathers.
+//   lsm_kernel_spec.cuh     kernels specialised at compile time on (dynamics, N, L) - the fast path
+//   lsm_kernel_generic.cuh  run-time N / L fallback for every other configuration
+//   lsm_step_common.cuh     dynamics, HJ filter resolution, grid interpolation shared by both
+//
+// Work decomposition ("warp per env group"): a warp owns EPW consecutive environments, G = next power
+// of two >= N lanes per environment. Per-agent phases run one lane per agent; the graph observation
+// (pairwise distances, radius-limited adjacency, node features) is built in the warp's shared-memory
+// slice and written with all 32 lanes. There is no block-level barrier: warps only __syncwarp(), so
+// one warp's stores overlap another warp's HJ-grid gathers.
 //
 // The reference mutates goal counters / done flags / velocities agent by agent WHILE it emits
 // observations (multiagent/environment.py:979-1029). Each agent's own update depends only on its
-// own state, so here every lane computes its agent's pre- and post-update state in parallel and
-// an observer i selects "post" for agents <= i and "pre" for agents > i.
-#include "lsm_device.cuh"
+// own state, so every lane computes its agent's pre- and post-update state in parallel and an
+// observer i selects "post" for agents <= i and "pre" for agents > i.
+#include "lsm_kernel_generic.cuh"
+#include "lsm_kernel_spec.cuh"
+#include "lsm_host.h"
 
 namespace lsm {
-
-__constant__ double c_mag_cos[kMagSegments];
-__constant__ double c_mag_sin[kMagSegments];
-
-// utils.py:276-321, with cos/sin(phi_k) tabulated by the host
-__device__ double magnetic_heading(double px, double py, double radius) {
-    if (fabs(px) < 1e-6) return 0.0;
-    const double scale_x = 0.5;
-    px = scale_x * px;
-    double bx = 0.0, by = 0.0;
-    for (int k = 0; k < kMagSegments; ++k) {
-        const double c = c_mag_cos[k], s = c_mag_sin[k];
-        const double Ly = -radius * c, Lz = -radius * s;
-        const double dLy = radius * s, dLz = -radius * c;
-        const double rx = px - 0.0, ry = py - Ly, rz = 0.0 - Lz;
-        const double rmag = sqrt((rx * rx + ry * ry) + rz * rz);
-        const double rmag3 = rmag * rmag * rmag;
-        const double cx = dLy * rz - dLz * ry;
-        const double cy = dLz * rx - 0.0 * rz;
-        bx = bx + cx / rmag3;
-        by = by + cy / rmag3;
-    }
-    bx = bx / scale_x;
-    return atan2(by, bx);
-}
-
-struct EnvSmem {
-    double *ax, *ay, *as2, *as3, *vpre_x, *vpre_y, *vpost_x, *vpost_y, *spd_post, *sth, *cth, *rawx, *rawy;
-    double *lx, *ly, *lh, *lsp, *lsin, *lcos, *daa;
-    float* dthr;
-    int *goal_pre, *goal_post, *reached_pre, *reached_post, *done_pre, *done_post;
-    unsigned *disc_pre, *disc_post, *keepm;
-    __device__ __forceinline__ void bind(unsigned char* base, const SmemLayout& sl) {
-        ax = (double*)(base + sl.ax); ay = (double*)(base + sl.ay); as2 = (double*)(base + sl.as2); as3 = (double*)(base + sl.as3);
-        vpre_x = (double*)(base + sl.vpre_x); vpre_y = (double*)(base + sl.vpre_y);
-        vpost_x = (double*)(base + sl.vpost_x); vpost_y = (double*)(base + sl.vpost_y);
-        spd_post = (double*)(base + sl.spd_post); sth = (double*)(base + sl.sth); cth = (double*)(base + sl.cth);
-        rawx = (double*)(base + sl.rawx); rawy = (double*)(base + sl.rawy);
-        lx = (double*)(base + sl.lx); ly = (double*)(base + sl.ly); lh = (double*)(base + sl.lh);
-        lsp = (double*)(base + sl.lsp); lsin = (double*)(base + sl.lsin); lcos = (double*)(base + sl.lcos);
-        daa = (double*)(base + sl.daa); dthr = (float*)(base + sl.dthr);
-        goal_pre = (int*)(base + sl.goal_pre); goal_post = (int*)(base + sl.goal_post);
-        reached_pre = (int*)(base + sl.reached_pre); reached_post = (int*)(base + sl.reached_post);
-        done_pre = (int*)(base + sl.done_pre); done_post = (int*)(base + sl.done_post);
-        disc_pre = (unsigned*)(base + sl.disc_pre); disc_post = (unsigned*)(base + sl.disc_post);
-        keepm = (unsigned*)(base + sl.keepm);
-    }
-};
-
-__device__ __forceinline__ int goal_index(int reached, int i, int N, int M) {   // navigation_graph_safe.py:576-582
-    int order = reached * N + i;
-    if (order >= M) order = (reached - 1) * N + i;
-    return order;
-}
-
-// relative state between ego and other (safety_filter.py:277-284, 356-362)
-template <int DYN>
-__device__ __forceinline__ void relative_state(double ex, double ey, double e2, double e3, double ox, double oy,
-                                               double o2, double o3, double (&r)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5]) {
-    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-        r[0] = ex - ox; r[1] = ey - oy; r[2] = e2 - o2; r[3] = e3 - o3;
-    } else {
-        const double ddx = ox - ex, ddy = oy - ey;
-        const double dist = sqrt(ddx * ddx + ddy * ddy);
-        const double ang = atan2(ddy, ddx);
-        r[0] = dist * cos(ang - e2);
-        r[1] = dist * sin(ang - e2);
-        r[2] = o2 - e2; r[3] = e3; r[4] = o3;
-    }
-}
-
-template <int DYN>
-__device__ __forceinline__ double hj_value(const KParams& kp, const Curriculum& q,
-                                           const double (&rel)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5], bool& in_range) {
-    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-    Stencil<ND> st;
-    stencil_setup<ND>(kp.vg, rel, st);
-    if (!st.valid) { in_range = false; return INFINITY; }
-    const double v = stencil_value<ND>(kp.vg, st);
-    if (isnan(v)) { in_range = false; return INFINITY; }
-    in_range = true;
-    return v - (q.sep - kp.vg.separation_distance);
-}
-
-// World.apply_safety_filter for ONE ego agent (core.py:648-677; safety_filter.py:203-260, 378-433)
-template <int DYN>
-__device__ void safety_filter_agent(const KParams& kp, const Curriculum& q, const EnvSmem& S, int i, int N,
-                                    double raw0, double raw1, double& safe0, double& safe1, int& filtered, int& deconf) {
-    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-    const lsm_config& c = kp.c;
-    safe0 = raw0; safe1 = raw1; filtered = 0; deconf = -1;
-    const double ex = S.ax[i], ey = S.ay[i], e2 = S.as2[i], e3 = S.as3[i];
-    double best_d = 0.0, best_v = 0.0; int kd = -1, kv = -1; bool kv_in_range = false;
-    for (int j = 0; j < N; ++j) {
-        if (j == i || S.done_pre[j]) continue;
-        const double ox = S.ax[j], oy = S.ay[j];
-        const double ddx = ox - ex, ddy = oy - ey;
-        const double dist = sqrt(ddx * ddx + ddy * ddy);
-        double rel[ND]; bool inr;
-        relative_state<DYN>(ex, ey, e2, e3, ox, oy, S.as2[j], S.as3[j], rel);
-        const double v = hj_value<DYN>(kp, q, rel, inr);
-        if (kd < 0 || dist < best_d) { kd = j; best_d = dist; }
-        if (kv < 0 || v < best_v) { kv = j; best_v = v; kv_in_range = inr; }
-    }
-    if (kv < 0) return;                         // no other active agent
-    deconf = kv;
-    if (best_d > c.coordination_range) return;
-    if (!kv_in_range) return;
-    double rel[ND];
-    relative_state<DYN>(ex, ey, e2, e3, S.ax[kv], S.ay[kv], S.as2[kv], S.as3[kv], rel);
-    const double uref[4] = { raw0, raw1, S.rawx[kv], S.rawy[kv] };
-    double g[ND];
-    {
-        Stencil<ND> st;
-        stencil_setup<ND>(kp.vg, rel, st);
-        stencil_grad<ND>(kp.vg, st, g);
-    }
-    const double eps_hj = 0.4;
-    double u[4]; bool aliased = false;
-    const double dt = c.dt;
-    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-        const double a[4] = { g[2], g[3], -g[2], -g[3] };
-        if (best_v < eps_hj) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = (a[k] < 0.0) ? -0.5 : 0.5;
-        } else {
-            double b = g[0] * rel[2] + g[1] * rel[3];
-            b = b + c.cbf_rate * best_v;
-            const double pinv[4] = { 1.0, 1.0, 1.0, 1.0 };
-            if (!qp_project(a, b, uref, pinv, u)) {
-                aliased = true;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) u[k] = uref[k];
-            }
-        }
-        const double axmax = (rel[2] < 0.5 - dt * 0.5) ? 0.5 : 0.0;
-        const double axmin = (rel[2] > -0.5 - dt * (-0.5)) ? -0.5 : 0.0;
-        u[0] = pymax(pymin(u[0], axmax), axmin);
-        const double aymax = (rel[3] < 0.5 - dt * 0.5) ? 0.5 : 0.0;
-        const double aymin = (rel[3] > -0.5 - dt * (-0.5)) ? -0.5 : 0.0;
-        u[1] = pymax(pymin(u[1], aymax), aymin);
-    } else {
-        const double wmax = 0.1, amin = -0.001, amax = 0.002;
-        const double vmin = 60 * 0.514444 * 0.001, vmax = 175 * 0.514444 * 0.001;
-        double a[4];
-        a[0] = (g[0] * rel[1] + g[1] * (-rel[0])) + g[2] * (-1.0);
-        a[1] = g[2]; a[2] = g[3]; a[3] = g[ND - 1];
-        const bool bang = best_v < eps_hj;
-        if (bang) {
-            double lo[4] = { f32r(-wmax), f32r(-wmax), f32r(amin), f32r(amin) };
-            double hi[4] = { f32r(wmax), f32r(wmax), f32r(amax), f32r(amax) };
-            // cascade of whole-vector jnp.where selections (safety_filter.py:70-78): the LAST true one wins
-            int which = 0;
-            if (rel[3] <= vmin) which = 1;
-            if (rel[3] >= vmax) which = 2;
-            if (rel[ND - 1] <= vmin) which = 3;
-            if (rel[ND - 1] >= vmax) which = 4;
-            if (which == 1) lo[2] = 0.0;
-            if (which == 2) hi[2] = 0.0;
-            if (which == 3) lo[3] = 0.0;
-            if (which == 4) hi[3] = 0.0;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) u[k] = (a[k] < 0.0) ? lo[k] : hi[k];
-        } else {
-            const double f0 = -rel[3] + rel[ND - 1] * cos(rel[2]);
-            const double f1 = rel[ND - 1] * sin(rel[2]);
-            double b = g[0] * f0 + g[1] * f1;
-            b = b + c.cbf_rate * best_v;
-            double pinv[4];
-            if (rel[0] < 0.0) { pinv[0] = 1.0 / 100.0; pinv[1] = 1.0 / 10.0; pinv[2] = 1.0 / 10.0; pinv[3] = 1.0 / 1.0; }
-            else { pinv[0] = 1.0 / 10.0; pinv[1] = 1.0 / 1.0; pinv[2] = 1.0 / 100.0; pinv[3] = 1.0 / 10.0; }
-            if (!qp_project(a, b, uref, pinv, u)) {
-                aliased = true;
-#pragma unroll
-                for (int k = 0; k < 4; ++k) u[k] = uref[k];
-            } else {
-                u[0] = pymax(pymin(u[0], wmax), -wmax);
-                u[2] = pymax(pymin(u[2], wmax), -wmax);
-            }
-        }
-        double cmax = (rel[3] < vmax - dt * amax) ? amax : 0.0;
-        double cmin = (rel[3] > vmin - dt * amin) ? amin : 0.0;
-        u[1] = pymax(pymin(u[1], cmax), cmin);
-        cmax = (rel[ND - 1] < vmax - dt * amax) ? amax : 0.0;
-        cmin = (rel[ND - 1] > vmin - dt * amin) ? amin : 0.0;
-        u[3] = pymax(pymin(u[3], cmax), cmin);
-        if (bang) { u[1] = f32r(u[1]); u[3] = f32r(u[3]); }
-    }
-    double nd = 0.0;
-    if (!aliased) {
-#pragma unroll
-        for (int k = 0; k < 4; ++k) { const double d = u[k] - uref[k]; nd = nd + d * d; }
-        nd = sqrt(nd);
-    }
-    filtered = nd > 1e-4;
-    safe0 = u[0]; safe1 = u[1];
-}
-
-// core.py:191-210 / :110-131, closed-form over one dt
-template <int DYN>
-__device__ __forceinline__ void integrate(double& x, double& y, double& s2, double& s3, double u0, double u1, double dt,
-                                          double& p_dist, double& state_time) {
-    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-        double vx = s2, vy = s3;
-        x = x + vx * dt + 0.5 * u0 * dt * dt;
-        y = y + vy * dt + 0.5 * u1 * dt * dt;
-        vx = vx + u0 * dt; vy = vy + u1 * dt;
-        double speed = sqrt(vx * vx + vy * vy);
-        const double max_speed = 0.5;
-        if (speed > max_speed) { vx = max_speed * vx / speed; vy = max_speed * vy / speed; }
-        s2 = vx; s3 = vy;
-        speed = sqrt(vx * vx + vy * vy);
-        p_dist += speed * dt;
-    } else {
-        const double vmin = 60 * 0.514444 * 0.001, vmax = 175 * 0.514444 * 0.001;
-        const double th0 = s2, v0 = s3, om = u0, ac = u1;
-        const double th1 = th0 + om * dt;
-        double v1 = v0 + ac * dt;
-        double ddx, ddy;
-        if (fabs(om * dt) < 1e-3) {
-            const double T = dt, c0 = cos(th0), s0 = sin(th0), o = om;
-            const double i0 = T, i1 = T * T / 2.0, i2 = T * T * T / 3.0, i3 = T * T * T * T / 4.0, i4 = T * T * T * T * T / 5.0;
-            const double cc0 = c0, cc1 = -s0 * o, cc2 = -c0 * o * o / 2.0, cc3 = s0 * o * o * o / 6.0;
-            const double sc0 = s0, sc1 = c0 * o, sc2 = -s0 * o * o / 2.0, sc3 = -c0 * o * o * o / 6.0;
-            ddx = v0 * (cc0 * i0 + cc1 * i1 + cc2 * i2 + cc3 * i3) + ac * (cc0 * i1 + cc1 * i2 + cc2 * i3 + cc3 * i4);
-            ddy = v0 * (sc0 * i0 + sc1 * i1 + sc2 * i2 + sc3 * i3) + ac * (sc0 * i1 + sc1 * i2 + sc2 * i3 + sc3 * i4);
-        } else {
-            const double s1 = sin(th1), c1 = cos(th1), s0 = sin(th0), c0 = cos(th0);
-            ddx = (v1 * s1 - v0 * s0) / om + ac * (c1 - c0) / (om * om);
-            ddy = (-(v1 * c1) + v0 * c0) / om + ac * (s1 - s0) / (om * om);
-        }
-        x = x + ddx; y = y + ddy;
-        s2 = th1;
-        if (v1 > vmax) v1 = vmax;
-        if (v1 < vmin) v1 = vmin;
-        s3 = v1;
-        p_dist += v1 * dt;
-    }
-    state_time += dt;
-}
-
-// ---------------------------------------------------------------------------------------------
-// the kernel
-// ---------------------------------------------------------------------------------------------
-#define AFP(f) (kp.b.agent_f64 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
-#define AIP(f) (kp.b.agent_i32 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
-#define EFP(f) (kp.b.env_f64 + (size_t)(f) * (size_t)n + (size_t)env)
-#define EIP(f) (kp.b.env_i32 + (size_t)(f) * (size_t)n + (size_t)env)
-
-template <int DYN>
-__global__ void __launch_bounds__(256) lsm_fused_kernel(const __grid_constant__ KParams kp) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const lsm_config& c = kp.c;
-    const int lane = threadIdx.x & 31;
-    const int warp_in_block = threadIdx.x >> 5;
-    const int warps_per_block = blockDim.x >> 5;
-    const int N = kp.N, L = kp.L, M = kp.M, E = kp.E, G = kp.G, EPW = kp.EPW, W = kp.W;
-    const int Dobs = kp.D, F = kp.F;
-    const long long n = kp.b.num_envs;
-    const int le = lane / G;            // local env of this lane in the per-agent phases
-    const int ai = lane - le * G;       // agent index of this lane
-    const unsigned group_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (le * G));
-    unsigned char* wbase = smem_raw + (size_t)warp_in_block * kp.smem_per_warp;
-    EnvSmem S;                          // this lane's env (per-agent phases)
-    S.bind(wbase + (size_t)le * kp.sl.bytes_per_env, kp.sl);
-    const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
-    const long long ngroups = (n + EPW - 1) / EPW;
-
-    for (long long grp = (long long)blockIdx.x * warps_per_block + warp_in_block; grp < ngroups;
-         grp += (long long)gridDim.x * warps_per_block) {
-        const long long env0 = grp * EPW;
-        const long long env = env0 + le;
-        bool env_on = env < n;
-        if (kp.mode == MODE_RESET && kp.env_mask != nullptr && env_on) env_on = kp.env_mask[env] != 0;
-        const bool agent_on = env_on && ai < N;
-        if (__ballot_sync(0xffffffffu, env_on) == 0u) continue;
-
-        // ---------------- P0: load ----------------
-        double x = 0, y = 0, s2 = 0, s3 = 0, p_dist = 0, state_time = 0, min_rel = INFINITY, goal_min_time = INFINITY;
-        double times_old = -1, dists_old = -1, dist_left = -1, ep_travel_dist = 0, ep_min_dist = INFINITY, action_diff = 0;
-        int reached = 0, done = 0, safety_filtered = 0, deconflict = -1, ncoll = 0;
-        int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0;
-        int current_step = 0, reset_count = 0, parity = 0;
-        double ratio = 0.0;
-        if (env_on) {
-            current_step = *EIP(LSM_EI_CURRENT_STEP); reset_count = *EIP(LSM_EI_RESET_COUNT);
-            parity = *EIP(LSM_EI_PARITY); ratio = *EFP(LSM_EF_CURRICULUM_RATIO);
-        }
-        if (agent_on) {
-            x = *AFP(LSM_AF_X); y = *AFP(LSM_AF_Y); s2 = *AFP(LSM_AF_S2); s3 = *AFP(LSM_AF_S3);
-            p_dist = *AFP(LSM_AF_P_DIST); state_time = *AFP(LSM_AF_STATE_TIME);
-            min_rel = *AFP(LSM_AF_MIN_REL_DIST); goal_min_time = *AFP(LSM_AF_GOAL_MIN_TIME);
-            times_old = *AFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A);
-            dists_old = *AFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A);
-            dist_left = *AFP(LSM_AF_DIST_LEFT); ep_travel_dist = *AFP(LSM_AF_EP_TRAVEL_DIST);
-            ep_min_dist = *AFP(LSM_AF_EP_MIN_DIST); action_diff = *AFP(LSM_AF_ACTION_DIFF);
-            reached = *AIP(LSM_AI_REACHED); done = *AIP(LSM_AI_DONE);
-            safety_filtered = *AIP(LSM_AI_SAFETY_FILTERED); deconflict = *AIP(LSM_AI_DECONFLICT_IDX);
-            ncoll = *AIP(LSM_AI_NUM_COLLISIONS); ep_len = *AIP(LSM_AI_EP_TRAVEL_LEN);
-            ep_conflict = *AIP(LSM_AI_EP_CONFLICT); ep_multi = *AIP(LSM_AI_EP_MULTI); ep_done = *AIP(LSM_AI_EP_DONE);
-        }
-        double times_req = times_old, dists_goal = dists_old;
-        // landmarks of the warp's EPW environments: contiguous runs per field
-        {
-            const long long total = (long long)EPW * M;
-            for (int f = 0; f < LSM_LF_COUNT; ++f) {
-                const double* src = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)env0) * (size_t)M;
-                int el = 0, m = lane;
-                while (m >= M) { m -= M; ++el; }
-                for (long long idx = lane; idx < total; idx += 32) {
-                    if (env0 + el < n) {
-                        unsigned char* eb = wbase + (size_t)el * kp.sl.bytes_per_env;
-                        const int off = f == 0 ? kp.sl.lx : f == 1 ? kp.sl.ly : f == 2 ? kp.sl.lh : f == 3 ? kp.sl.lsp
-                                        : f == 4 ? kp.sl.lsin : kp.sl.lcos;
-                        ((double*)(eb + off))[m] = src[idx];
-                    }
-                    m += 32;
-                    while (m >= M) { m -= M; ++el; }
-                }
-            }
-        }
-        Curriculum q = curriculum(kp, ratio);
-        if (agent_on) {
-            S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
-            S.done_pre[ai] = done; S.reached_pre[ai] = reached;
-        }
-        __syncwarp();
-
-        bool all_done_env = false;
-
-        if (kp.mode == MODE_STEP) {
-            // ---------------- P1: action decode, safety filter, dynamics ----------------
-            current_step += 1;
-            double raw0 = 0.0, raw1 = 0.0;
-            if (agent_on) {
-                int idx;
-                if (kp.action_idx != nullptr) idx = kp.action_idx[(size_t)env * N + ai];
-                else {   // np.argmax over the one-hot row: first maximum
-                    const float* row = kp.action_onehot + ((size_t)env * N + ai) * LSM_NUM_ACTIONS;
-                    idx = 0; float best = row[0];
-                    for (int k = 1; k < LSM_NUM_ACTIONS; ++k) { const float v = row[k]; if (v > best) { best = v; idx = k; } }
-                }
-                const int i0 = idx / 5, i1 = idx - i0 * 5;
-                raw0 = c.act_tab0[i0]; raw1 = c.act_tab1[i1];
-                S.rawx[ai] = raw0; S.rawy[ai] = raw1;
-            }
-            __syncwarp();
-            double safe0 = raw0, safe1 = raw1;
-            for (int it = 0; it < c.num_internal_step; ++it) {
-                if (agent_on && q.world_filter) {   // world.use_safety_filter is per env (curriculum, Q5)
-                    int filt = 0, dec = -1;
-                    safe0 = raw0; safe1 = raw1;
-                    if (!done) safety_filter_agent<DYN>(kp, q, S, ai, N, raw0, raw1, safe0, safe1, filt, dec);
-                    deconflict = dec; safety_filtered = filt;
-                }
-                __syncwarp();   // everyone has read the pre-integration states
-                if (agent_on) {
-                    const double d0 = raw0 - safe0, d1 = raw1 - safe1;
-                    action_diff = sqrt(d0 * d0 + d1 * d1);
-                    if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time);
-                    S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
-                }
-                __syncwarp();
-            }
-            // ---------------- P2: agent-agent distances, goal / reward / done ----------------
-            int goal_pre = 0, goal_post = 0, reached_post = reached, done_post = done;
-            double rew = 0.0;
-            double vpx = 0, vpy = 0, vqx = 0, vqy = 0;   // world-frame velocity pre / post own update
-            double theta = 0, speed = 0;
-            bool reached_now = false;
-            if (agent_on) {
-                // core.py:696-709 (+ the agent block of calculate_distances)
-                double m = INFINITY;
-                for (int j = 0; j < N; ++j) {
-                    const double dx = x - S.ax[j], dy = y - S.ay[j];
-                    const double d = sqrt(dx * dx + dy * dy);
-                    S.daa[ai * N + j] = d;
-                    if (j != ai && !done && !S.done_pre[j] && d < m) m = d;
-                }
-                min_rel = m;
-                theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
-                goal_pre = goal_index(reached, ai, N, M);
-                const double gx = S.lx[goal_pre], gy = S.ly[goal_pre], gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
-                // observation (pre-update goal): navigation_graph_safe.py:855-875, utils.py:114-137
-                float* o = kp.b.obs + ((size_t)env * N + ai) * Dobs;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                    o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(gx - x); o[3] = (float)(gy - y);
-                    o[4] = (float)S.lsin[goal_pre]; o[5] = (float)S.lcos[goal_pre]; o[6] = (float)gs;
-                } else {
-                    double rx, ry; rotate_into(gx - x, gy - y, S.cth[ai], S.sth[ai], rx, ry);
-                    const double rh = gh - s2;
-                    o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                    o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)gs;
-                }
-                // reward_reach_goal: navigation_graph_safe.py:691-791
-                const double he = direction_alignment_error(theta, gh);
-                const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
-                const double se = fabs(speed - gs);
-                const double sen = clipd(se / q.speed_thresh, 0.0, 1.0);
-                double cra = ratio_sloped(ratio, 0.25, 0.75);
-                if (use_filter_arg) cra = 1.0;
-                reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
-                if (reached_now) {
-                    const double spr = 1.0 - sen;
-                    const double pdx = gx - x, pdy = gy - y;
-                    double cte = pdx * sin(theta) - pdy * cos(theta);
-                    const double nrm = norm2(pdx, pdy);
-                    cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
-                    cte = clipd(cte, 0.0, 1.0);
-                    const double pr = hpr * spr * (1.0 - cte);
-                    double goal_rew;
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) goal_rew = c.goal_rew * pr;
-                    else goal_rew = c.goal_rew * (pr * cra + (1.0 - cra));
-                    if (!done) rew += goal_rew;
-                }
-                if (!done) {
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        if (!use_filter_arg) {   // utils.py:323-349
-                            const double cg = cos(gh), sg = sin(gh);
-                            double rpx, rpy, rvx, rvy;
-                            rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
-                            const double dist = norm2(rpx, rpy);
-                            const double ang = atan2(rpy, rpx);
-                            const double ang_range = kPi / 6;
-                            rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
-                            const double rh = magnetic_heading(rpx, rpy, 2.0 * q.dist_thresh);
-                            double ref_speed = pymax(gs, 0.1);
-                            const double dr = clipd(dist / 1.5, 0.0, 1.0);
-                            ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
-                            const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
-                            const double err = norm2(ex, ey);
-                            double pen;
-                            if (cos(ang) < cos(ang_range)) pen = err;
-                            else {
-                                const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
-                                pen = err * (1.0 - ar) + dist * ar;
-                            }
-                            double hap = 3.0 * pen;
-                            hap = clipd(1.0 - q.sloped, 0.0, 1.0) * hap;
-                            rew -= hap;
-                        }
-                        if (use_filter_arg) rew -= 1.0; else rew -= 1.0 * q.sloped;
-                    } else {
-                        double rpx, rpy;
-                        rotate_into(x - gx, y - gy, cos(gh), sin(gh), rpx, rpy);
-                        const double rs[4] = { rpx, rpy, theta - gh, speed };
-                        Stencil<4> st;
-                        stencil_setup<4>(kp.tg, rs, st);
-                        double ttr = st.valid ? stencil_value<4>(kp.tg, st) : NAN;
-                        if (isnan(ttr)) ttr = kp.tg.ttr_max;
-                        rew -= 0.04 * ttr;
-                        rew -= sen * cra;
-                    }
-                }
-                // update_reached_goal_and_done (+ freeze_agent): navigation_graph_safe.py:658-675, 1091-1099
-                if (reached_now && !done) reached_post = reached + 1;
-                done_post = done;
-                vqx = vpx; vqy = vpy;
-                if (reached_post >= L) {
-                    done_post = 1;
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { s2 = 0.0; s3 = 0.0; } else s3 = 0.0;
-                    vqx = 0.0; vqy = 0.0;
-                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) { vqx = s3 * S.cth[ai]; vqy = s3 * S.sth[ai]; }
-                }
-                goal_post = goal_index(reached_post, ai, N, M);
-                S.vpre_x[ai] = vpx; S.vpre_y[ai] = vpy; S.vpost_x[ai] = vqx; S.vpost_y[ai] = vqy;
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal_pre[ai] = goal_pre; S.goal_post[ai] = goal_post;
-                S.reached_post[ai] = reached_post; S.done_post[ai] = done_post;
-                S.as2[ai] = s2; S.as3[ai] = s3;
-            }
-            __syncwarp();
-            if (agent_on) {
-                // remaining reward terms see agents < i after and agents > i before their own update
-                if (c.flags & LSM_FLAG_SAFETY_VIOLATION) {         // navigation_graph_safe.py:793-798
-                    double r = 0.0;
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
-                        if (S.daa[ai * N + a] < q.sep && !adone) r += q.conflict_rew;
-                    }
-                    rew += r;
-                }
-                if (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) {       // navigation_graph_safe.py:800-823
-                    int count = 0; double pen = 0.0;
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
-                        const double rd = S.daa[ai * N + a];
-                        if (rd < q.eng && !adone) {
-                            const double rx = S.ax[a] - x, ry = S.ay[a] - y;
-                            const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
-                            const double dir = atan2(ry, rx);
-                            const double vax = a < ai ? S.vpost_x[a] : S.vpre_x[a];
-                            const double vay = a < ai ? S.vpost_y[a] : S.vpre_y[a];
-                            double change = cos(dir) * (vax - vpx) + sin(dir) * (vay - vpy);
-                            change = fabs(pymin(0.0, change));
-                            pen += change * closeness;
-                            count += 1;
-                        }
-                    }
-                    if (count > 1) rew += q.multi_rew * pen;
-                }
-                if ((c.flags & LSM_FLAG_DIFF_FROM_FILTERED_ACTION) && use_filter_arg) {   // :825-828
-                    if (!done) rew += q.diff_rew * action_diff;
-                }
-                if (c.flags & LSM_FLAG_HJ_VALUE) {                 // :830-837, core.py:459-468
-                    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-                    double r = 0.0;
-                    // the ego state is still the pre-update one here (reward runs before the update)
-                    const double e2 = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? vpx : theta;
-                    const double e3 = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? vpy : speed;
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
-                        if (adone) continue;
-                        // an agent that is not done has identical pre / post state
-                        double rel[ND]; bool inr;
-                        double o2, o3;
-                        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { o2 = S.vpre_x[a]; o3 = S.vpre_y[a]; }
-                        else { o2 = S.as2[a]; o3 = S.as3[a]; }
-                        relative_state<DYN>(x, y, e2, e3, S.ax[a], S.ay[a], o2, o3, rel);
-                        const double v = hj_value<DYN>(kp, q, rel, inr);
-                        const double cvp = fabs(pymin(v - 0.4, 0.0));
-                        r += q.cvalue_rew * cvp;
-                    }
-                    rew += r;
-                }
-                rew = clipd(rew, c.min_reward, c.max_reward);
-
-                // episode statistics: environment.py:1004-1022 (uses agent i's row of its own masked adj)
-                if (!done_post) {
-                    ep_len += 1;
-                    ep_travel_dist += norm2(vqx, vqy) * c.dt;
-                    int cnt = 0; bool have = false; double mn = INFINITY;
-                    for (int j = 0; j < N; ++j) {
-                        const int jdisc = j <= ai ? S.done_post[j] : S.done_pre[j];
-                        double d = jdisc ? 0.0 : S.daa[ai * N + j];
-                        d = (d < c.coordination_range && d > 0.0) ? d : 0.0;
-                        if (d != 0.0) { have = true; if (d < c.engagement_distance_ref) cnt++; if (d < mn) mn = d; }
-                    }
-                    if (have) {
-                        if (cnt > 1) ep_multi += 1;
-                        if (mn < c.separation_distance_target) ep_conflict += 1;
-                        if (mn < ep_min_dist) ep_min_dist = mn;
-                    }
-                }
-                if (done_post) ep_done = 1;
-                // info_callback state: navigation_graph_safe.py:386-413 (post-update goal and velocity)
-                {
-                    const double gx = S.lx[goal_post], gy = S.ly[goal_post];
-                    const double dx = x - gx, dy = y - gy;
-                    const double dist = sqrt(dx * dx + dy * dy);
-                    const double th2 = theta_of<DYN>(s2, s3), sp2 = speed_of<DYN>(s2, s3);
-                    const bool r2 = goal_reached<DYN>(x, y, th2, sp2, gx, gy, S.lh[goal_post], S.lsp[goal_post], q);
-                    if (r2 && times_req == -1.0) { times_req = (double)current_step * c.dt; dists_goal = p_dist; dist_left = dist; }
-                    if (times_req == -1.0) { dists_goal = p_dist; dist_left = dist; }
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        if (S.daa[ai * N + a] < 1.05 * (0.050 + 0.050)) ncoll += 1;
-                    }
-                }
-            }
-            if (agent_on && kp.b.reward_individual != nullptr) kp.b.reward_individual[(size_t)env * N + ai] = (float)rew;
-            // shared reward: sequential sum in agent order (environment.py:1032-1037)
-            if (c.flags & LSM_FLAG_SHARED_REWARD) {
-                double s = 0.0;
-                for (int k = 0; k < N; ++k) s += __shfl_sync(0xffffffffu, rew, le * G + k);
-                rew = s;
-            }
-            const bool done_out = done_post || (current_step >= c.episode_length);   // environment.py:260-268
-            const unsigned not_done = __ballot_sync(0xffffffffu, agent_on && !done_out);
-            all_done_env = env_on && ((not_done & group_mask) == 0u);
-            if (agent_on) {
-                kp.b.reward[(size_t)env * N + ai] = (float)rew;
-                kp.b.done[(size_t)env * N + ai] = (uint8_t)done_out;
-                kp.b.safe_action[((size_t)env * N + ai) * 2] = safe0;
-                kp.b.safe_action[((size_t)env * N + ai) * 2 + 1] = safe1;
-            }
-            reached = reached_post; done = done_post;
-            parity ^= 1;
-        } else {
-            // RESET / OBSERVE: pre == post
-            if (agent_on) {
-                double vx, vy;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
-                const int g = goal_index(reached, ai, N, M);
-                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal_pre[ai] = g; S.goal_post[ai] = g;
-                S.reached_post[ai] = reached; S.done_post[ai] = done;
-            }
-            __syncwarp();
-        }
-
-        // ---------------- P3: reset (graphworker auto-reset or explicit) ----------------
-        const bool do_reset = (kp.mode == MODE_STEP && kp.flag && all_done_env) || (kp.mode == MODE_RESET && env_on);
-        const bool sample = (kp.mode == MODE_STEP) ? true : (kp.flag != 0);
-        const unsigned reset_lanes = __ballot_sync(0xffffffffu, do_reset);
-        if (reset_lanes != 0u) {
-            // episode summary: environment.py:895-926 (sequential sums in agent order)
-            double s_len = 0, s_dist = 0, s_done = 0, s_reached = 0, s_conf = 0, s_min = 0, s_multi = 0, mn = INFINITY;
-            const double len_i = ep_len == 0 ? 1.0 : (double)ep_len;
-            for (int k = 0; k < N; ++k) {
-                const int src = le * G + k;
-                s_len += (double)__shfl_sync(0xffffffffu, ep_len, src);
-                s_dist += __shfl_sync(0xffffffffu, ep_travel_dist, src);
-                s_done += (double)__shfl_sync(0xffffffffu, ep_done, src);
-                s_reached += (double)__shfl_sync(0xffffffffu, reached, src);
-                s_conf += __shfl_sync(0xffffffffu, (double)ep_conflict / len_i, src);
-                s_multi += __shfl_sync(0xffffffffu, (double)ep_multi / len_i, src);
-                const double md = __shfl_sync(0xffffffffu, ep_min_dist, src);
-                s_min += md;
-                if (md < mn) mn = md;
-            }
-            if (do_reset && ai == 0) {
-                double* out = kp.b.ep_info + (size_t)env * LSM_EP_COUNT;
-                out[LSM_EP_TRAVEL_TIME_MEAN] = c.dt * (s_len / N);
-                out[LSM_EP_TRAVEL_DISTANCE_MEAN] = s_dist / N;
-                out[LSM_EP_DONE_PERCENTAGE] = s_done / N;
-                out[LSM_EP_NUM_REACHED_GOAL_MEAN] = s_reached / N;
-                out[LSM_EP_CONFLICT_PERCENTAGE] = s_conf / N;
-                const double mm = s_min / N;
-                out[LSM_EP_MIN_DISTANCE_MEAN] = isinf(mm) ? c.coordination_range : mm;
-                out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
-                out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
-            }
-            if (do_reset) {
-                current_step = 0;
-                ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
-                q = curriculum(kp, ratio);
-            }
-            if (do_reset && sample && ai == 0) {
-                // Scenario.random_scenario: navigation_graph_safe.py:1199-1367, utils.py:39-68
-                Rng r; r.init(kp.seed, (uint32_t)(kp.b.env_id_base + env), (uint32_t)reset_count);
-                const double ws = c.world_size;
-                double cra = ratio_sloped(ratio, 0.25, 0.75);
-                if (use_filter_arg) cra = 1.0;
-                for (int i = 0; i < N; ++i) {
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        S.ax[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.ay[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.as2[i] = 0.0; S.as3[i] = 0.0;
-                    } else {
-                        const double xmin = -0.5 * ws;
-                        const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
-                        const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
-                        S.ax[i] = r.uniform(xmin, xmax); S.ay[i] = ry;
-                        const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
-                        S.as2[i] = r.uniform(0.0, 2.0 * kPi);
-                        S.as3[i] = sp;
-                    }
-                }
-                for (int i = 0; i < N; ++i) {
-                    // the L goals of agent i live at landmark slots l*N + i; the previous agent's at l*N + i-1
-                    double xlo, xhi, ylo, yhi, min_d, max_d;
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        xlo = -0.5 * ws; xhi = 0.5 * ws; ylo = -0.5 * ws; yhi = 0.5 * ws;
-                        min_d = 0.25 * c.coordination_range; max_d = 0.75 * c.coordination_range;
-                    } else {
-                        const double yw = 0.1 * (1.0 - cra) + 0.5 * cra;
-                        xlo = 0.0; xhi = 0.75 * ws; ylo = -yw * ws; yhi = yw * ws;
-                        min_d = 0.5 * c.coordination_range; max_d = c.coordination_range;
-                    }
-                    for (int l = 0; l < L; ++l) {
-                        double gx = 0.0, gy = 0.0;
-                        if (l > 0) {
-                            for (int j = 0; j < 1000; ++j) {
-                                gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi);
-                                double dm = INFINITY;
-                                for (int k = 0; k < l; ++k) {
-                                    const double d = norm2(S.lx[k * N + i] - gx, S.ly[k * N + i] - gy);
-                                    if (d < dm) dm = d;
-                                }
-                                if (dm > min_d && dm < max_d) break;
-                            }
-                        } else { gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi); }
-                        S.lx[l * N + i] = gx; S.ly[l * N + i] = gy;
-                    }
-                    if (i > 0) for (int l = 0; l < L; ++l) if (r.uniform(0.0, 1.0) < 0.5) {
-                        S.lx[l * N + i] = S.lx[l * N + i - 1]; S.ly[l * N + i] = S.ly[l * N + i - 1];
-                    }
-                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
-                        if (S.lx[i] > S.lx[N + i]) {
-                            const double tx = S.lx[i], ty = S.ly[i];
-                            S.lx[i] = S.lx[N + i]; S.ly[i] = S.ly[N + i]; S.lx[N + i] = tx; S.ly[N + i] = ty;
-                        }
-                    }
-                    for (int l = 0; l < L - 1; ++l)
-                        S.lh[l * N + i] = atan2(S.ly[(l + 1) * N + i] - S.ly[l * N + i], S.lx[(l + 1) * N + i] - S.lx[l * N + i]);
-                    const double last_heading = S.lh[(L - 2) * N + i];
-                    const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
-                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
-                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
-                    } else {
-                        // goal_speeds_random is drawn before var_random; keep the draws in lsp, then decide
-                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
-                        const double var = r.uniform(0.0, 1.0);
-                        if (!(var < pymin(cr, 1.0 - 0.2))) {
-                            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
-                            S.lsp[(L - 1) * N + i] = c.goal_speed_min;
-                        }
-                    }
-                    for (int l = 0; l < L - 1; ++l) {
-                        const double pr = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? cr * 0.25 * kPi : cra * 0.1 * kPi;
-                        S.lh[l * N + i] += r.uniform(-pr, pr);
-                    }
-                    S.lh[(L - 1) * N + i] = last_heading;
-                    for (int l = 0; l < L; ++l) {
-                        S.lsin[l * N + i] = sin(S.lh[l * N + i]);
-                        S.lcos[l * N + i] = cos(S.lh[l * N + i]);
-                    }
-                }
-            }
-            __syncwarp();
-            if (do_reset && agent_on) {
-                if (sample) { x = S.ax[ai]; y = S.ay[ai]; s2 = S.as2[ai]; s3 = S.as3[ai]; }
-                done = 0; reached = 0;
-                p_dist = 0.0; state_time = 0.0;
-                goal_min_time = norm2(x - S.lx[ai], y - S.ly[ai]) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
-                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
-                ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
-                double vx, vy;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
-                S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
-                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal_pre[ai] = ai; S.goal_post[ai] = ai;
-                S.reached_pre[ai] = 0; S.reached_post[ai] = 0; S.done_pre[ai] = 0; S.done_post[ai] = 0;
-                // reset observation
-                const int g = ai;
-                float* o = kp.b.obs + ((size_t)env * N + ai) * Dobs;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                    o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(S.lx[g] - x); o[3] = (float)(S.ly[g] - y);
-                    o[4] = (float)S.lsin[g]; o[5] = (float)S.lcos[g]; o[6] = (float)S.lsp[g];
-                } else {
-                    double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
-                    const double rh = S.lh[g] - s2;
-                    o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                    o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
-                }
-            }
-            if (do_reset && sample) reset_count += 1;
-            __syncwarp();
-            // write the new landmarks back (sampled envs only)
-            if (sample) {
-                for (int el = 0; el < EPW; ++el) {
-                    if (!((reset_lanes >> (el * G)) & 1u)) continue;
-                    unsigned char* eb = wbase + (size_t)el * kp.sl.bytes_per_env;
-                    for (int f = 0; f < LSM_LF_COUNT; ++f) {
-                        const int off = f == 0 ? kp.sl.lx : f == 1 ? kp.sl.ly : f == 2 ? kp.sl.lh : f == 3 ? kp.sl.lsp
-                                        : f == 4 ? kp.sl.lsin : kp.sl.lcos;
-                        double* dst = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)(env0 + el)) * (size_t)M;
-                        for (int m = lane; m < M; m += 32) dst[m] = ((const double*)(eb + off))[m];
-                    }
-                }
-            }
-        } else if (kp.mode == MODE_OBSERVE && agent_on) {
-            // observation of the injected state
-            const int g = S.goal_pre[ai];
-            float* o = kp.b.obs + ((size_t)env * N + ai) * Dobs;
-            if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(S.lx[g] - x); o[3] = (float)(S.ly[g] - y);
-                o[4] = (float)S.lsin[g]; o[5] = (float)S.lcos[g]; o[6] = (float)S.lsp[g];
-            } else {
-                double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
-                const double rh = S.lh[g] - s2;
-                o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
-            }
-        }
-
-        // ---------------- state write-back ----------------
-        if (kp.mode != MODE_OBSERVE) {
-            if (env_on && ai == 0) {
-                *EIP(LSM_EI_CURRENT_STEP) = current_step; *EIP(LSM_EI_RESET_COUNT) = reset_count;
-                *EIP(LSM_EI_PARITY) = parity; *EIP(LSM_EI_JUST_RESET) = do_reset ? 1 : 0;
-                *EFP(LSM_EF_CURRICULUM_RATIO) = ratio;
-            }
-            if (agent_on) {
-                *AFP(LSM_AF_X) = x; *AFP(LSM_AF_Y) = y; *AFP(LSM_AF_S2) = s2; *AFP(LSM_AF_S3) = s3;
-                *AFP(LSM_AF_P_DIST) = p_dist; *AFP(LSM_AF_STATE_TIME) = state_time;
-                *AFP(LSM_AF_MIN_REL_DIST) = min_rel; *AFP(LSM_AF_GOAL_MIN_TIME) = goal_min_time;
-                // the slot named by `parity` receives the newest values; the other keeps last step's
-                *AFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) = times_req;
-                *AFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) = dists_goal;
-                if (do_reset) {
-                    *AFP(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) = times_req;
-                    *AFP(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) = dists_goal;
-                }
-                *AFP(LSM_AF_DIST_LEFT) = dist_left; *AFP(LSM_AF_EP_TRAVEL_DIST) = ep_travel_dist;
-                *AFP(LSM_AF_EP_MIN_DIST) = ep_min_dist; *AFP(LSM_AF_ACTION_DIFF) = action_diff;
-                *AIP(LSM_AI_REACHED) = reached; *AIP(LSM_AI_DONE) = done;
-                *AIP(LSM_AI_SAFETY_FILTERED) = safety_filtered; *AIP(LSM_AI_DECONFLICT_IDX) = deconflict;
-                *AIP(LSM_AI_NUM_COLLISIONS) = ncoll; *AIP(LSM_AI_EP_TRAVEL_LEN) = ep_len;
-                *AIP(LSM_AI_EP_CONFLICT) = ep_conflict; *AIP(LSM_AI_EP_MULTI) = ep_multi; *AIP(LSM_AI_EP_DONE) = ep_done;
-            }
-        }
-        __syncwarp();
-
-        // ---------------- P4: graph observation for the warp's environments ----------------
-        for (int el = 0; el < EPW; ++el) {
-            const long long ee = env0 + el;
-            if (ee >= n) break;
-            if (kp.mode == MODE_RESET && kp.env_mask != nullptr && kp.env_mask[ee] == 0) continue;
-            EnvSmem T;
-            T.bind(wbase + (size_t)el * kp.sl.bytes_per_env, kp.sl);
-            // (a) pairwise distances, thresholded by the sensing radius (core.py:514-543 and the strict
-            //     0 < d < R test of navigation_graph_safe.py:991)
-            for (int e = lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
-            for (int p = lane; p < kp.num_pairs; p += 32) {
-                const int a = kp.pair_tab[2 * p], b2 = kp.pair_tab[2 * p + 1];
-                const double pax = a < N ? T.ax[a] : T.lx[a - N], pay = a < N ? T.ay[a] : T.ly[a - N];
-                const double pbx = b2 < N ? T.ax[b2] : T.lx[b2 - N], pby = b2 < N ? T.ay[b2] : T.ly[b2 - N];
-                const double dx = pax - pbx, dy = pay - pby;
-                const double d = sqrt(dx * dx + dy * dy);
-                const float v = (d < c.coordination_range && d > 0.0) ? (float)d : 0.0f;
-                T.dthr[a * E + b2] = v; T.dthr[b2 * E + a] = v;
-            }
-            // (b) disconnected-entity bit masks, before and after this step's goal updates
-            unsigned any_disc = 0u;
-            for (int w = 0; w < W; ++w) {
-                const int e = w * 32 + lane;
-                bool dpre = false, dpost = false;
-                if (e < N) { dpre = T.done_pre[e] != 0; dpost = T.done_post[e] != 0; }
-                else if (e < E) {
-                    const int m = e - N, owner = m % N, order = m / N;
-                    dpre = T.reached_pre[owner] > order; dpost = T.reached_post[owner] > order;
-                }
-                const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
-                if (lane == 0) { T.disc_pre[w] = bpre; T.disc_post[w] = bpost; }
-                any_disc |= bpost;
-            }
-            __syncwarp();
-            // keep mask of observer i: entities owned by agents <= i are seen post-update, the others pre-update
-            for (int k = lane; k < N * W; k += 32) {
-                const int w = k % W;
-                const unsigned sel = kp.sel_tab[k];
-                T.keepm[k] = ~((T.disc_post[w] & sel) | (T.disc_pre[w] & ~sel));
-            }
-            __syncwarp();
-            // (c) node features: one lane per (observer, entity) row
-            {
-                float* nbase = kp.b.node_obs + (size_t)ee * N * E * F;
-                const int rows = N * E;
-                int i = 0, e = lane;
-                while (e >= E) { e -= E; ++i; }
-                for (int r = lane; r < rows; r += 32) {
-                    float* o = nbase + (size_t)r * F;
-                    const double xi = T.ax[i], yi = T.ay[i];
-                    const double vix = T.vpost_x[i], viy = T.vpost_y[i];
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        float f0, f1, f2, f3, f4, f5, f6, f7, f8, f9;
-                        if (e < N) {
-                            const bool post = e <= i;
-                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
-                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
-                            f0 = (float)(T.ax[e] - xi); f1 = (float)(T.ay[e] - yi);
-                            f2 = (float)(vex - vix); f3 = (float)(vey - viy);
-                            f4 = (float)(T.lx[g] - xi); f5 = (float)(T.ly[g] - yi);
-                            f6 = (float)T.lsin[g]; f7 = (float)T.lcos[g]; f8 = (float)T.lsp[g]; f9 = 0.0f;
-                        } else {
-                            const int m = e - N;
-                            f0 = (float)(T.lx[m] - xi); f1 = (float)(T.ly[m] - yi);
-                            f2 = (float)(-vix); f3 = (float)(-viy); f4 = f0; f5 = f1;
-                            f6 = (float)T.lsin[m]; f7 = (float)T.lcos[m]; f8 = (float)T.lsp[m]; f9 = 1.0f;
-                        }
-                        float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
-                        o2[0] = make_float2(f0, f1); o2[1] = make_float2(f2, f3); o2[2] = make_float2(f4, f5);
-                        o2[3] = make_float2(f6, f7); o2[4] = make_float2(f8, f9);
-                    } else {
-                        const double ci = T.cth[i], si = T.sth[i];
-                        if (e < N) {
-                            const bool post = e <= i;
-                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
-                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
-                            double rx, ry, gx, gy;
-                            rotate_into(T.ax[e] - xi, T.ay[e] - yi, ci, si, rx, ry);
-                            rotate_into(T.lx[g] - xi, T.ly[g] - yi, ci, si, gx, gy);
-                            // sin/cos(theta_e - theta_i) and sin/cos(goal_heading - theta_i) by angle difference
-                            const double ce = T.cth[e], se = T.sth[e];
-                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(vex - vix, vey - viy);
-                            o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
-                            o[5] = (float)gx; o[6] = (float)gy;
-                            o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
-                            o[9] = (float)T.lsp[g]; o[10] = 0.0f;
-                        } else {
-                            const int m = e - N;
-                            double rx, ry;
-                            rotate_into(T.lx[m] - xi, T.ly[m] - yi, ci, si, rx, ry);
-                            const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
-                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
-                            o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
-                            o[9] = (float)T.lsp[m]; o[10] = 1.0f;
-                        }
-                    }
-                    e += 32;
-                    while (e >= E) { e -= E; ++i; }
-                }
-            }
-            // (d) adjacency: observer i keeps entity k unless it is disconnected as seen after agents <= i updated
-            {
-                float* abase = kp.b.adj + (size_t)ee * N * E * E;
-                const int EE = E * E;
-                if (kp.adj_vec == 4) {
-                    const int chunks = EE / 4, cpr = E / 4;
-                    for (int ch = lane; ch < chunks; ch += 32) {
-                        const int a = ch / cpr, b4 = (ch - a * cpr) * 4;
-                        const float4 v = *reinterpret_cast<const float4*>(T.dthr + a * E + b4);
-                        float* dst = abase + a * E + b4;
-                        if (any_disc == 0u) {
-                            for (int i = 0; i < N; ++i) *reinterpret_cast<float4*>(dst + (size_t)i * EE) = v;
-                        } else {
-                            for (int i = 0; i < N; ++i) {
-                                const bool ka = (T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u;
-                                const unsigned nib = ka ? ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu) : 0u;
-                                float4 o;
-                                o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
-                                o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-                                *reinterpret_cast<float4*>(dst + (size_t)i * EE) = o;
-                            }
-                        }
-                    }
-                } else {
-                    for (int idx = lane; idx < EE; idx += 32) {
-                        const int a = idx / E, b2 = idx - a * E;
-                        const float v = T.dthr[idx];
-                        for (int i = 0; i < N; ++i) {
-                            const bool keep = ((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
-                                              ((T.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u);
-                            abase[(size_t)i * EE + idx] = keep ? v : 0.0f;
-                        }
-                    }
-                }
-            }
-            __syncwarp();
-        }
-        __syncwarp();
-    }
-}
 
 // ---------------------------------------------------------------------------------------------
 // host-side launch helpers (used by lsm_capi.cu)
 // ---------------------------------------------------------------------------------------------
-static const void* kernel_ptr(int dynamics) {
-    return dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? (const void*)lsm_fused_kernel<LSM_DYN_DOUBLE_INTEGRATOR>
-                                                 : (const void*)lsm_fused_kernel<LSM_DYN_AIRTAXI>;
+#define LSM_SPEC_LIST(X)                         \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2)           \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2)           \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2)          \
+    X(LSM_DYN_AIRTAXI, 10, 2)
+
+constexpr int kSpecBlock = 128;
+constexpr int kSpecMinBlocks = 4;
+
+static const void* generic_ptr(int dynamics) {
+    return dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? (const void*)lsm_generic_kernel<LSM_DYN_DOUBLE_INTEGRATOR>
+                                                 : (const void*)lsm_generic_kernel<LSM_DYN_AIRTAXI>;
 }
 
-cudaError_t fused_kernel_prepare(int dynamics, int smem_bytes, int block_threads, int* regs, int* blocks_per_sm) {
-    const void* fn = kernel_ptr(dynamics);
+static const void* spec_ptr(int dynamics, int N, int L, int* bytes_per_env) {
+#define X(DYN_, N_, L_)                                                                           \
+    if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
+        *bytes_per_env = (int)sizeof(EnvShared<DYN_, N_, L_>);                                    \
+        return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, kSpecMinBlocks>;            \
+    }
+    LSM_SPEC_LIST(X)
+#undef X
+    return nullptr;
+}
+
+bool spec_available(int dynamics, int N, int L, int* bytes_per_env, int* block_threads) {
+    *block_threads = kSpecBlock;
+    return spec_ptr(dynamics, N, L, bytes_per_env) != nullptr;
+}
+
+cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,
+                           int* blocks_per_sm) {
+    int dummy = 0;
+    const void* fn = spec ? spec_ptr(dynamics, N, L, &dummy) : generic_ptr(dynamics);
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
@@ -984,8 +72,8 @@ cudaError_t upload_magnetic_tables(const double* cos_tab, const double* sin_tab)
     return cudaMemcpyToSymbol(c_mag_sin, sin_tab, sizeof(double) * kMagSegments);
 }
 
-cudaError_t fused_kernel_launch(const KParams& kp, int grid_blocks, int block_threads, int smem_bytes,
-                                cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int block_threads, int smem_bytes,
+                          cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)grid_blocks, 1, 1);
     cfg.blockDim = dim3((unsigned)block_threads, 1, 1);
@@ -1005,9 +93,10 @@ cudaError_t fused_kernel_launch(const KParams& kp, int grid_blocks, int block_th
     }
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
-    if (kp.c.dynamics == LSM_DYN_DOUBLE_INTEGRATOR)
-        return cudaLaunchKernelEx(&cfg, lsm_fused_kernel<LSM_DYN_DOUBLE_INTEGRATOR>, kp);
-    return cudaLaunchKernelEx(&cfg, lsm_fused_kernel<LSM_DYN_AIRTAXI>, kp);
+    void* args[] = { (void*)&kp };
+    int dummy = 0;
+    const void* fn = spec ? spec_ptr(kp.c.dynamics, kp.N, kp.L, &dummy) : generic_ptr(kp.c.dynamics);
+    return cudaLaunchKernelExC(&cfg, fn, args);
 }
 
 }  // namespace lsm
