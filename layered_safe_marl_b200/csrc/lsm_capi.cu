@@ -37,6 +37,7 @@ struct lsm_handle {
     int blocks_per_sm = 0;
     uint16_t* d_pair_tab = nullptr;
     uint32_t* d_sel_tab = nullptr;
+    uint32_t* d_pair32 = nullptr;
     size_t persist_bytes = 0;
     size_t max_window = 0;
     bool spec = false;          // compile-time specialised kernel available for (dynamics, N, L)
@@ -44,6 +45,7 @@ struct lsm_handle {
     int epw_max = 1;            // 32 / G
     int smem_optin = 0;
     int forced_epw = 0;         // LSM_EPW environment override (experiments)
+    int stage_bytes = 0;        // per-warp node-row staging buffer of the specialised kernels
 };
 
 extern "C" {
@@ -101,13 +103,38 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
         const double phase = stair * 0.5 * lsm::kPi;
         kp.sep_ratio_tab[k] = 1.0 - std::cos(phase);
     }
-    // exact squared radius: d < R  <=>  d2 < r2_lt for d = sqrt_rn(d2)  (sqrt_rn is monotone)
+    // exact squared thresholds: sqrt_rn is monotone, so {t : sqrt_rn(t) >= T} is [lt(T), inf)
     {
+        auto lt = [](double T) {
+            if (!(T > 0.0)) return 0.0;
+            double t = T * T;
+            while (t > 0.0 && std::sqrt(t) >= T) t = std::nextafter(t, 0.0);
+            while (std::sqrt(t) < T) t = std::nextafter(t, INFINITY);
+            return t;
+        };
+        auto gt = [](double T) {
+            if (T < 0.0) return 0.0;
+            double t = T * T;
+            while (t > 0.0 && std::sqrt(t) > T) t = std::nextafter(t, 0.0);
+            while (!(std::sqrt(t) > T)) t = std::nextafter(t, INFINITY);
+            return t;
+        };
         const double R = cfg->coordination_range;
-        double t = R * R;
-        while (std::sqrt(t) >= R) t = std::nextafter(t, 0.0);
-        while (std::sqrt(t) < R) t = std::nextafter(t, INFINITY);
-        kp.r2_lt = t;
+        kp.r2_lt = lt(R); kp.r2_gt = gt(R);
+        kp.col2_lt = lt(1.05 * (0.050 + 0.050));
+        kp.engref2_lt = lt(cfg->engagement_distance_ref);
+        kp.septgt2_lt = lt(cfg->separation_distance_target);
+        for (int k = 0; k < 5; ++k) {
+            // scenario.separation_distance / engagement_distance at stair level k (same expressions as the kernel)
+            const double sep_ratio = kp.sep_ratio_tab[k];
+            const double sep_init = (cfg->flags & LSM_FLAG_SEPARATION_DISTANCE_CURRICULUM) ? 0.0 : cfg->separation_distance_target;
+            volatile double a = sep_init * (1.0 - sep_ratio);
+            volatile double b = cfg->separation_distance_target * sep_ratio;
+            const double sep = a + b;
+            volatile double dlt = sep - cfg->engagement_ref_separation;
+            const double eng = cfg->engagement_distance_ref + dlt;
+            kp.sep2_lt[k] = lt(sep); kp.eng2_lt[k] = lt(eng);
+        }
     }
     // shared-memory layout of one environment (generic kernel; the specialised kernels use a struct)
     lsm::SmemLayout& sl = kp.sl;
@@ -131,14 +158,16 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
 
     int spec_bytes = 0, spec_block = 0;
     const char* force_generic = std::getenv("LSM_FORCE_GENERIC");
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &spec_bytes, &spec_block) &&
+    int spec_stage = 0;
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &spec_bytes, &spec_block, &spec_stage) &&
               !(force_generic != nullptr && force_generic[0] == '1');
     const char* fe = std::getenv("LSM_EPW");
     h->forced_epw = fe ? std::atoi(fe) : 0;
     if (h->spec) {
         h->bytes_per_env = spec_bytes;
+        h->stage_bytes = spec_stage;
         int wpb = spec_block / 32;
-        while (wpb > 1 && spec_bytes * wpb > h->smem_optin) --wpb;     // 32-agent records are ~60 KB each
+        while (wpb > 1 && (spec_bytes + spec_stage) * wpb > h->smem_optin) --wpb;     // 32-agent records are ~60 KB each
         h->warps_per_block = wpb;
         h->block_threads = 32 * wpb;
     } else {
@@ -154,7 +183,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     // provisional geometry (re-evaluated in lsm_bind_buffers once num_envs is known)
     if (h->spec) kp.EPW = 1;
     kp.smem_per_warp = h->bytes_per_env * kp.EPW;
-    h->smem_per_block = kp.smem_per_warp * h->warps_per_block;
+    h->smem_per_block = (kp.smem_per_warp + h->stage_bytes) * h->warps_per_block;
     if (h->smem_per_block > h->smem_optin) {
         delete h;
         return fail(4, "lsm_create: one environment group does not fit in shared memory");
@@ -168,7 +197,6 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     std::vector<uint16_t> pairs;
     pairs.reserve((size_t)E * (E - 1));
     for (int a = 0; a < E; ++a) for (int b = a + 1; b < E; ++b) {
-        if (h->spec && b < N) continue;   // the specialised kernels take agent-agent distances from the float64 block
         pairs.push_back((uint16_t)a); pairs.push_back((uint16_t)b);
     }
     kp.num_pairs = (int)(pairs.size() / 2);
@@ -182,7 +210,12 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     if (e == cudaSuccess) e = cudaMalloc(&h->d_sel_tab, sel.size() * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemcpy(h->d_sel_tab, sel.data(), sel.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { lsm_destroy(h); return cuda_fail(e, "table upload"); }
-    kp.pair_tab = h->d_pair_tab; kp.sel_tab = h->d_sel_tab;
+    std::vector<uint32_t> pair32(pairs.size() / 2);
+    for (size_t k2 = 0; k2 < pair32.size(); ++k2) pair32[k2] = ((uint32_t)pairs[2 * k2] << 16) | (uint32_t)pairs[2 * k2 + 1];
+    if (e == cudaSuccess) e = cudaMalloc(&h->d_pair32, pair32.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_pair32, pair32.data(), pair32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { lsm_destroy(h); return cuda_fail(e, "table upload"); }
+    kp.pair_tab = h->d_pair_tab; kp.sel_tab = h->d_sel_tab; kp.pair32 = h->d_pair32;
     // cos/sin(phi_k) of utils.py:291 (np.linspace(0, 2pi, 50, endpoint=False)), host libm
     double ctab[lsm::kMagSegments], stab[lsm::kMagSegments];
     const double step = (2.0 * lsm::kPi - 0.0) / (double)lsm::kMagSegments;
@@ -200,6 +233,7 @@ int lsm_destroy(lsm_handle* h) {
     if (h == nullptr) return 0;
     if (h->d_pair_tab) cudaFree(h->d_pair_tab);
     if (h->d_sel_tab) cudaFree(h->d_sel_tab);
+    if (h->d_pair32) cudaFree(h->d_pair32);
     delete h;
     return 0;
 }
@@ -215,6 +249,7 @@ static int fill_grid(const lsm_grid_desc* g, lsm::GridDev* d, int want_ndim, boo
         d->shape[k] = g->shape[k]; d->periodic[k] = g->periodic[k] ? 1 : 0; d->lo[k] = g->lo[k];
         const double n = (double)g->shape[k];
         d->spacing[k] = g->periodic[k] ? (g->hi[k] - g->lo[k]) / n : (g->hi[k] - g->lo[k]) / (n - 1.0);
+        d->inv_spacing[k] = 1.0 / d->spacing[k];
     }
     d->separation_distance = g->separation_distance; d->ttr_max = g->ttr_max;
     d->values = g->values; d->grads = g->grads;
@@ -259,7 +294,7 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
         int best_epw = h->epw_max, best_bps = 0;
         const lsm_config& c = h->kp.c;
         for (int epw = 1; epw <= h->epw_max; epw *= 2) {
-            const int smem = h->bytes_per_env * epw * h->warps_per_block;
+            const int smem = (h->bytes_per_env * epw + h->stage_bytes) * h->warps_per_block;
             if (smem > h->smem_optin) break;
             int regs = 0, bps = 0;
             cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, smem, h->block_threads, &regs, &bps);
@@ -273,12 +308,12 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
         if (best_bps == 0) {
             // nothing fits in one wave: densest packing that fits in shared memory
             int epw = h->epw_max;
-            while (epw > 1 && h->bytes_per_env * epw * h->warps_per_block > h->smem_optin) epw /= 2;
+            while (epw > 1 && (h->bytes_per_env * epw + h->stage_bytes) * h->warps_per_block > h->smem_optin) epw /= 2;
             best_epw = epw;
         }
         h->kp.EPW = best_epw;
         h->kp.smem_per_warp = h->bytes_per_env * best_epw;
-        h->smem_per_block = h->kp.smem_per_warp * h->warps_per_block;
+        h->smem_per_block = (h->kp.smem_per_warp + h->stage_bytes) * h->warps_per_block;
         cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, h->smem_per_block, h->block_threads,
                                             &h->regs, &h->blocks_per_sm);
         if (e != cudaSuccess) return cuda_fail(e, "kernel_prepare");
@@ -311,6 +346,8 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     kp.mode = mode; kp.flag = flag; kp.action_idx = action_idx; kp.action_onehot = action_onehot;
     kp.env_mask = env_mask; kp.episode = (long long)episode; kp.seed = (unsigned long long)seed;
     const long long ngroups = (kp.b.num_envs + kp.EPW - 1) / kp.EPW;
+    kp.ngroups = (int)ngroups;
+    { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
     if (blocks > h->grid_cap) blocks = h->grid_cap;
     const void* persist = (mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;

@@ -26,6 +26,7 @@ struct GridDev {
     int periodic[5];
     double lo[5];
     double spacing[5];
+    double inv_spacing[5];     // RN(1/spacing): exact division through the reciprocal (spec kernels)
     double separation_distance;
     double ttr_max;
     const float* values;
@@ -68,9 +69,18 @@ struct KParams {
     int smem_per_warp;
     SmemLayout sl;
     const uint16_t* pair_tab;  // [num_pairs][2] entity pairs a < b
+    const uint32_t* pair32;    // [num_pairs] the same pairs packed (a << 16) | b
     int num_pairs;
+    int ngroups;               // ceil(num_envs / EPW)
+    int debug;                 // LSM_DEBUG experiment switches (0 in production): 1 skip graph emission, 2 skip HJ pair lookups, 4 skip node rows, 8 skip adjacency stores
     const uint32_t* sel_tab;   // [N][W] entities whose owner agent is <= i
-    double r2_lt;              // smallest double whose correctly rounded sqrt is >= coordination_range
+    // exact squared thresholds (host): lt(T) = min{t : sqrt_rn(t) >= T} so that d < T <=> d2 < lt(T);
+    //                                  gt(T) = min{t : sqrt_rn(t) >  T} so that d > T <=> d2 >= gt(T)
+    double r2_lt, r2_gt;       // coordination_range (adjacency radius / filter range)
+    double col2_lt;            // 1.05 * (size + size) agent collision distance
+    double engref2_lt;         // world.engagement_distance (episode statistics)
+    double septgt2_lt;         // world.separation_distance_target (episode statistics)
+    double sep2_lt[5], eng2_lt[5];   // scenario separation / engagement distance per curriculum stair level
 };
 
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -1,17 +1,22 @@
 // lsm_kernel_spec.cuh - step kernel specialised at compile time on (dynamics, N agents, L landmarks
 // per agent): constant-size shared-memory records, unrolled loops, immediate-offset stores.
 //
-// Differences from the generic kernel (same arithmetic for every thresholded quantity):
-//   * envs per warp (EPW) is a LAUNCH choice (1 .. 32/G): small batches run one environment per warp
-//     so that the whole batch is resident in one wave; large batches pack 32/G environments per warp.
-//   * the HJ value lookups run pair-parallel: every (ego, other) pair of the warp's environments is
-//     one lane-task (N*N tasks per env), results go to shared memory, the agent lane then takes the
-//     first minimum in `other` order exactly like np.argmin.
-//   * agent-agent distances (needed in float64 for thresholds) are pair-parallel too; agent-landmark
-//     and landmark-landmark distances only feed the float32 adjacency, so they use d^2 in float64
-//     against an EXACT squared threshold (host-computed smallest double whose correctly rounded sqrt
-//     is >= R) and a correctly rounded float32 sqrt for the stored value.
-//   * node features read float32 per-entity tables (sin/cos/speed of headings converted once per env).
+// Same decisions as the generic kernel for every thresholded quantity, organised for far fewer instructions:
+//   * envs per warp (EPW) is a LAUNCH choice (1 .. 32/G): small batches spread over more warps so the
+//     whole batch is resident in one wave; large batches pack 32/G environments per warp.
+//   * the HJ value lookups run pair-parallel: every (ego, other) pair of the warp's environments is one
+//     lane-task, results go to shared memory, the agent lane then takes the first minimum in `other`
+//     order exactly like np.argmin. The stencil uses 32-bit indices and an exactly rounded division by
+//     the grid spacing through its precomputed reciprocal (Markstein: q0 = a*y, r = fma(-b,q0,a),
+//     q = fma(r,y,q0) equals RN(a/b); checked on the CPU in tests/test_host_logic.py).
+//   * distances are kept SQUARED in float64; every `d < T` / `d > T` test of the reference becomes
+//     `d2 < T2` against a host-computed exact squared threshold (sqrt_rn is monotone, so
+//     {t : sqrt_rn(t) >= T} is an interval whose lower end the host finds with nextafter). Square roots
+//     are taken only where a distance VALUE is stored (min distance, float32 adjacency).
+//   * the float32 adjacency value is d2f * rsqrt(d2f) (<= 4e-7 relative from the float64 reference, bar
+//     1e-5); which entries are non-zero is decided exactly in float64.
+//   * node features are branch-free rows over unified per-entity tables (landmarks carry zero velocity and
+//     their own position as "goal"), read with 16-byte shared-memory loads.
 #pragma once
 #include "lsm_step_common.cuh"
 
@@ -22,50 +27,457 @@ struct __align__(16) EnvShared {
     static constexpr int M = N * L;
     static constexpr int E = N + M;
     static constexpr int W = (E + 31) / 32;
-    // agent state after the dynamics (as2/as3 hold the PRE-update velocity / heading+speed)
-    double ax[N], ay[N], as2[N], as3[N];
-    double vpre_x[N], vpre_y[N], vpost_x[N], vpost_y[N];   // world-frame velocity before / after own goal update
-    double spd_post[N], sth[N], cth[N];                    // airtaxi: speed after update, sin/cos(theta)
-    double rawx[N], rawy[N];                               // decoded raw controls
-    double lx[M], ly[M], lh[M], lsp[M], lsin[M], lcos[M];
-    double daa[N * N];                                     // agent-agent distances (P1: pre-integration, P2: post)
-    double fval[N * N];                                    // HJ value of (ego i, other j); +inf = out of range
-    float dthr[E * E];                                     // radius-thresholded distance matrix
-    float lsinf[M], lcosf[M], lspf[M];                     // float32 landmark tables for node features
-    int goal_pre[N], goal_post[N], reached_pre[N], reached_post[N], done_pre[N], done_post[N];
-    unsigned disc_pre[W], disc_post[W], keepm[N * W];
-    double cur_sep;                                        // scenario.separation_distance of this env (curriculum)
-    int cur_filter;                                        // world.use_safety_filter of this env (curriculum, Q5)
+    // unified per-entity tables for the branch-free node-feature rows:
+    //   pos[e]                     position of entity e (agents after the dynamics, then landmarks)
+    //   pos[E + s*N + a]           goal position of agent a before (s=0) / after (s=1) its own goal update
+    //   vel[s*N + a], vel[2N] = 0  world-frame velocity of agent a before / after its update; landmarks use slot 2N
+    //   cst[m], cst[M + s*N + a]   (sin heading, cos heading, speed, type) of landmark m / of agent a's goal
+    double2 pos[E + 2 * N];
+    double2 vel[2 * N + 1];
+    float4 cst[M + 2 * N];
+    double as2[N], as3[N];     // state components 2,3 BEFORE the own goal update (vx,vy | theta,speed)
+    double rawx[N], rawy[N];   // decoded raw controls
+    double sth[N], cth[N], spd_post[N];       // airtaxi: sin/cos(theta), speed after the own update
+    double lh[M], lsp[M], lsin[M], lcos[M];   // landmark heading, speed, sin/cos(heading)
+    union alignas(16) {
+        float dthr[E * E];     // P4: radius-thresholded distance matrix (float32, what adj stores)
+        struct {
+            double d2aa[N * N];    // P1/P2: squared agent-agent distances (before / after the dynamics)
+            double fval[N * N];    // P1: HJ value of (ego i, other j); +inf = out of range
+        };
+    };
+    int goal[2][N], reached[2][N], done[2][N];
+    unsigned disc[2][W], keepm[N * W];
+    double cur_sep;            // scenario.separation_distance of this env (curriculum)
+    int cur_filter;            // world.use_safety_filter of this env (curriculum, Q5)
 };
 
 template <int N> struct Pow2 { static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
 
-// HJ value of one (ego, other) pair: safety_filter.py:192-201, 345-354
-template <int DYN, class S>
-__device__ __forceinline__ double pair_value(const KParams& kp, const Curriculum& q, const S& s, int i, int j) {
-    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-    double rel[ND]; bool inr;
-    relative_state<DYN>(s.ax[i], s.ay[i], s.as2[i], s.as3[i], s.ax[j], s.ay[j], s.as2[j], s.as3[j], rel);
-    return hj_value<DYN>(kp, q, rel, inr);   // +inf when out of range
+// ---------------------------------------------------------------------------------------------
+// lean stencil: 32-bit indices, exact division through the reciprocal, weight prefixes shared
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double div_exact(double a, double b, double y /* RN(1/b) */) {
+    const double q0 = a * y;
+    const double r = fma(-b, q0, a);
+    return fma(r, y, q0);
 }
 
-#define SAFP(f) (kp.b.agent_f64 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
-#define SAIP(f) (kp.b.agent_i32 + ((size_t)(f) * (size_t)n + (size_t)env) * (size_t)N + (size_t)ai)
-#define SEFP(f) (kp.b.env_f64 + (size_t)(f) * (size_t)n + (size_t)env)
-#define SEIP(f) (kp.b.env_i32 + (size_t)(f) * (size_t)n + (size_t)env)
+template <int ND>
+struct Stencil32 {
+    int lo[ND], hi[ND];        // linear offset contributions
+    double wlo[ND], whi[ND];
+    bool valid;
+};
 
-template <int DYN, int N, int L>
-__device__ __forceinline__ void emit_obs_row(const EnvShared<DYN, N, L>& S, int ai, int g, double x, double y,
-                                             double s2, double s3, float* o) {
+template <int ND>
+__device__ __forceinline__ void stencil32_setup(const GridDev& g, const double (&x)[ND], Stencil32<ND>& s) {
+    s.valid = true;
+    int mul = 1;
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+        double pos = div_exact(x[d] - g.lo[d], g.spacing[d], g.inv_spacing[d]);
+        if (isnan(pos)) s.valid = false;
+        if (!(fabs(pos) <= 1.0e9)) pos = pos < 0.0 ? -1.0e9 : 1.0e9;     // declared clamp; never taken in-grid
+        const double fl = floor(pos);
+        const double whi = pos - fl;
+        s.wlo[d] = 1.0 - whi; s.whi[d] = whi;
+        const int n = g.shape[d];
+        int il = (int)fl, ih = il + 1;          // |fl| <= 1e9 fits in int32
+        if (g.periodic[d]) {
+            il %= n; if (il < 0) il += n;
+            ih %= n; if (ih < 0) ih += n;
+        } else {
+            il = min(max(il, 0), n - 1);
+            ih = min(max(ih, 0), n - 1);
+        }
+        s.lo[d] = il * mul; s.hi[d] = ih * mul;
+        mul *= n;
+    }
+}
+
+// value: sum over corners (binary counting, dim 0 slowest) of ((w0*w1)*w2..)*v, sequential adds
+template <int ND>
+__device__ __forceinline__ double stencil32_value(const GridDev& g, const Stencil32<ND>& s) {
+    double acc = 0.0;
+    if (ND == 4) {
+#pragma unroll
+        for (int c0 = 0; c0 < 2; ++c0) {
+            const double w0 = c0 ? s.whi[0] : s.wlo[0]; const int o0 = c0 ? s.hi[0] : s.lo[0];
+#pragma unroll
+            for (int c1 = 0; c1 < 2; ++c1) {
+                const double w1 = w0 * (c1 ? s.whi[1] : s.wlo[1]); const int o1 = o0 + (c1 ? s.hi[1] : s.lo[1]);
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const double w2 = w1 * (c2 ? s.whi[2] : s.wlo[2]); const int o2 = o1 + (c2 ? s.hi[2] : s.lo[2]);
+                    acc = acc + (w2 * s.wlo[3]) * (double)__ldg(g.values + o2 + s.lo[3]);
+                    acc = acc + (w2 * s.whi[3]) * (double)__ldg(g.values + o2 + s.hi[3]);
+                }
+            }
+        }
+    } else {
+#pragma unroll
+        for (int corner = 0; corner < (1 << ND); ++corner) {
+            double weight = 0.0; int lin = 0;
+#pragma unroll
+            for (int d = 0; d < ND; ++d) {
+                const int bit = (corner >> (ND - 1 - d)) & 1;
+                const double wd = bit ? s.whi[d] : s.wlo[d];
+                weight = (d == 0) ? wd : weight * wd;
+                lin += bit ? s.hi[d] : s.lo[d];
+            }
+            acc = acc + weight * (double)__ldg(g.values + lin);
+        }
+    }
+    return acc;
+}
+
+// all gradient components in one pass over the corners (same corner / weight order as the value)
+template <int ND>
+__device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32<ND>& s, double (&out)[ND]) {
+#pragma unroll
+    for (int d = 0; d < ND; ++d) out[d] = 0.0;
+#pragma unroll
+    for (int corner = 0; corner < (1 << ND); ++corner) {
+        double weight = 0.0; int lin = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int bit = (corner >> (ND - 1 - d)) & 1;
+            const double wd = bit ? s.whi[d] : s.wlo[d];
+            weight = (d == 0) ? wd : weight * wd;
+            lin += bit ? s.hi[d] : s.lo[d];
+        }
+        if (ND == 4) {
+            const float4 v = __ldg(reinterpret_cast<const float4*>(g.grads) + lin);
+            out[0] = out[0] + weight * (double)v.x; out[1] = out[1] + weight * (double)v.y;
+            out[2] = out[2] + weight * (double)v.z; out[3] = out[3] + weight * (double)v.w;
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; ++d) out[d] = out[d] + weight * (double)__ldg(g.grads + lin * ND + d);
+        }
+    }
+}
+
+struct LeanGrad {
+    template <int ND>
+    __device__ __forceinline__ static void eval(const GridDev& g, const double (&rel)[ND], double (&out)[ND]) {
+        Stencil32<ND> st;
+        stencil32_setup<ND>(g, rel, st);
+        stencil32_grad<ND>(g, st, out);
+    }
+};
+
+template <int DYN, class ES>
+__device__ __forceinline__ double pair_value(const KParams& kp, double sep, const ES& s, int i, int j) {
+    // safety_filter.py:192-201, 345-354 (+ the value shift of HjDataHandle.update_separation_distance)
+    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    double rel[ND];
+    const double2 pi = s.pos[i], pj = s.pos[j];
+    relative_state<DYN>(pi.x, pi.y, s.as2[i], s.as3[i], pj.x, pj.y, s.as2[j], s.as3[j], rel);
+    Stencil32<ND> st;
+    stencil32_setup<ND>(kp.vg, rel, st);
+    if (!st.valid) return INFINITY;
+    const double v = stencil32_value<ND>(kp.vg, st);
+    if (isnan(v)) return INFINITY;
+    return v - (sep - kp.vg.separation_distance);
+}
+
+template <int DYN, class ES>
+__device__ __forceinline__ void emit_obs_row(const ES& S, int ai, int g /* landmark index */, double x, double y,
+                                             double s2, double s3, float* o, int N) {
     // navigation_graph_safe.py:855-875, utils.py:114-137
+    const double2 gp = S.pos[N + g];
     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-        o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(S.lx[g] - x); o[3] = (float)(S.ly[g] - y);
+        o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(gp.x - x); o[3] = (float)(gp.y - y);
         o[4] = (float)S.lsin[g]; o[5] = (float)S.lcos[g]; o[6] = (float)S.lsp[g];
     } else {
-        double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
+        double rx, ry; rotate_into(gp.x - x, gp.y - y, S.cth[ai], S.sth[ai], rx, ry);
         const double rh = S.lh[g] - s2;
         o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
         o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk store (UBLKCP): shared -> global, asynchronous, issued by one lane; frees the warp from
+// the store loop and its LSU back-pressure. Source and destination 16-byte aligned, size % 16 == 0.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(PENDING) : "memory"); }
+
+// Graph observation of ONE environment (navigation_graph_safe.py:932-994 + utils.py:139-255), all 32 lanes.
+template <int DYN, int N, int L>
+__device__ __noinline__ void emit_graph(float* __restrict__ node_obs, float* __restrict__ adj,
+                                       const uint32_t* __restrict__ sel_tab, const double r2_lt,
+                                       EnvShared<DYN, N, L>& T, float* __restrict__ stage, int ee, int lane, int debug) {
+    // arguments by value: a noinline callee would otherwise re-read the kernel parameter block through generic loads
+    using ES = EnvShared<DYN, N, L>;
+    constexpr int M = ES::M, E = ES::E, W = ES::W, EE = E * E;
+    constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
+    // (a) thresholded distance matrix: d2 in float64 against the exact squared radius; the stored
+    //     float32 value is d2f * rsqrt(d2f). One lane-task per unordered entity pair, enumerated without a
+    //     table as (a, a + d mod E) for d = 1 .. E/2 (for even E the last distance only needs a < E/2).
+    for (int e = lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
+    constexpr int NPAIR = E * (E - 1) / 2;
+    auto pair_task = [&](int p) {
+        const int dm1 = p / E, a = p - dm1 * E;
+        int b = a + dm1 + 1; if (b >= E) b -= E;
+        const double2 pa = T.pos[a], pb = T.pos[b];
+        const double dx = pa.x - pb.x, dy = pa.y - pb.y;
+        const double d2 = dx * dx + dy * dy;
+        const float d2f = fmaxf((float)d2, 1.0e-30f);
+        float rs;
+        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(d2f));
+        const float v = (d2 < r2_lt && d2 > 0.0) ? d2f * rs : 0.0f;
+        T.dthr[a * E + b] = v; T.dthr[b * E + a] = v;
+    };
+    {
+        int p = lane;
+        for (; p + 32 < NPAIR; p += 64) { pair_task(p); pair_task(p + 32); }   // two independent tasks in flight
+        if (p < NPAIR) pair_task(p);
+    }
+    // (b) disconnected-entity bit masks before / after this step's goal updates (ballots)
+    unsigned any_change = 0u, any_disc = 0u;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const int e = w * 32 + lane;
+        bool dpre = false, dpost = false;
+        if (e < N) { dpre = T.done[0][e] != 0; dpost = T.done[1][e] != 0; }
+        else if (e < E) {
+            const int m = e - N, order = m / N, owner = m - order * N;
+            dpre = T.reached[0][owner] > order; dpost = T.reached[1][owner] > order;
+        }
+        const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
+        if (lane == 0) { T.disc[0][w] = bpre; T.disc[1][w] = bpost; }
+        any_change |= (bpre ^ bpost); any_disc |= bpost;
+    }
+    __syncwarp();
+    if (any_disc != 0u) {
+        for (int k = lane; k < N * W; k += 32) {
+            const int w = k % W;
+            const unsigned sel = sel_tab[k];
+            T.keepm[k] = ~((T.disc[1][w] & sel) | (T.disc[0][w] & ~sel));
+        }
+    }
+    __syncwarp();
+    // (d) adjacency (issued BEFORE the node rows so that the asynchronous copies overlap their computation)
+    if (!(debug & 8)) {
+        float* abase = adj + (size_t)ee * (N * EE);
+        if (E % 2 == 0 && any_change == 0u) {
+            // every observer sees the same matrix this step: mask it once in place, then N bulk copies
+            if (any_disc != 0u) {
+                for (int idx = lane; idx < EE; idx += 32) {
+                    const int a = idx / E, b2 = idx - a * E;
+                    const bool keep = ((T.keepm[a >> 5] >> (a & 31)) & 1u) && ((T.keepm[b2 >> 5] >> (b2 & 31)) & 1u);
+                    if (!keep) T.dthr[idx] = 0.0f;
+                }
+            }
+            bulk_store_fence();
+            __syncwarp();
+            if (lane < N) { bulk_store(abase + lane * EE, T.dthr, (unsigned)EE * 4u); bulk_store_commit(); }
+        } else if (E % 4 == 0) {
+            constexpr int CPR = E / 4, CHUNKS = EE / 4;
+            for (int ch = lane; ch < CHUNKS; ch += 32) {
+                const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
+                const float4 v = *reinterpret_cast<const float4*>(T.dthr + ch * 4);
+                float* dst = abase + ch * 4;
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const bool ka = any_disc == 0u || ((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u);
+                    const unsigned nib = !ka ? 0u : (any_disc == 0u ? 0xFu : ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu));
+                    float4 o;
+                    o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
+                    o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
+                    __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                }
+            }
+        } else {
+            for (int idx = lane; idx < EE; idx += 32) {
+                const int a = idx / E, b2 = idx - a * E;
+                const float v = T.dthr[idx];
+#pragma unroll
+                for (int i = 0; i < N; ++i) {
+                    const bool keep = any_disc == 0u ||
+                                      (((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
+                                       ((T.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u));
+                    __stcs(abase + i * EE + idx, keep ? v : 0.0f);
+                }
+            }
+        }
+    }
+    // (c) node features: one lane per (observer, entity) row. Rows are 40 / 44 bytes, so they are staged in a
+    //     per-warp double-buffered shared-memory buffer (32 rows at a time) and flushed with fully coalesced vector stores.
+    if (!(debug & 4)) {
+        float* nbase = node_obs + (size_t)ee * (N * E * F);
+        constexpr int ROWS = N * E, CH = 32;
+        constexpr int VEC = ((ROWS * F) % 4 == 0 && (CH * F) % 4 == 0) ? 4 : (((ROWS * F) % 2 == 0 && (CH * F) % 2 == 0) ? 2 : 1);
+        auto node_row = [&](int r, float* o) {
+            const int i = r / E, e = r - i * E;
+            const double2 pi = T.pos[i], vi = T.vel[N + i];
+            const bool is_agent = e < N;
+            const int sel = (e <= i) ? N : 0;     // agents <= i are seen after their own update
+            const int vidx = is_agent ? sel + e : 2 * N;
+            const int gidx = is_agent ? E + sel + e : e;
+            const int cidx = is_agent ? M + sel + e : e - N;
+            if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                // utils.py:201-255: [p_e - p_i, v_e - v_i, goal_e - p_i, sin gh, cos gh, gspeed, type]
+                const double2 pe = T.pos[e], ve = T.vel[vidx], ge = T.pos[gidx];
+                const float4 cc = T.cst[cidx];
+                float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
+                o2[0] = make_float2((float)(pe.x - pi.x), (float)(pe.y - pi.y));
+                o2[1] = make_float2((float)(ve.x - vi.x), (float)(ve.y - vi.y));
+                o2[2] = make_float2((float)(ge.x - pi.x), (float)(ge.y - pi.y));
+                o2[3] = make_float2(cc.x, cc.y);
+                o2[4] = make_float2(cc.z, cc.w);
+            } else {
+                const double ci = T.cth[i], si = T.sth[i];
+                if (e < N) {
+                    const int g = T.goal[sel ? 1 : 0][e];
+                    const double2 pe = T.pos[e], ve = T.vel[vidx], ge = T.pos[gidx];
+                    double rx, ry, gx, gy;
+                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
+                    rotate_into(ge.x - pi.x, ge.y - pi.y, ci, si, gx, gy);
+                    const double ce = T.cth[e], se = T.sth[e];
+                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(ve.x - vi.x, ve.y - vi.y);
+                    o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
+                    o[5] = (float)gx; o[6] = (float)gy;
+                    o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
+                    o[9] = (float)T.lsp[g]; o[10] = 0.0f;
+                } else {
+                    const int m = e - N;
+                    const double2 pe = T.pos[e];
+                    double rx, ry;
+                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
+                    const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
+                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
+                    o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
+                    o[9] = (float)T.lsp[m]; o[10] = 1.0f;
+                }
+            }
+        };
+        constexpr bool BULK = (VEC == 4);
+        int chunk = 0;
+        for (int r0 = 0; r0 < ROWS; r0 += CH, ++chunk) {
+            float* buf = stage + (chunk & 1) * (CH * F);
+            if (BULK && chunk >= 2) {       // the copy that last read this buffer must have finished reading it
+                if (lane == 0) bulk_store_wait_read<1>();
+                __syncwarp();
+            }
+            const int ra = r0 + lane;
+            if (ra < ROWS) node_row(ra, buf + lane * F);
+            const int nfl = ((ROWS - r0) < CH ? (ROWS - r0) : CH) * F;   // floats in this chunk
+            float* gdst = nbase + r0 * F;
+            if (BULK) {
+                bulk_store_fence();
+                __syncwarp();
+                if (lane == 0) { bulk_store(gdst, buf, (unsigned)nfl * 4u); bulk_store_commit(); }
+            } else {
+                __syncwarp();
+                if (VEC == 2) {
+                    for (int q = lane; q < nfl / 2; q += 32)
+                        __stcs(reinterpret_cast<float2*>(gdst) + q, reinterpret_cast<const float2*>(buf)[q]);
+                } else {
+                    for (int q = lane; q < nfl; q += 32) __stcs(gdst + q, buf[q]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    // every bulk copy issued by this call has finished READING shared memory before the records are reused
+    bulk_store_wait_read<0>();
+    __syncwarp();
+}
+
+// Scenario.random_scenario for ONE environment, executed by the env's leader lane
+// (navigation_graph_safe.py:1199-1367, utils.py:39-68); Philox stream keyed by (seed, env, reset_count).
+template <int DYN, int N, int L>
+__device__ __noinline__ void sample_scenario(const KParams& kp, EnvShared<DYN, N, L>& S, int env, int reset_count,
+                                            double ratio) {
+    using ES = EnvShared<DYN, N, L>;
+    constexpr int M = ES::M;
+    const lsm_config& c = kp.c;
+    const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
+    Rng r; r.init(kp.seed, (uint32_t)(kp.b.env_id_base + env), (uint32_t)reset_count);
+    const double ws = c.world_size;
+    double cra = ratio_sloped(ratio, 0.25, 0.75);
+    if (use_filter_arg) cra = 1.0;
+    for (int i = 0; i < N; ++i) {
+        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+            const double px = r.uniform(-0.8 * ws, 0.8 * ws);
+            const double py = r.uniform(-0.8 * ws, 0.8 * ws);
+            S.pos[i] = make_double2(px, py);
+            S.as2[i] = 0.0; S.as3[i] = 0.0;
+        } else {
+            const double xmin = -0.5 * ws;
+            const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
+            const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
+            const double rx = r.uniform(xmin, xmax);
+            S.pos[i] = make_double2(rx, ry);
+            const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
+            S.as2[i] = r.uniform(0.0, 2.0 * kPi);
+            S.as3[i] = sp;
+        }
+    }
+    double2* lp = S.pos + N;    // landmark positions, slot l*N + i
+    for (int i = 0; i < N; ++i) {
+        double xlo, xhi, ylo, yhi, min_d, max_d;
+        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+            xlo = -0.5 * ws; xhi = 0.5 * ws; ylo = -0.5 * ws; yhi = 0.5 * ws;
+            min_d = 0.25 * c.coordination_range; max_d = 0.75 * c.coordination_range;
+        } else {
+            const double yw = 0.1 * (1.0 - cra) + 0.5 * cra;
+            xlo = 0.0; xhi = 0.75 * ws; ylo = -yw * ws; yhi = yw * ws;
+            min_d = 0.5 * c.coordination_range; max_d = c.coordination_range;
+        }
+        for (int l = 0; l < L; ++l) {
+            double gx = 0.0, gy = 0.0;
+            if (l > 0) {
+                for (int j = 0; j < 1000; ++j) {
+                    gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi);
+                    double dm = INFINITY;
+                    for (int k = 0; k < l; ++k) {
+                        const double d = norm2(lp[k * N + i].x - gx, lp[k * N + i].y - gy);
+                        if (d < dm) dm = d;
+                    }
+                    if (dm > min_d && dm < max_d) break;
+                }
+            } else { gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi); }
+            lp[l * N + i] = make_double2(gx, gy);
+        }
+        if (i > 0) for (int l = 0; l < L; ++l) if (r.uniform(0.0, 1.0) < 0.5) lp[l * N + i] = lp[l * N + i - 1];
+        if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+            if (lp[i].x > lp[N + i].x) { const double2 t = lp[i]; lp[i] = lp[N + i]; lp[N + i] = t; }
+        }
+        for (int l = 0; l < L - 1; ++l)
+            S.lh[l * N + i] = atan2(lp[(l + 1) * N + i].y - lp[l * N + i].y, lp[(l + 1) * N + i].x - lp[l * N + i].x);
+        const double last_heading = S.lh[(L - 2) * N + i];
+        const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
+        if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
+        } else {
+            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
+            const double var = r.uniform(0.0, 1.0);
+            if (!(var < pymin(cr, 1.0 - 0.2))) {
+                for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
+                S.lsp[(L - 1) * N + i] = c.goal_speed_min;
+            }
+        }
+        for (int l = 0; l < L - 1; ++l) {
+            const double pr = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? cr * 0.25 * kPi : cra * 0.1 * kPi;
+            S.lh[l * N + i] += r.uniform(-pr, pr);
+        }
+        S.lh[(L - 1) * N + i] = last_heading;
+    }
+    for (int m = 0; m < M; ++m) {
+        const double sv = sin(S.lh[m]), cv = cos(S.lh[m]);
+        S.lsin[m] = sv; S.lcos[m] = cv;
+        S.cst[m] = make_float4((float)sv, (float)cv, (float)S.lsp[m], 1.0f);
     }
 }
 
@@ -76,32 +488,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
     constexpr int G = Pow2<N>::value;
     constexpr int Dobs = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
     constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
-    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const lsm_config& c = kp.c;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
     const int EPW = kp.EPW;                       // launch choice, 1 .. 32/G
-    const long long n = kp.b.num_envs;
+    const int n = (int)kp.b.num_envs;
     const int le = lane / G;
     const int ai = lane - le * G;
-    ES* const Sw = reinterpret_cast<ES*>(smem_raw) + (size_t)warp_in_block * EPW;   // this warp's env records
+    ES* const Sw = reinterpret_cast<ES*>(smem_raw) + warp_in_block * EPW;   // this warp's env records
     const bool lane_has_env = le < EPW;
+    // per-warp staging buffer for node-feature rows (after all environment records of the block)
+    float* const stage = reinterpret_cast<float*>(smem_raw + (size_t)warps_per_block * EPW * sizeof(ES)) + warp_in_block * (2 * 32 * F);
     ES& S = Sw[lane_has_env ? le : 0];
     const unsigned group_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((le * G) & 31));
     const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
-    const long long ngroups = (n + EPW - 1) / EPW;
+    const int ngroups = kp.ngroups;               // ceil(n / EPW), from the host
+    const size_t fstride = (size_t)n * N;         // elements between two fields of the agent SoA
 
-    for (long long grp = (long long)blockIdx.x * warps_per_block + warp_in_block; grp < ngroups;
-         grp += (long long)gridDim.x * warps_per_block) {
-        const long long env0 = grp * EPW;
-        const long long env = env0 + le;
+    for (int grp = blockIdx.x * warps_per_block + warp_in_block; grp < ngroups; grp += gridDim.x * warps_per_block) {
+        const int env0 = grp * EPW;
+        const int env = env0 + le;
         bool env_on = lane_has_env && env < n;
         if (kp.mode == MODE_RESET && kp.env_mask != nullptr && env_on) env_on = kp.env_mask[env] != 0;
         const bool agent_on = env_on && ai < N;
         if (__ballot_sync(0xffffffffu, env_on) == 0u) continue;
-        const int nenv = (int)((n - env0) < (long long)EPW ? (n - env0) : (long long)EPW);   // envs of this group
+        const int nenv = (n - env0) < EPW ? (n - env0) : EPW;   // envs of this group
 
         // ---------------- P0: load ----------------
         double x = 0, y = 0, s2 = 0, s3 = 0, p_dist = 0, state_time = 0, min_rel = INFINITY, goal_min_time = INFINITY;
@@ -110,45 +523,50 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
         int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0;
         int current_step = 0, reset_count = 0, parity = 0;
         double ratio = 0.0;
+        double* const af = kp.b.agent_f64 + ((size_t)env * N + ai);
+        int* const aip = kp.b.agent_i32 + ((size_t)env * N + ai);
         if (env_on) {
-            current_step = *SEIP(LSM_EI_CURRENT_STEP); reset_count = *SEIP(LSM_EI_RESET_COUNT);
-            parity = *SEIP(LSM_EI_PARITY); ratio = *SEFP(LSM_EF_CURRICULUM_RATIO);
+            current_step = kp.b.env_i32[(size_t)LSM_EI_CURRENT_STEP * n + env];
+            reset_count = kp.b.env_i32[(size_t)LSM_EI_RESET_COUNT * n + env];
+            parity = kp.b.env_i32[(size_t)LSM_EI_PARITY * n + env];
+            ratio = kp.b.env_f64[(size_t)LSM_EF_CURRICULUM_RATIO * n + env];
         }
         if (agent_on) {
-            x = *SAFP(LSM_AF_X); y = *SAFP(LSM_AF_Y); s2 = *SAFP(LSM_AF_S2); s3 = *SAFP(LSM_AF_S3);
-            p_dist = *SAFP(LSM_AF_P_DIST); state_time = *SAFP(LSM_AF_STATE_TIME);
-            min_rel = *SAFP(LSM_AF_MIN_REL_DIST); goal_min_time = *SAFP(LSM_AF_GOAL_MIN_TIME);
-            times_req = *SAFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A);
-            dists_goal = *SAFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A);
-            dist_left = *SAFP(LSM_AF_DIST_LEFT); ep_travel_dist = *SAFP(LSM_AF_EP_TRAVEL_DIST);
-            ep_min_dist = *SAFP(LSM_AF_EP_MIN_DIST); action_diff = *SAFP(LSM_AF_ACTION_DIFF);
-            reached = *SAIP(LSM_AI_REACHED); done = *SAIP(LSM_AI_DONE);
-            safety_filtered = *SAIP(LSM_AI_SAFETY_FILTERED); deconflict = *SAIP(LSM_AI_DECONFLICT_IDX);
-            ncoll = *SAIP(LSM_AI_NUM_COLLISIONS); ep_len = *SAIP(LSM_AI_EP_TRAVEL_LEN);
-            ep_conflict = *SAIP(LSM_AI_EP_CONFLICT); ep_multi = *SAIP(LSM_AI_EP_MULTI); ep_done = *SAIP(LSM_AI_EP_DONE);
+            x = af[LSM_AF_X * fstride]; y = af[LSM_AF_Y * fstride]; s2 = af[LSM_AF_S2 * fstride]; s3 = af[LSM_AF_S3 * fstride];
+            p_dist = af[LSM_AF_P_DIST * fstride]; state_time = af[LSM_AF_STATE_TIME * fstride];
+            min_rel = af[LSM_AF_MIN_REL_DIST * fstride]; goal_min_time = af[LSM_AF_GOAL_MIN_TIME * fstride];
+            times_req = af[(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) * fstride];
+            dists_goal = af[(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) * fstride];
+            dist_left = af[LSM_AF_DIST_LEFT * fstride]; ep_travel_dist = af[LSM_AF_EP_TRAVEL_DIST * fstride];
+            ep_min_dist = af[LSM_AF_EP_MIN_DIST * fstride]; action_diff = af[LSM_AF_ACTION_DIFF * fstride];
+            reached = aip[LSM_AI_REACHED * fstride]; done = aip[LSM_AI_DONE * fstride];
+            safety_filtered = aip[LSM_AI_SAFETY_FILTERED * fstride]; deconflict = aip[LSM_AI_DECONFLICT_IDX * fstride];
+            ncoll = aip[LSM_AI_NUM_COLLISIONS * fstride]; ep_len = aip[LSM_AI_EP_TRAVEL_LEN * fstride];
+            ep_conflict = aip[LSM_AI_EP_CONFLICT * fstride]; ep_multi = aip[LSM_AI_EP_MULTI * fstride];
+            ep_done = aip[LSM_AI_EP_DONE * fstride];
         }
         // landmark tables of the group's environments: contiguous runs per field
         {
             const int total = nenv * M;
-#pragma unroll
-            for (int f = 0; f < LSM_LF_COUNT; ++f) {
-                const double* src = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)env0) * (size_t)M;
-                for (int idx = lane; idx < total; idx += 32) {
-                    const int el = idx / M, m = idx - el * M;
-                    const double v = src[idx];
-                    ES& T = Sw[el];
-                    if (f == 0) T.lx[m] = v; else if (f == 1) T.ly[m] = v; else if (f == 2) T.lh[m] = v;
-                    else if (f == 3) { T.lsp[m] = v; T.lspf[m] = (float)v; }
-                    else if (f == 4) { T.lsin[m] = v; T.lsinf[m] = (float)v; }
-                    else { T.lcos[m] = v; T.lcosf[m] = (float)v; }
-                }
+            const size_t lstride = (size_t)n * M;
+            const double* src = kp.b.landmarks + (size_t)env0 * M;
+            for (int idx = lane; idx < total; idx += 32) {
+                const int el = idx / M, m = idx - el * M;
+                ES& T = Sw[el];
+                const double lxv = src[LSM_LF_X * lstride + idx], lyv = src[LSM_LF_Y * lstride + idx];
+                const double lhv = src[LSM_LF_HEADING * lstride + idx], lsv = src[LSM_LF_SPEED * lstride + idx];
+                const double sv = src[LSM_LF_SIN * lstride + idx], cv = src[LSM_LF_COS * lstride + idx];
+                T.pos[N + m] = make_double2(lxv, lyv);
+                T.lh[m] = lhv; T.lsp[m] = lsv; T.lsin[m] = sv; T.lcos[m] = cv;
+                T.cst[m] = make_float4((float)sv, (float)cv, (float)lsv, 1.0f);   // landmark rows: type 1
             }
         }
         Curriculum q = curriculum(kp, ratio);
+        const int lvl = (int)(q.stair * 4.0);     // curriculum stair level: index of the squared-threshold tables
         if (agent_on) {
-            S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
-            S.done_pre[ai] = done; S.reached_pre[ai] = reached;
-            if (ai == 0) { S.cur_sep = q.sep; S.cur_filter = q.world_filter ? 1 : 0; }
+            S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
+            S.done[0][ai] = done; S.reached[0][ai] = reached;
+            if (ai == 0) { S.cur_sep = q.sep; S.cur_filter = q.world_filter ? 1 : 0; S.vel[2 * N] = make_double2(0.0, 0.0); }
         }
         __syncwarp();
 
@@ -174,18 +592,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
             __syncwarp();
             double safe0 = raw0, safe1 = raw1;
             for (int it = 0; it < c.num_internal_step; ++it) {
-                if (any_filter != 0u) {
-                    // (a) pair-parallel: distance and HJ value of every (ego, other) pair of the group
+                if (any_filter != 0u && !(kp.debug & 2)) {
+                    // (a) pair-parallel: squared distance and HJ value of every (ego, other) pair of the group
                     for (int t = lane; t < nenv * N * N; t += 32) {
                         const int el = t / (N * N), r = t - el * (N * N);
                         const int i = r / N, j = r - i * N;
                         ES& T = Sw[el];
-                        if (!T.cur_filter || i == j || T.done_pre[i] || T.done_pre[j]) continue;
-                        const double ddx = T.ax[j] - T.ax[i], ddy = T.ay[j] - T.ay[i];
-                        T.daa[r] = sqrt(ddx * ddx + ddy * ddy);
-                        Curriculum qe = q;
-                        qe.sep = T.cur_sep;          // the only curriculum scalar the HJ value depends on
-                        T.fval[r] = pair_value<DYN>(kp, qe, T, i, j);
+                        if (!T.cur_filter || i == j || T.done[0][i] || T.done[0][j]) continue;
+                        const double2 pi = T.pos[i], pj = T.pos[j];
+                        const double ddx = pj.x - pi.x, ddy = pj.y - pi.y;
+                        T.d2aa[r] = ddx * ddx + ddy * ddy;
+                        T.fval[r] = pair_value<DYN>(kp, T.cur_sep, T, i, j);
                     }
                     __syncwarp();
                 }
@@ -194,19 +611,21 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                     int filt = 0, dec = -1;
                     safe0 = raw0; safe1 = raw1;
                     if (!done) {
-                        double best_d = 0.0, best_v = 0.0; int kd = -1, kv = -1;
+                        double best_d2 = 0.0, best_v = 0.0; int kd = -1, kv = -1;
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
-                            if (j == ai || S.done_pre[j]) continue;
-                            const double dist = S.daa[ai * N + j], v = S.fval[ai * N + j];
-                            if (kd < 0 || dist < best_d) { kd = j; best_d = dist; }
+                            if (j == ai || S.done[0][j]) continue;
+                            const double d2 = S.d2aa[ai * N + j], v = S.fval[ai * N + j];
+                            if (kd < 0 || d2 < best_d2) { kd = j; best_d2 = d2; }
                             if (kv < 0 || v < best_v) { kv = j; best_v = v; }
                         }
                         if (kv >= 0) {
                             dec = kv;
-                            const bool kv_in_range = !isinf(best_v);
-                            filter_resolve<DYN>(kp, best_d, best_v, kv_in_range, x, y, s2, s3, S.ax[kv], S.ay[kv], S.as2[kv],
-                                                S.as3[kv], raw0, raw1, S.rawx[kv], S.rawy[kv], safe0, safe1, filt);
+                            // `min distance > coordination_range` as an exact test on the squared distance
+                            const double best_d = (best_d2 >= kp.r2_gt) ? INFINITY : 0.0;
+                            const double2 po = S.pos[kv];
+                            filter_resolve<DYN, LeanGrad>(kp, best_d, best_v, !isinf(best_v), x, y, s2, s3, po.x, po.y, S.as2[kv], S.as3[kv],
+                                                raw0, raw1, S.rawx[kv], S.rawy[kv], safe0, safe1, filt);
                         }
                     }
                     deconflict = dec; safety_filtered = filt;
@@ -216,40 +635,33 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                     const double d0 = raw0 - safe0, d1 = raw1 - safe1;
                     action_diff = sqrt(d0 * d0 + d1 * d1);
                     if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time);
-                    S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
+                    S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
                 }
                 __syncwarp();
             }
-            // ---------------- P2: agent-agent distances (pair-parallel), goal / reward / done ----------------
+            // ---------------- P2: squared agent-agent distances (pair-parallel), goal / reward / done ----------------
             for (int t = lane; t < nenv * N * N; t += 32) {
                 const int el = t / (N * N), r = t - el * (N * N);
                 const int i = r / N, j = r - i * N;
                 ES& T = Sw[el];
-                const double dx = T.ax[i] - T.ax[j], dy = T.ay[i] - T.ay[j];
-                T.daa[r] = sqrt(dx * dx + dy * dy);
+                const double2 pi = T.pos[i], pj = T.pos[j];
+                const double dx = pi.x - pj.x, dy = pi.y - pj.y;
+                T.d2aa[r] = dx * dx + dy * dy;
             }
             __syncwarp();
             int goal_pre = 0, goal_post = 0, reached_post = reached, done_post = done;
             double rew = 0.0;
             double vpx = 0, vpy = 0, vqx = 0, vqy = 0;
             double theta = 0, speed = 0;
+            bool reached_now = false;
             if (agent_on) {
-                // core.py:696-709
-                double m = INFINITY;
-                if (!done) {
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        const double d = S.daa[ai * N + j];
-                        if (j != ai && !S.done_pre[j] && d < m) m = d;
-                    }
-                }
-                min_rel = m;
                 theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
                 else { const double ct = cos(s2), st = sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
                 goal_pre = goal_index(reached, ai, N, M);
-                const double gx = S.lx[goal_pre], gy = S.ly[goal_pre], gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
-                emit_obs_row<DYN, N, L>(S, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+                const double2 gp = S.pos[N + goal_pre];
+                const double gx = gp.x, gy = gp.y, gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
+                emit_obs_row<DYN>(S, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
                 // reward_reach_goal: navigation_graph_safe.py:691-791
                 const double he = direction_alignment_error(theta, gh);
                 const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
@@ -257,7 +669,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 const double sen = clipd(se / q.speed_thresh, 0.0, 1.0);
                 double cra = ratio_sloped(ratio, 0.25, 0.75);
                 if (use_filter_arg) cra = 1.0;
-                const bool reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
+                reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
                 if (reached_now) {
                     const double spr = 1.0 - sen;
                     const double pdx = gx - x, pdy = gy - y;
@@ -302,9 +714,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                         double rpx, rpy;
                         rotate_into(x - gx, y - gy, cos(gh), sin(gh), rpx, rpy);
                         const double rs[4] = { rpx, rpy, theta - gh, speed };
-                        Stencil<4> st;
-                        stencil_setup<4>(kp.tg, rs, st);
-                        double ttr = st.valid ? stencil_value<4>(kp.tg, st) : NAN;
+                        Stencil32<4> st;
+                        stencil32_setup<4>(kp.tg, rs, st);
+                        double ttr = st.valid ? stencil32_value<4>(kp.tg, st) : NAN;
                         if (isnan(ttr)) ttr = kp.tg.ttr_max;
                         rew -= 0.04 * ttr;
                         rew -= sen * cra;
@@ -321,46 +733,57 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                     else { s3q = 0.0; vqx = s3q * S.cth[ai]; vqy = s3q * S.sth[ai]; }
                 }
                 goal_post = goal_index(reached_post, ai, N, M);
-                S.vpre_x[ai] = vpx; S.vpre_y[ai] = vpy; S.vpost_x[ai] = vqx; S.vpost_y[ai] = vqy;
+                S.vel[ai] = make_double2(vpx, vpy); S.vel[N + ai] = make_double2(vqx, vqy);
+                S.pos[E + ai] = gp; S.pos[E + N + ai] = S.pos[N + goal_post];
+                { float4 t = S.cst[goal_pre]; t.w = 0.0f; S.cst[M + ai] = t; }
+                { float4 t = S.cst[goal_post]; t.w = 0.0f; S.cst[M + N + ai] = t; }
                 S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3q;
-                S.goal_pre[ai] = goal_pre; S.goal_post[ai] = goal_post;
-                S.reached_post[ai] = reached_post; S.done_post[ai] = done_post;
-                // keep the PRE-update state in as2/as3 (the HJ_VALUE term of later agents reads an agent that
-                // is not done, whose pre and post states coincide); the lane's registers take the post state
+                S.goal[0][ai] = goal_pre; S.goal[1][ai] = goal_post;
+                S.reached[1][ai] = reached_post; S.done[1][ai] = done_post;
+                // as2/as3 keep the PRE-update state (the HJ_VALUE term of later agents only reads agents that are
+                // not done, whose pre and post states coincide); the lane's registers take the post state
                 s2 = s2q; s3 = s3q;
             }
             __syncwarp();
             if (agent_on) {
-                if (c.flags & LSM_FLAG_SAFETY_VIOLATION) {         // navigation_graph_safe.py:793-798
-                    double r = 0.0;
+                // one pass over the other agents: min distance, collisions, episode statistics, proximity rewards.
+                // Agent a is seen after its own update if a < i (rewards) / a <= i (statistics), else before.
+                double mind2 = INFINITY;                       // core.py:696-709
+                double stat_mind2 = INFINITY; int cnt = 0;      // environment.py:1004-1022
+                double r_sv = 0.0;                              // navigation_graph_safe.py:793-798
+                int pc_count = 0; double pc_pen = 0.0;          // navigation_graph_safe.py:800-823
+                const bool want_sv = (c.flags & LSM_FLAG_SAFETY_VIOLATION) != 0;
+                const bool want_pc = (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) != 0;
 #pragma unroll
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
-                        if (S.daa[ai * N + a] < q.sep && !adone) r += q.conflict_rew;
+                for (int a = 0; a < N; ++a) {
+                    if (a == ai) continue;
+                    const double d2 = S.d2aa[ai * N + a];
+                    const int apre = S.done[0][a], apost = S.done[1][a];
+                    if (!done && !apre && d2 < mind2) mind2 = d2;
+                    if (d2 < kp.col2_lt) ncoll += 1;           // navigation_graph_safe.py:405-413, 497-501
+                    const int adone_r = a < ai ? apost : apre;
+                    if (want_sv && d2 < kp.sep2_lt[lvl] && !adone_r) r_sv += q.conflict_rew;
+                    if (want_pc && d2 < kp.eng2_lt[lvl] && !adone_r) {
+                        const double rd = sqrt(d2);
+                        const double2 pa = S.pos[a];
+                        const double rx = pa.x - x, ry = pa.y - y;
+                        const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
+                        const double dir = atan2(ry, rx);
+                        const double2 va = S.vel[(a < ai ? N : 0) + a];
+                        double change = cos(dir) * (va.x - vpx) + sin(dir) * (va.y - vpy);
+                        change = fabs(pymin(0.0, change));
+                        pc_pen += change * closeness;
+                        pc_count += 1;
                     }
-                    rew += r;
-                }
-                if (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) {       // navigation_graph_safe.py:800-823
-                    int count = 0; double pen = 0.0;
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
-                        const double rd = S.daa[ai * N + a];
-                        if (rd < q.eng && !adone) {
-                            const double rx = S.ax[a] - x, ry = S.ay[a] - y;
-                            const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
-                            const double dir = atan2(ry, rx);
-                            const double vax = a < ai ? S.vpost_x[a] : S.vpre_x[a];
-                            const double vay = a < ai ? S.vpost_y[a] : S.vpre_y[a];
-                            double change = cos(dir) * (vax - vpx) + sin(dir) * (vay - vpy);
-                            change = fabs(pymin(0.0, change));
-                            pen += change * closeness;
-                            count += 1;
-                        }
+                    const int adone_s = a <= ai ? apost : apre;
+                    if (!adone_s && d2 < kp.r2_lt && d2 > 0.0) {
+                        if (d2 < kp.engref2_lt) cnt++;
+                        if (d2 < stat_mind2) stat_mind2 = d2;
                     }
-                    if (count > 1) rew += q.multi_rew * pen;
                 }
+                min_rel = sqrt(mind2);
+                if (want_sv) rew += r_sv;
+                if (want_pc && pc_count > 1) rew += q.multi_rew * pc_pen;
                 if ((c.flags & LSM_FLAG_DIFF_FROM_FILTERED_ACTION) && use_filter_arg) {   // :825-828
                     if (!done) rew += q.diff_rew * action_diff;
                 }
@@ -368,52 +791,39 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                     double r = 0.0;
                     for (int a = 0; a < N; ++a) {
                         if (a == ai) continue;
-                        const int adone = a < ai ? S.done_post[a] : S.done_pre[a];
+                        const int adone = a < ai ? S.done[1][a] : S.done[0][a];
                         if (adone) continue;
-                        const double v = pair_value<DYN>(kp, q, S, ai, a);   // as2/as3 hold the pre-update states
+                        const double v = pair_value<DYN>(kp, q.sep, S, ai, a);   // as2/as3 hold the pre-update states
                         const double cvp = fabs(pymin(v - 0.4, 0.0));
                         r += q.cvalue_rew * cvp;
                     }
                     rew += r;
                 }
                 rew = clipd(rew, c.min_reward, c.max_reward);
-
-                // episode statistics: environment.py:1004-1022
                 if (!done_post) {
                     ep_len += 1;
                     ep_travel_dist += norm2(vqx, vqy) * c.dt;
-                    int cnt = 0; bool have = false; double mn = INFINITY;
-#pragma unroll
-                    for (int j = 0; j < N; ++j) {
-                        const int jdisc = j <= ai ? S.done_post[j] : S.done_pre[j];
-                        double d = jdisc ? 0.0 : S.daa[ai * N + j];
-                        d = (d < c.coordination_range && d > 0.0) ? d : 0.0;
-                        if (d != 0.0) { have = true; if (d < c.engagement_distance_ref) cnt++; if (d < mn) mn = d; }
-                    }
-                    if (have) {
+                    if (stat_mind2 < INFINITY) {
                         if (cnt > 1) ep_multi += 1;
-                        if (mn < c.separation_distance_target) ep_conflict += 1;
+                        if (stat_mind2 < kp.septgt2_lt) ep_conflict += 1;
+                        const double mn = sqrt(stat_mind2);
                         if (mn < ep_min_dist) ep_min_dist = mn;
                     }
                 }
                 if (done_post) ep_done = 1;
                 // info_callback state: navigation_graph_safe.py:386-413 (post-update goal and velocity)
-                {
-                    const double gx = S.lx[goal_post], gy = S.ly[goal_post];
-                    const double dx = x - gx, dy = y - gy;
-                    const double dist = sqrt(dx * dx + dy * dy);
-                    if (times_req == -1.0) {
-                        // a set times_required freezes all three fields, so the goal test is only needed here
+                if (times_req == -1.0) {
+                    // once times_required is set all three fields are frozen, so the goal test is only needed here
+                    const double2 gq = S.pos[N + goal_post];
+                    const double dx = x - gq.x, dy = y - gq.y;
+                    // same goal and same (unfrozen) state as before the update -> same answer as `reached_now`
+                    bool r2 = reached_now;
+                    if (goal_post != goal_pre || done_post != done) {
                         const double th2 = theta_of<DYN>(s2, s3), sp2 = speed_of<DYN>(s2, s3);
-                        const bool r2 = goal_reached<DYN>(x, y, th2, sp2, gx, gy, S.lh[goal_post], S.lsp[goal_post], q);
-                        if (r2) times_req = (double)current_step * c.dt;
-                        dists_goal = p_dist; dist_left = dist;
+                        r2 = goal_reached<DYN>(x, y, th2, sp2, gq.x, gq.y, S.lh[goal_post], S.lsp[goal_post], q);
                     }
-#pragma unroll
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        if (S.daa[ai * N + a] < 1.05 * (0.050 + 0.050)) ncoll += 1;
-                    }
+                    if (r2) times_req = (double)current_step * c.dt;
+                    dists_goal = p_dist; dist_left = sqrt(dx * dx + dy * dy);
                 }
             }
             if (agent_on && kp.b.reward_individual != nullptr) kp.b.reward_individual[(size_t)env * N + ai] = (float)rew;
@@ -439,10 +849,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
                 else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
                 const int g = goal_index(reached, ai, N, M);
-                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
+                S.vel[ai] = make_double2(vx, vy); S.vel[N + ai] = make_double2(vx, vy);
+                const double2 gp = S.pos[N + g];
+                S.pos[E + ai] = gp; S.pos[E + N + ai] = gp;
+                float4 cc = S.cst[g]; cc.w = 0.0f;
+                S.cst[M + ai] = cc; S.cst[M + N + ai] = cc;
                 S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal_pre[ai] = g; S.goal_post[ai] = g;
-                S.reached_post[ai] = reached; S.done_post[ai] = done;
+                S.goal[0][ai] = g; S.goal[1][ai] = g;
+                S.reached[1][ai] = reached; S.done[1][ai] = done;
             }
             __syncwarp();
         }
@@ -483,297 +897,84 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
                 q = curriculum(kp, ratio);
             }
-            if (do_reset && sample && ai == 0) {
-                // Scenario.random_scenario: navigation_graph_safe.py:1199-1367, utils.py:39-68
-                Rng r; r.init(kp.seed, (uint32_t)(kp.b.env_id_base + env), (uint32_t)reset_count);
-                const double ws = c.world_size;
-                double cra = ratio_sloped(ratio, 0.25, 0.75);
-                if (use_filter_arg) cra = 1.0;
-                for (int i = 0; i < N; ++i) {
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        S.ax[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.ay[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.as2[i] = 0.0; S.as3[i] = 0.0;
-                    } else {
-                        const double xmin = -0.5 * ws;
-                        const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
-                        const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
-                        S.ax[i] = r.uniform(xmin, xmax); S.ay[i] = ry;
-                        const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
-                        S.as2[i] = r.uniform(0.0, 2.0 * kPi);
-                        S.as3[i] = sp;
-                    }
-                }
-                for (int i = 0; i < N; ++i) {
-                    double xlo, xhi, ylo, yhi, min_d, max_d;
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        xlo = -0.5 * ws; xhi = 0.5 * ws; ylo = -0.5 * ws; yhi = 0.5 * ws;
-                        min_d = 0.25 * c.coordination_range; max_d = 0.75 * c.coordination_range;
-                    } else {
-                        const double yw = 0.1 * (1.0 - cra) + 0.5 * cra;
-                        xlo = 0.0; xhi = 0.75 * ws; ylo = -yw * ws; yhi = yw * ws;
-                        min_d = 0.5 * c.coordination_range; max_d = c.coordination_range;
-                    }
-                    for (int l = 0; l < L; ++l) {
-                        double gx = 0.0, gy = 0.0;
-                        if (l > 0) {
-                            for (int j = 0; j < 1000; ++j) {
-                                gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi);
-                                double dm = INFINITY;
-                                for (int k = 0; k < l; ++k) {
-                                    const double d = norm2(S.lx[k * N + i] - gx, S.ly[k * N + i] - gy);
-                                    if (d < dm) dm = d;
-                                }
-                                if (dm > min_d && dm < max_d) break;
-                            }
-                        } else { gx = r.uniform(xlo, xhi); gy = r.uniform(ylo, yhi); }
-                        S.lx[l * N + i] = gx; S.ly[l * N + i] = gy;
-                    }
-                    if (i > 0) for (int l = 0; l < L; ++l) if (r.uniform(0.0, 1.0) < 0.5) {
-                        S.lx[l * N + i] = S.lx[l * N + i - 1]; S.ly[l * N + i] = S.ly[l * N + i - 1];
-                    }
-                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
-                        if (S.lx[i] > S.lx[N + i]) {
-                            const double tx = S.lx[i], ty = S.ly[i];
-                            S.lx[i] = S.lx[N + i]; S.ly[i] = S.ly[N + i]; S.lx[N + i] = tx; S.ly[N + i] = ty;
-                        }
-                    }
-                    for (int l = 0; l < L - 1; ++l)
-                        S.lh[l * N + i] = atan2(S.ly[(l + 1) * N + i] - S.ly[l * N + i], S.lx[(l + 1) * N + i] - S.lx[l * N + i]);
-                    const double last_heading = S.lh[(L - 2) * N + i];
-                    const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
-                    if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
-                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
-                    } else {
-                        for (int l = 0; l < L; ++l) S.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
-                        const double var = r.uniform(0.0, 1.0);
-                        if (!(var < pymin(cr, 1.0 - 0.2))) {
-                            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
-                            S.lsp[(L - 1) * N + i] = c.goal_speed_min;
-                        }
-                    }
-                    for (int l = 0; l < L - 1; ++l) {
-                        const double pr = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? cr * 0.25 * kPi : cra * 0.1 * kPi;
-                        S.lh[l * N + i] += r.uniform(-pr, pr);
-                    }
-                    S.lh[(L - 1) * N + i] = last_heading;
-                    for (int l = 0; l < L; ++l) {
-                        const int m = l * N + i;
-                        S.lsin[m] = sin(S.lh[m]); S.lcos[m] = cos(S.lh[m]);
-                        S.lsinf[m] = (float)S.lsin[m]; S.lcosf[m] = (float)S.lcos[m]; S.lspf[m] = (float)S.lsp[m];
-                    }
-                }
-            }
+            if (do_reset && sample && ai == 0) sample_scenario<DYN, N, L>(kp, S, env, reset_count, ratio);
             __syncwarp();
             if (do_reset && agent_on) {
-                if (sample) { x = S.ax[ai]; y = S.ay[ai]; s2 = S.as2[ai]; s3 = S.as3[ai]; }
+                if (sample) { const double2 p = S.pos[ai]; x = p.x; y = p.y; s2 = S.as2[ai]; s3 = S.as3[ai]; }
                 done = 0; reached = 0;
                 p_dist = 0.0; state_time = 0.0;
-                goal_min_time = norm2(x - S.lx[ai], y - S.ly[ai]) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
+                const double2 g0 = S.pos[N + ai];
+                goal_min_time = norm2(x - g0.x, y - g0.y) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
                 times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
                 else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
-                S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
-                S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
+                S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
+                S.vel[ai] = make_double2(vx, vy); S.vel[N + ai] = make_double2(vx, vy);
+                S.pos[E + ai] = g0; S.pos[E + N + ai] = g0;
+                float4 cc = S.cst[ai]; cc.w = 0.0f;
+                S.cst[M + ai] = cc; S.cst[M + N + ai] = cc;
                 S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal_pre[ai] = ai; S.goal_post[ai] = ai;
-                S.reached_pre[ai] = 0; S.reached_post[ai] = 0; S.done_pre[ai] = 0; S.done_post[ai] = 0;
-                emit_obs_row<DYN, N, L>(S, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+                S.goal[0][ai] = ai; S.goal[1][ai] = ai;
+                S.reached[0][ai] = 0; S.reached[1][ai] = 0; S.done[0][ai] = 0; S.done[1][ai] = 0;
+                emit_obs_row<DYN>(S, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
             }
             if (do_reset && sample) reset_count += 1;
             __syncwarp();
             if (sample) {
+                const size_t lstride = (size_t)n * M;
                 for (int el = 0; el < nenv; ++el) {
                     if (!((reset_lanes >> ((el * G) & 31)) & 1u)) continue;
                     const ES& T = Sw[el];
-#pragma unroll
-                    for (int f = 0; f < LSM_LF_COUNT; ++f) {
-                        const double* srcp = f == 0 ? T.lx : f == 1 ? T.ly : f == 2 ? T.lh : f == 3 ? T.lsp : f == 4 ? T.lsin : T.lcos;
-                        double* dst = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)(env0 + el)) * (size_t)M;
-                        for (int m = lane; m < M; m += 32) dst[m] = srcp[m];
+                    double* dst = kp.b.landmarks + (size_t)(env0 + el) * M;
+                    for (int m = lane; m < M; m += 32) {
+                        const double2 p = T.pos[N + m];
+                        dst[LSM_LF_X * lstride + m] = p.x; dst[LSM_LF_Y * lstride + m] = p.y;
+                        dst[LSM_LF_HEADING * lstride + m] = T.lh[m]; dst[LSM_LF_SPEED * lstride + m] = T.lsp[m];
+                        dst[LSM_LF_SIN * lstride + m] = T.lsin[m]; dst[LSM_LF_COS * lstride + m] = T.lcos[m];
                     }
                 }
             }
         } else if (kp.mode == MODE_OBSERVE && agent_on) {
-            emit_obs_row<DYN, N, L>(S, ai, S.goal_pre[ai], x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+            emit_obs_row<DYN>(S, ai, S.goal[0][ai], x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
         }
 
         // ---------------- state write-back ----------------
         if (kp.mode != MODE_OBSERVE) {
             if (env_on && ai == 0) {
-                *SEIP(LSM_EI_CURRENT_STEP) = current_step; *SEIP(LSM_EI_RESET_COUNT) = reset_count;
-                *SEIP(LSM_EI_PARITY) = parity; *SEIP(LSM_EI_JUST_RESET) = do_reset ? 1 : 0;
-                *SEFP(LSM_EF_CURRICULUM_RATIO) = ratio;
+                kp.b.env_i32[(size_t)LSM_EI_CURRENT_STEP * n + env] = current_step;
+                kp.b.env_i32[(size_t)LSM_EI_RESET_COUNT * n + env] = reset_count;
+                kp.b.env_i32[(size_t)LSM_EI_PARITY * n + env] = parity;
+                kp.b.env_i32[(size_t)LSM_EI_JUST_RESET * n + env] = do_reset ? 1 : 0;
+                kp.b.env_f64[(size_t)LSM_EF_CURRICULUM_RATIO * n + env] = ratio;
             }
             if (agent_on) {
-                *SAFP(LSM_AF_X) = x; *SAFP(LSM_AF_Y) = y; *SAFP(LSM_AF_S2) = s2; *SAFP(LSM_AF_S3) = s3;
-                *SAFP(LSM_AF_P_DIST) = p_dist; *SAFP(LSM_AF_STATE_TIME) = state_time;
-                *SAFP(LSM_AF_MIN_REL_DIST) = min_rel; *SAFP(LSM_AF_GOAL_MIN_TIME) = goal_min_time;
-                *SAFP(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) = times_req;
-                *SAFP(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) = dists_goal;
+                af[LSM_AF_X * fstride] = x; af[LSM_AF_Y * fstride] = y; af[LSM_AF_S2 * fstride] = s2; af[LSM_AF_S3 * fstride] = s3;
+                af[LSM_AF_P_DIST * fstride] = p_dist; af[LSM_AF_STATE_TIME * fstride] = state_time;
+                af[LSM_AF_MIN_REL_DIST * fstride] = min_rel; af[LSM_AF_GOAL_MIN_TIME * fstride] = goal_min_time;
+                af[(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) * fstride] = times_req;
+                af[(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) * fstride] = dists_goal;
                 if (do_reset) {
-                    *SAFP(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) = times_req;
-                    *SAFP(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) = dists_goal;
+                    af[(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) * fstride] = times_req;
+                    af[(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) * fstride] = dists_goal;
                 }
-                *SAFP(LSM_AF_DIST_LEFT) = dist_left; *SAFP(LSM_AF_EP_TRAVEL_DIST) = ep_travel_dist;
-                *SAFP(LSM_AF_EP_MIN_DIST) = ep_min_dist; *SAFP(LSM_AF_ACTION_DIFF) = action_diff;
-                *SAIP(LSM_AI_REACHED) = reached; *SAIP(LSM_AI_DONE) = done;
-                *SAIP(LSM_AI_SAFETY_FILTERED) = safety_filtered; *SAIP(LSM_AI_DECONFLICT_IDX) = deconflict;
-                *SAIP(LSM_AI_NUM_COLLISIONS) = ncoll; *SAIP(LSM_AI_EP_TRAVEL_LEN) = ep_len;
-                *SAIP(LSM_AI_EP_CONFLICT) = ep_conflict; *SAIP(LSM_AI_EP_MULTI) = ep_multi; *SAIP(LSM_AI_EP_DONE) = ep_done;
+                af[LSM_AF_DIST_LEFT * fstride] = dist_left; af[LSM_AF_EP_TRAVEL_DIST * fstride] = ep_travel_dist;
+                af[LSM_AF_EP_MIN_DIST * fstride] = ep_min_dist; af[LSM_AF_ACTION_DIFF * fstride] = action_diff;
+                aip[LSM_AI_REACHED * fstride] = reached; aip[LSM_AI_DONE * fstride] = done;
+                aip[LSM_AI_SAFETY_FILTERED * fstride] = safety_filtered; aip[LSM_AI_DECONFLICT_IDX * fstride] = deconflict;
+                aip[LSM_AI_NUM_COLLISIONS * fstride] = ncoll; aip[LSM_AI_EP_TRAVEL_LEN * fstride] = ep_len;
+                aip[LSM_AI_EP_CONFLICT * fstride] = ep_conflict; aip[LSM_AI_EP_MULTI * fstride] = ep_multi;
+                aip[LSM_AI_EP_DONE * fstride] = ep_done;
             }
         }
         __syncwarp();
 
         // ---------------- P4: graph observation ----------------
         for (int el = 0; el < nenv; ++el) {
-            const long long ee = env0 + el;
+            const int ee = env0 + el;
             if (kp.mode == MODE_RESET && kp.env_mask != nullptr && kp.env_mask[ee] == 0) continue;
-            ES& T = Sw[el];
-            // (a) thresholded distance matrix. Agent-agent block from the float64 distances of P2 (recomputed
-            //     when the env was just reset or nothing was stepped) ...
-            const bool fresh_positions = (kp.mode != MODE_STEP) || ((reset_lanes >> ((el * G) & 31)) & 1u);
-            for (int r = lane; r < N * N; r += 32) {
-                const int i = r / N, j = r - i * N;
-                const double d = fresh_positions ? norm2(T.ax[i] - T.ax[j], T.ay[i] - T.ay[j]) : T.daa[r];
-                T.dthr[i * E + j] = (d < c.coordination_range && d > 0.0) ? (float)d : 0.0f;
-            }
-            // ... agent-landmark and landmark-landmark pairs: d^2 in float64 vs the exact squared threshold
-            constexpr int NPAIR = N * M + M * (M - 1) / 2;
-            for (int p = lane; p < NPAIR; p += 32) {
-                const unsigned short pa = kp.pair_tab[2 * p], pb = kp.pair_tab[2 * p + 1];   // pa < pb, pb >= N
-                const double pax = pa < N ? T.ax[pa] : T.lx[pa - N], pay = pa < N ? T.ay[pa] : T.ly[pa - N];
-                const double dx = pax - T.lx[pb - N], dy = pay - T.ly[pb - N];
-                const double d2 = dx * dx + dy * dy;
-                const float v = (d2 < kp.r2_lt && d2 > 0.0) ? __fsqrt_rn((float)d2) : 0.0f;
-                T.dthr[pa * E + pb] = v; T.dthr[pb * E + pa] = v;
-            }
-            for (int e = N + lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
-            // (b) disconnected-entity bit masks before / after this step's goal updates (ballots)
-            unsigned any_change = 0u;
-#pragma unroll
-            for (int w = 0; w < W; ++w) {
-                const int e = w * 32 + lane;
-                bool dpre = false, dpost = false;
-                if (e < N) { dpre = T.done_pre[e] != 0; dpost = T.done_post[e] != 0; }
-                else if (e < E) {
-                    const int m = e - N, order = m / N, owner = m - order * N;
-                    dpre = T.reached_pre[owner] > order; dpost = T.reached_post[owner] > order;
-                }
-                const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
-                if (lane == 0) { T.disc_pre[w] = bpre; T.disc_post[w] = bpost; }
-                any_change |= (bpre ^ bpost);
-            }
-            __syncwarp();
-            for (int k = lane; k < N * W; k += 32) {
-                const int w = k % W;
-                const unsigned sel = kp.sel_tab[k];
-                T.keepm[k] = ~((T.disc_post[w] & sel) | (T.disc_pre[w] & ~sel));
-            }
-            __syncwarp();
-            // (c) node features: one lane per (observer, entity) row
-            {
-                float* nbase = kp.b.node_obs + (size_t)ee * (N * E * F);
-                for (int r = lane; r < N * E; r += 32) {
-                    const int i = r / E, e = r - i * E;
-                    float* o = nbase + r * F;
-                    const double xi = T.ax[i], yi = T.ay[i];
-                    const double vix = T.vpost_x[i], viy = T.vpost_y[i];
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        float f0, f1, f2, f3, f4, f5, f6, f7, f8, f9;
-                        if (e < N) {
-                            const bool post = e <= i;
-                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
-                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
-                            f0 = (float)(T.ax[e] - xi); f1 = (float)(T.ay[e] - yi);
-                            f2 = (float)(vex - vix); f3 = (float)(vey - viy);
-                            f4 = (float)(T.lx[g] - xi); f5 = (float)(T.ly[g] - yi);
-                            f6 = T.lsinf[g]; f7 = T.lcosf[g]; f8 = T.lspf[g]; f9 = 0.0f;
-                        } else {
-                            const int m = e - N;
-                            f0 = (float)(T.lx[m] - xi); f1 = (float)(T.ly[m] - yi);
-                            f2 = (float)(-vix); f3 = (float)(-viy); f4 = f0; f5 = f1;
-                            f6 = T.lsinf[m]; f7 = T.lcosf[m]; f8 = T.lspf[m]; f9 = 1.0f;
-                        }
-                        float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
-                        o2[0] = make_float2(f0, f1); o2[1] = make_float2(f2, f3); o2[2] = make_float2(f4, f5);
-                        o2[3] = make_float2(f6, f7); o2[4] = make_float2(f8, f9);
-                    } else {
-                        const double ci = T.cth[i], si = T.sth[i];
-                        if (e < N) {
-                            const bool post = e <= i;
-                            const int g = post ? T.goal_post[e] : T.goal_pre[e];
-                            const double vex = post ? T.vpost_x[e] : T.vpre_x[e], vey = post ? T.vpost_y[e] : T.vpre_y[e];
-                            double rx, ry, gx, gy;
-                            rotate_into(T.ax[e] - xi, T.ay[e] - yi, ci, si, rx, ry);
-                            rotate_into(T.lx[g] - xi, T.ly[g] - yi, ci, si, gx, gy);
-                            const double ce = T.cth[e], se = T.sth[e];
-                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(vex - vix, vey - viy);
-                            o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
-                            o[5] = (float)gx; o[6] = (float)gy;
-                            o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
-                            o[9] = T.lspf[g]; o[10] = 0.0f;
-                        } else {
-                            const int m = e - N;
-                            double rx, ry;
-                            rotate_into(T.lx[m] - xi, T.ly[m] - yi, ci, si, rx, ry);
-                            const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
-                            o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
-                            o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
-                            o[9] = T.lspf[m]; o[10] = 1.0f;
-                        }
-                    }
-                }
-            }
-            // (d) adjacency
-            {
-                float* abase = kp.b.adj + (size_t)ee * (N * EE);
-                const unsigned any_disc = [&] { unsigned a = 0u; for (int w = 0; w < W; ++w) a |= T.disc_post[w]; return a; }();
-                if (E % 4 == 0) {
-                    constexpr int CPR = E / 4, CHUNKS = EE / 4;
-                    for (int ch = lane; ch < CHUNKS; ch += 32) {
-                        const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
-                        const float4 v = *reinterpret_cast<const float4*>(T.dthr + a * E + b4);
-                        float* dst = abase + a * E + b4;
-                        if (any_disc == 0u) {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), v);
-                        } else if (any_change == 0u) {
-                            // no goal update this step: every observer sees the same mask
-                            const bool ka = (T.keepm[a >> 5] >> (a & 31)) & 1u;
-                            const unsigned nib = ka ? ((T.keepm[b4 >> 5] >> (b4 & 31)) & 0xFu) : 0u;
-                            float4 o;
-                            o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
-                            o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-#pragma unroll
-                            for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
-                        } else {
-#pragma unroll
-                            for (int i = 0; i < N; ++i) {
-                                const bool ka = (T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u;
-                                const unsigned nib = ka ? ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu) : 0u;
-                                float4 o;
-                                o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
-                                o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-                                __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
-                            }
-                        }
-                    }
-                } else {
-                    for (int idx = lane; idx < EE; idx += 32) {
-                        const int a = idx / E, b2 = idx - a * E;
-                        const float v = T.dthr[idx];
-#pragma unroll
-                        for (int i = 0; i < N; ++i) {
-                            const bool keep = ((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
-                                              ((T.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u);
-                            __stcs(abase + i * EE + idx, keep ? v : 0.0f);
-                        }
-                    }
-                }
-            }
+            if (!(kp.debug & 1)) emit_graph<DYN, N, L>(kp.b.node_obs, kp.b.adj, kp.sel_tab, kp.r2_lt, Sw[el], stage, ee, lane, kp.debug);
             __syncwarp();
         }
         __syncwarp();

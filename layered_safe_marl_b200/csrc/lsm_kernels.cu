@@ -18,6 +18,8 @@
 #include "lsm_kernel_spec.cuh"
 #include "lsm_host.h"
 
+#include <cstdlib>
+
 namespace lsm {
 
 // ---------------------------------------------------------------------------------------------
@@ -30,27 +32,37 @@ namespace lsm {
     X(LSM_DYN_AIRTAXI, 10, 2)
 
 constexpr int kSpecBlock = 128;
-constexpr int kSpecMinBlocks = 4;
+
+// register budgets: MINB blocks of 128 threads per SM -> 65536 / (128 * MINB) registers per thread
+static int spec_minb() {
+    const char* e = std::getenv("LSM_MINB");
+    const int v = e ? std::atoi(e) : 4;
+    return (v == 6 || v == 7) ? v : 4;
+}
 
 static const void* generic_ptr(int dynamics) {
     return dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? (const void*)lsm_generic_kernel<LSM_DYN_DOUBLE_INTEGRATOR>
                                                  : (const void*)lsm_generic_kernel<LSM_DYN_AIRTAXI>;
 }
 
-static const void* spec_ptr(int dynamics, int N, int L, int* bytes_per_env) {
+static const void* spec_ptr(int dynamics, int N, int L, int* bytes_per_env, int* stage_bytes = nullptr) {
+    const int minb = spec_minb();
 #define X(DYN_, N_, L_)                                                                           \
     if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
         *bytes_per_env = (int)sizeof(EnvShared<DYN_, N_, L_>);                                    \
-        return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, kSpecMinBlocks>;            \
+        if (stage_bytes) *stage_bytes = 2 * 32 * (DYN_ == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11) * 4;   \
+        if (minb == 6) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 6>;          \
+        if (minb == 7) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 7>;          \
+        return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 4>;                         \
     }
     LSM_SPEC_LIST(X)
 #undef X
     return nullptr;
 }
 
-bool spec_available(int dynamics, int N, int L, int* bytes_per_env, int* block_threads) {
+bool spec_available(int dynamics, int N, int L, int* bytes_per_env, int* block_threads, int* stage_bytes) {
     *block_threads = kSpecBlock;
-    return spec_ptr(dynamics, N, L, bytes_per_env) != nullptr;
+    return spec_ptr(dynamics, N, L, bytes_per_env, stage_bytes) != nullptr;
 }
 
 cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,

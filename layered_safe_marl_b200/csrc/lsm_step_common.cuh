@@ -67,7 +67,16 @@ __device__ __forceinline__ double hj_value(const KParams& kp, const Curriculum& 
 // Second half of the safety handles (safety_filter.py:225-260, 400-433) once the deconflicting agent
 // `kv` (first minimum of the HJ value) and the smallest distance are known: gradient lookup,
 // least-restrictive bang-bang or CBF-QP, control clipping, filtered flag.
-template <int DYN>
+struct ClassicGrad {
+    template <int ND>
+    __device__ __forceinline__ static void eval(const GridDev& g, const double (&rel)[ND], double (&out)[ND]) {
+        Stencil<ND> st;
+        stencil_setup<ND>(g, rel, st);
+        stencil_grad<ND>(g, st, out);
+    }
+};
+
+template <int DYN, class GRAD = ClassicGrad>
 __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d, double best_v, bool kv_in_range,
                                                double ex, double ey, double e2, double e3,
                                                double ox, double oy, double o2, double o3,
@@ -81,11 +90,7 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
     relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
     const double uref[4] = { raw0, raw1, oraw0, oraw1 };
     double g[ND];
-    {
-        Stencil<ND> st;
-        stencil_setup<ND>(kp.vg, rel, st);
-        stencil_grad<ND>(kp.vg, st, g);
-    }
+    GRAD::template eval<ND>(kp.vg, rel, g);
     const double eps_hj = 0.4;
     double u[4]; bool aliased = false;
     const double dt = c.dt;

@@ -14,7 +14,11 @@ import re
 import sys
 
 
+OUTER_FILE = "lsm_kernels.cu"
+
+
 def parse_dis(path, kernel_sub):
+    """path: output of `nvdisasm -gi -c <cubin>` (inline chains) or `-g` (innermost only)."""
     lines = open(path).read().splitlines()
     start = None
     for i, l in enumerate(lines):
@@ -22,34 +26,38 @@ def parse_dis(path, kernel_sub):
             start = i
             break
     assert start is not None, "kernel not found in disassembly"
-    out = []            # (innermost (file, line), outermost-in-kernels.cu line)
-    cur = None
-    stack = []
+    out = []            # (innermost (file, line), outermost line inside OUTER_FILE, sass text)
+    cur = []            # annotation block attached to the next instruction(s)
+    fresh = True
+    pat = re.compile(r'//## File "([^"]+)", line (\d+)(?: inlined at "([^"]+)", line (\d+))?')
     for l in lines[start + 1:]:
         if l.startswith('.text.') or l.startswith('\t.section'):
             break
-        m = re.search(r'//## File "([^"]+)", line (\d+)(.*)', l)
+        m = pat.search(l)
         if m:
-            f, ln, rest = m.group(1), int(m.group(2)), m.group(3)
-            if 'inlined at' in rest:
-                stack.append((f, ln))
-            else:
-                stack = [(f, ln)]
-            cur = list(stack)
+            if fresh:
+                cur = []
+                fresh = False
+            cur.append((m.group(1), int(m.group(2))))
+            if m.group(3):
+                cur.append((m.group(3), int(m.group(4))))
             continue
         if re.match(r'\s+/\*[0-9a-f]{4,}\*/', l):
+            fresh = True
             inner = cur[0] if cur else ('?', 0)
             outer = 0
-            if cur:
-                for f, ln in cur:
-                    if f.endswith('lsm_kernels.cu'):
-                        outer = ln
+            for f, ln in cur:
+                if f.endswith(OUTER_FILE):
+                    outer = ln
             out.append((inner, outer, l.strip()[:100]))
     return out
 
 
 def main():
+    global OUTER_FILE
     sass_csv, dis, ksub = sys.argv[1], sys.argv[2], sys.argv[3]
+    if len(sys.argv) > 5:
+        OUTER_FILE = sys.argv[5]
     dis_rows = parse_dis(dis, ksub)
     rows = list(csv.reader(open(sass_csv)))
     # find the block for this kernel (first occurrence)
