@@ -128,6 +128,8 @@ typedef struct lsm_buffers {
 typedef struct lsm_launch_info {
     int32_t grid_blocks, block_threads, warps_per_block, envs_per_warp;
     int32_t smem_bytes_per_block, regs_per_thread, blocks_per_sm, sm_count;
+    int32_t specialised;          /* 1: compile-time (dynamics, N, L) kernel, 0: generic run-time-N kernel */
+    int32_t _pad;
 } lsm_launch_info;
 
 typedef struct lsm_handle lsm_handle;

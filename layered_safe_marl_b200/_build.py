@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, 'csrc')
 LIB_PATH = os.path.join(HERE, 'liblsm_b200.so')
 SOURCES = [os.path.join(CSRC, 'lsm_kernels.cu'), os.path.join(CSRC, 'lsm_capi.cu')]
-DEPS = SOURCES + [os.path.join(CSRC, 'lsm_device.cuh'), os.path.join(CSRC, 'lsm_host.h'),
-                  os.path.join(os.path.dirname(HERE), 'include', 'lsm_b200.h')]
+DEPS = SOURCES + [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith(('.cuh', '.h'))] + \
+    [os.path.join(os.path.dirname(HERE), 'include', 'lsm_b200.h')]
 
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-O3', '-lineinfo', '-std=c++17',
               # no FMA contraction: float64 intermediates must round like the reference's numpy arithmetic

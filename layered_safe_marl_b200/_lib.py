@@ -43,7 +43,7 @@ class LsmBuffers(C.Structure):
 class LsmLaunchInfo(C.Structure):
     _fields_ = [('grid_blocks', C.c_int32), ('block_threads', C.c_int32), ('warps_per_block', C.c_int32),
                 ('envs_per_warp', C.c_int32), ('smem_bytes_per_block', C.c_int32), ('regs_per_thread', C.c_int32),
-                ('blocks_per_sm', C.c_int32), ('sm_count', C.c_int32)]
+                ('blocks_per_sm', C.c_int32), ('sm_count', C.c_int32), ('specialised', C.c_int32), ('_pad', C.c_int32)]
 
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',

@@ -331,6 +331,7 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     out->grid_blocks = (int32_t)blocks; out->block_threads = h->block_threads; out->warps_per_block = h->warps_per_block;
     out->envs_per_warp = h->kp.EPW; out->smem_bytes_per_block = h->smem_per_block; out->regs_per_thread = h->regs;
     out->blocks_per_sm = h->blocks_per_sm; out->sm_count = h->sm_count;
+    out->specialised = h->spec ? 1 : 0; out->_pad = 0;
     return 0;
 }
 

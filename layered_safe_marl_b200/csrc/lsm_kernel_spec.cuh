@@ -96,38 +96,29 @@ __device__ __forceinline__ void stencil32_setup(const GridDev& g, const double (
     }
 }
 
-// value: sum over corners (binary counting, dim 0 slowest) of ((w0*w1)*w2..)*v, sequential adds
+// value: sum over corners (binary counting, dim 0 slowest) of ((w0*w1)*w2..)*v, sequential adds.
+// All 2^ND loads are issued first (one memory round trip per lookup instead of 2^ND dependent ones).
 template <int ND>
 __device__ __forceinline__ double stencil32_value(const GridDev& g, const Stencil32<ND>& s) {
+    constexpr int NC = 1 << ND;
+    float v[NC];
+#pragma unroll
+    for (int corner = 0; corner < NC; ++corner) {
+        int lin = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) lin += ((corner >> (ND - 1 - d)) & 1) ? s.hi[d] : s.lo[d];
+        v[corner] = __ldg(g.values + lin);
+    }
     double acc = 0.0;
-    if (ND == 4) {
 #pragma unroll
-        for (int c0 = 0; c0 < 2; ++c0) {
-            const double w0 = c0 ? s.whi[0] : s.wlo[0]; const int o0 = c0 ? s.hi[0] : s.lo[0];
+    for (int corner = 0; corner < NC; ++corner) {
+        double weight = 0.0;
 #pragma unroll
-            for (int c1 = 0; c1 < 2; ++c1) {
-                const double w1 = w0 * (c1 ? s.whi[1] : s.wlo[1]); const int o1 = o0 + (c1 ? s.hi[1] : s.lo[1]);
-#pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const double w2 = w1 * (c2 ? s.whi[2] : s.wlo[2]); const int o2 = o1 + (c2 ? s.hi[2] : s.lo[2]);
-                    acc = acc + (w2 * s.wlo[3]) * (double)__ldg(g.values + o2 + s.lo[3]);
-                    acc = acc + (w2 * s.whi[3]) * (double)__ldg(g.values + o2 + s.hi[3]);
-                }
-            }
+        for (int d = 0; d < ND; ++d) {
+            const double wd = ((corner >> (ND - 1 - d)) & 1) ? s.whi[d] : s.wlo[d];
+            weight = (d == 0) ? wd : weight * wd;
         }
-    } else {
-#pragma unroll
-        for (int corner = 0; corner < (1 << ND); ++corner) {
-            double weight = 0.0; int lin = 0;
-#pragma unroll
-            for (int d = 0; d < ND; ++d) {
-                const int bit = (corner >> (ND - 1 - d)) & 1;
-                const double wd = bit ? s.whi[d] : s.wlo[d];
-                weight = (d == 0) ? wd : weight * wd;
-                lin += bit ? s.hi[d] : s.lo[d];
-            }
-            acc = acc + weight * (double)__ldg(g.values + lin);
-        }
+        acc = acc + weight * (double)v[corner];
     }
     return acc;
 }
@@ -168,18 +159,38 @@ struct LeanGrad {
 };
 
 template <int DYN, class ES>
-__device__ __forceinline__ double pair_value(const KParams& kp, double sep, const ES& s, int i, int j) {
+__device__ __forceinline__ double pair_value(const GridDev& vg, double sep, const ES& s, int i, int j) {
     // safety_filter.py:192-201, 345-354 (+ the value shift of HjDataHandle.update_separation_distance)
     constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
     double rel[ND];
     const double2 pi = s.pos[i], pj = s.pos[j];
     relative_state<DYN>(pi.x, pi.y, s.as2[i], s.as3[i], pj.x, pj.y, s.as2[j], s.as3[j], rel);
     Stencil32<ND> st;
-    stencil32_setup<ND>(kp.vg, rel, st);
+    stencil32_setup<ND>(vg, rel, st);
     if (!st.valid) return INFINITY;
-    const double v = stencil32_value<ND>(kp.vg, st);
+    const double v = stencil32_value<ND>(vg, st);
     if (isnan(v)) return INFINITY;
-    return v - (sep - kp.vg.separation_distance);
+    return v - (sep - vg.separation_distance);
+}
+
+// (a) of the safety filter, pair-parallel over the warp's environments: squared distance and HJ value of every
+// (ego, other) pair. A separate function so that the lookup gets its own register allocation (all 2^d
+// loads of a stencil in flight) instead of competing with the per-agent state carried by the kernel body.
+// `vg` points to the block's shared-memory copy of the grid descriptor.
+template <int DYN, int N, int L>
+__device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EnvShared<DYN, N, L>* Sw, int nenv, int lane) {
+    using ES = EnvShared<DYN, N, L>;
+    const GridDev g = *vg;
+    for (int t = lane; t < nenv * N * N; t += 32) {
+        const int el = t / (N * N), r = t - el * (N * N);
+        const int i = r / N, j = r - i * N;
+        ES& T = Sw[el];
+        if (!T.cur_filter || i == j || T.done[0][i] || T.done[0][j]) continue;
+        const double2 pi = T.pos[i], pj = T.pos[j];
+        const double ddx = pj.x - pi.x, ddy = pj.y - pi.y;
+        T.d2aa[r] = ddx * ddx + ddy * ddy;
+        T.fval[r] = pair_value<DYN>(g, T.cur_sep, T, i, j);
+    }
 }
 
 template <int DYN, class ES>
@@ -269,8 +280,10 @@ __device__ __noinline__ void emit_graph(float* __restrict__ node_obs, float* __r
     // (d) adjacency (issued BEFORE the node rows so that the asynchronous copies overlap their computation)
     if (!(debug & 8)) {
         float* abase = adj + (size_t)ee * (N * EE);
-        if (E % 2 == 0 && any_change == 0u) {
-            // every observer sees the same matrix this step: mask it once in place, then N bulk copies
+        if (E % 2 == 0 && any_change == 0u && (E % 4 != 0 || (debug & 16))) {
+            // every observer sees the same matrix: mask it once in place, then N bulk copies. Used when rows are not
+            // 16-byte multiples (E % 4 != 0, e.g. cfg3's E = 30), where it beats the scalar store loop; with E % 4 == 0
+            // the float4 loop below is faster (N back-to-back UBLKCP issues stall ~400 cycles each).
             if (any_disc != 0u) {
                 for (int idx = lane; idx < EE; idx += 32) {
                     const int a = idx / E, b2 = idx - a * E;
@@ -287,14 +300,27 @@ __device__ __noinline__ void emit_graph(float* __restrict__ node_obs, float* __r
                 const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
                 const float4 v = *reinterpret_cast<const float4*>(T.dthr + ch * 4);
                 float* dst = abase + ch * 4;
+                if (any_disc == 0u) {               // nothing disconnected: the same chunk for every observer
 #pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const bool ka = any_disc == 0u || ((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u);
-                    const unsigned nib = !ka ? 0u : (any_disc == 0u ? 0xFu : ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu));
+                    for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), v);
+                } else if (any_change == 0u) {      // no goal update this step: one mask for every observer
+                    const bool ka = (T.keepm[a >> 5] >> (a & 31)) & 1u;
+                    const unsigned nib = ka ? ((T.keepm[b4 >> 5] >> (b4 & 31)) & 0xFu) : 0u;
                     float4 o;
                     o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
                     o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-                    __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+#pragma unroll
+                    for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const bool ka = (T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u;
+                        const unsigned nib = ka ? ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu) : 0u;
+                        float4 o;
+                        o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
+                        o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
+                        __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                    }
                 }
             }
         } else {
@@ -489,6 +515,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
     constexpr int Dobs = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
     constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GridDev s_vg;                      // block copy of the value-grid descriptor for pair_phase
+    if (threadIdx.x == 0) s_vg = kp.vg;
+    __syncthreads();
     const lsm_config& c = kp.c;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
@@ -593,17 +622,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
             double safe0 = raw0, safe1 = raw1;
             for (int it = 0; it < c.num_internal_step; ++it) {
                 if (any_filter != 0u && !(kp.debug & 2)) {
-                    // (a) pair-parallel: squared distance and HJ value of every (ego, other) pair of the group
-                    for (int t = lane; t < nenv * N * N; t += 32) {
-                        const int el = t / (N * N), r = t - el * (N * N);
-                        const int i = r / N, j = r - i * N;
-                        ES& T = Sw[el];
-                        if (!T.cur_filter || i == j || T.done[0][i] || T.done[0][j]) continue;
-                        const double2 pi = T.pos[i], pj = T.pos[j];
-                        const double ddx = pj.x - pi.x, ddy = pj.y - pi.y;
-                        T.d2aa[r] = ddx * ddx + ddy * ddy;
-                        T.fval[r] = pair_value<DYN>(kp, T.cur_sep, T, i, j);
-                    }
+                    pair_phase<DYN, N, L>(&s_vg, Sw, nenv, lane);
                     __syncwarp();
                 }
                 if (agent_on && q.world_filter) {
@@ -793,7 +812,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                         if (a == ai) continue;
                         const int adone = a < ai ? S.done[1][a] : S.done[0][a];
                         if (adone) continue;
-                        const double v = pair_value<DYN>(kp, q.sep, S, ai, a);   // as2/as3 hold the pre-update states
+                        const double v = pair_value<DYN>(kp.vg, q.sep, S, ai, a);   // as2/as3 hold the pre-update states
                         const double cvp = fabs(pymin(v - 0.4, 0.0));
                         r += q.cvalue_rew * cvp;
                     }

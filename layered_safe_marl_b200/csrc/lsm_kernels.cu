@@ -36,8 +36,8 @@ constexpr int kSpecBlock = 128;
 // register budgets: MINB blocks of 128 threads per SM -> 65536 / (128 * MINB) registers per thread
 static int spec_minb() {
     const char* e = std::getenv("LSM_MINB");
-    const int v = e ? std::atoi(e) : 4;
-    return (v == 6 || v == 7) ? v : 4;
+    const int v = e ? std::atoi(e) : 2;
+    return (v == 3 || v == 4) ? v : 2;
 }
 
 static const void* generic_ptr(int dynamics) {
@@ -51,8 +51,8 @@ static const void* spec_ptr(int dynamics, int N, int L, int* bytes_per_env, int*
     if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
         *bytes_per_env = (int)sizeof(EnvShared<DYN_, N_, L_>);                                    \
         if (stage_bytes) *stage_bytes = 2 * 32 * (DYN_ == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11) * 4;   \
-        if (minb == 6) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 6>;          \
-        if (minb == 7) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 7>;          \
+        if (minb == 2) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 2>;          \
+        if (minb == 3) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 3>;          \
         return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 4>;                         \
     }
     LSM_SPEC_LIST(X)
