@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LSM_ABI_VERSION 1
+#define LSM_ABI_VERSION 2
 
 enum { LSM_DYN_DOUBLE_INTEGRATOR = 0, LSM_DYN_AIRTAXI = 1 };
 
@@ -128,8 +128,12 @@ typedef struct lsm_buffers {
 typedef struct lsm_launch_info {
     int32_t grid_blocks, block_threads, warps_per_block, envs_per_warp;
     int32_t smem_bytes_per_block, regs_per_thread, blocks_per_sm, sm_count;
-    int32_t specialised;          /* 1: compile-time (dynamics, N, L) kernel, 0: generic run-time-N kernel */
-    int32_t _pad;
+    int32_t specialised;          /* 1: compile-time (dynamics, N, L) three-launch pipeline, 0: generic fused kernel */
+    /* specialised pipeline only: the graph-emission kernel (one block per env) and the pair kernel */
+    int32_t emit_block_threads, emit_smem_bytes_per_block, emit_regs_per_thread, emit_blocks_per_sm;
+    int32_t pair_regs_per_thread;
+    int32_t launches_per_step;    /* kernels one lsm_step launches in steady state */
+    int32_t emit_record_bytes;    /* per-env record handed from the agent kernel to the emit kernel */
 } lsm_launch_info;
 
 typedef struct lsm_handle lsm_handle;
@@ -159,6 +163,17 @@ int lsm_reset(lsm_handle *h, const uint8_t *env_mask, int64_t episode, uint64_t 
 
 /* Re-emit obs / node_obs / adj from the bound state without stepping. */
 int lsm_observe(lsm_handle *h, void *stream);
+
+/* Tell the library that the caller edited the bound state tensors (agent_f64 / agent_i32 / env_f64) directly.
+ * The specialised pipeline keeps the HJ pair values of the current state from the previous launch
+ * (safety_filter.py:192-201 evaluated one step ahead); after an edit the next lsm_step recomputes them first. */
+int lsm_invalidate(lsm_handle *h);
+
+/* Measurement hook (specialised pipeline only): relaunch the graph-emission kernel alone on the per-env
+ * records the last lsm_step / lsm_reset / lsm_observe left behind. Idempotent: rewrites node_obs and adj
+ * (graph_observation, navigation_graph_safe.py:932-994) with the same values. Returns 6 when the
+ * configuration has no separate emission launch. */
+int lsm_emit_only(lsm_handle *h, void *stream);
 
 #ifdef __cplusplus
 }

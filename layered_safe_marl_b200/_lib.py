@@ -43,12 +43,15 @@ class LsmBuffers(C.Structure):
 class LsmLaunchInfo(C.Structure):
     _fields_ = [('grid_blocks', C.c_int32), ('block_threads', C.c_int32), ('warps_per_block', C.c_int32),
                 ('envs_per_warp', C.c_int32), ('smem_bytes_per_block', C.c_int32), ('regs_per_thread', C.c_int32),
-                ('blocks_per_sm', C.c_int32), ('sm_count', C.c_int32), ('specialised', C.c_int32), ('_pad', C.c_int32)]
+                ('blocks_per_sm', C.c_int32), ('sm_count', C.c_int32), ('specialised', C.c_int32),
+                ('emit_block_threads', C.c_int32), ('emit_smem_bytes_per_block', C.c_int32),
+                ('emit_regs_per_thread', C.c_int32), ('emit_blocks_per_sm', C.c_int32),
+                ('pair_regs_per_thread', C.c_int32), ('launches_per_step', C.c_int32), ('emit_record_bytes', C.c_int32)]
 
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
-                    'lsm_observe')
+                    'lsm_observe', 'lsm_emit_only', 'lsm_invalidate')
 
 _lib = None
 
@@ -81,8 +84,10 @@ def load():
     lib.lsm_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_void_p]
     lib.lsm_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.c_void_p]
     lib.lsm_observe.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lsm_emit_only.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lsm_invalidate.argtypes = [C.c_void_p]
     for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
-                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe'):
+                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate'):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -40,12 +40,16 @@ struct lsm_handle {
     uint32_t* d_pair32 = nullptr;
     size_t persist_bytes = 0;
     size_t max_window = 0;
-    bool spec = false;          // compile-time specialised kernel available for (dynamics, N, L)
-    int bytes_per_env = 0;      // shared memory of one environment record
+    bool spec = false;          // compile-time specialised pipeline available for (dynamics, N, L)
+    int bytes_per_env = 0;      // shared memory of one environment (agent kernel: emit record + scratch)
     int epw_max = 1;            // 32 / G
     int smem_optin = 0;
     int forced_epw = 0;         // LSM_EPW environment override (experiments)
-    int stage_bytes = 0;        // per-warp node-row staging buffer of the specialised kernels
+    lsm::SpecGeometry geo = {};
+    int emit_regs = 0, emit_blocks_per_sm = 0, pair_regs = 0;
+    bool pairval_valid = false;         // d_pairval holds the HJ pair values of the CURRENT state (written by the last emit launch)
+    double* d_pairval = nullptr;        // library-owned scratch of the specialised pipeline
+    unsigned char* d_emit_rec = nullptr;
 };
 
 extern "C" {
@@ -156,18 +160,17 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.bytes_per_env = align_up(off, 16);
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    int spec_bytes = 0, spec_block = 0;
     const char* force_generic = std::getenv("LSM_FORCE_GENERIC");
-    int spec_stage = 0;
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &spec_bytes, &spec_block, &spec_stage) &&
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) &&
               !(force_generic != nullptr && force_generic[0] == '1');
     const char* fe = std::getenv("LSM_EPW");
     h->forced_epw = fe ? std::atoi(fe) : 0;
     if (h->spec) {
-        h->bytes_per_env = spec_bytes;
-        h->stage_bytes = spec_stage;
-        int wpb = spec_block / 32;
-        while (wpb > 1 && (spec_bytes + spec_stage) * wpb > h->smem_optin) --wpb;     // 32-agent records are ~60 KB each
+        h->bytes_per_env = h->geo.rec_bytes + h->geo.scratch_bytes;
+        // agent kernel: one lane per agent, 32/G envs per warp (LSM_EPW overrides for experiments)
+        if (h->forced_epw >= 1 && h->forced_epw <= h->epw_max) kp.EPW = h->forced_epw;
+        int wpb = h->geo.agent_block / 32;
+        while (wpb > 1 && h->bytes_per_env * kp.EPW * wpb > h->smem_optin) --wpb;
         h->warps_per_block = wpb;
         h->block_threads = 32 * wpb;
     } else {
@@ -180,10 +183,8 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
         h->warps_per_block = wpb;
         h->block_threads = 32 * wpb;
     }
-    // provisional geometry (re-evaluated in lsm_bind_buffers once num_envs is known)
-    if (h->spec) kp.EPW = 1;
     kp.smem_per_warp = h->bytes_per_env * kp.EPW;
-    h->smem_per_block = (kp.smem_per_warp + h->stage_bytes) * h->warps_per_block;
+    h->smem_per_block = kp.smem_per_warp * h->warps_per_block;
     if (h->smem_per_block > h->smem_optin) {
         delete h;
         return fail(4, "lsm_create: one environment group does not fit in shared memory");
@@ -192,6 +193,12 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "kernel_prepare"); }
     if (h->blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: kernel does not fit on an SM"); }
     h->grid_cap = h->sm_count * h->blocks_per_sm;
+    if (h->spec) {
+        if (h->geo.emit_smem > h->smem_optin) { delete h; return fail(4, "lsm_create: emit record does not fit in shared memory"); }
+        e = lsm::spec_prepare_aux(cfg->dynamics, N, L, &h->emit_regs, &h->emit_blocks_per_sm, &h->pair_regs);
+        if (e != cudaSuccess) { delete h; return cuda_fail(e, "spec_prepare_aux"); }
+        if (h->emit_blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: emit kernel does not fit on an SM"); }
+    }
 
     // lookup tables
     std::vector<uint16_t> pairs;
@@ -234,6 +241,8 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_pair_tab) cudaFree(h->d_pair_tab);
     if (h->d_sel_tab) cudaFree(h->d_sel_tab);
     if (h->d_pair32) cudaFree(h->d_pair32);
+    if (h->d_pairval) cudaFree(h->d_pairval);
+    if (h->d_emit_rec) cudaFree(h->d_emit_rec);
     delete h;
     return 0;
 }
@@ -288,37 +297,15 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
     h->kp.b = *b;
     h->have_buffers = true;
     if (h->spec) {
-        // Envs per warp is a launch choice. If even the densest packing needs more than one wave the batch is
-        // throughput-bound: pack epw_max envs per warp (fewest instructions per env). Otherwise take the
-        // SMALLEST packing whose warps are all resident at once (most parallelism inside the single wave).
-        int best_epw = h->epw_max, best_bps = 0;
-        const lsm_config& c = h->kp.c;
-        for (int epw = 1; epw <= h->epw_max; epw *= 2) {
-            const int smem = (h->bytes_per_env * epw + h->stage_bytes) * h->warps_per_block;
-            if (smem > h->smem_optin) break;
-            int regs = 0, bps = 0;
-            cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, smem, h->block_threads, &regs, &bps);
-            if (e != cudaSuccess) return cuda_fail(e, "kernel_prepare");
-            if (bps < 1) break;
-            const long long ngroups = (b->num_envs + epw - 1) / epw;
-            const long long capacity = (long long)h->sm_count * bps * h->warps_per_block;
-            if (h->forced_epw == epw || (h->forced_epw == 0 && ngroups <= capacity)) { best_epw = epw; best_bps = bps; break; }
-            if (epw == h->epw_max) { best_epw = epw; best_bps = bps; }
-        }
-        if (best_bps == 0) {
-            // nothing fits in one wave: densest packing that fits in shared memory
-            int epw = h->epw_max;
-            while (epw > 1 && (h->bytes_per_env * epw + h->stage_bytes) * h->warps_per_block > h->smem_optin) epw /= 2;
-            best_epw = epw;
-        }
-        h->kp.EPW = best_epw;
-        h->kp.smem_per_warp = h->bytes_per_env * best_epw;
-        h->smem_per_block = (h->kp.smem_per_warp + h->stage_bytes) * h->warps_per_block;
-        cudaError_t e = lsm::kernel_prepare(c.dynamics, c.num_agents, c.num_landmarks, true, h->smem_per_block, h->block_threads,
-                                            &h->regs, &h->blocks_per_sm);
-        if (e != cudaSuccess) return cuda_fail(e, "kernel_prepare");
-        if (h->blocks_per_sm < 1) return fail(4, "lsm_bind_buffers: kernel does not fit on an SM");
-        h->grid_cap = h->sm_count * h->blocks_per_sm;
+        // library-owned scratch between the launches of one step
+        if (h->d_pairval) { cudaFree(h->d_pairval); h->d_pairval = nullptr; }
+        if (h->d_emit_rec) { cudaFree(h->d_emit_rec); h->d_emit_rec = nullptr; }
+        const size_t N = (size_t)h->kp.N;
+        cudaError_t e = cudaMalloc(&h->d_pairval, (size_t)b->num_envs * N * N * sizeof(double));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_emit_rec, (size_t)b->num_envs * (size_t)h->geo.rec_bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "lsm_bind_buffers: scratch allocation");
+        h->kp.emit_rec = h->d_emit_rec;
+        h->pairval_valid = false;
     }
     return 0;
 }
@@ -327,11 +314,17 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     if (h == nullptr || out == nullptr) return fail(1, "lsm_get_launch_info: null argument");
     const long long ngroups = h->have_buffers ? (h->kp.b.num_envs + h->kp.EPW - 1) / h->kp.EPW : 0;
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
-    if (blocks > h->grid_cap) blocks = h->grid_cap;
+    if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;
     out->grid_blocks = (int32_t)blocks; out->block_threads = h->block_threads; out->warps_per_block = h->warps_per_block;
     out->envs_per_warp = h->kp.EPW; out->smem_bytes_per_block = h->smem_per_block; out->regs_per_thread = h->regs;
     out->blocks_per_sm = h->blocks_per_sm; out->sm_count = h->sm_count;
-    out->specialised = h->spec ? 1 : 0; out->_pad = 0;
+    out->specialised = h->spec ? 1 : 0;
+    out->emit_block_threads = h->spec ? h->geo.emit_threads : 0;
+    out->emit_smem_bytes_per_block = h->spec ? h->geo.emit_smem : 0;
+    out->emit_regs_per_thread = h->emit_regs; out->emit_blocks_per_sm = h->emit_blocks_per_sm;
+    out->pair_regs_per_thread = h->pair_regs;
+    out->launches_per_step = h->spec ? 2 : 1;   // + lsm_pair_kernel on the first step after the state was edited
+    out->emit_record_bytes = h->spec ? h->geo.rec_bytes : 0;
     return 0;
 }
 
@@ -350,11 +343,34 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     kp.ngroups = (int)ngroups;
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
-    if (blocks > h->grid_cap) blocks = h->grid_cap;
+    if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;   // generic kernel: persistent grid
     const void* persist = (mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
-    cudaError_t e = lsm::kernel_launch(kp, h->spec, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
-                                       persist, h->persist_bytes);
+    cudaError_t e;
+    kp.pairval = nullptr;
+    const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
+    if (pair_path && mode == lsm::MODE_STEP) {
+        // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
+        // previous launch's emit kernel; recomputed here (K_a) when the state was edited in between
+        kp.pairval = h->d_pairval;
+        if (!h->pairval_valid || (kp.debug & 32)) {
+            e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
+            if (e != cudaSuccess) return cuda_fail(e, who);
+        }
+    }
+    // K_b (specialised: per-agent physics) or the fused generic kernel
+    e = lsm::kernel_launch(kp, h->spec, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
+                           persist, h->persist_bytes);
     if (e != cudaSuccess) return cuda_fail(e, who);
+    if (h->spec) {
+        if (!(kp.debug & 1)) {
+            // K_c: graph observation, one block per env (+ the pair values of the next step)
+            kp.pairval = (pair_path && !(kp.debug & 32)) ? h->d_pairval : nullptr;
+            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes);
+            if (e != cudaSuccess) return cuda_fail(e, who);
+            if (kp.pairval != nullptr) { if (env_mask == nullptr) h->pairval_valid = true; }
+            else h->pairval_valid = false;
+        } else h->pairval_valid = false;
+    }
     return 0;
 }
 
@@ -371,6 +387,26 @@ int lsm_reset(lsm_handle* h, const uint8_t* env_mask, int64_t episode, uint64_t 
 
 int lsm_observe(lsm_handle* h, void* stream) {
     return launch(h, lsm::MODE_OBSERVE, 0, nullptr, nullptr, nullptr, 0, 0, stream, "lsm_observe");
+}
+
+int lsm_invalidate(lsm_handle* h) {
+    if (h == nullptr) return fail(1, "lsm_invalidate: null handle");
+    h->pairval_valid = false;
+    return 0;
+}
+
+int lsm_emit_only(lsm_handle* h, void* stream) {
+    if (h == nullptr) return fail(1, "lsm_emit_only: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_emit_only: lsm_bind_buffers has not been called");
+    if (!h->spec) return fail(6, "lsm_emit_only: this configuration runs the fused generic kernel (no separate emission launch)");
+    lsm::KParams kp = h->kp;
+    kp.mode = lsm::MODE_OBSERVE; kp.env_mask = nullptr;
+    { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
+    const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 32);
+    kp.pairval = pair_path ? h->d_pairval : nullptr;
+    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, pair_path ? (const void*)kp.vg.values : nullptr, h->persist_bytes);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_emit_only");
+    return 0;
 }
 
 }  // extern "C"

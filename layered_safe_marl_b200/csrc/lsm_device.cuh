@@ -81,6 +81,9 @@ struct KParams {
     double engref2_lt;         // world.engagement_distance (episode statistics)
     double septgt2_lt;         // world.separation_distance_target (episode statistics)
     double sep2_lt[5], eng2_lt[5];   // scenario separation / engagement distance per curriculum stair level
+    // specialised pipeline (library-owned scratch, L2 resident between the launches of one step)
+    double* pairval;           // [num_envs][N][N] raw HJ value of (ego, other) from lsm_pair_kernel; NULL = compute in-kernel
+    unsigned char* emit_rec;   // [num_envs][sizeof(EmitRec)] per-env record consumed by lsm_emit_kernel
 };
 
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }

@@ -3,10 +3,20 @@
 #include "lsm_device.cuh"
 
 namespace lsm {
-bool spec_available(int dynamics, int N, int L, int* bytes_per_env, int* block_threads, int* stage_bytes);
+struct SpecGeometry {
+    int rec_bytes;        // sizeof(EmitRec): per-env record between the agent and the emit kernel
+    int scratch_bytes;    // sizeof(AgentScratch): per-env physics scratch of the agent kernel
+    int agent_block, pair_block;
+    int emit_smem, emit_threads;
+};
+bool spec_available(int dynamics, int N, int L, SpecGeometry* g);
+// agent kernel (specialised) or the fused generic kernel
 cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,
                            int* blocks_per_sm);
+cudaError_t spec_prepare_aux(int dynamics, int N, int L, int* emit_regs, int* emit_blocks_per_sm, int* pair_regs);
 cudaError_t upload_magnetic_tables(const double* cos_tab, const double* sin_tab);
 cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int block_threads, int smem_bytes,
                           cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
+cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
+cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
 }  // namespace lsm

@@ -1,14 +1,23 @@
-// lsm_kernel_spec.cuh - step kernel specialised at compile time on (dynamics, N agents, L landmarks
-// per agent): constant-size shared-memory records, unrolled loops, immediate-offset stores.
+// lsm_kernel_spec.cuh - the step pipeline specialised at compile time on (dynamics, N agents, L landmarks
+// per agent): constant-size records, unrolled loops, immediate-offset stores.
 //
-// Same decisions as the generic kernel for every thresholded quantity, organised for far fewer instructions:
-//   * envs per warp (EPW) is a LAUNCH choice (1 .. 32/G): small batches spread over more warps so the
-//     whole batch is resident in one wave; large batches pack 32/G environments per warp.
-//   * the HJ value lookups run pair-parallel: every (ego, other) pair of the warp's environments is one
-//     lane-task, results go to shared memory, the agent lane then takes the first minimum in `other`
-//     order exactly like np.argmin. The stencil uses 32-bit indices and an exactly rounded division by
-//     the grid spacing through its precomputed reciprocal (Markstein: q0 = a*y, r = fma(-b,q0,a),
-//     q = fma(r,y,q0) equals RN(a/b); checked on the CPU in tests/test_host_logic.py).
+// One env.step is THREE launches, each at the natural parallelism of its phase (a fused single kernel
+// needs ~250 registers for the physics and then runs the store-bound graph emission at 7 warps per SM;
+// measured in profiles/r01_v3_*: 17 % issue utilisation, latency-bound):
+//
+//   lsm_pair_kernel   one THREAD per ordered (env, ego, other) pair: relative state + multilinear HJ value
+//                     lookup (safety_filter.py:192-201, 345-354) -> pairval[env][ego][other] (float64, L2 resident)
+//   lsm_agent_kernel  one LANE per agent, 32/G envs per warp: action decode, argmin / gradient / bang-bang or QP,
+//                     dynamics, goal / reward / done, episode statistics, auto-reset, state write-back; leaves
+//                     a compact per-env "emit record" (positions, velocities, goal tables, pre/post flags)
+//   lsm_emit_kernel   one BLOCK (WPE warps) per env, low register count / high occupancy: radius-thresholded
+//                     distance matrix, disconnected-entity masks, adjacency and node-feature stores - the
+//                     HBM-bound part (>= 96 % of the algorithmic bytes)
+//
+// Same decisions as the generic kernel for every thresholded quantity:
+//   * the HJ stencil uses 32-bit indices and an exactly rounded division by the grid spacing through its
+//     precomputed reciprocal (Markstein: q0 = a*y, r = fma(-b,q0,a), q = fma(r,y,q0) equals RN(a/b);
+//     checked on the CPU in tests/test_host_logic.py).
 //   * distances are kept SQUARED in float64; every `d < T` / `d > T` test of the reference becomes
 //     `d2 < T2` against a host-computed exact squared threshold (sqrt_rn is monotone, so
 //     {t : sqrt_rn(t) >= T} is an interval whose lower end the host finds with nextafter). Square roots
@@ -22,35 +31,56 @@
 
 namespace lsm {
 
+// airtaxi-only part of the emit record (rotations into the observer frame need float64 sin / cos)
 template <int DYN, int N, int L>
-struct __align__(16) EnvShared {
+struct AirExtra {
+    double sth[N], cth[N], spd_post[N];           // sin/cos(theta), speed after the own update
+    double theta[N];                              // heading (never changed by the goal update)
+    double lsin[N * L], lcos[N * L], lsp[N * L];   // landmark sin/cos(heading), speed
+    int goal[2][N];                                // landmark index of the goal before / after the own update
+};
+template <int N, int L>
+struct AirExtra<LSM_DYN_DOUBLE_INTEGRATOR, N, L> {};
+
+// What the graph emission needs from the physics of one environment (written by lsm_agent_kernel, read by
+// lsm_emit_kernel). Unified per-entity tables for the branch-free node-feature rows:
+//   pos[e]                     position of entity e (agents after the dynamics, then landmarks)
+//   pos[E + s*N + a]           goal position of agent a before (s=0) / after (s=1) its own goal update
+//   vel[s*N + a], vel[2N] = 0  world-frame velocity of agent a before / after its update; landmarks use slot 2N
+//   cst[m], cst[M + s*N + a]   (sin heading, cos heading, speed, type) of landmark m / of agent a's goal
+template <int DYN, int N, int L>
+struct __align__(16) EmitRec {
     static constexpr int M = N * L;
     static constexpr int E = N + M;
     static constexpr int W = (E + 31) / 32;
-    // unified per-entity tables for the branch-free node-feature rows:
-    //   pos[e]                     position of entity e (agents after the dynamics, then landmarks)
-    //   pos[E + s*N + a]           goal position of agent a before (s=0) / after (s=1) its own goal update
-    //   vel[s*N + a], vel[2N] = 0  world-frame velocity of agent a before / after its update; landmarks use slot 2N
-    //   cst[m], cst[M + s*N + a]   (sin heading, cos heading, speed, type) of landmark m / of agent a's goal
     double2 pos[E + 2 * N];
     double2 vel[2 * N + 1];
     float4 cst[M + 2 * N];
+    int reached[2][N], done[2][N];
+    int next_filter;           // world.use_safety_filter this env will have at the NEXT step (curriculum after a reset)
+    int _pad[3];
+    AirExtra<DYN, N, L> air;
+};
+
+// physics-only shared-memory scratch of one environment inside lsm_agent_kernel
+template <int DYN, int N, int L>
+struct __align__(16) AgentScratch {
+    static constexpr int M = N * L;
     double as2[N], as3[N];     // state components 2,3 BEFORE the own goal update (vx,vy | theta,speed)
     double rawx[N], rawy[N];   // decoded raw controls
-    double sth[N], cth[N], spd_post[N];       // airtaxi: sin/cos(theta), speed after the own update
     double lh[M], lsp[M], lsin[M], lcos[M];   // landmark heading, speed, sin/cos(heading)
-    union alignas(16) {
-        float dthr[E * E];     // P4: radius-thresholded distance matrix (float32, what adj stores)
-        struct {
-            double d2aa[N * N];    // P1/P2: squared agent-agent distances (before / after the dynamics)
-            double fval[N * N];    // P1: HJ value of (ego i, other j); +inf = out of range
-        };
-    };
-    int goal[2][N], reached[2][N], done[2][N];
-    unsigned disc[2][W], keepm[N * W];
+    double fval[N * N];        // HJ value of (ego i, other j) when computed in-kernel (internal steps > 1)
     double cur_sep;            // scenario.separation_distance of this env (curriculum)
     int cur_filter;            // world.use_safety_filter of this env (curriculum, Q5)
+    int _pad;
 };
+
+// Programmatic dependent launch (griddepcontrol): every kernel of the pipeline is launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, lets its successor become resident early (launch_dependents at
+// the top) and waits for the complete, flushed predecessor before it touches global memory (wait). This hides the
+// launch + block-dispatch latency (~6 us per launch in the bench's event timing) behind the predecessor's tail.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 template <int N> struct Pow2 { static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
 
@@ -158,54 +188,88 @@ struct LeanGrad {
     }
 };
 
-template <int DYN, class ES>
-__device__ __forceinline__ double pair_value(const GridDev& vg, double sep, const ES& s, int i, int j) {
-    // safety_filter.py:192-201, 345-354 (+ the value shift of HjDataHandle.update_separation_distance)
+// raw (unshifted) HJ value of the pair (ego, other); +inf = outside the declared range / NaN
+template <int DYN>
+__device__ __forceinline__ double pair_value_raw(const GridDev& vg, double ex, double ey, double e2, double e3,
+                                                 double ox, double oy, double o2, double o3) {
+    // safety_filter.py:192-201, 345-354
     constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
     double rel[ND];
-    const double2 pi = s.pos[i], pj = s.pos[j];
-    relative_state<DYN>(pi.x, pi.y, s.as2[i], s.as3[i], pj.x, pj.y, s.as2[j], s.as3[j], rel);
+    relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
     Stencil32<ND> st;
     stencil32_setup<ND>(vg, rel, st);
     if (!st.valid) return INFINITY;
     const double v = stencil32_value<ND>(vg, st);
     if (isnan(v)) return INFINITY;
-    return v - (sep - vg.separation_distance);
+    return v;
 }
 
-// (a) of the safety filter, pair-parallel over the warp's environments: squared distance and HJ value of every
-// (ego, other) pair. A separate function so that the lookup gets its own register allocation (all 2^d
-// loads of a stencil in flight) instead of competing with the per-agent state carried by the kernel body.
-// `vg` points to the block's shared-memory copy of the grid descriptor.
+// value shift of HjDataHandle.update_separation_distance (safety_filter.py:170-174); inf stays inf
+__device__ __forceinline__ double shift_value(double raw, double sep, const GridDev& vg) {
+    return raw - (sep - vg.separation_distance);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_a: HJ values of every ordered agent pair, one thread per (env, ego, other)
+// ---------------------------------------------------------------------------------------------
+template <int DYN, int N>
+__global__ void __launch_bounds__(256) lsm_pair_kernel(const __grid_constant__ KParams kp) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long n = kp.b.num_envs;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * (N * N)) return;
+    const int env = (int)(t / (N * N)), r = (int)(t - (long long)env * (N * N));
+    const int i = r / N, j = r - i * N;
+    if (i == j) return;
+    // world.use_safety_filter of this env (curriculum, navigation_graph_safe.py:351-357)
+    const lsm_config& c = kp.c;
+    if (!(c.flags & LSM_FLAG_INITIAL_PHASE_USE_SAFETY_FILTER)) {
+        const double ratio = kp.b.env_f64[(size_t)LSM_EF_CURRICULUM_RATIO * n + env];
+        if (!(ratio_sloped(ratio, 0.25, 0.75) > 0.0)) return;
+    }
+    const size_t fs = (size_t)n * N;
+    const size_t ia = (size_t)env * N + i, ja = (size_t)env * N + j;
+    const int* dn = kp.b.agent_i32 + LSM_AI_DONE * fs;
+    if (dn[ia] || dn[ja]) return;
+    const double* af = kp.b.agent_f64;
+    const double v = pair_value_raw<DYN>(kp.vg, af[LSM_AF_X * fs + ia], af[LSM_AF_Y * fs + ia], af[LSM_AF_S2 * fs + ia],
+                                         af[LSM_AF_S3 * fs + ia], af[LSM_AF_X * fs + ja], af[LSM_AF_Y * fs + ja],
+                                         af[LSM_AF_S2 * fs + ja], af[LSM_AF_S3 * fs + ja]);
+    kp.pairval[t] = v;
+}
+
+// in-kernel variant for internal steps after the first (states changed inside the launch): pair-parallel over
+// the warp's environments, shifted values into P.fval
 template <int DYN, int N, int L>
-__device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EnvShared<DYN, N, L>* Sw, int nenv, int lane) {
-    using ES = EnvShared<DYN, N, L>;
+__device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EmitRec<DYN, N, L>* Rw, AgentScratch<DYN, N, L>* Pw,
+                                       int nenv, int lane) {
     const GridDev g = *vg;
     for (int t = lane; t < nenv * N * N; t += 32) {
         const int el = t / (N * N), r = t - el * (N * N);
         const int i = r / N, j = r - i * N;
-        ES& T = Sw[el];
-        if (!T.cur_filter || i == j || T.done[0][i] || T.done[0][j]) continue;
-        const double2 pi = T.pos[i], pj = T.pos[j];
-        const double ddx = pj.x - pi.x, ddy = pj.y - pi.y;
-        T.d2aa[r] = ddx * ddx + ddy * ddy;
-        T.fval[r] = pair_value<DYN>(g, T.cur_sep, T, i, j);
+        const EmitRec<DYN, N, L>& R = Rw[el];
+        AgentScratch<DYN, N, L>& P = Pw[el];
+        if (!P.cur_filter || i == j || R.done[0][i] || R.done[0][j]) continue;
+        const double2 pi = R.pos[i], pj = R.pos[j];
+        P.fval[r] = shift_value(pair_value_raw<DYN>(g, pi.x, pi.y, P.as2[i], P.as3[i], pj.x, pj.y, P.as2[j], P.as3[j]),
+                                P.cur_sep, g);
     }
 }
 
-template <int DYN, class ES>
-__device__ __forceinline__ void emit_obs_row(const ES& S, int ai, int g /* landmark index */, double x, double y,
-                                             double s2, double s3, float* o, int N) {
+template <int DYN, int N, int L>
+__device__ __forceinline__ void emit_obs_row(const EmitRec<DYN, N, L>& R, const AgentScratch<DYN, N, L>& P, int ai,
+                                             int g /* landmark index */, double x, double y, double s2, double s3, float* o) {
     // navigation_graph_safe.py:855-875, utils.py:114-137
-    const double2 gp = S.pos[N + g];
-    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+    const double2 gp = R.pos[N + g];
+    if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
         o[0] = (float)s2; o[1] = (float)s3; o[2] = (float)(gp.x - x); o[3] = (float)(gp.y - y);
-        o[4] = (float)S.lsin[g]; o[5] = (float)S.lcos[g]; o[6] = (float)S.lsp[g];
+        o[4] = (float)P.lsin[g]; o[5] = (float)P.lcos[g]; o[6] = (float)P.lsp[g];
     } else {
-        double rx, ry; rotate_into(gp.x - x, gp.y - y, S.cth[ai], S.sth[ai], rx, ry);
-        const double rh = S.lh[g] - s2;
+        double rx, ry; rotate_into(gp.x - x, gp.y - y, R.air.cth[ai], R.air.sth[ai], rx, ry);
+        const double rh = P.lh[g] - s2;
         o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-        o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
+        o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)P.lsp[g];
     }
 }
 
@@ -222,211 +286,12 @@ __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bul
 template <int PENDING>
 __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" :: "n"(PENDING) : "memory"); }
 
-// Graph observation of ONE environment (navigation_graph_safe.py:932-994 + utils.py:139-255), all 32 lanes.
-template <int DYN, int N, int L>
-__device__ __noinline__ void emit_graph(float* __restrict__ node_obs, float* __restrict__ adj,
-                                       const uint32_t* __restrict__ sel_tab, const double r2_lt,
-                                       EnvShared<DYN, N, L>& T, float* __restrict__ stage, int ee, int lane, int debug) {
-    // arguments by value: a noinline callee would otherwise re-read the kernel parameter block through generic loads
-    using ES = EnvShared<DYN, N, L>;
-    constexpr int M = ES::M, E = ES::E, W = ES::W, EE = E * E;
-    constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
-    // (a) thresholded distance matrix: d2 in float64 against the exact squared radius; the stored
-    //     float32 value is d2f * rsqrt(d2f). One lane-task per unordered entity pair, enumerated without a
-    //     table as (a, a + d mod E) for d = 1 .. E/2 (for even E the last distance only needs a < E/2).
-    for (int e = lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
-    constexpr int NPAIR = E * (E - 1) / 2;
-    auto pair_task = [&](int p) {
-        const int dm1 = p / E, a = p - dm1 * E;
-        int b = a + dm1 + 1; if (b >= E) b -= E;
-        const double2 pa = T.pos[a], pb = T.pos[b];
-        const double dx = pa.x - pb.x, dy = pa.y - pb.y;
-        const double d2 = dx * dx + dy * dy;
-        const float d2f = fmaxf((float)d2, 1.0e-30f);
-        float rs;
-        asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(d2f));
-        const float v = (d2 < r2_lt && d2 > 0.0) ? d2f * rs : 0.0f;
-        T.dthr[a * E + b] = v; T.dthr[b * E + a] = v;
-    };
-    {
-        int p = lane;
-        for (; p + 32 < NPAIR; p += 64) { pair_task(p); pair_task(p + 32); }   // two independent tasks in flight
-        if (p < NPAIR) pair_task(p);
-    }
-    // (b) disconnected-entity bit masks before / after this step's goal updates (ballots)
-    unsigned any_change = 0u, any_disc = 0u;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const int e = w * 32 + lane;
-        bool dpre = false, dpost = false;
-        if (e < N) { dpre = T.done[0][e] != 0; dpost = T.done[1][e] != 0; }
-        else if (e < E) {
-            const int m = e - N, order = m / N, owner = m - order * N;
-            dpre = T.reached[0][owner] > order; dpost = T.reached[1][owner] > order;
-        }
-        const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
-        if (lane == 0) { T.disc[0][w] = bpre; T.disc[1][w] = bpost; }
-        any_change |= (bpre ^ bpost); any_disc |= bpost;
-    }
-    __syncwarp();
-    if (any_disc != 0u) {
-        for (int k = lane; k < N * W; k += 32) {
-            const int w = k % W;
-            const unsigned sel = sel_tab[k];
-            T.keepm[k] = ~((T.disc[1][w] & sel) | (T.disc[0][w] & ~sel));
-        }
-    }
-    __syncwarp();
-    // (d) adjacency (issued BEFORE the node rows so that the asynchronous copies overlap their computation)
-    if (!(debug & 8)) {
-        float* abase = adj + (size_t)ee * (N * EE);
-        if (E % 2 == 0 && any_change == 0u && (E % 4 != 0 || (debug & 16))) {
-            // every observer sees the same matrix: mask it once in place, then N bulk copies. Used when rows are not
-            // 16-byte multiples (E % 4 != 0, e.g. cfg3's E = 30), where it beats the scalar store loop; with E % 4 == 0
-            // the float4 loop below is faster (N back-to-back UBLKCP issues stall ~400 cycles each).
-            if (any_disc != 0u) {
-                for (int idx = lane; idx < EE; idx += 32) {
-                    const int a = idx / E, b2 = idx - a * E;
-                    const bool keep = ((T.keepm[a >> 5] >> (a & 31)) & 1u) && ((T.keepm[b2 >> 5] >> (b2 & 31)) & 1u);
-                    if (!keep) T.dthr[idx] = 0.0f;
-                }
-            }
-            bulk_store_fence();
-            __syncwarp();
-            if (lane < N) { bulk_store(abase + lane * EE, T.dthr, (unsigned)EE * 4u); bulk_store_commit(); }
-        } else if (E % 4 == 0) {
-            constexpr int CPR = E / 4, CHUNKS = EE / 4;
-            for (int ch = lane; ch < CHUNKS; ch += 32) {
-                const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
-                const float4 v = *reinterpret_cast<const float4*>(T.dthr + ch * 4);
-                float* dst = abase + ch * 4;
-                if (any_disc == 0u) {               // nothing disconnected: the same chunk for every observer
-#pragma unroll
-                    for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), v);
-                } else if (any_change == 0u) {      // no goal update this step: one mask for every observer
-                    const bool ka = (T.keepm[a >> 5] >> (a & 31)) & 1u;
-                    const unsigned nib = ka ? ((T.keepm[b4 >> 5] >> (b4 & 31)) & 0xFu) : 0u;
-                    float4 o;
-                    o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
-                    o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-#pragma unroll
-                    for (int i = 0; i < N; ++i) __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
-                } else {
-#pragma unroll
-                    for (int i = 0; i < N; ++i) {
-                        const bool ka = (T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u;
-                        const unsigned nib = ka ? ((T.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu) : 0u;
-                        float4 o;
-                        o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
-                        o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
-                        __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
-                    }
-                }
-            }
-        } else {
-            for (int idx = lane; idx < EE; idx += 32) {
-                const int a = idx / E, b2 = idx - a * E;
-                const float v = T.dthr[idx];
-#pragma unroll
-                for (int i = 0; i < N; ++i) {
-                    const bool keep = any_disc == 0u ||
-                                      (((T.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
-                                       ((T.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u));
-                    __stcs(abase + i * EE + idx, keep ? v : 0.0f);
-                }
-            }
-        }
-    }
-    // (c) node features: one lane per (observer, entity) row. Rows are 40 / 44 bytes, so they are staged in a
-    //     per-warp double-buffered shared-memory buffer (32 rows at a time) and flushed with fully coalesced vector stores.
-    if (!(debug & 4)) {
-        float* nbase = node_obs + (size_t)ee * (N * E * F);
-        constexpr int ROWS = N * E, CH = 32;
-        constexpr int VEC = ((ROWS * F) % 4 == 0 && (CH * F) % 4 == 0) ? 4 : (((ROWS * F) % 2 == 0 && (CH * F) % 2 == 0) ? 2 : 1);
-        auto node_row = [&](int r, float* o) {
-            const int i = r / E, e = r - i * E;
-            const double2 pi = T.pos[i], vi = T.vel[N + i];
-            const bool is_agent = e < N;
-            const int sel = (e <= i) ? N : 0;     // agents <= i are seen after their own update
-            const int vidx = is_agent ? sel + e : 2 * N;
-            const int gidx = is_agent ? E + sel + e : e;
-            const int cidx = is_agent ? M + sel + e : e - N;
-            if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                // utils.py:201-255: [p_e - p_i, v_e - v_i, goal_e - p_i, sin gh, cos gh, gspeed, type]
-                const double2 pe = T.pos[e], ve = T.vel[vidx], ge = T.pos[gidx];
-                const float4 cc = T.cst[cidx];
-                float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
-                o2[0] = make_float2((float)(pe.x - pi.x), (float)(pe.y - pi.y));
-                o2[1] = make_float2((float)(ve.x - vi.x), (float)(ve.y - vi.y));
-                o2[2] = make_float2((float)(ge.x - pi.x), (float)(ge.y - pi.y));
-                o2[3] = make_float2(cc.x, cc.y);
-                o2[4] = make_float2(cc.z, cc.w);
-            } else {
-                const double ci = T.cth[i], si = T.sth[i];
-                if (e < N) {
-                    const int g = T.goal[sel ? 1 : 0][e];
-                    const double2 pe = T.pos[e], ve = T.vel[vidx], ge = T.pos[gidx];
-                    double rx, ry, gx, gy;
-                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
-                    rotate_into(ge.x - pi.x, ge.y - pi.y, ci, si, gx, gy);
-                    const double ce = T.cth[e], se = T.sth[e];
-                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(ve.x - vi.x, ve.y - vi.y);
-                    o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
-                    o[5] = (float)gx; o[6] = (float)gy;
-                    o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
-                    o[9] = (float)T.lsp[g]; o[10] = 0.0f;
-                } else {
-                    const int m = e - N;
-                    const double2 pe = T.pos[e];
-                    double rx, ry;
-                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
-                    const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
-                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
-                    o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
-                    o[9] = (float)T.lsp[m]; o[10] = 1.0f;
-                }
-            }
-        };
-        constexpr bool BULK = (VEC == 4);
-        int chunk = 0;
-        for (int r0 = 0; r0 < ROWS; r0 += CH, ++chunk) {
-            float* buf = stage + (chunk & 1) * (CH * F);
-            if (BULK && chunk >= 2) {       // the copy that last read this buffer must have finished reading it
-                if (lane == 0) bulk_store_wait_read<1>();
-                __syncwarp();
-            }
-            const int ra = r0 + lane;
-            if (ra < ROWS) node_row(ra, buf + lane * F);
-            const int nfl = ((ROWS - r0) < CH ? (ROWS - r0) : CH) * F;   // floats in this chunk
-            float* gdst = nbase + r0 * F;
-            if (BULK) {
-                bulk_store_fence();
-                __syncwarp();
-                if (lane == 0) { bulk_store(gdst, buf, (unsigned)nfl * 4u); bulk_store_commit(); }
-            } else {
-                __syncwarp();
-                if (VEC == 2) {
-                    for (int q = lane; q < nfl / 2; q += 32)
-                        __stcs(reinterpret_cast<float2*>(gdst) + q, reinterpret_cast<const float2*>(buf)[q]);
-                } else {
-                    for (int q = lane; q < nfl; q += 32) __stcs(gdst + q, buf[q]);
-                }
-                __syncwarp();
-            }
-        }
-    }
-    // every bulk copy issued by this call has finished READING shared memory before the records are reused
-    bulk_store_wait_read<0>();
-    __syncwarp();
-}
-
 // Scenario.random_scenario for ONE environment, executed by the env's leader lane
 // (navigation_graph_safe.py:1199-1367, utils.py:39-68); Philox stream keyed by (seed, env, reset_count).
 template <int DYN, int N, int L>
-__device__ __noinline__ void sample_scenario(const KParams& kp, EnvShared<DYN, N, L>& S, int env, int reset_count,
-                                            double ratio) {
-    using ES = EnvShared<DYN, N, L>;
-    constexpr int M = ES::M;
+__device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, L>& R, AgentScratch<DYN, N, L>& P,
+                                            int env, int reset_count, double ratio) {
+    constexpr int M = N * L;
     const lsm_config& c = kp.c;
     const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
     Rng r; r.init(kp.seed, (uint32_t)(kp.b.env_id_base + env), (uint32_t)reset_count);
@@ -437,20 +302,20 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EnvShared<DYN, N
         if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
             const double px = r.uniform(-0.8 * ws, 0.8 * ws);
             const double py = r.uniform(-0.8 * ws, 0.8 * ws);
-            S.pos[i] = make_double2(px, py);
-            S.as2[i] = 0.0; S.as3[i] = 0.0;
+            R.pos[i] = make_double2(px, py);
+            P.as2[i] = 0.0; P.as3[i] = 0.0;
         } else {
             const double xmin = -0.5 * ws;
             const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
             const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
             const double rx = r.uniform(xmin, xmax);
-            S.pos[i] = make_double2(rx, ry);
+            R.pos[i] = make_double2(rx, ry);
             const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
-            S.as2[i] = r.uniform(0.0, 2.0 * kPi);
-            S.as3[i] = sp;
+            P.as2[i] = r.uniform(0.0, 2.0 * kPi);
+            P.as3[i] = sp;
         }
     }
-    double2* lp = S.pos + N;    // landmark positions, slot l*N + i
+    double2* lp = R.pos + N;    // landmark positions, slot l*N + i
     for (int i = 0; i < N; ++i) {
         double xlo, xhi, ylo, yhi, min_d, max_d;
         if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
@@ -481,43 +346,133 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EnvShared<DYN, N
             if (lp[i].x > lp[N + i].x) { const double2 t = lp[i]; lp[i] = lp[N + i]; lp[N + i] = t; }
         }
         for (int l = 0; l < L - 1; ++l)
-            S.lh[l * N + i] = atan2(lp[(l + 1) * N + i].y - lp[l * N + i].y, lp[(l + 1) * N + i].x - lp[l * N + i].x);
-        const double last_heading = S.lh[(L - 2) * N + i];
+            P.lh[l * N + i] = atan2(lp[(l + 1) * N + i].y - lp[l * N + i].y, lp[(l + 1) * N + i].x - lp[l * N + i].x);
+        const double last_heading = P.lh[(L - 2) * N + i];
         const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
         if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
-            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
+            for (int l = 0; l < L; ++l) P.lsp[l * N + i] = c.goal_speed_max;
         } else {
-            for (int l = 0; l < L; ++l) S.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
+            for (int l = 0; l < L; ++l) P.lsp[l * N + i] = r.uniform(c.goal_speed_min, c.goal_speed_max);
             const double var = r.uniform(0.0, 1.0);
             if (!(var < pymin(cr, 1.0 - 0.2))) {
-                for (int l = 0; l < L; ++l) S.lsp[l * N + i] = c.goal_speed_max;
-                S.lsp[(L - 1) * N + i] = c.goal_speed_min;
+                for (int l = 0; l < L; ++l) P.lsp[l * N + i] = c.goal_speed_max;
+                P.lsp[(L - 1) * N + i] = c.goal_speed_min;
             }
         }
         for (int l = 0; l < L - 1; ++l) {
             const double pr = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? cr * 0.25 * kPi : cra * 0.1 * kPi;
-            S.lh[l * N + i] += r.uniform(-pr, pr);
+            P.lh[l * N + i] += r.uniform(-pr, pr);
         }
-        S.lh[(L - 1) * N + i] = last_heading;
+        P.lh[(L - 1) * N + i] = last_heading;
     }
     for (int m = 0; m < M; ++m) {
-        const double sv = sin(S.lh[m]), cv = cos(S.lh[m]);
-        S.lsin[m] = sv; S.lcos[m] = cv;
-        S.cst[m] = make_float4((float)sv, (float)cv, (float)S.lsp[m], 1.0f);
+        const double sv = sin(P.lh[m]), cv = cos(P.lh[m]);
+        P.lsin[m] = sv; P.lcos[m] = cv;
+        R.cst[m] = make_float4((float)sv, (float)cv, (float)P.lsp[m], 1.0f);
     }
 }
+// ---------------------------------------------------------------------------------------------
+// Cold paths of the per-agent kernel, kept OUT OF LINE: the kernel runs its straight-line code once per
+// warp, so its cost is dominated by instruction fetch (profiles/r01_v4b: stall_no_instruction 5.8 per
+// issue); every rarely-taken block that is inlined becomes a far jump over kilobytes of SASS.
+// ---------------------------------------------------------------------------------------------
+// utils.py:323-349 (double integrator without the safety-filter argument): heading/velocity penalty
+__device__ __noinline__ double magnetic_penalty(double x, double y, double s2, double s3, double gx, double gy,
+                                               double gh, double gs, double dist_thresh, double sloped) {
+    const double cg = cos(gh), sg = sin(gh);
+    double rpx, rpy, rvx, rvy;
+    rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
+    const double dist = norm2(rpx, rpy);
+    const double ang = atan2(rpy, rpx);
+    const double ang_range = kPi / 6;
+    rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
+    const double rh = magnetic_heading(rpx, rpy, 2.0 * dist_thresh);
+    double ref_speed = pymax(gs, 0.1);
+    const double dr = clipd(dist / 1.5, 0.0, 1.0);
+    ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
+    const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
+    const double err = norm2(ex, ey);
+    double pen;
+    if (cos(ang) < cos(ang_range)) pen = err;
+    else {
+        const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
+        pen = err * (1.0 - ar) + dist * ar;
+    }
+    double hap = 3.0 * pen;
+    hap = clipd(1.0 - sloped, 0.0, 1.0) * hap;
+    return hap;
+}
 
+// navigation_graph_safe.py:700-720: heading * speed * cross-track factor of the goal reward (only on the step a goal is reached)
+__device__ __noinline__ double goal_reward_factor(double theta, double pdx, double pdy, double hpr, double sen) {
+    const double spr = 1.0 - sen;
+    double cte = pdx * sin(theta) - pdy * cos(theta);
+    const double nrm = norm2(pdx, pdy);
+    cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
+    cte = clipd(cte, 0.0, 1.0);
+    return hpr * spr * (1.0 - cte);
+}
+
+// reward_multiple_engagement (navigation_graph_safe.py:800-823) over the agents flagged in `mask`
+template <int DYN, int N, int L>
+__device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, L>& R, unsigned mask, int ai, double x, double y,
+                                                         double vpx, double vpy, double sep, double eng) {
+    double pc_pen = 0.0;
+    for (int a = 0; a < N; ++a) {
+        if (!((mask >> a) & 1u)) continue;
+        const double2 pa = R.pos[a];
+        const double rx = pa.x - x, ry = pa.y - y;
+        const double dx = x - pa.x, dy = y - pa.y;
+        const double rd = sqrt(dx * dx + dy * dy);
+        const double closeness = 1.0 - clipd((rd - sep) / (eng - sep), 0.0, 1.0);
+        const double dir = atan2(ry, rx);
+        const double2 va = R.vel[(a < ai ? N : 0) + a];
+        double change = cos(dir) * (va.x - vpx) + sin(dir) * (va.y - vpy);
+        change = fabs(pymin(0.0, change));
+        pc_pen += change * closeness;
+    }
+    return pc_pen;
+}
+
+// reward_hj_value (navigation_graph_safe.py:830-837, core.py:459-468)
+template <int DYN, int N, int L>
+__device__ __noinline__ double hj_value_reward(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L>& R,
+                                              const AgentScratch<DYN, N, L>& P, int ai, double x, double y, double sep, double cvalue_rew) {
+    const GridDev g = *vg;
+    double r = 0.0;
+    for (int a = 0; a < N; ++a) {
+        if (a == ai) continue;
+        const int adone = a < ai ? R.done[1][a] : R.done[0][a];
+        if (adone) continue;
+        // as2/as3 hold the pre-update states
+        const double2 pa = R.pos[a];
+        const double v = shift_value(pair_value_raw<DYN>(g, x, y, P.as2[ai], P.as3[ai], pa.x, pa.y, P.as2[a], P.as3[a]), sep, g);
+        const double cvp = fabs(pymin(v - 0.4, 0.0));
+        r += cvalue_rew * cvp;
+    }
+    return r;
+}
+
+template <int DYN>
+__device__ __noinline__ bool goal_reached_cold(double x, double y, double s2, double s3, double gx, double gy, double gh, double gs,
+                                              double dist_thresh, double heading_thresh, double speed_thresh) {
+    const double th2 = theta_of<DYN>(s2, s3), sp2 = speed_of<DYN>(s2, s3);
+    Curriculum q;
+    q.dist_thresh = dist_thresh; q.heading_thresh = heading_thresh; q.speed_thresh = speed_thresh;
+    return goal_reached<DYN>(x, y, th2, sp2, gx, gy, gh, gs, q);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_b: per-agent physics. A warp owns EPW consecutive environments, G = next_pow2(N) lanes each.
+// ---------------------------------------------------------------------------------------------
 template <int DYN, int N, int L, int BLOCK, int MINB>
-__global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_constant__ KParams kp) {
-    using ES = EnvShared<DYN, N, L>;
-    constexpr int M = ES::M, E = ES::E, W = ES::W, EE = E * E;
+__global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_constant__ KParams kp) {
+    using REC = EmitRec<DYN, N, L>;
+    using SCR = AgentScratch<DYN, N, L>;
+    constexpr int M = REC::M, E = REC::E;
     constexpr int G = Pow2<N>::value;
     constexpr int Dobs = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
-    constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ GridDev s_vg;                      // block copy of the value-grid descriptor for pair_phase
-    if (threadIdx.x == 0) s_vg = kp.vg;
-    __syncthreads();
     const lsm_config& c = kp.c;
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
@@ -526,15 +481,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
     const int n = (int)kp.b.num_envs;
     const int le = lane / G;
     const int ai = lane - le * G;
-    ES* const Sw = reinterpret_cast<ES*>(smem_raw) + warp_in_block * EPW;   // this warp's env records
+    // this warp's records: EPW emit records (contiguous: dumped to global memory in one run), then EPW scratch blocks
+    unsigned char* const wbase = smem_raw + (size_t)warp_in_block * EPW * (sizeof(REC) + sizeof(SCR));
+    REC* const Rw = reinterpret_cast<REC*>(wbase);
+    SCR* const Pw = reinterpret_cast<SCR*>(wbase + (size_t)EPW * sizeof(REC));
     const bool lane_has_env = le < EPW;
-    // per-warp staging buffer for node-feature rows (after all environment records of the block)
-    float* const stage = reinterpret_cast<float*>(smem_raw + (size_t)warps_per_block * EPW * sizeof(ES)) + warp_in_block * (2 * 32 * F);
-    ES& S = Sw[lane_has_env ? le : 0];
+    REC& R = Rw[lane_has_env ? le : 0];
+    SCR& P = Pw[lane_has_env ? le : 0];
     const unsigned group_mask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((le * G) & 31));
     const bool use_filter_arg = (c.flags & LSM_FLAG_USE_SAFETY_FILTER) != 0;
     const int ngroups = kp.ngroups;               // ceil(n / EPW), from the host
     const size_t fstride = (size_t)n * N;         // elements between two fields of the agent SoA
+    pdl_launch_dependents();
+    pdl_wait();
 
     for (int grp = blockIdx.x * warps_per_block + warp_in_block; grp < ngroups; grp += gridDim.x * warps_per_block) {
         const int env0 = grp * EPW;
@@ -581,26 +540,27 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
             const double* src = kp.b.landmarks + (size_t)env0 * M;
             for (int idx = lane; idx < total; idx += 32) {
                 const int el = idx / M, m = idx - el * M;
-                ES& T = Sw[el];
                 const double lxv = src[LSM_LF_X * lstride + idx], lyv = src[LSM_LF_Y * lstride + idx];
                 const double lhv = src[LSM_LF_HEADING * lstride + idx], lsv = src[LSM_LF_SPEED * lstride + idx];
                 const double sv = src[LSM_LF_SIN * lstride + idx], cv = src[LSM_LF_COS * lstride + idx];
-                T.pos[N + m] = make_double2(lxv, lyv);
+                Rw[el].pos[N + m] = make_double2(lxv, lyv);
+                SCR& T = Pw[el];
                 T.lh[m] = lhv; T.lsp[m] = lsv; T.lsin[m] = sv; T.lcos[m] = cv;
-                T.cst[m] = make_float4((float)sv, (float)cv, (float)lsv, 1.0f);   // landmark rows: type 1
+                Rw[el].cst[m] = make_float4((float)sv, (float)cv, (float)lsv, 1.0f);   // landmark rows: type 1
             }
         }
         Curriculum q = curriculum(kp, ratio);
         const int lvl = (int)(q.stair * 4.0);     // curriculum stair level: index of the squared-threshold tables
         if (agent_on) {
-            S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
-            S.done[0][ai] = done; S.reached[0][ai] = reached;
-            if (ai == 0) { S.cur_sep = q.sep; S.cur_filter = q.world_filter ? 1 : 0; S.vel[2 * N] = make_double2(0.0, 0.0); }
+            R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
+            R.done[0][ai] = done; R.reached[0][ai] = reached;
+            if (ai == 0) { P.cur_sep = q.sep; P.cur_filter = q.world_filter ? 1 : 0; R.vel[2 * N] = make_double2(0.0, 0.0); }
         }
         __syncwarp();
 
         bool all_done_env = false;
         const unsigned any_filter = __ballot_sync(0xffffffffu, env_on && q.world_filter);
+        int goal_obs = 0;                         // landmark index of the goal the env-level observation uses
 
         if (kp.mode == MODE_STEP) {
             // ---------------- P1: action decode, safety filter, dynamics ----------------
@@ -616,25 +576,39 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 }
                 const int i0 = idx / 5, i1 = idx - i0 * 5;
                 raw0 = c.act_tab0[i0]; raw1 = c.act_tab1[i1];
-                S.rawx[ai] = raw0; S.rawy[ai] = raw1;
+                P.rawx[ai] = raw0; P.rawy[ai] = raw1;
             }
             __syncwarp();
             double safe0 = raw0, safe1 = raw1;
             for (int it = 0; it < c.num_internal_step; ++it) {
-                if (any_filter != 0u && !(kp.debug & 2)) {
-                    pair_phase<DYN, N, L>(&s_vg, Sw, nenv, lane);
+                // HJ values of (ego, other): from lsm_pair_kernel for the states this launch started with, in-kernel
+                // for later internal steps
+                const bool precomputed = it == 0 && kp.pairval != nullptr;
+                if (any_filter != 0u && !precomputed) {
+                    pair_phase<DYN, N, L>(&kp.vg, Rw, Pw, nenv, lane);
                     __syncwarp();
                 }
                 if (agent_on && q.world_filter) {
-                    // (b) np.argmin over the others (first minimum, ascending agent index), then resolve
+                    // np.argmin over the others (first minimum, ascending agent index), then resolve
                     int filt = 0, dec = -1;
                     safe0 = raw0; safe1 = raw1;
                     if (!done) {
                         double best_d2 = 0.0, best_v = 0.0; int kd = -1, kv = -1;
+                        const double* pv = kp.pairval + ((size_t)env * N + ai) * N;
+                        double vj[N];
 #pragma unroll
                         for (int j = 0; j < N; ++j) {
-                            if (j == ai || S.done[0][j]) continue;
-                            const double d2 = S.d2aa[ai * N + j], v = S.fval[ai * N + j];
+                            vj[j] = INFINITY;
+                            if (j == ai || R.done[0][j]) continue;
+                            vj[j] = precomputed ? pv[j] : P.fval[ai * N + j];
+                        }
+#pragma unroll
+                        for (int j = 0; j < N; ++j) {
+                            if (j == ai || R.done[0][j]) continue;
+                            const double2 pj = R.pos[j];
+                            const double ddx = pj.x - x, ddy = pj.y - y;
+                            const double d2 = ddx * ddx + ddy * ddy;
+                            const double v = precomputed ? shift_value(vj[j], q.sep, kp.vg) : vj[j];
                             if (kd < 0 || d2 < best_d2) { kd = j; best_d2 = d2; }
                             if (kv < 0 || v < best_v) { kv = j; best_v = v; }
                         }
@@ -642,9 +616,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                             dec = kv;
                             // `min distance > coordination_range` as an exact test on the squared distance
                             const double best_d = (best_d2 >= kp.r2_gt) ? INFINITY : 0.0;
-                            const double2 po = S.pos[kv];
-                            filter_resolve<DYN, LeanGrad>(kp, best_d, best_v, !isinf(best_v), x, y, s2, s3, po.x, po.y, S.as2[kv], S.as3[kv],
-                                                raw0, raw1, S.rawx[kv], S.rawy[kv], safe0, safe1, filt);
+                            const double2 po = R.pos[kv];
+                            filter_resolve<DYN, LeanGrad>(kp, best_d, best_v, !isinf(best_v), x, y, s2, s3, po.x, po.y, P.as2[kv], P.as3[kv],
+                                                raw0, raw1, P.rawx[kv], P.rawy[kv], safe0, safe1, filt);
                         }
                     }
                     deconflict = dec; safety_filtered = filt;
@@ -654,33 +628,25 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                     const double d0 = raw0 - safe0, d1 = raw1 - safe1;
                     action_diff = sqrt(d0 * d0 + d1 * d1);
                     if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time);
-                    S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
+                    R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
                 }
                 __syncwarp();
             }
-            // ---------------- P2: squared agent-agent distances (pair-parallel), goal / reward / done ----------------
-            for (int t = lane; t < nenv * N * N; t += 32) {
-                const int el = t / (N * N), r = t - el * (N * N);
-                const int i = r / N, j = r - i * N;
-                ES& T = Sw[el];
-                const double2 pi = T.pos[i], pj = T.pos[j];
-                const double dx = pi.x - pj.x, dy = pi.y - pj.y;
-                T.d2aa[r] = dx * dx + dy * dy;
-            }
-            __syncwarp();
+            // ---------------- P2: goal / reward / done ----------------
             int goal_pre = 0, goal_post = 0, reached_post = reached, done_post = done;
             double rew = 0.0;
             double vpx = 0, vpy = 0, vqx = 0, vqy = 0;
             double theta = 0, speed = 0;
+            double cth = 1.0, sth = 0.0;
             bool reached_now = false;
             if (agent_on) {
                 theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
+                else { cth = cos(s2); sth = sin(s2); vpx = s3 * cth; vpy = s3 * sth; R.air.cth[ai] = cth; R.air.sth[ai] = sth; }
                 goal_pre = goal_index(reached, ai, N, M);
-                const double2 gp = S.pos[N + goal_pre];
-                const double gx = gp.x, gy = gp.y, gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
-                emit_obs_row<DYN>(S, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
+                const double2 gp = R.pos[N + goal_pre];
+                const double gx = gp.x, gy = gp.y, gh = P.lh[goal_pre], gs = P.lsp[goal_pre];
+                emit_obs_row<DYN, N, L>(R, P, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
                 // reward_reach_goal: navigation_graph_safe.py:691-791
                 const double he = direction_alignment_error(theta, gh);
                 const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
@@ -690,44 +656,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 if (use_filter_arg) cra = 1.0;
                 reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
                 if (reached_now) {
-                    const double spr = 1.0 - sen;
-                    const double pdx = gx - x, pdy = gy - y;
-                    double cte = pdx * sin(theta) - pdy * cos(theta);
-                    const double nrm = norm2(pdx, pdy);
-                    cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
-                    cte = clipd(cte, 0.0, 1.0);
-                    const double pr = hpr * spr * (1.0 - cte);
+                    const double pr = goal_reward_factor(theta, gx - x, gy - y, hpr, sen);
                     double goal_rew;
                     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) goal_rew = c.goal_rew * pr;
                     else goal_rew = c.goal_rew * (pr * cra + (1.0 - cra));
                     if (!done) rew += goal_rew;
                 }
                 if (!done) {
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        if (!use_filter_arg) {   // utils.py:323-349
-                            const double cg = cos(gh), sg = sin(gh);
-                            double rpx, rpy, rvx, rvy;
-                            rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
-                            const double dist = norm2(rpx, rpy);
-                            const double ang = atan2(rpy, rpx);
-                            const double ang_range = kPi / 6;
-                            rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
-                            const double rh = magnetic_heading(rpx, rpy, 2.0 * q.dist_thresh);
-                            double ref_speed = pymax(gs, 0.1);
-                            const double dr = clipd(dist / 1.5, 0.0, 1.0);
-                            ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
-                            const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
-                            const double err = norm2(ex, ey);
-                            double pen;
-                            if (cos(ang) < cos(ang_range)) pen = err;
-                            else {
-                                const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
-                                pen = err * (1.0 - ar) + dist * ar;
-                            }
-                            double hap = 3.0 * pen;
-                            hap = clipd(1.0 - q.sloped, 0.0, 1.0) * hap;
-                            rew -= hap;
-                        }
+                    if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        if (!use_filter_arg) rew -= magnetic_penalty(x, y, s2, s3, gx, gy, gh, gs, q.dist_thresh, q.sloped);
                         if (use_filter_arg) rew -= 1.0; else rew -= 1.0 * q.sloped;
                     } else {
                         double rpx, rpy;
@@ -749,16 +686,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 if (reached_post >= L) {
                     done_post = 1;
                     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { s2q = 0.0; s3q = 0.0; vqx = 0.0; vqy = 0.0; }
-                    else { s3q = 0.0; vqx = s3q * S.cth[ai]; vqy = s3q * S.sth[ai]; }
+                    else { s3q = 0.0; vqx = s3q * cth; vqy = s3q * sth; }
                 }
                 goal_post = goal_index(reached_post, ai, N, M);
-                S.vel[ai] = make_double2(vpx, vpy); S.vel[N + ai] = make_double2(vqx, vqy);
-                S.pos[E + ai] = gp; S.pos[E + N + ai] = S.pos[N + goal_post];
-                { float4 t = S.cst[goal_pre]; t.w = 0.0f; S.cst[M + ai] = t; }
-                { float4 t = S.cst[goal_post]; t.w = 0.0f; S.cst[M + N + ai] = t; }
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3q;
-                S.goal[0][ai] = goal_pre; S.goal[1][ai] = goal_post;
-                S.reached[1][ai] = reached_post; S.done[1][ai] = done_post;
+                R.vel[ai] = make_double2(vpx, vpy); R.vel[N + ai] = make_double2(vqx, vqy);
+                R.pos[E + ai] = gp; R.pos[E + N + ai] = R.pos[N + goal_post];
+                { float4 t = R.cst[goal_pre]; t.w = 0.0f; R.cst[M + ai] = t; }
+                { float4 t = R.cst[goal_post]; t.w = 0.0f; R.cst[M + N + ai] = t; }
+                if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+                    R.air.spd_post[ai] = s3q; R.air.goal[0][ai] = goal_pre; R.air.goal[1][ai] = goal_post;
+                }
+                R.reached[1][ai] = reached_post; R.done[1][ai] = done_post;
                 // as2/as3 keep the PRE-update state (the HJ_VALUE term of later agents only reads agents that are
                 // not done, whose pre and post states coincide); the lane's registers take the post state
                 s2 = s2q; s3 = s3q;
@@ -770,30 +708,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 double mind2 = INFINITY;                       // core.py:696-709
                 double stat_mind2 = INFINITY; int cnt = 0;      // environment.py:1004-1022
                 double r_sv = 0.0;                              // navigation_graph_safe.py:793-798
-                int pc_count = 0; double pc_pen = 0.0;          // navigation_graph_safe.py:800-823
+                int pc_count = 0;                               // navigation_graph_safe.py:800-823
                 const bool want_sv = (c.flags & LSM_FLAG_SAFETY_VIOLATION) != 0;
                 const bool want_pc = (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) != 0;
+                unsigned pc_mask = 0u;
 #pragma unroll
                 for (int a = 0; a < N; ++a) {
                     if (a == ai) continue;
-                    const double d2 = S.d2aa[ai * N + a];
-                    const int apre = S.done[0][a], apost = S.done[1][a];
+                    // squared distance after the dynamics; (p_i - p_a)^2 == (p_a - p_i)^2 exactly, so both lanes of a
+                    // pair see the same value (core.py:514-543)
+                    const double2 pa = R.pos[a];
+                    const double dx = x - pa.x, dy = y - pa.y;
+                    const double d2 = dx * dx + dy * dy;
+                    const int apre = R.done[0][a], apost = R.done[1][a];
                     if (!done && !apre && d2 < mind2) mind2 = d2;
                     if (d2 < kp.col2_lt) ncoll += 1;           // navigation_graph_safe.py:405-413, 497-501
                     const int adone_r = a < ai ? apost : apre;
                     if (want_sv && d2 < kp.sep2_lt[lvl] && !adone_r) r_sv += q.conflict_rew;
-                    if (want_pc && d2 < kp.eng2_lt[lvl] && !adone_r) {
-                        const double rd = sqrt(d2);
-                        const double2 pa = S.pos[a];
-                        const double rx = pa.x - x, ry = pa.y - y;
-                        const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
-                        const double dir = atan2(ry, rx);
-                        const double2 va = S.vel[(a < ai ? N : 0) + a];
-                        double change = cos(dir) * (va.x - vpx) + sin(dir) * (va.y - vpy);
-                        change = fabs(pymin(0.0, change));
-                        pc_pen += change * closeness;
-                        pc_count += 1;
-                    }
+                    if (want_pc && d2 < kp.eng2_lt[lvl] && !adone_r) { pc_mask |= 1u << a; pc_count += 1; }
                     const int adone_s = a <= ai ? apost : apre;
                     if (!adone_s && d2 < kp.r2_lt && d2 > 0.0) {
                         if (d2 < kp.engref2_lt) cnt++;
@@ -802,22 +734,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 }
                 min_rel = sqrt(mind2);
                 if (want_sv) rew += r_sv;
-                if (want_pc && pc_count > 1) rew += q.multi_rew * pc_pen;
+                if (pc_count > 1)
+                    rew += q.multi_rew * potential_conflict_penalty<DYN, N, L>(R, pc_mask, ai, x, y, vpx, vpy, q.sep, q.eng);
                 if ((c.flags & LSM_FLAG_DIFF_FROM_FILTERED_ACTION) && use_filter_arg) {   // :825-828
                     if (!done) rew += q.diff_rew * action_diff;
                 }
-                if (c.flags & LSM_FLAG_HJ_VALUE) {                 // :830-837, core.py:459-468
-                    double r = 0.0;
-                    for (int a = 0; a < N; ++a) {
-                        if (a == ai) continue;
-                        const int adone = a < ai ? S.done[1][a] : S.done[0][a];
-                        if (adone) continue;
-                        const double v = pair_value<DYN>(kp.vg, q.sep, S, ai, a);   // as2/as3 hold the pre-update states
-                        const double cvp = fabs(pymin(v - 0.4, 0.0));
-                        r += q.cvalue_rew * cvp;
-                    }
-                    rew += r;
-                }
+                if (c.flags & LSM_FLAG_HJ_VALUE)
+                    rew += hj_value_reward<DYN, N, L>(&kp.vg, R, P, ai, x, y, q.sep, q.cvalue_rew);
                 rew = clipd(rew, c.min_reward, c.max_reward);
                 if (!done_post) {
                     ep_len += 1;
@@ -833,14 +756,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 // info_callback state: navigation_graph_safe.py:386-413 (post-update goal and velocity)
                 if (times_req == -1.0) {
                     // once times_required is set all three fields are frozen, so the goal test is only needed here
-                    const double2 gq = S.pos[N + goal_post];
+                    const double2 gq = R.pos[N + goal_post];
                     const double dx = x - gq.x, dy = y - gq.y;
                     // same goal and same (unfrozen) state as before the update -> same answer as `reached_now`
                     bool r2 = reached_now;
-                    if (goal_post != goal_pre || done_post != done) {
-                        const double th2 = theta_of<DYN>(s2, s3), sp2 = speed_of<DYN>(s2, s3);
-                        r2 = goal_reached<DYN>(x, y, th2, sp2, gq.x, gq.y, S.lh[goal_post], S.lsp[goal_post], q);
-                    }
+                    if (goal_post != goal_pre || done_post != done)
+                        r2 = goal_reached_cold<DYN>(x, y, s2, s3, gq.x, gq.y, P.lh[goal_post], P.lsp[goal_post], q.dist_thresh, q.heading_thresh,
+                                                    q.speed_thresh);
                     if (r2) times_req = (double)current_step * c.dt;
                     dists_goal = p_dist; dist_left = sqrt(dx * dx + dy * dy);
                 }
@@ -865,17 +787,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
         } else {
             if (agent_on) {
                 double vx, vy;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
+                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
                 const int g = goal_index(reached, ai, N, M);
-                S.vel[ai] = make_double2(vx, vy); S.vel[N + ai] = make_double2(vx, vy);
-                const double2 gp = S.pos[N + g];
-                S.pos[E + ai] = gp; S.pos[E + N + ai] = gp;
-                float4 cc = S.cst[g]; cc.w = 0.0f;
-                S.cst[M + ai] = cc; S.cst[M + N + ai] = cc;
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal[0][ai] = g; S.goal[1][ai] = g;
-                S.reached[1][ai] = reached; S.done[1][ai] = done;
+                goal_obs = g;
+                R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
+                const double2 gp = R.pos[N + g];
+                R.pos[E + ai] = gp; R.pos[E + N + ai] = gp;
+                float4 cc = R.cst[g]; cc.w = 0.0f;
+                R.cst[M + ai] = cc; R.cst[M + N + ai] = cc;
+                if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+                    R.air.spd_post[ai] = s3; R.air.goal[0][ai] = g; R.air.goal[1][ai] = g;
+                }
+                R.reached[1][ai] = reached; R.done[1][ai] = done;
             }
             __syncwarp();
         }
@@ -916,28 +840,29 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
                 q = curriculum(kp, ratio);
             }
-            if (do_reset && sample && ai == 0) sample_scenario<DYN, N, L>(kp, S, env, reset_count, ratio);
+            if (do_reset && sample && ai == 0) sample_scenario<DYN, N, L>(kp, R, P, env, reset_count, ratio);
             __syncwarp();
             if (do_reset && agent_on) {
-                if (sample) { const double2 p = S.pos[ai]; x = p.x; y = p.y; s2 = S.as2[ai]; s3 = S.as3[ai]; }
+                if (sample) { const double2 p = R.pos[ai]; x = p.x; y = p.y; s2 = P.as2[ai]; s3 = P.as3[ai]; }
                 done = 0; reached = 0;
                 p_dist = 0.0; state_time = 0.0;
-                const double2 g0 = S.pos[N + ai];
+                const double2 g0 = R.pos[N + ai];
                 goal_min_time = norm2(x - g0.x, y - g0.y) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
                 times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
-                if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
-                S.pos[ai] = make_double2(x, y); S.as2[ai] = s2; S.as3[ai] = s3;
-                S.vel[ai] = make_double2(vx, vy); S.vel[N + ai] = make_double2(vx, vy);
-                S.pos[E + ai] = g0; S.pos[E + N + ai] = g0;
-                float4 cc = S.cst[ai]; cc.w = 0.0f;
-                S.cst[M + ai] = cc; S.cst[M + N + ai] = cc;
-                S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
-                S.goal[0][ai] = ai; S.goal[1][ai] = ai;
-                S.reached[0][ai] = 0; S.reached[1][ai] = 0; S.done[0][ai] = 0; S.done[1][ai] = 0;
-                emit_obs_row<DYN>(S, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
+                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
+                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
+                R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
+                R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
+                R.pos[E + ai] = g0; R.pos[E + N + ai] = g0;
+                float4 cc = R.cst[ai]; cc.w = 0.0f;
+                R.cst[M + ai] = cc; R.cst[M + N + ai] = cc;
+                if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+                    R.air.spd_post[ai] = s3; R.air.goal[0][ai] = ai; R.air.goal[1][ai] = ai;
+                }
+                R.reached[0][ai] = 0; R.reached[1][ai] = 0; R.done[0][ai] = 0; R.done[1][ai] = 0;
+                emit_obs_row<DYN, N, L>(R, P, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
             }
             if (do_reset && sample) reset_count += 1;
             __syncwarp();
@@ -945,18 +870,19 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 const size_t lstride = (size_t)n * M;
                 for (int el = 0; el < nenv; ++el) {
                     if (!((reset_lanes >> ((el * G) & 31)) & 1u)) continue;
-                    const ES& T = Sw[el];
+                    const REC& T = Rw[el];
+                    const SCR& U = Pw[el];
                     double* dst = kp.b.landmarks + (size_t)(env0 + el) * M;
                     for (int m = lane; m < M; m += 32) {
                         const double2 p = T.pos[N + m];
                         dst[LSM_LF_X * lstride + m] = p.x; dst[LSM_LF_Y * lstride + m] = p.y;
-                        dst[LSM_LF_HEADING * lstride + m] = T.lh[m]; dst[LSM_LF_SPEED * lstride + m] = T.lsp[m];
-                        dst[LSM_LF_SIN * lstride + m] = T.lsin[m]; dst[LSM_LF_COS * lstride + m] = T.lcos[m];
+                        dst[LSM_LF_HEADING * lstride + m] = U.lh[m]; dst[LSM_LF_SPEED * lstride + m] = U.lsp[m];
+                        dst[LSM_LF_SIN * lstride + m] = U.lsin[m]; dst[LSM_LF_COS * lstride + m] = U.lcos[m];
                     }
                 }
             }
         } else if (kp.mode == MODE_OBSERVE && agent_on) {
-            emit_obs_row<DYN>(S, ai, S.goal[0][ai], x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs, N);
+            emit_obs_row<DYN, N, L>(R, P, ai, goal_obs, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
         }
 
         // ---------------- state write-back ----------------
@@ -987,17 +913,320 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_spec_kernel(const __grid_cons
                 aip[LSM_AI_EP_DONE * fstride] = ep_done;
             }
         }
+        // ---------------- emit records -> global memory (consumed by lsm_emit_kernel; L2 resident) ----------------
+        if (env_on && ai == 0) R.next_filter = q.world_filter ? 1 : 0;     // q follows a reset's new curriculum ratio
+        if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
+            if (agent_on) R.air.theta[ai] = s2;
+            for (int idx = lane; idx < nenv * M; idx += 32) {
+                const int el = idx / M, m = idx - el * M;
+                Rw[el].air.lsin[m] = Pw[el].lsin[m]; Rw[el].air.lcos[m] = Pw[el].lcos[m]; Rw[el].air.lsp[m] = Pw[el].lsp[m];
+            }
+        }
         __syncwarp();
-
-        // ---------------- P4: graph observation ----------------
-        for (int el = 0; el < nenv; ++el) {
-            const int ee = env0 + el;
-            if (kp.mode == MODE_RESET && kp.env_mask != nullptr && kp.env_mask[ee] == 0) continue;
-            if (!(kp.debug & 1)) emit_graph<DYN, N, L>(kp.b.node_obs, kp.b.adj, kp.sel_tab, kp.r2_lt, Sw[el], stage, ee, lane, kp.debug);
-            __syncwarp();
+        {
+            constexpr int Q = (int)(sizeof(REC) / 16);
+            const unsigned on_mask = __ballot_sync(0xffffffffu, env_on && ai == 0);
+            for (int el = 0; el < nenv; ++el) {
+                if (!((on_mask >> ((el * G) & 31)) & 1u)) continue;
+                const int4* src = reinterpret_cast<const int4*>(&Rw[el]);
+                int4* dst = reinterpret_cast<int4*>(kp.emit_rec + (size_t)(env0 + el) * sizeof(REC));
+                for (int k = lane; k < Q; k += 32) dst[k] = src[k];
+            }
         }
         __syncwarp();
     }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_c: graph observation (navigation_graph_safe.py:932-994 + utils.py:139-255). Persistent blocks of WPE warps
+// loop over environments; the outputs of one environment (N adjacency matrices + N*E node rows, >= 96 % of the
+// step's bytes) are assembled in shared memory and leave through TMA bulk copies, so the stores of environment k
+// drain to HBM while environment k+1 is being computed. The next record is prefetched with cp.async.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(sdst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" :: "r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int DYN, int N, int L>
+struct EmitGeom {
+    using REC = EmitRec<DYN, N, L>;
+    static constexpr int E = REC::E, W = REC::W, EE = E * E;
+    static constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
+    static constexpr int ROWS = N * E;
+    // node rows leave in chunks of CR rows (<= 16 KB, CR % 4 == 0 so that the byte count is a multiple of 16)
+    static constexpr int CR_MAX = (16384 / (F * 4)) / 4 * 4;
+    static constexpr bool NODE_BULK = (ROWS % 4 == 0);
+    static constexpr int CR = NODE_BULK ? (ROWS < CR_MAX ? ROWS : CR_MAX) : 32;
+    static constexpr int NCHUNK = (ROWS + CR - 1) / CR;
+    static constexpr bool ADJ_BULK = (EE % 4 == 0);             // 16-byte multiple per observer matrix
+    // double-buffer the per-env tiles when they are small; one buffer (wait for the drain) when a tile is tens of KB
+    static constexpr int NBUF = (EE * 4 + CR * F * 4) <= 24 * 1024 ? 2 : 1;
+};
+
+template <int DYN, int N, int L, int WPE>
+struct __align__(16) EmitShared {
+    using GEO = EmitGeom<DYN, N, L>;
+    using REC = EmitRec<DYN, N, L>;
+    REC rec[2];                                              // current / prefetched record
+    alignas(16) float dthr[GEO::NBUF][GEO::EE];              // radius-thresholded distance matrix (float32, what adj stores)
+    alignas(16) float nodes[GEO::NBUF][GEO::CR * GEO::F];    // node-row chunk
+    unsigned disc[2][GEO::W], keepm[N * GEO::W];
+};
+
+template <int DYN, int N, int L, int WPE, int MINB>
+__global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_constant__ KParams kp) {
+    using ES = EmitShared<DYN, N, L, WPE>;
+    using REC = EmitRec<DYN, N, L>;
+    using GEO = EmitGeom<DYN, N, L>;
+    constexpr int M = REC::M, E = REC::E, W = REC::W, EE = E * E;
+    constexpr int F = GEO::F, ROWS = GEO::ROWS, CR = GEO::CR, NCHUNK = GEO::NCHUNK, NBUF = GEO::NBUF;
+    constexpr int T = 32 * WPE;
+    constexpr int Q = (int)(sizeof(REC) / 16);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ES& S = *reinterpret_cast<ES*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = (int)kp.b.num_envs;
+    const double r2_lt = kp.r2_lt;
+    const int debug = kp.debug;
+    pdl_launch_dependents();
+    pdl_wait();
+    if (debug & 64) return;          // experiments: launch + block dispatch floor
+    const bool masked_reset = kp.mode == MODE_RESET && kp.env_mask != nullptr;
+
+    auto prefetch = [&](int env, int slot) {
+        const int4* src = reinterpret_cast<const int4*>(kp.emit_rec + (size_t)env * sizeof(REC));
+        int4* dst = reinterpret_cast<int4*>(&S.rec[slot]);
+        for (int k = tid; k < Q; k += T) cp_async16(dst + k, src + k);
+    };
+    int it = 0, tiles = 0;
+    if ((int)blockIdx.x < n) prefetch(blockIdx.x, 0);
+    cp_async_commit();
+    for (int ee = blockIdx.x; ee < n; ee += gridDim.x, ++it) {
+        const int rb = it & 1;                         // record slot
+        const int tb = NBUF == 2 ? (tiles & 1) : 0;    // tile buffer (alternates per PROCESSED environment)
+        cp_async_wait_all();
+        // the bulk copies that last read this iteration's tile buffers have finished reading them
+        if (tid == 0) { if (NBUF == 2) bulk_store_wait_read<1>(); else bulk_store_wait_read<0>(); }
+        __syncthreads();
+        if (ee + (int)gridDim.x < n) prefetch(ee + gridDim.x, rb ^ 1);
+        cp_async_commit();
+        if (masked_reset && kp.env_mask[ee] == 0) continue;
+        if (debug & 128) continue;   // experiments: + record load
+        ++tiles;
+        const REC& R = S.rec[rb];
+        float* const dthr = S.dthr[tb];
+        if (debug & 256) {           // experiments: the bulk copies alone (whatever the tiles hold), no compute
+            if (tid == 0) {
+                if (GEO::ADJ_BULK) for (int i = 0; i < N; ++i) bulk_store(kp.b.adj + ((size_t)ee * N + i) * EE, dthr, (unsigned)EE * 4u);
+                if (GEO::NODE_BULK && NCHUNK == 1) bulk_store(kp.b.node_obs + (size_t)ee * (ROWS * F), S.nodes[tb], (unsigned)(ROWS * F) * 4u);
+                bulk_store_commit();
+            }
+            continue;
+        }
+        // (a) thresholded distance matrix: d2 in float64 against the exact squared radius; the stored float32 value is
+        //     d2f * rsqrt(d2f). Thread a (one per entity) walks the circular distances d = 1 .. E/2 to entity a + d
+        //     (for even E the last distance only needs a < E/2), so every unordered pair is visited once.
+        {
+            constexpr int HALF = E / 2;                                  // circular distances 1 .. HALF
+            constexpr int NSPLIT = (T / E) < 1 ? 1 : ((T / E) > HALF ? HALF : (T / E));   // threads per entity
+            constexpr int DCH = (HALF + NSPLIT - 1) / NSPLIT;            // distances per thread
+            for (int t = tid; t < E * NSPLIT; t += T) {
+                const int part = t / E, a = t - part * E;
+                const double2 pa = R.pos[a];
+                if (part == 0) dthr[a * E + a] = 0.0f;
+                const int d0 = part * DCH + 1;
+                const int d1 = (d0 + DCH - 1) < HALF ? (d0 + DCH - 1) : HALF;
+                int b = a + d0 - 1; if (b >= E) b -= E;
+#pragma unroll 4
+                for (int d = d0; d <= d1; ++d) {
+                    b = b + 1; if (b >= E) b -= E;
+                    if (E % 2 == 0 && d == HALF && a >= HALF) break;
+                    const double2 pb = R.pos[b];
+                    const double dx = pa.x - pb.x, dy = pa.y - pb.y;
+                    const double d2 = dx * dx + dy * dy;
+                    const float d2f = fmaxf((float)d2, 1.0e-30f);
+                    float rs;
+                    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(d2f));
+                    const float v = (d2 < r2_lt && d2 > 0.0) ? d2f * rs : 0.0f;
+                    dthr[a * E + b] = v; dthr[b * E + a] = v;
+                }
+            }
+        }
+        // (b) disconnected-entity bit masks before / after this step's goal updates (every warp computes the ballots,
+        //     thread 0 publishes them)
+        unsigned any_change = 0u, any_disc = 0u;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int e = w * 32 + lane;
+            bool dpre = false, dpost = false;
+            if (e < N) { dpre = R.done[0][e] != 0; dpost = R.done[1][e] != 0; }
+            else if (e < E) {
+                const int m = e - N, order = m / N, owner = m - order * N;
+                dpre = R.reached[0][owner] > order; dpost = R.reached[1][owner] > order;
+            }
+            const unsigned bpre = __ballot_sync(0xffffffffu, dpre), bpost = __ballot_sync(0xffffffffu, dpost);
+            if (tid == 0) { S.disc[0][w] = bpre; S.disc[1][w] = bpost; }
+            any_change |= (bpre ^ bpost); any_disc |= bpost;
+        }
+        __syncthreads();
+        if (any_disc != 0u) {
+            for (int k = tid; k < N * W; k += T) {
+                const int w = k % W;
+                const unsigned sel = kp.sel_tab[k];
+                S.keepm[k] = ~((S.disc[1][w] & sel) | (S.disc[0][w] & ~sel));
+            }
+            __syncthreads();
+        }
+        // (d) adjacency
+        float* abase = kp.b.adj + (size_t)ee * (N * EE);
+        const bool adj_bulk = GEO::ADJ_BULK && any_change == 0u && !(debug & 16);
+        if (!(debug & 8)) {
+            if (adj_bulk) {
+                // every observer sees the same matrix: mask it once in place; thread 0 sends it N times below
+                if (any_disc != 0u) {
+                    for (int idx = tid; idx < EE; idx += T) {
+                        const int a = idx / E, b2 = idx - a * E;
+                        const bool keep = ((S.keepm[a >> 5] >> (a & 31)) & 1u) && ((S.keepm[b2 >> 5] >> (b2 & 31)) & 1u);
+                        if (!keep) dthr[idx] = 0.0f;
+                    }
+                }
+            } else if (E % 4 == 0) {
+                constexpr int CPR = E / 4, CHUNKS = EE / 4;
+                for (int ch = tid; ch < CHUNKS; ch += T) {
+                    const int a = ch / CPR, b4 = (ch - a * CPR) * 4;
+                    const float4 v = *reinterpret_cast<const float4*>(dthr + ch * 4);
+                    float* dst = abase + ch * 4;
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const bool ka = any_disc == 0u || ((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u);
+                        const unsigned nib = !ka ? 0u : (any_disc == 0u ? 0xFu : ((S.keepm[i * W + (b4 >> 5)] >> (b4 & 31)) & 0xFu));
+                        float4 o;
+                        o.x = (nib & 1u) ? v.x : 0.0f; o.y = (nib & 2u) ? v.y : 0.0f;
+                        o.z = (nib & 4u) ? v.z : 0.0f; o.w = (nib & 8u) ? v.w : 0.0f;
+                        __stcs(reinterpret_cast<float4*>(dst + i * EE), o);
+                    }
+                }
+            } else {
+                for (int idx = tid; idx < EE; idx += T) {
+                    const int a = idx / E, b2 = idx - a * E;
+                    const float v = dthr[idx];
+#pragma unroll
+                    for (int i = 0; i < N; ++i) {
+                        const bool keep = any_disc == 0u ||
+                                          (((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) &&
+                                           ((S.keepm[i * W + (b2 >> 5)] >> (b2 & 31)) & 1u));
+                        __stcs(abase + i * EE + idx, keep ? v : 0.0f);
+                    }
+                }
+            }
+        }
+        // (c) node features: one thread per (observer, entity) row, assembled row-major in shared memory
+        float* nbase = kp.b.node_obs + (size_t)ee * (ROWS * F);
+        auto node_row = [&](int r, float* o) {
+            const int i = r / E, e = r - i * E;
+            const double2 pi = R.pos[i], vi = R.vel[N + i];
+            const bool is_agent = e < N;
+            const int sel = (e <= i) ? N : 0;     // agents <= i are seen after their own update
+            const int vidx = is_agent ? sel + e : 2 * N;
+            const int gidx = is_agent ? E + sel + e : e;
+            const int cidx = is_agent ? M + sel + e : e - N;
+            if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                // utils.py:201-255: [p_e - p_i, v_e - v_i, goal_e - p_i, sin gh, cos gh, gspeed, type]
+                const double2 pe = R.pos[e], ve = R.vel[vidx], ge = R.pos[gidx];
+                const float4 cc = R.cst[cidx];
+                float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
+                o2[0] = make_float2((float)(pe.x - pi.x), (float)(pe.y - pi.y));
+                o2[1] = make_float2((float)(ve.x - vi.x), (float)(ve.y - vi.y));
+                o2[2] = make_float2((float)(ge.x - pi.x), (float)(ge.y - pi.y));
+                o2[3] = make_float2(cc.x, cc.y);
+                o2[4] = make_float2(cc.z, cc.w);
+            } else {
+                const double ci = R.air.cth[i], si = R.air.sth[i];
+                if (e < N) {
+                    const int g = R.air.goal[sel ? 1 : 0][e];
+                    const double2 pe = R.pos[e], ve = R.vel[vidx], ge = R.pos[gidx];
+                    double rx, ry, gx, gy;
+                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
+                    rotate_into(ge.x - pi.x, ge.y - pi.y, ci, si, gx, gy);
+                    const double ce = R.air.cth[e], se = R.air.sth[e];
+                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)norm2(ve.x - vi.x, ve.y - vi.y);
+                    o[3] = (float)(se * ci - ce * si); o[4] = (float)(ce * ci + se * si);
+                    o[5] = (float)gx; o[6] = (float)gy;
+                    o[7] = (float)(R.air.lsin[g] * ci - R.air.lcos[g] * si); o[8] = (float)(R.air.lcos[g] * ci + R.air.lsin[g] * si);
+                    o[9] = (float)R.air.lsp[g]; o[10] = 0.0f;
+                } else {
+                    const int m = e - N;
+                    const double2 pe = R.pos[e];
+                    double rx, ry;
+                    rotate_into(pe.x - pi.x, pe.y - pi.y, ci, si, rx, ry);
+                    const float sh = (float)(R.air.lsin[m] * ci - R.air.lcos[m] * si), ch = (float)(R.air.lcos[m] * ci + R.air.lsin[m] * si);
+                    o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)R.air.spd_post[i];
+                    o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
+                    o[9] = (float)R.air.lsp[m]; o[10] = 1.0f;
+                }
+            }
+        };
+        bool adj_sent = false;
+        for (int c = 0; c < NCHUNK; ++c) {
+            const int r0 = c * CR;
+            const int nrows = (ROWS - r0) < CR ? (ROWS - r0) : CR;
+            const int nb = NBUF == 2 ? tb : 0;
+            if (c > 0) {
+                // the previous chunk's copy has finished reading the buffer this chunk is written to
+                if (tid == 0) bulk_store_wait_read<0>();
+                __syncthreads();
+            }
+            float* buf = S.nodes[nb];
+            if (!(debug & 4))
+                for (int r = tid; r < nrows; r += T) node_row(r0 + r, buf + r * F);
+            if (GEO::NODE_BULK || adj_bulk) bulk_store_fence();
+            __syncthreads();
+            if (tid == 0) {
+                if (adj_bulk && !adj_sent && !(debug & 8)) {
+#pragma unroll 1
+                    for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u);
+                }
+                if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u);
+                bulk_store_commit();
+            }
+            adj_sent = true;
+            if (!GEO::NODE_BULK && !(debug & 4)) {
+                const int nfl = nrows * F;
+                if (F % 2 == 0 && (ROWS * F) % 2 == 0) {
+                    for (int q = tid; q < nfl / 2; q += T)
+                        __stcs(reinterpret_cast<float2*>(nbase + r0 * F) + q, reinterpret_cast<const float2*>(buf)[q]);
+                } else {
+                    for (int q = tid; q < nfl; q += T) __stcs(nbase + r0 * F + q, buf[q]);
+                }
+                __syncthreads();
+            }
+        }
+        // (e) HJ values of every ordered agent pair for the NEXT step (safety_filter.py:192-201, 345-354): they depend only on
+        //     the state this step leaves behind, and the L2 gathers overlap this environment's copies draining to HBM. The
+        //     agent kernel of the next lsm_step consumes them (lsm_pair_kernel recomputes them if the state was edited).
+        if (kp.pairval != nullptr && R.next_filter) {
+            double* pv = kp.pairval + (size_t)ee * (N * N);
+            for (int t = tid; t < N * N; t += T) {
+                const int i = t / N, j = t - i * N;
+                if (i == j || R.done[1][i] || R.done[1][j]) continue;
+                const double2 pi = R.pos[i], pj = R.pos[j];
+                double i2, i3, j2, j3;
+                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                    const double2 vi = R.vel[N + i], vj = R.vel[N + j];
+                    i2 = vi.x; i3 = vi.y; j2 = vj.x; j3 = vj.y;
+                } else {
+                    i2 = R.air.theta[i]; i3 = R.air.spd_post[i]; j2 = R.air.theta[j]; j3 = R.air.spd_post[j];
+                }
+                pv[t] = pair_value_raw<DYN>(kp.vg, pi.x, pi.y, i2, i3, pj.x, pj.y, j2, j3);
+            }
+        }
+    }
+    // every bulk copy issued by this block has finished READING shared memory before the block retires
+    if (tid == 0) bulk_store_wait_read<0>();
+    cp_async_wait_all();
 }
 
 }  // namespace lsm

@@ -4,11 +4,10 @@
 //   lsm_kernel_generic.cuh  run-time N / L fallback for every other configuration
 //   lsm_step_common.cuh     dynamics, HJ filter resolution, grid interpolation shared by both
 //
-// Work decomposition ("warp per env group"): a warp owns EPW consecutive environments, G = next power
-// of two >= N lanes per environment. Per-agent phases run one lane per agent; the graph observation
-// (pairwise distances, radius-limited adjacency, node features) is built in the warp's shared-memory
-// slice and written with all 32 lanes. There is no block-level barrier: warps only __syncwarp(), so
-// one warp's stores overlap another warp's HJ-grid gathers.
+// Specialised path: three launches per step (pair values -> per-agent physics -> graph emission), see
+// lsm_kernel_spec.cuh. Generic path ("warp per env group", one fused launch): a warp owns EPW consecutive
+// environments, G = next power of two >= N lanes per environment; per-agent phases run one lane per
+// agent; the graph observation is built in the warp's shared-memory slice and written with all 32 lanes.
 //
 // The reference mutates goal counters / done flags / velocities agent by agent WHILE it emits
 // observations (multiagent/environment.py:979-1029). Each agent's own update depends only on its
@@ -25,19 +24,58 @@ namespace lsm {
 // ---------------------------------------------------------------------------------------------
 // host-side launch helpers (used by lsm_capi.cu)
 // ---------------------------------------------------------------------------------------------
-#define LSM_SPEC_LIST(X)                         \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2)           \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2)           \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2)          \
-    X(LSM_DYN_AIRTAXI, 10, 2)
+// (dynamics, N, L, warps per env of the emit kernel, resident emit blocks per SM the register budget targets)
+#define LSM_SPEC_LIST(X)                               \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 4, 4)           \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2, 1, 16)          \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2, 4, 3)          \
+    X(LSM_DYN_AIRTAXI, 10, 2, 2, 5)
 
-constexpr int kSpecBlock = 128;
+constexpr int kAgentBlock = 128;
+constexpr int kAgentMinB = 2;
+constexpr int kPairBlock = 256;
 
-// register budgets: MINB blocks of 128 threads per SM -> 65536 / (128 * MINB) registers per thread
-static int spec_minb() {
-    const char* e = std::getenv("LSM_MINB");
-    const int v = e ? std::atoi(e) : 2;
-    return (v == 3 || v == 4) ? v : 2;
+struct SpecFns {
+    const void* pair; const void* agent; const void* emit;
+    int rec_bytes, scratch_bytes, emit_smem, emit_threads;
+};
+
+// experiments: LSM_WPE=2|4 selects an alternative emit-kernel shape for the cfg2 specialisation
+template <int WPE_, int EMINB_>
+static void cfg2_emit_variant(SpecFns* f) {
+    f->emit = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_>;
+    f->emit_smem = (int)sizeof(EmitShared<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_>);
+    f->emit_threads = 32 * WPE_;
+}
+
+static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f);
+static bool spec_fns(int dynamics, int N, int L, SpecFns* f) {
+    if (!spec_fns_base(dynamics, N, L, f)) return false;
+    if (dynamics == LSM_DYN_DOUBLE_INTEGRATOR && N == 8 && L == 2) {
+        const char* e = std::getenv("LSM_WPE");
+        const int w = e ? std::atoi(e) : 0;
+        if (w == 1) cfg2_emit_variant<1, 8>(f);
+        if (w == 2) cfg2_emit_variant<2, 8>(f);
+        if (w == 24) cfg2_emit_variant<2, 4>(f);    // two warps per block at half the occupancy target
+    }
+    return true;
+}
+
+static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
+#define X(DYN_, N_, L_, WPE_, EMINB_)                                                             \
+    if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
+        f->pair = (const void*)lsm_pair_kernel<DYN_, N_>;                                         \
+        f->agent = (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>;          \
+        f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
+        f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
+        f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \
+        f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, WPE_>);                               \
+        f->emit_threads = 32 * WPE_;                                                              \
+        return true;                                                                              \
+    }
+    LSM_SPEC_LIST(X)
+#undef X
+    return false;
 }
 
 static const void* generic_ptr(int dynamics) {
@@ -45,30 +83,15 @@ static const void* generic_ptr(int dynamics) {
                                                  : (const void*)lsm_generic_kernel<LSM_DYN_AIRTAXI>;
 }
 
-static const void* spec_ptr(int dynamics, int N, int L, int* bytes_per_env, int* stage_bytes = nullptr) {
-    const int minb = spec_minb();
-#define X(DYN_, N_, L_)                                                                           \
-    if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
-        *bytes_per_env = (int)sizeof(EnvShared<DYN_, N_, L_>);                                    \
-        if (stage_bytes) *stage_bytes = 2 * 32 * (DYN_ == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11) * 4;   \
-        if (minb == 2) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 2>;          \
-        if (minb == 3) return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 3>;          \
-        return (const void*)lsm_spec_kernel<DYN_, N_, L_, kSpecBlock, 4>;                         \
-    }
-    LSM_SPEC_LIST(X)
-#undef X
-    return nullptr;
+bool spec_available(int dynamics, int N, int L, SpecGeometry* g) {
+    SpecFns f;
+    if (!spec_fns(dynamics, N, L, &f)) return false;
+    g->rec_bytes = f.rec_bytes; g->scratch_bytes = f.scratch_bytes; g->agent_block = kAgentBlock;
+    g->emit_smem = f.emit_smem; g->emit_threads = f.emit_threads; g->pair_block = kPairBlock;
+    return true;
 }
 
-bool spec_available(int dynamics, int N, int L, int* bytes_per_env, int* block_threads, int* stage_bytes) {
-    *block_threads = kSpecBlock;
-    return spec_ptr(dynamics, N, L, bytes_per_env, stage_bytes) != nullptr;
-}
-
-cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,
-                           int* blocks_per_sm) {
-    int dummy = 0;
-    const void* fn = spec ? spec_ptr(dynamics, N, L, &dummy) : generic_ptr(dynamics);
+static cudaError_t prepare_one(const void* fn, int block_threads, int smem_bytes, int* regs, int* blocks_per_sm) {
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     if (e != cudaSuccess) return e;
     cudaFuncAttributes fa;
@@ -78,37 +101,91 @@ cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, block_threads, smem_bytes);
 }
 
+cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,
+                           int* blocks_per_sm) {
+    SpecFns f;
+    const void* fn = generic_ptr(dynamics);
+    if (spec) { if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue; fn = f.agent; }
+    return prepare_one(fn, block_threads, smem_bytes, regs, blocks_per_sm);
+}
+
+cudaError_t spec_prepare_aux(int dynamics, int N, int L, int* emit_regs, int* emit_blocks_per_sm, int* pair_regs) {
+    SpecFns f;
+    if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
+    cudaError_t e = prepare_one(f.emit, f.emit_threads, f.emit_smem, emit_regs, emit_blocks_per_sm);
+    if (e != cudaSuccess) return e;
+    int bps = 0;
+    return prepare_one(f.pair, kPairBlock, 0, pair_regs, &bps);
+}
+
 cudaError_t upload_magnetic_tables(const double* cos_tab, const double* sin_tab) {
     cudaError_t e = cudaMemcpyToSymbol(c_mag_cos, cos_tab, sizeof(double) * kMagSegments);
     if (e != cudaSuccess) return e;
     return cudaMemcpyToSymbol(c_mag_sin, sin_tab, sizeof(double) * kMagSegments);
 }
 
-cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int block_threads, int smem_bytes,
-                          cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+static cudaError_t launch_one(const void* fn, const KParams& kp, unsigned grid_blocks, int block_threads, int smem_bytes,
+                              cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool pdl) {
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)grid_blocks, 1, 1);
+    cfg.gridDim = dim3(grid_blocks, 1, 1);
     cfg.blockDim = dim3((unsigned)block_threads, 1, 1);
     cfg.dynamicSmemBytes = (size_t)smem_bytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     int nattr = 0;
-    if (persist_ptr != nullptr && persist_bytes > 0) {
+    static const bool no_pdl = std::getenv("LSM_NO_PDL") != nullptr;
+    if (pdl && !no_pdl) {
+        attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[nattr].val.programmaticStreamSerializationAllowed = 1;
+        ++nattr;
+    }
+    static const bool no_persist = std::getenv("LSM_NO_PERSIST") != nullptr;
+    if (!no_persist && persist_ptr != nullptr && persist_bytes > 0) {
         // keep the HJ value grid resident in L2 while the observation stream flows through it
-        attr[0].id = cudaLaunchAttributeAccessPolicyWindow;
-        attr[0].val.accessPolicyWindow.base_ptr = const_cast<void*>(persist_ptr);
-        attr[0].val.accessPolicyWindow.num_bytes = persist_bytes;
-        attr[0].val.accessPolicyWindow.hitRatio = 1.0f;
-        attr[0].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-        attr[0].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-        nattr = 1;
+        attr[nattr].id = cudaLaunchAttributeAccessPolicyWindow;
+        attr[nattr].val.accessPolicyWindow.base_ptr = const_cast<void*>(persist_ptr);
+        attr[nattr].val.accessPolicyWindow.num_bytes = persist_bytes;
+        attr[nattr].val.accessPolicyWindow.hitRatio = 1.0f;
+        attr[nattr].val.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+        attr[nattr].val.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+        ++nattr;
     }
     cfg.attrs = attr;
     cfg.numAttrs = nattr;
     void* args[] = { (void*)&kp };
-    int dummy = 0;
-    const void* fn = spec ? spec_ptr(kp.c.dynamics, kp.N, kp.L, &dummy) : generic_ptr(kp.c.dynamics);
     return cudaLaunchKernelExC(&cfg, fn, args);
+}
+
+cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int block_threads, int smem_bytes,
+                          cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+    SpecFns f;
+    const void* fn = generic_ptr(kp.c.dynamics);
+    if (spec) { if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue; fn = f.agent; }
+    return launch_one(fn, kp, (unsigned)grid_blocks, block_threads, smem_bytes, stream, persist_ptr, persist_bytes, spec);
+}
+
+cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+    SpecFns f;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    const long long tasks = (long long)kp.b.num_envs * kp.N * kp.N;
+    const long long blocks = (tasks + kPairBlock - 1) / kPairBlock;
+    return launch_one(f.pair, kp, (unsigned)blocks, kPairBlock, 0, stream, persist_ptr, persist_bytes, true);
+}
+
+cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+    SpecFns f;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    // persistent blocks: as many as are resident at once, each loops over environments
+    static int sm_count = 0;
+    if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    int bps = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, f.emit, f.emit_threads, f.emit_smem);
+    if (e != cudaSuccess) return e;
+    if (bps < 1) return cudaErrorLaunchOutOfResources;
+    unsigned grid = (unsigned)sm_count * (unsigned)bps;
+    if (grid > (unsigned)kp.b.num_envs) grid = (unsigned)kp.b.num_envs;
+    if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
+    return launch_one(f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
 }
 
 }  // namespace lsm

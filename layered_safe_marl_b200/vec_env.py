@@ -269,6 +269,10 @@ class B200GraphVecEnv:
         _lib.check(self.lib.lsm_observe(self._h, self._stream()), 'lsm_observe')
         return self._outputs(False, False)
 
+    def emit_only(self):
+        """Relaunch the graph-emission kernel alone (measurement hook; rewrites node_obs / adj with the same values)."""
+        _lib.check(self.lib.lsm_emit_only(self._h, self._stream()), 'lsm_emit_only')
+
     def step_async(self, actions, num_current_episode=None):
         self._pending_actions = actions
         self._pending_episode = num_current_episode
@@ -304,8 +308,13 @@ class B200GraphVecEnv:
 
     # ------------------------------------------------------------------------------------------
     # named-state interchange (checkpoint / parity injection); leading axis = env
+    def invalidate(self):
+        """Call after writing the state tensors (agent_f64, agent_i32, env_f64, landmarks) directly."""
+        _lib.check(self.lib.lsm_invalidate(self._h), 'lsm_invalidate')
+
     def set_state(self, s: dict):
         dev = self.device
+        self.invalidate()
 
         def t(v, dtype):
             return torch.as_tensor(np.asarray(v), dtype=dtype, device=dev)

@@ -62,8 +62,9 @@ def main():
     rows = list(csv.reader(open(sass_csv)))
     # find the block for this kernel (first occurrence)
     k0 = None
+    nsub = sys.argv[6] if len(sys.argv) > 6 else ksub.replace('ILi0E', '<(int)0>').split('<')[0]
     for i, r in enumerate(rows):
-        if r and r[0] == 'Kernel Name' and ksub.replace('ILi0E', '<(int)0>').split('<')[0] in r[1]:
+        if r and r[0] == 'Kernel Name' and nsub in r[1]:
             k0 = i
             break
     if k0 is None:
