@@ -50,7 +50,9 @@ enum {
     LSM_FLAG_DIFF_FROM_FILTERED_ACTION = 1 << 5,
     LSM_FLAG_USE_SAFETY_FILTER = 1 << 6,   /* the --use_safety_filter argument */
     LSM_FLAG_SHARED_REWARD = 1 << 7,       /* --collaborative */
-    LSM_FLAG_USE_MASKING = 1 << 8          /* --use_masking (required, reference quirk Q9) */
+    LSM_FLAG_USE_MASKING = 1 << 8,         /* --use_masking (required, reference quirk Q9) */
+    LSM_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9    /* --graph_feat_type global: 7-wide observer-independent node features
+                                              (navigation_graph_safe.py:1017-1036); default is 'relative' */
 };
 
 /* state layout: agent_f64[field][env][agent], agent_i32[field][env][agent],
@@ -116,7 +118,7 @@ typedef struct lsm_buffers {
     int32_t *env_i32;             /* [LSM_EI_COUNT][num_envs] */
     /* outputs */
     float *obs;                   /* [num_envs][N][D]       D = 7 (DI) | 6 (airtaxi) */
-    float *node_obs;              /* [num_envs][N][E][F]    F = 10 (DI) | 11 (airtaxi), E = N(1+L) */
+    float *node_obs;              /* [num_envs][N][E][F]    F = 10 (DI) | 11 (airtaxi) | 7 (global features), E = N(1+L) */
     float *adj;                   /* [num_envs][N][E][E] */
     float *reward;                /* [num_envs][N] */
     uint8_t *done;                /* [num_envs][N] */

@@ -93,6 +93,7 @@ FLAG_DIFF_FROM_FILTERED_ACTION = 1 << 5
 FLAG_USE_SAFETY_FILTER = 1 << 6   # the --use_safety_filter ARGUMENT (not the per-episode world flag)
 FLAG_SHARED_REWARD = 1 << 7       # --collaborative
 FLAG_USE_MASKING = 1 << 8         # --use_masking
+FLAG_GRAPH_FEAT_GLOBAL = 1 << 9   # --graph_feat_type global
 
 
 def reward_flags_from(binary_cfg=RewardBinaryConfig) -> int:
@@ -157,6 +158,8 @@ class ScenarioParams:
 
     @property
     def node_feat_dim(self) -> int:
+        if self.flags & FLAG_GRAPH_FEAT_GLOBAL:     # [vel, pos, goal_pos, type], navigation_graph_safe.py:1017-1036
+            return 7
         return 10 if self.dynamics == DYN_DOUBLE_INTEGRATOR else 11
 
     def asdict(self):
@@ -180,8 +183,9 @@ def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
         raise ValueError("obstacle 0 not supported")
     if int(getattr(args, 'num_scripted_agents', 0)) != 0 or int(getattr(args, 'num_walls', 0)) != 0:
         raise NotImplementedError("scripted agents / walls are not part of the shipped scenario")
-    if getattr(args, 'graph_feat_type', 'relative') != 'relative':
-        raise NotImplementedError("graph_feat_type='global' is not built yet (all shipped scripts use 'relative')")
+    graph_feat_type = getattr(args, 'graph_feat_type', 'relative')
+    if graph_feat_type not in ('relative', 'global'):
+        raise ValueError(f"graph_feat_type {graph_feat_type!r}")
     if not bool(getattr(args, 'use_masking', True)):
         # reference quirk Q9: without masking a parked agent overruns its landmark list and get_entity raises
         raise NotImplementedError("use_masking=False makes the reference raise once an agent parks (Q9)")
@@ -194,6 +198,8 @@ def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
         flags |= FLAG_USE_SAFETY_FILTER
     if bool(getattr(args, 'collaborative', False)):
         flags |= FLAG_SHARED_REWARD
+    if graph_feat_type == 'global':
+        flags |= FLAG_GRAPH_FEAT_GLOBAL
     num_total_episode = int(args.num_env_steps) // int(args.episode_length) // int(args.n_rollout_threads)
     return ScenarioParams(
         dynamics=dyn,

@@ -96,7 +96,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     const int M = N * L, E = N + M;
     kp.N = N; kp.L = L; kp.M = M; kp.E = E;
     kp.D = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
-    kp.F = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
+    kp.F = (cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) ? 7 : (cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11);
     kp.G = next_pow2(N);
     kp.EPW = 32 / kp.G;
     h->epw_max = kp.EPW;
@@ -161,7 +161,8 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
     const char* force_generic = std::getenv("LSM_FORCE_GENERIC");
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) &&
+    // the specialised pipeline emits the 'relative' node features every shipped script uses; 'global' runs the generic kernel
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) &&
               !(force_generic != nullptr && force_generic[0] == '1');
     const char* fe = std::getenv("LSM_EPW");
     h->forced_epw = fe ? std::atoi(fe) : 0;

@@ -668,7 +668,20 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     float* o = nbase + (size_t)r * F;
                     const double xi = T.ax[i], yi = T.ay[i];
                     const double vix = T.vpost_x[i], viy = T.vpost_y[i];
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                    if (kp.c.flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) {
+                        // _get_entity_feat_global (navigation_graph_safe.py:1017-1036): [vel, pos, goal_pos, type]; an agent's
+                        // goal is its FIRST landmark (optimal_match_index = arange, :179), a landmark's goal is itself
+                        if (e < N) {
+                            const bool post = e <= i;
+                            o[0] = (float)(post ? T.vpost_x[e] : T.vpre_x[e]); o[1] = (float)(post ? T.vpost_y[e] : T.vpre_y[e]);
+                            o[2] = (float)T.ax[e]; o[3] = (float)T.ay[e];
+                            o[4] = (float)T.lx[e]; o[5] = (float)T.ly[e]; o[6] = 0.0f;
+                        } else {
+                            const int m = e - N;
+                            o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)T.lx[m]; o[3] = (float)T.ly[m];
+                            o[4] = o[2]; o[5] = o[3]; o[6] = 1.0f;
+                        }
+                    } else if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
                         float f0, f1, f2, f3, f4, f5, f6, f7, f8, f9;
                         if (e < N) {
                             const bool post = e <= i;

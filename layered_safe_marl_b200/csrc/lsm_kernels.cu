@@ -35,6 +35,12 @@ constexpr int kAgentBlock = 128;
 constexpr int kAgentMinB = 2;
 constexpr int kPairBlock = 256;
 
+// experiments: LSM_AGENT_MINB=3 trades ~100-400 B of spills for 12 instead of 8 resident physics warps per SM
+static int agent_minb() {
+    static const int v = [] { const char* e = std::getenv("LSM_AGENT_MINB"); return e ? std::atoi(e) : 0; }();
+    return v;
+}
+
 struct SpecFns {
     const void* pair; const void* agent; const void* emit;
     int rec_bytes, scratch_bytes, emit_smem, emit_threads;
@@ -65,7 +71,8 @@ static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
 #define X(DYN_, N_, L_, WPE_, EMINB_)                                                             \
     if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
         f->pair = (const void*)lsm_pair_kernel<DYN_, N_>;                                         \
-        f->agent = (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>;          \
+        f->agent = agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, 3>          \
+                                     : (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>; \
         f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
         f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
         f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \

@@ -211,6 +211,11 @@ CASES = [
          flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=36, seed=10, greedy_agents=(0, 1, 2, 3, 4),
          injections=(('near_goal', 0, 0.6, 1), ('near_goal', 1, 0.7, 0, 0.05), ('pair', 5, 6, 2.0, 0.08),
                      ('pair', 7, 8, 3.5, 0.06))),
+    # graph_feat_type='global' (navigation_graph_safe.py:1017-1036): observer-independent 7-wide node features
+    dict(name='di3_global_feat', args_kw=dict(DI, num_agents=3, episode_length=50, graph_feat_type='global'), flags={},
+         episode=3000, T=30, seed=12, greedy_agents=(0, 1), injections=(('near_goal', 0, 0.45, 1), ('near_goal', 1, 0.40, 0, 0.05))),
+    dict(name='at4_global_feat', args_kw=dict(AT, num_agents=4, episode_length=30, graph_feat_type='global'), flags={},
+         episode=0, T=12, seed=13, greedy_agents=(0,), injections=(('near_goal', 0, 0.5, 1),)),
     dict(name='at6_allflags', args_kw=dict(AT, num_agents=6, use_safety_filter=True, world_size=3, episode_length=350),
          flags=ALL_FLAGS, episode=4000, T=30, seed=11, greedy_agents=(0, 1),
          injections=(('near_goal', 0, 0.5, 1), ('pair', 2, 3, 1.5, 0.085), ('pair', 4, 5, 2.5, 0.035))),

@@ -533,9 +533,31 @@ static void emit_obs(const env_t *w, int i, float *out) {
     }
 }
 /* navigation_graph_safe.py:1038-1089 + utils.py:139-255 */
+static int node_feat_dim(const env_t *w) {
+    if (w->p->flags & LSMO_FLAG_GRAPH_FEAT_GLOBAL) return 7;
+    return w->dyn == LSMO_DYN_DI ? 10 : 11;
+}
+
 static void emit_node_obs(const env_t *w, int i, float *out) {
     int N = w->N, E = w->E;
     double vi[2]; a_vel(w, i, vi);
+    if (w->p->flags & LSMO_FLAG_GRAPH_FEAT_GLOBAL) {
+        /* _get_entity_feat_global, navigation_graph_safe.py:1017-1036: [vel, pos, goal_pos, type]; an agent's goal
+         * is landmark `optimal_match_index[id]` = its FIRST landmark (:179), a landmark's goal is its own position */
+        for (int e = 0; e < E; ++e) {
+            float *o = out + (size_t)e * 7;
+            if (e < N) {
+                double ve[2]; a_vel(w, e, ve);
+                o[0] = (float)ve[0]; o[1] = (float)ve[1]; o[2] = (float)w->x[e]; o[3] = (float)w->y[e];
+                o[4] = (float)w->lx[e]; o[5] = (float)w->ly[e]; o[6] = 0.0f;
+            } else {
+                int m = e - N;
+                o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)w->lx[m]; o[3] = (float)w->ly[m];
+                o[4] = o[2]; o[5] = o[3]; o[6] = 1.0f;
+            }
+        }
+        return;
+    }
     for (int e = 0; e < E; ++e) {
         if (w->dyn == LSMO_DYN_DI) {
             float *o = out + (size_t)e * 10;
@@ -908,7 +930,7 @@ static void episode_summary(const env_t *w, double out[LSMO_EP_COUNT]) {
 
 static void emit_all(env_t *w, const lsmo_buffers *b, int64_t e) {
     int N = w->N, E = w->E;
-    int D = w->dyn == LSMO_DYN_DI ? 7 : 6, F = w->dyn == LSMO_DYN_DI ? 10 : 11;
+    int D = w->dyn == LSMO_DYN_DI ? 7 : 6, F = node_feat_dim(w);
     calculate_distances(w);
     for (int i = 0; i < N; ++i) {
         emit_obs(w, i, b->obs + ((size_t)e * N + i) * D);
@@ -955,7 +977,7 @@ static void env_step(env_t *w, const lsmo_buffers *b, int64_t e, const int32_t *
                      uint64_t seed, int auto_reset) {
     const lsmo_params *p = w->p;
     int N = w->N, E = w->E;
-    int D = w->dyn == LSMO_DYN_DI ? 7 : 6, F = w->dyn == LSMO_DYN_DI ? 10 : 11;
+    int D = w->dyn == LSMO_DYN_DI ? 7 : 6, F = node_feat_dim(w);
     w->current_step += 1;
     double raw[MAXN][2], safe[MAXN][2];
     for (int i = 0; i < N; ++i) {          /* _set_action, environment.py:387-410 */

@@ -34,7 +34,8 @@ enum {
     LSMO_FLAG_DIFF_FROM_FILTERED_ACTION = 1 << 5,
     LSMO_FLAG_USE_SAFETY_FILTER = 1 << 6,
     LSMO_FLAG_SHARED_REWARD = 1 << 7,
-    LSMO_FLAG_USE_MASKING = 1 << 8
+    LSMO_FLAG_USE_MASKING = 1 << 8,
+    LSMO_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9    /* --graph_feat_type global (navigation_graph_safe.py:1017-1036) */
 };
 
 /* per-agent float64 fields: agent_f64[field][env][agent] */

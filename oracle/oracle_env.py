@@ -145,7 +145,7 @@ class OracleEnv(object):
         self.E = self.N + self.M
         self.dyn = int(self.pd['dynamics'])
         self.D = 7 if self.dyn == 0 else 6
-        self.F = 10 if self.dyn == 0 else 11
+        self.F = 7 if (int(params["flags"]) & (1 << 9)) else (10 if self.dyn == 0 else 11)   # 7: global node features
         self.seed = int(seed)
         self.nthreads = int(nthreads)
         self.vg, self._vg_keep = make_grid(value_grid)

@@ -16,13 +16,14 @@ CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 3"
 $CMD > $O/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
 $CMD > $O/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:lsm_spec -s 5 -c 2 -f -o $O/${TAG}_prof_cfg2 $CMD > $O/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lsm_ -s 12 -c 4 -f -o $O/${TAG}_prof_cfg2 $CMD > $O/${TAG}_ncu2.log 2>&1
 tail -3 $O/${TAG}_pytest.log; cat $O/${TAG}_smoke.log | tail -2
 python - <<PY
 import json
 for w in ('cfg2','cfg1','cfg3','cfg4'):
     try:
         d=json.loads(open('$O/${TAG}_bench_%s.json'%w).read().strip().splitlines()[-1])
-        print(w, 'ms', round(d['ms_per_step'],4), 'b2b', round(d['ms_per_step_back_to_back'],4), 'frac', round(d['roofline']['frac'],3), 'e2e', d['e2e']['value'], 'cpu', (d.get('cpu_baseline') or {}).get('value'))
+        r=d['roofline']
+        print(w, 'step_ms', round(d['ms_per_step'],4), 'b2b', round(d['ms_per_step_back_to_back'],4), 'emit_ms', round(r['mean_launch_ms'],4), 'emit_frac', round(r['frac'],3), 'step_frac', round(r['whole_step']['frac'],3), 'e2e', d['e2e']['value'], 'cpu', (d.get('cpu_baseline') or {}).get('value'))
     except Exception as e: print(w, 'ERR', e)
 PY
