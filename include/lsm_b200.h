@@ -166,6 +166,13 @@ int lsm_reset(lsm_handle *h, const uint8_t *env_mask, int64_t episode, uint64_t 
 /* Re-emit obs / node_obs / adj from the bound state without stepping. */
 int lsm_observe(lsm_handle *h, void *stream);
 
+/* Re-point the per-step OUTPUT arrays (any of them NULL = keep the current binding). Cheap (no allocation, no
+ * launch): lets a device-resident rollout buffer receive every step directly in its slot for that step instead
+ * of copying it there afterwards (the reference copies twice: np.stack in GraphSubprocVecEnv.step_wait,
+ * env_wrappers.py:985-996, and .copy() in GraphReplayBuffer.insert, graph_buffer.py:223-228).
+ * node_obs and adj must be 16-byte aligned. */
+int lsm_set_output_buffers(lsm_handle *h, float *obs, float *node_obs, float *adj, float *reward, uint8_t *done);
+
 /* Tell the library that the caller edited the bound state tensors (agent_f64 / agent_i32 / env_f64) directly.
  * The specialised pipeline keeps the HJ pair values of the current state from the previous launch
  * (safety_filter.py:192-201 evaluated one step ahead); after an edit the next lsm_step recomputes them first. */

@@ -51,7 +51,7 @@ class LsmLaunchInfo(C.Structure):
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
-                    'lsm_observe', 'lsm_emit_only', 'lsm_invalidate')
+                    'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers')
 
 _lib = None
 
@@ -86,8 +86,9 @@ def load():
     lib.lsm_observe.argtypes = [C.c_void_p, C.c_void_p]
     lib.lsm_emit_only.argtypes = [C.c_void_p, C.c_void_p]
     lib.lsm_invalidate.argtypes = [C.c_void_p]
+    lib.lsm_set_output_buffers.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
-                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate'):
+                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers'):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

@@ -390,6 +390,19 @@ int lsm_observe(lsm_handle* h, void* stream) {
     return launch(h, lsm::MODE_OBSERVE, 0, nullptr, nullptr, nullptr, 0, 0, stream, "lsm_observe");
 }
 
+int lsm_set_output_buffers(lsm_handle* h, float* obs, float* node_obs, float* adj, float* reward, uint8_t* done) {
+    if (h == nullptr) return fail(1, "lsm_set_output_buffers: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_set_output_buffers: lsm_bind_buffers has not been called");
+    if (((uintptr_t)adj & 15u) || ((uintptr_t)node_obs & 15u))
+        return fail(2, "lsm_set_output_buffers: adj and node_obs must be 16-byte aligned");
+    if (obs) h->kp.b.obs = obs;
+    if (node_obs) h->kp.b.node_obs = node_obs;
+    if (adj) h->kp.b.adj = adj;
+    if (reward) h->kp.b.reward = reward;
+    if (done) h->kp.b.done = done;
+    return 0;
+}
+
 int lsm_invalidate(lsm_handle* h) {
     if (h == nullptr) return fail(1, "lsm_invalidate: null handle");
     h->pairval_valid = false;

@@ -308,6 +308,24 @@ class B200GraphVecEnv:
 
     # ------------------------------------------------------------------------------------------
     # named-state interchange (checkpoint / parity injection); leading axis = env
+    def set_output_buffers(self, obs=None, node_obs=None, adj=None, reward=None, done=None):
+        """Re-point the per-step outputs at caller-owned CUDA tensors (e.g. a rollout-buffer slot). The env keeps
+        references so the memory stays alive; `step`/`reset` then return these tensors."""
+        def chk(t, like, name):
+            if t is None:
+                return None
+            assert t.is_cuda and t.is_contiguous() and t.dtype == like.dtype and tuple(t.shape) == tuple(like.shape), \
+                f"{name}: need a contiguous {like.dtype} CUDA tensor of shape {tuple(like.shape)}"
+            return t
+        obs, node_obs, adj = chk(obs, self.obs, 'obs'), chk(node_obs, self.node_obs, 'node_obs'), chk(adj, self.adj, 'adj')
+        reward, done = chk(reward, self.reward, 'reward'), chk(done, self.done, 'done')
+        ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+        _lib.check(self.lib.lsm_set_output_buffers(self._h, ptr(obs), ptr(node_obs), ptr(adj), ptr(reward), ptr(done)),
+                   'lsm_set_output_buffers')
+        for name, t in (('obs', obs), ('node_obs', node_obs), ('adj', adj), ('reward', reward), ('done', done)):
+            if t is not None:
+                setattr(self, name, t)
+
     def invalidate(self):
         """Call after writing the state tensors (agent_f64, agent_i32, env_f64, landmarks) directly."""
         _lib.check(self.lib.lsm_invalidate(self._h), 'lsm_invalidate')
@@ -387,3 +405,18 @@ class B200GraphVecEnv:
             vals = self.ep_info.mean(dim=0).cpu().numpy()
             return {k: float(vals[j]) for j, k in enumerate(LY.EP_INFO_KEYS)}
         return allreduce_episode_stats(self.ep_info, None if reduce_group is True else reduce_group)
+
+
+class B200GraphDummyVecEnv(B200GraphVecEnv):
+    """`GraphDummyVecEnv` surface (reference onpolicy/envs/env_wrappers.py:904-948): the in-process vec-env the
+    reference uses for rendering / CSV evaluation (graph_mpe_runner.py:649-940). Differences from the
+    subprocess variant, reproduced here: `step` returns an 8-tuple ending in `reset_count` (always 0) and
+    environments are NOT auto-reset when all their agents are done."""
+
+    def __init__(self, args, num_envs=None, **kw):
+        kw['auto_reset'] = False
+        super().__init__(args, num_envs=num_envs, **kw)
+
+    def step_wait(self, copy: bool = False):
+        out = super().step_wait(copy=copy)
+        return (*out, 0)
