@@ -173,6 +173,18 @@ int lsm_observe(lsm_handle *h, void *stream);
  * node_obs and adj must be 16-byte aligned. */
 int lsm_set_output_buffers(lsm_handle *h, float *obs, float *node_obs, float *adj, float *reward, uint8_t *done);
 
+/* Compacted COO edge list of the adjacency output in the order the reference's GNN builds on every forward
+ * (TransformerConvNet.process_adj, onpolicy/algorithms/utils/gnn.py:376-407): graphs = num_envs * N, row-major
+ * non-zeros of each E x E matrix;
+ *   edge_index  DEVICE int64 [2][capacity]: row 0 = graph * E + row, row 1 = graph * E + col
+ *   edge_attr   DEVICE float [capacity]
+ *   counts      DEVICE int32 [graphs]         non-zeros per graph
+ *   offsets     DEVICE int64 [graphs + 1]     exclusive prefix sum; offsets[graphs] = nnz (entries past `capacity`
+ *                                             are not written - check nnz <= capacity)
+ * adj = NULL reads the bound adj output of the last step. */
+int lsm_edge_list(lsm_handle *h, const float *adj, int64_t *edge_index, float *edge_attr, int32_t *counts,
+                  int64_t *offsets, int64_t capacity, void *stream);
+
 /* Tell the library that the caller edited the bound state tensors (agent_f64 / agent_i32 / env_f64) directly.
  * The specialised pipeline keeps the HJ pair values of the current state from the previous launch
  * (safety_filter.py:192-201 evaluated one step ahead); after an edit the next lsm_step recomputes them first. */

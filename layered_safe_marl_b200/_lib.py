@@ -51,7 +51,7 @@ class LsmLaunchInfo(C.Structure):
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
-                    'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers')
+                    'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list')
 
 _lib = None
 
@@ -87,8 +87,9 @@ def load():
     lib.lsm_emit_only.argtypes = [C.c_void_p, C.c_void_p]
     lib.lsm_invalidate.argtypes = [C.c_void_p]
     lib.lsm_set_output_buffers.argtypes = [C.c_void_p] + [C.c_void_p] * 5
+    lib.lsm_edge_list.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
-                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers'):
+                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list'):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

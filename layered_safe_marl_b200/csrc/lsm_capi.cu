@@ -403,6 +403,21 @@ int lsm_set_output_buffers(lsm_handle* h, float* obs, float* node_obs, float* ad
     return 0;
 }
 
+int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* edge_attr, int32_t* counts, int64_t* offsets,
+                  int64_t capacity, void* stream) {
+    if (h == nullptr) return fail(1, "lsm_edge_list: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_edge_list: lsm_bind_buffers has not been called");
+    if (edge_index == nullptr || edge_attr == nullptr || counts == nullptr || offsets == nullptr)
+        return fail(1, "lsm_edge_list: null output");
+    if (capacity < 1) return fail(2, "lsm_edge_list: capacity must be >= 1");
+    const float* a = adj ? adj : h->kp.b.adj;
+    const long long graphs = (long long)h->kp.b.num_envs * h->kp.N;
+    cudaError_t e = lsm::edge_list_launch(a, counts, (long long*)offsets, (long long*)edge_index, edge_attr, graphs, h->kp.E,
+                                          (long long)capacity, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_edge_list");
+    return 0;
+}
+
 int lsm_invalidate(lsm_handle* h) {
     if (h == nullptr) return fail(1, "lsm_invalidate: null handle");
     h->pairval_valid = false;

@@ -19,4 +19,6 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
                           cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
 cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
 cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
+cudaError_t edge_list_launch(const float* adj, int32_t* counts, long long* offsets, long long* edge_index, float* edge_attr,
+                             long long num_graphs, int E, long long capacity, cudaStream_t stream);
 }  // namespace lsm

@@ -15,6 +15,7 @@
 // observer i selects "post" for agents <= i and "pre" for agents > i.
 #include "lsm_kernel_generic.cuh"
 #include "lsm_kernel_spec.cuh"
+#include "lsm_edges.cuh"
 #include "lsm_host.h"
 
 #include <cstdlib>
@@ -193,6 +194,16 @@ cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void*
     if (grid > (unsigned)kp.b.num_envs) grid = (unsigned)kp.b.num_envs;
     if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
     return launch_one(f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
+}
+
+cudaError_t edge_list_launch(const float* adj, int32_t* counts, long long* offsets, long long* edge_index, float* edge_attr,
+                             long long num_graphs, int E, long long capacity, cudaStream_t stream) {
+    const int wpb = 8;   // warps (graphs) per block
+    const unsigned blocks = (unsigned)((num_graphs + wpb - 1) / wpb);
+    lsm_edge_count_kernel<<<blocks, wpb * 32, 0, stream>>>(adj, counts, num_graphs, E * E);
+    lsm_edge_scan_kernel<<<1, 1024, 0, stream>>>(counts, offsets, num_graphs);
+    lsm_edge_fill_kernel<<<blocks, wpb * 32, 0, stream>>>(adj, offsets, edge_index, edge_attr, num_graphs, E, capacity);
+    return cudaGetLastError();
 }
 
 }  // namespace lsm

@@ -326,6 +326,29 @@ class B200GraphVecEnv:
             if t is not None:
                 setattr(self, name, t)
 
+    def edge_list(self, adj=None, capacity=None):
+        """(edge_index (2, nnz) int64, edge_attr (nnz, 1) float32) of `adj` (default: the last step's adjacency) in
+        the order of the reference's TransformerConvNet.process_adj (gnn.py:376-407) for the (num_envs*N, E, E)
+        batch the runner feeds the policy - without materialising adj.nonzero(). One host sync (reads nnz)."""
+        a = self.adj if adj is None else adj
+        assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous() and a.numel() == self.n * self.N * self.E * self.E
+        graphs = self.n * self.N
+        cap = int(capacity) if capacity is not None else graphs * self.E * (self.E - 1)
+        if getattr(self, '_edge_cap', 0) < cap:
+            self._edge_index = torch.empty((2, cap), dtype=torch.int64, device=self.device)
+            self._edge_attr = torch.empty((cap,), dtype=torch.float32, device=self.device)
+            self._edge_counts = torch.empty((graphs,), dtype=torch.int32, device=self.device)
+            self._edge_offsets = torch.empty((graphs + 1,), dtype=torch.int64, device=self.device)
+            self._edge_cap = cap
+        _lib.check(self.lib.lsm_edge_list(self._h, C.c_void_p(a.data_ptr()), C.c_void_p(self._edge_index.data_ptr()),
+                                          C.c_void_p(self._edge_attr.data_ptr()), C.c_void_p(self._edge_counts.data_ptr()),
+                                          C.c_void_p(self._edge_offsets.data_ptr()), self._edge_cap, self._stream()),
+                   'lsm_edge_list')
+        nnz = int(self._edge_offsets[graphs].item())
+        if nnz > self._edge_cap:
+            raise RuntimeError(f"edge list needs {nnz} entries, capacity is {self._edge_cap}")
+        return self._edge_index[:, :nnz], self._edge_attr[:nnz].unsqueeze(1)
+
     def invalidate(self):
         """Call after writing the state tensors (agent_f64, agent_i32, env_f64, landmarks) directly."""
         _lib.check(self.lib.lsm_invalidate(self._h), 'lsm_invalidate')

@@ -174,3 +174,39 @@ def test_eval_scenarios_cuda_matches_oracle(name, N):
         np.testing.assert_array_equal(ora.adj != 0, out[3].cpu().numpy() != 0)
         G.assert_close(out[2].cpu().numpy(), ora.node_obs, f't={t} node_obs')
         G.assert_close(out[4].cpu().numpy(), ora.reward, f't={t} reward')
+
+
+def _process_adj(adj):
+    """TransformerConvNet.process_adj, reference onpolicy/algorithms/utils/gnn.py:376-407 (3-D case), verbatim semantics."""
+    batch_size, num_nodes, _ = adj.shape
+    edge_index = adj.nonzero(as_tuple=False)
+    edge_attr = adj[edge_index[:, 0], edge_index[:, 1], edge_index[:, 2]]
+    batch = edge_index[:, 0] * num_nodes
+    edge_index = torch.stack([batch + edge_index[:, 1], batch + edge_index[:, 2]], dim=0)
+    return edge_index, edge_attr.unsqueeze(1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,dyn', [(8, 'double_integrator'), (3, 'double_integrator'), (10, 'airtaxi')])
+def test_edge_list_matches_process_adj(N, dyn):
+    """N2: the device COO builder against the reference's own torch code on the adjacency of real steps
+    (bit-exact integer indices, bit-exact float32 attributes, ragged graphs incl. empty ones)."""
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=False, episode_length=12,
+                          world_size=8 if dyn == 'double_integrator' else 12)     # sparse: many pairs beyond the radius
+    env = B200GraphVecEnv(args, num_envs=97, seed=5)
+    env.reset(0)
+    gen = torch.Generator(device='cpu'); gen.manual_seed(2)
+    for t in range(14):                                   # crosses an auto-reset
+        a = torch.randint(0, 25, (97, N), generator=gen, dtype=torch.int32).to(env.device)
+        out = env.step(a, 0)
+        adj = out[3]
+        ei, ea = env.edge_list()
+        ri, ra = _process_adj(adj.reshape(-1, env.E, env.E))
+        assert ei.dtype == torch.int64 and ea.dtype == torch.float32 and ea.shape == ra.shape
+        assert torch.equal(ei, ri), f't={t}'
+        assert torch.equal(ea, ra), f't={t}'
+    # an all-zero adjacency (no edges at all) and a user-supplied tensor
+    z = torch.zeros_like(env.adj)
+    ei, ea = env.edge_list(z)
+    assert ei.shape == (2, 0) and ea.shape == (0, 1)
