@@ -47,6 +47,7 @@ struct lsm_handle {
     int forced_epw = 0;         // LSM_EPW environment override (experiments)
     lsm::SpecGeometry geo = {};
     int emit_regs = 0, emit_blocks_per_sm = 0, pair_regs = 0;
+    bool l2_persist = false;            // LSM_L2_PERSIST=1: persisting access-policy window on the value grid
     bool pairval_valid = false;         // d_pairval holds the HJ pair values of the CURRENT state (written by the last emit launch)
     double* d_pairval = nullptr;        // library-owned scratch of the specialised pipeline
     unsigned char* d_emit_rec = nullptr;
@@ -84,7 +85,11 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaGetDeviceProperties"); }
     h->sm_count = prop.multiProcessorCount;
     h->max_window = (size_t)prop.accessPolicyMaxWindowSize;
-    if (prop.persistingL2CacheMaxSize > 0) {
+    // An L2 persisting set-aside for the HJ grid is OFF by default: carving 32 MB out of the 126 MB L2 slowed the
+    // step's 107 MB store stream by 25-35 % on B200 (plain 16-byte stores of the adjacency bytes: 22.6 -> 16.8 us;
+    // whole cfg2 step 52.5 -> 47.9 us), while the 3-24 MB grids stay L2-resident on their own. LSM_L2_PERSIST=1 opts in.
+    h->l2_persist = std::getenv("LSM_L2_PERSIST") != nullptr;
+    if (prop.persistingL2CacheMaxSize > 0 && h->l2_persist) {
         size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (want > ((size_t)32 << 20)) want = (size_t)32 << 20;
         cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want);   // best effort
@@ -345,7 +350,7 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
     if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;   // generic kernel: persistent grid
-    const void* persist = (mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
+    const void* persist = (h->l2_persist && mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
     cudaError_t e;
     kp.pairval = nullptr;
     const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
@@ -433,7 +438,8 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
     const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 32);
     kp.pairval = pair_path ? h->d_pairval : nullptr;
-    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, pair_path ? (const void*)kp.vg.values : nullptr, h->persist_bytes);
+    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, (pair_path && h->l2_persist) ? (const void*)kp.vg.values : nullptr,
+                                          h->persist_bytes);
     if (e != cudaSuccess) return cuda_fail(e, "lsm_emit_only");
     return 0;
 }

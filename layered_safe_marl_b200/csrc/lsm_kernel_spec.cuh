@@ -994,6 +994,36 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
     pdl_launch_dependents();
     pdl_wait();
     if (debug & 64) return;          // experiments: launch + block dispatch floor
+    if (debug & 512) {               // experiments: every bulk copy of this block back to back, nothing else
+        if (tid == 0) {
+            for (int ee = blockIdx.x; ee < n; ee += gridDim.x) {
+                if (GEO::ADJ_BULK) for (int i = 0; i < N; ++i) bulk_store(kp.b.adj + ((size_t)ee * N + i) * EE, S.dthr[0], (unsigned)EE * 4u);
+                if (GEO::NODE_BULK && NCHUNK == 1) bulk_store(kp.b.node_obs + (size_t)ee * (ROWS * F), S.nodes[0], (unsigned)(ROWS * F) * 4u);
+                bulk_store_commit();
+            }
+            bulk_store_wait_read<0>();
+        }
+        return;
+    }
+    if (debug & 2048) {              // experiments: the same bytes, classic grid-strided 16-byte stores (compact moving window)
+        const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+        float4* a4 = reinterpret_cast<float4*>(kp.b.adj);
+        const size_t na = (size_t)n * N * EE / 4, nn = (size_t)n * ROWS * F / 4;
+        if (!(debug & 8)) for (size_t k = (size_t)blockIdx.x * T + tid; k < na; k += (size_t)gridDim.x * T) a4[k] = v;
+        float4* n4 = reinterpret_cast<float4*>(kp.b.node_obs);
+        if (!(debug & 4)) for (size_t k = (size_t)blockIdx.x * T + tid; k < nn; k += (size_t)gridDim.x * T) n4[k] = v;
+        return;
+    }
+    if (debug & 1024) {              // experiments: the same bytes with coalesced 16-byte stores from registers
+        const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+        for (int ee = blockIdx.x; ee < n; ee += gridDim.x) {
+            float4* a4 = reinterpret_cast<float4*>(kp.b.adj + (size_t)ee * N * EE);
+            if (!(debug & 8)) for (int k = tid; k < N * EE / 4; k += T) a4[k] = v;
+            float4* n4 = reinterpret_cast<float4*>(kp.b.node_obs + (size_t)ee * (ROWS * F));
+            if (!(debug & 4)) for (int k = tid; k < ROWS * F / 4; k += T) n4[k] = v;
+        }
+        return;
+    }
     const bool masked_reset = kp.mode == MODE_RESET && kp.env_mask != nullptr;
 
     auto prefetch = [&](int env, int slot) {

@@ -147,8 +147,7 @@ static cudaError_t launch_one(const void* fn, const KParams& kp, unsigned grid_b
         attr[nattr].val.programmaticStreamSerializationAllowed = 1;
         ++nattr;
     }
-    static const bool no_persist = std::getenv("LSM_NO_PERSIST") != nullptr;
-    if (!no_persist && persist_ptr != nullptr && persist_bytes > 0) {
+    if (persist_ptr != nullptr && persist_bytes > 0) {
         // keep the HJ value grid resident in L2 while the observation stream flows through it
         attr[nattr].id = cudaLaunchAttributeAccessPolicyWindow;
         attr[nattr].val.accessPolicyWindow.base_ptr = const_cast<void*>(persist_ptr);
