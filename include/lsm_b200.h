@@ -196,6 +196,12 @@ int lsm_invalidate(lsm_handle *h);
  * configuration has no separate emission launch. */
 int lsm_emit_only(lsm_handle *h, void *stream);
 
+/* Diagnostics (never on the product path): per-kernel timeline of the launches that follow. If `out_ns` is non-NULL
+ * and a timeline is armed, synchronises the device and copies 7 %globaltimer values (ns) out: pair first-block-in,
+ * pair last-body-out, agent in / out, emit in / out, pair grid out. `arm` != 0 (re)arms the recording for the next
+ * launches, 0 disables it. */
+int lsm_debug_timeline(lsm_handle *h, int arm, uint64_t *out_ns);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,6 +51,8 @@ struct lsm_handle {
     bool pairval_valid = false;         // d_pairval holds the HJ pair values of the CURRENT state (written by the last emit launch)
     double* d_pairval = nullptr;        // library-owned scratch of the specialised pipeline
     unsigned char* d_emit_rec = nullptr;
+    unsigned long long* d_timeline = nullptr;   // diagnostics only (lsm_debug_timeline)
+    float* d_vpacked = nullptr;          // corner-packed copy of the value grid (GridDev::packed)
 };
 
 extern "C" {
@@ -249,6 +251,8 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_pair32) cudaFree(h->d_pair32);
     if (h->d_pairval) cudaFree(h->d_pairval);
     if (h->d_emit_rec) cudaFree(h->d_emit_rec);
+    if (h->d_timeline) cudaFree(h->d_timeline);
+    if (h->d_vpacked) cudaFree(h->d_vpacked);
     delete h;
     return 0;
 }
@@ -281,6 +285,22 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     for (int k = 0; k < g->ndim; ++k) cells *= (size_t)g->shape[k];
     h->persist_bytes = cells * sizeof(float);
     if (h->persist_bytes > h->max_window) h->persist_bytes = h->max_window;
+    // corner-packed copy for the pair kernel (one aligned chunk per lookup). LSM_NO_PACKED=1 keeps the scattered gathers;
+    // tables larger than LSM_PACKED_MAX_MB (default 2048) are not built.
+    if (h->d_vpacked) { cudaFree(h->d_vpacked); h->d_vpacked = nullptr; }
+    h->kp.vg.packed = nullptr;
+    if (h->spec && std::getenv("LSM_NO_PACKED") == nullptr) {
+        const char* mx = std::getenv("LSM_PACKED_MAX_MB");
+        const size_t max_bytes = (size_t)(mx ? std::atoll(mx) : 2048) << 20;
+        const size_t bytes = cells * ((size_t)1 << g->ndim) * sizeof(float);
+        if (bytes <= max_bytes && cells * ((size_t)1 << g->ndim) / 4 < (size_t)0x7fffffff) {
+            cudaError_t e = cudaMalloc(&h->d_vpacked, bytes);
+            if (e == cudaSuccess) e = lsm::pack_grid_launch(h->kp.vg, h->d_vpacked, (long long)cells);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) return cuda_fail(e, "lsm_set_value_grid: corner-packed table");
+            h->kp.vg.packed = h->d_vpacked;
+        }
+    }
     return 0;
 }
 
@@ -328,8 +348,13 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     out->emit_block_threads = h->spec ? h->geo.emit_threads : 0;
     out->emit_smem_bytes_per_block = h->spec ? h->geo.emit_smem : 0;
     out->emit_regs_per_thread = h->emit_regs; out->emit_blocks_per_sm = h->emit_blocks_per_sm;
+    if (h->spec) {   // the grid lsm_step launches (room left for the pair kernel when the filter is on)
+        int bps = 0;
+        const bool pair_path = (h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg;
+        if (lsm::spec_emit_blocks_per_sm(h->kp.c.dynamics, h->kp.N, h->kp.L, pair_path, &bps) == cudaSuccess) out->emit_blocks_per_sm = bps;
+    }
     out->pair_regs_per_thread = h->pair_regs;
-    out->launches_per_step = h->spec ? 2 : 1;   // + lsm_pair_kernel on the first step after the state was edited
+    out->launches_per_step = h->spec ? (((h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg) ? 3 : 2) : 1;   // agent, emit, pair (filter on)
     out->emit_record_bytes = h->spec ? h->geo.rec_bytes : 0;
     return 0;
 }
@@ -353,12 +378,14 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     const void* persist = (h->l2_persist && mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
     cudaError_t e;
     kp.pairval = nullptr;
+    kp.pair_late = 0;
     const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
+    const bool pair_up_front = (kp.debug & 32) != 0;   // experiments: K_a in front of the agent kernel on every step
     if (pair_path && mode == lsm::MODE_STEP) {
         // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
-        // previous launch's emit kernel; recomputed here (K_a) when the state was edited in between
+        // pair kernel launched behind the previous emit kernel; recomputed here when the state was edited in between
         kp.pairval = h->d_pairval;
-        if (!h->pairval_valid || (kp.debug & 32)) {
+        if (!h->pairval_valid || pair_up_front) {
             e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
             if (e != cudaSuccess) return cuda_fail(e, who);
         }
@@ -368,14 +395,20 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
                            persist, h->persist_bytes);
     if (e != cudaSuccess) return cuda_fail(e, who);
     if (h->spec) {
+        h->pairval_valid = false;
         if (!(kp.debug & 1)) {
-            // K_c: graph observation, one block per env (+ the pair values of the next step)
-            kp.pairval = (pair_path && !(kp.debug & 32)) ? h->d_pairval : nullptr;
-            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes);
+            // K_c: graph observation (persistent blocks)
+            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes, pair_path && !pair_up_front);
             if (e != cudaSuccess) return cuda_fail(e, who);
-            if (kp.pairval != nullptr) { if (env_mask == nullptr) h->pairval_valid = true; }
-            else h->pairval_valid = false;
-        } else h->pairval_valid = false;
+        }
+        if (pair_path && !pair_up_front) {
+            // K_a for the NEXT step, beside the emit kernel's drain (see lsm_pair_kernel)
+            kp.pairval = h->d_pairval;
+            kp.pair_late = (kp.debug & 1) ? 0 : 1;
+            e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
+            if (e != cudaSuccess) return cuda_fail(e, who);
+            h->pairval_valid = true;
+        }
     }
     return 0;
 }
@@ -436,11 +469,32 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     lsm::KParams kp = h->kp;
     kp.mode = lsm::MODE_OBSERVE; kp.env_mask = nullptr;
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
-    const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 32);
-    kp.pairval = pair_path ? h->d_pairval : nullptr;
-    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, (pair_path && h->l2_persist) ? (const void*)kp.vg.values : nullptr,
-                                          h->persist_bytes);
+    kp.pairval = nullptr; kp.pair_late = 0;
+    const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & (2 | 32));
+    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, nullptr, 0, pair_path);   // same grid as inside lsm_step
     if (e != cudaSuccess) return cuda_fail(e, "lsm_emit_only");
+    return 0;
+}
+
+int lsm_debug_timeline(lsm_handle* h, int arm, uint64_t* out_ns) {
+    if (h == nullptr) return fail(1, "lsm_debug_timeline: null handle");
+    cudaError_t e;
+    if (out_ns != nullptr && h->d_timeline != nullptr) {
+        if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(e, "lsm_debug_timeline");
+        if ((e = cudaMemcpy(out_ns, h->d_timeline, sizeof(uint64_t) * lsm::TL_COUNT, cudaMemcpyDeviceToHost)) != cudaSuccess)
+            return cuda_fail(e, "lsm_debug_timeline");
+    }
+    if (arm) {
+        if (h->d_timeline == nullptr && (e = cudaMalloc(&h->d_timeline, sizeof(uint64_t) * lsm::TL_COUNT)) != cudaSuccess)
+            return cuda_fail(e, "lsm_debug_timeline");
+        uint64_t init[lsm::TL_COUNT];
+        for (int k = 0; k < lsm::TL_COUNT; ++k) init[k] = 0;
+        init[lsm::TL_PAIR_START] = init[lsm::TL_AGENT_START] = init[lsm::TL_EMIT_START] = ~0ull;
+        if ((e = cudaMemcpy(h->d_timeline, init, sizeof(init), cudaMemcpyHostToDevice)) != cudaSuccess) return cuda_fail(e, "lsm_debug_timeline");
+        h->kp.timeline = h->d_timeline;
+    } else {
+        h->kp.timeline = nullptr;
+    }
     return 0;
 }
 

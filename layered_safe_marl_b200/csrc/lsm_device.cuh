@@ -31,6 +31,11 @@ struct GridDev {
     double ttr_max;
     const float* values;
     const float* grads;
+    // corner-packed copy of `values` (library-owned, built by lsm_set_value_grid): for every "lower corner" index tuple
+    // the 2^ndim stencil values it anchors, contiguous in the corner order of the interpolation (binary counting, dim 0
+    // slowest; upper index = lower + 1, wrapped on periodic dims, clamped at the last node otherwise). One lookup reads
+    // one 64-byte (4-D) / 128-byte (5-D) aligned chunk instead of 2^ndim scattered words. NULL = not built.
+    const float* packed;
 };
 
 // per-env shared-memory block: element offsets (in bytes from the env block base)
@@ -84,7 +89,15 @@ struct KParams {
     // specialised pipeline (library-owned scratch, L2 resident between the launches of one step)
     double* pairval;           // [num_envs][N][N] raw HJ value of (ego, other) from lsm_pair_kernel; NULL = compute in-kernel
     unsigned char* emit_rec;   // [num_envs][sizeof(EmitRec)] per-env record consumed by lsm_emit_kernel
+    int pair_late;             // lsm_pair_kernel launched BEHIND the emit kernel of the same step (runs beside its drain)
+    unsigned long long* timeline;   // diagnostics (lsm_debug_timeline), NULL in production: globaltimer min-start / max-end per kernel
 };
+
+// timeline slots: first block in / last block out of each kernel of the pipeline (ns, %globaltimer)
+enum { TL_PAIR_START = 0, TL_PAIR_BODY_END, TL_AGENT_START, TL_AGENT_END, TL_EMIT_START, TL_EMIT_END, TL_PAIR_END, TL_COUNT };
+__device__ __forceinline__ unsigned long long globaltimer_ns() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+__device__ __forceinline__ void tl_start(unsigned long long* tl, int slot) { if (tl != nullptr && threadIdx.x == 0) atomicMin(tl + slot, globaltimer_ns()); }
+__device__ __forceinline__ void tl_end(unsigned long long* tl, int slot) { if (tl != nullptr && threadIdx.x == 0) atomicMax(tl + slot, globaltimer_ns()); }
 
 __device__ __forceinline__ double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
 __device__ __forceinline__ double pymax(double a, double b) { return (b > a) ? b : a; }

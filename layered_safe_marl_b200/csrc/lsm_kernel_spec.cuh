@@ -82,6 +82,28 @@ struct __align__(16) AgentScratch {
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// fire-and-forget L2 prefetch: the per-agent kernel is a latency chain, and every input it touches late (pair values,
+// actions, landmark tables, the parity-selected info slots) would otherwise be one more dependent DRAM round trip
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" :: "l"(p)); }
+
+// L2 eviction-priority hints (createpolicy): the 100 MB - 10 GB observation stream of one step is written evict-first
+// and the HJ grids are gathered evict-last, so the stream does not push the few-MB grids out of the 126 MB L2 - without
+// them the pair kernel's gathers miss to HBM and its reads interleave with the emit kernel's write stream.
+__device__ __forceinline__ unsigned long long l2_evict_first() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_last() {
+    unsigned long long p; asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p)); return p;
+}
+__device__ __forceinline__ float ldg_hint(const float* p, unsigned long long pol) {
+    float v; asm("ld.global.nc.L2::cache_hint.f32 %0, [%1], %2;" : "=f"(v) : "l"(p), "l"(pol)); return v;
+}
+__device__ __forceinline__ float4 ldg_hint(const float4* p, unsigned long long pol) {
+    float4 v;
+    asm("ld.global.nc.L2::cache_hint.v4.f32 {%0, %1, %2, %3}, [%4], %5;" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p), "l"(pol));
+    return v;
+}
+
 template <int N> struct Pow2 { static constexpr int value = N <= 1 ? 1 : N <= 2 ? 2 : N <= 4 ? 4 : N <= 8 ? 8 : N <= 16 ? 16 : 32; };
 
 // ---------------------------------------------------------------------------------------------
@@ -132,12 +154,13 @@ template <int ND>
 __device__ __forceinline__ double stencil32_value(const GridDev& g, const Stencil32<ND>& s) {
     constexpr int NC = 1 << ND;
     float v[NC];
+    const unsigned long long keep = l2_evict_last();
 #pragma unroll
     for (int corner = 0; corner < NC; ++corner) {
         int lin = 0;
 #pragma unroll
         for (int d = 0; d < ND; ++d) lin += ((corner >> (ND - 1 - d)) & 1) ? s.hi[d] : s.lo[d];
-        v[corner] = __ldg(g.values + lin);
+        v[corner] = ldg_hint(g.values + lin, keep);
     }
     double acc = 0.0;
 #pragma unroll
@@ -158,6 +181,7 @@ template <int ND>
 __device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32<ND>& s, double (&out)[ND]) {
 #pragma unroll
     for (int d = 0; d < ND; ++d) out[d] = 0.0;
+    const unsigned long long keep = l2_evict_last();
 #pragma unroll
     for (int corner = 0; corner < (1 << ND); ++corner) {
         double weight = 0.0; int lin = 0;
@@ -169,12 +193,12 @@ __device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32
             lin += bit ? s.hi[d] : s.lo[d];
         }
         if (ND == 4) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(g.grads) + lin);
+            const float4 v = ldg_hint(reinterpret_cast<const float4*>(g.grads) + lin, keep);
             out[0] = out[0] + weight * (double)v.x; out[1] = out[1] + weight * (double)v.y;
             out[2] = out[2] + weight * (double)v.z; out[3] = out[3] + weight * (double)v.w;
         } else {
 #pragma unroll
-            for (int d = 0; d < ND; ++d) out[d] = out[d] + weight * (double)__ldg(g.grads + lin * ND + d);
+            for (int d = 0; d < ND; ++d) out[d] = out[d] + weight * (double)ldg_hint(g.grads + lin * ND + d, keep);
         }
     }
 }
@@ -188,14 +212,78 @@ struct LeanGrad {
     }
 };
 
-// raw (unshifted) HJ value of the pair (ego, other); +inf = outside the declared range / NaN
-template <int DYN>
-__device__ __forceinline__ double pair_value_raw(const GridDev& vg, double ex, double ey, double e2, double e3,
-                                                 double ox, double oy, double o2, double o3) {
-    // safety_filter.py:192-201, 345-354
-    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-    double rel[ND];
-    relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+// ---------------------------------------------------------------------------------------------
+// corner-packed table (GridDev::packed): builder + lookup. The lookup reproduces stencil32_setup + stencil32_value
+// bit for bit (same positions, weights, corner order, sequential adds); positions whose lower index falls outside
+// [0, n-1] on a non-periodic dim (the declared clamp region) take the scattered path instead.
+// ---------------------------------------------------------------------------------------------
+template <int ND>
+__global__ void __launch_bounds__(256) lsm_pack_grid_kernel(const float* __restrict__ values, float* __restrict__ packed,
+                                                          GridDev g, long long cells) {
+    constexpr int NC = 1 << ND;
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cells * NC) return;
+    const long long cell = t / NC; const int corner = (int)(t - cell * NC);
+    long long rem = cell, lin = 0, mul = 1;
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+        const int n = g.shape[d];
+        const int il = (int)(rem % n); rem /= n;
+        int ih = il + 1;
+        if (g.periodic[d]) { if (ih >= n) ih -= n; } else if (ih > n - 1) ih = n - 1;
+        lin += (long long)(((corner >> (ND - 1 - d)) & 1) ? ih : il) * mul;
+        mul *= n;
+    }
+    packed[t] = values[lin];
+}
+
+template <int ND>
+__device__ __forceinline__ bool packed_value(const GridDev& g, const double (&x)[ND], double& out) {
+    constexpr int NC = 1 << ND;
+    double wlo[ND], whi[ND];
+    bool ok = true;
+    int cell = 0, mul = 1;
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+        const double pos = div_exact(x[d] - g.lo[d], g.spacing[d], g.inv_spacing[d]);
+        const double fl = floor(pos);
+        const double w = pos - fl;
+        wlo[d] = 1.0 - w; whi[d] = w;
+        const int n = g.shape[d];
+        // NaN / out-of-box positions fail these comparisons and go to the scattered path
+        if (g.periodic[d]) {
+            if (!(fabs(pos) <= 1.0e9)) ok = false;
+            int il = (int)fl % n; if (il < 0) il += n;
+            cell += il * mul;
+        } else {
+            if (!(fl >= 0.0 && fl <= (double)(n - 1))) ok = false;
+            cell += (int)fl * mul;
+        }
+        mul *= n;
+    }
+    if (!ok) return false;
+    const float4* src = reinterpret_cast<const float4*>(g.packed) + (size_t)cell * (NC / 4);
+    float4 q[NC / 4];
+#pragma unroll
+    for (int k = 0; k < NC / 4; ++k) q[k] = __ldg(src + k);
+    const float* v = reinterpret_cast<const float*>(q);
+    double acc = 0.0;
+#pragma unroll
+    for (int corner = 0; corner < NC; ++corner) {
+        double weight = 0.0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const double wd = ((corner >> (ND - 1 - d)) & 1) ? whi[d] : wlo[d];
+            weight = (d == 0) ? wd : weight * wd;
+        }
+        acc = acc + weight * (double)v[corner];
+    }
+    out = acc;
+    return true;
+}
+
+template <int ND>
+__device__ __noinline__ double pair_value_scattered(const GridDev& vg, const double (&rel)[ND]) {
     Stencil32<ND> st;
     stencil32_setup<ND>(vg, rel, st);
     if (!st.valid) return INFINITY;
@@ -204,39 +292,70 @@ __device__ __forceinline__ double pair_value_raw(const GridDev& vg, double ex, d
     return v;
 }
 
+// raw (unshifted) HJ value of the pair (ego, other); +inf = outside the declared range / NaN
+template <int DYN>
+__device__ __forceinline__ double pair_value_raw(const GridDev& vg, double ex, double ey, double e2, double e3,
+                                                 double ox, double oy, double o2, double o3) {
+    // safety_filter.py:192-201, 345-354
+    constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    double rel[ND];
+    relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+    if (vg.packed != nullptr) {
+        double v;
+        if (packed_value<ND>(vg, rel, v)) return isnan(v) ? INFINITY : v;
+    }
+    return pair_value_scattered<ND>(vg, rel);
+}
+
 // value shift of HjDataHandle.update_separation_distance (safety_filter.py:170-174); inf stays inf
 __device__ __forceinline__ double shift_value(double raw, double sep, const GridDev& vg) {
     return raw - (sep - vg.separation_distance);
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_a: HJ values of every ordered agent pair, one thread per (env, ego, other)
+// K_a: HJ values of every ordered agent pair, one thread per (env, ego, other).
+//
+// The values feed the NEXT step's filter (safety_filter.py:192-201 evaluates V(x_i - x_j) at the start of a step) and
+// depend only on the state the agent kernel of THIS step left behind. Normal placement ("late"): launched right behind
+// the emit kernel with programmatic dependent launch and WITHOUT a grid-dependency wait at its top - the emit kernel
+// releases its dependents only after its own wait, i.e. once the agent kernel is complete and flushed - so these
+// latency-bound L2 gathers run on the issue slots the store-bound emit kernel leaves idle, at full thread-per-pair
+// parallelism. Block 0 waits for the emit kernel before it retires, which keeps "this grid complete" => "emit grid
+// complete" for the next step's agent kernel. Fallback placement (pair_late == 0): in front of the agent kernel, when
+// the state was edited from outside (lsm_invalidate / set_state).
 // ---------------------------------------------------------------------------------------------
+constexpr int kPairThreads = 128;
 template <int DYN, int N>
-__global__ void __launch_bounds__(256) lsm_pair_kernel(const __grid_constant__ KParams kp) {
+__global__ void __launch_bounds__(kPairThreads) lsm_pair_kernel(const __grid_constant__ KParams kp) {
     pdl_launch_dependents();
-    pdl_wait();
+    if (!kp.pair_late) pdl_wait();
+    tl_start(kp.timeline, TL_PAIR_START);
     const long long n = kp.b.num_envs;
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n * (N * N)) return;
-    const int env = (int)(t / (N * N)), r = (int)(t - (long long)env * (N * N));
-    const int i = r / N, j = r - i * N;
-    if (i == j) return;
-    // world.use_safety_filter of this env (curriculum, navigation_graph_safe.py:351-357)
-    const lsm_config& c = kp.c;
-    if (!(c.flags & LSM_FLAG_INITIAL_PHASE_USE_SAFETY_FILTER)) {
-        const double ratio = kp.b.env_f64[(size_t)LSM_EF_CURRICULUM_RATIO * n + env];
-        if (!(ratio_sloped(ratio, 0.25, 0.75) > 0.0)) return;
-    }
-    const size_t fs = (size_t)n * N;
-    const size_t ia = (size_t)env * N + i, ja = (size_t)env * N + j;
-    const int* dn = kp.b.agent_i32 + LSM_AI_DONE * fs;
-    if (dn[ia] || dn[ja]) return;
-    const double* af = kp.b.agent_f64;
-    const double v = pair_value_raw<DYN>(kp.vg, af[LSM_AF_X * fs + ia], af[LSM_AF_Y * fs + ia], af[LSM_AF_S2 * fs + ia],
-                                         af[LSM_AF_S3 * fs + ia], af[LSM_AF_X * fs + ja], af[LSM_AF_Y * fs + ja],
-                                         af[LSM_AF_S2 * fs + ja], af[LSM_AF_S3 * fs + ja]);
-    kp.pairval[t] = v;
+    [&] {
+        if (t >= n * (N * N)) return;
+        const int env = (int)(t / (N * N)), r = (int)(t - (long long)env * (N * N));
+        const int i = r / N, j = r - i * N;
+        if (i == j) return;
+        // world.use_safety_filter of this env (curriculum, navigation_graph_safe.py:351-357)
+        const lsm_config& c = kp.c;
+        if (!(c.flags & LSM_FLAG_INITIAL_PHASE_USE_SAFETY_FILTER)) {
+            const double ratio = kp.b.env_f64[(size_t)LSM_EF_CURRICULUM_RATIO * n + env];
+            if (!(ratio_sloped(ratio, 0.25, 0.75) > 0.0)) return;
+        }
+        const size_t fs = (size_t)n * N;
+        const size_t ia = (size_t)env * N + i, ja = (size_t)env * N + j;
+        const int* dn = kp.b.agent_i32 + LSM_AI_DONE * fs;
+        if (dn[ia] || dn[ja]) return;
+        const double* af = kp.b.agent_f64;
+        const double v = pair_value_raw<DYN>(kp.vg, af[LSM_AF_X * fs + ia], af[LSM_AF_Y * fs + ia], af[LSM_AF_S2 * fs + ia],
+                                             af[LSM_AF_S3 * fs + ia], af[LSM_AF_X * fs + ja], af[LSM_AF_Y * fs + ja],
+                                             af[LSM_AF_S2 * fs + ja], af[LSM_AF_S3 * fs + ja]);
+        kp.pairval[t] = v;
+    }();
+    tl_end(kp.timeline, TL_PAIR_BODY_END);
+    if (kp.pair_late && blockIdx.x == 0 && threadIdx.x == 0) pdl_wait();
+    tl_end(kp.timeline, TL_PAIR_END);
 }
 
 // in-kernel variant for internal steps after the first (states changed inside the launch): pair-parallel over
@@ -281,6 +400,11 @@ __device__ __forceinline__ void bulk_store_fence() { asm volatile("fence.proxy.a
 __device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" :: "l"(gdst), "r"(saddr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_store(void* gdst, const void* ssrc, unsigned bytes, unsigned long long pol) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(ssrc);
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group.L2::cache_hint [%0], [%1], %2, %3;"
+                 :: "l"(gdst), "r"(saddr), "r"(bytes), "l"(pol) : "memory");
 }
 __device__ __forceinline__ void bulk_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int PENDING>
@@ -494,6 +618,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
     const size_t fstride = (size_t)n * N;         // elements between two fields of the agent SoA
     pdl_launch_dependents();
     pdl_wait();
+    tl_start(kp.timeline, TL_AGENT_START);
 
     for (int grp = blockIdx.x * warps_per_block + warp_in_block; grp < ngroups; grp += gridDim.x * warps_per_block) {
         const int env0 = grp * EPW;
@@ -505,6 +630,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
         const int nenv = (n - env0) < EPW ? (n - env0) : EPW;   // envs of this group
 
         // ---------------- P0: load ----------------
+        // everything this warp will touch later is requested now, so that the chain below pays ONE DRAM round trip
+        if (agent_on) {
+            const size_t a = (size_t)env * N + ai;
+            if (kp.mode == MODE_STEP) {
+                if (kp.action_idx != nullptr) prefetch_l2(kp.action_idx + a);
+                else { prefetch_l2(kp.action_onehot + a * LSM_NUM_ACTIONS); prefetch_l2(kp.action_onehot + a * LSM_NUM_ACTIONS + LSM_NUM_ACTIONS - 1); }
+                if (kp.pairval != nullptr) {
+#pragma unroll
+                    for (int k = 0; k < N * 8; k += 128) prefetch_l2(kp.pairval + a * N + k / 8);
+                }
+            }
+            const double* afp = kp.b.agent_f64 + a;
+            prefetch_l2(afp + LSM_AF_TIMES_REQ_A * fstride); prefetch_l2(afp + LSM_AF_TIMES_REQ_B * fstride);
+            prefetch_l2(afp + LSM_AF_DISTS_GOAL_A * fstride); prefetch_l2(afp + LSM_AF_DISTS_GOAL_B * fstride);
+        }
+        {
+            const size_t lstride = (size_t)n * M;
+            const double* src = kp.b.landmarks + (size_t)env0 * M;
+            for (int idx = lane * 16; idx < nenv * M; idx += 32 * 16) {      // one request per 128-byte line and field
+#pragma unroll
+                for (int f = 0; f < LSM_LF_COUNT; ++f) {
+                    prefetch_l2(src + f * lstride + idx);
+                    prefetch_l2(src + f * lstride + (idx + 15 < nenv * M ? idx + 15 : nenv * M - 1));   // runs are not line aligned
+                }
+            }
+        }
         double x = 0, y = 0, s2 = 0, s3 = 0, p_dist = 0, state_time = 0, min_rel = INFINITY, goal_min_time = INFINITY;
         double times_req = -1, dists_goal = -1, dist_left = -1, ep_travel_dist = 0, ep_min_dist = INFINITY, action_diff = 0;
         int reached = 0, done = 0, safety_filtered = 0, deconflict = -1, ncoll = 0;
@@ -935,6 +1086,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
         }
         __syncwarp();
     }
+    tl_end(kp.timeline, TL_AGENT_END);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -991,8 +1143,11 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
     const int n = (int)kp.b.num_envs;
     const double r2_lt = kp.r2_lt;
     const int debug = kp.debug;
-    pdl_launch_dependents();
+    // the dependents (normally lsm_pair_kernel, which does not wait at its top) are released only once the agent kernel
+    // this launch depends on is complete and flushed
     pdl_wait();
+    pdl_launch_dependents();
+    tl_start(kp.timeline, TL_EMIT_START);
     if (debug & 64) return;          // experiments: launch + block dispatch floor
     if (debug & 512) {               // experiments: every bulk copy of this block back to back, nothing else
         if (tid == 0) {
@@ -1215,11 +1370,20 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             if (GEO::NODE_BULK || adj_bulk) bulk_store_fence();
             __syncthreads();
             if (tid == 0) {
-                if (adj_bulk && !adj_sent && !(debug & 8)) {
+                if (debug & 4096) {      // experiments: no eviction-priority hint on the stream
+                    if (adj_bulk && !adj_sent && !(debug & 8)) {
 #pragma unroll 1
-                    for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u);
+                        for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u);
+                    }
+                    if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u);
+                } else {
+                    const unsigned long long stream_pol = l2_evict_first();
+                    if (adj_bulk && !adj_sent && !(debug & 8)) {
+#pragma unroll 1
+                        for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u, stream_pol);
+                    }
+                    if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
                 }
-                if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u);
                 bulk_store_commit();
             }
             adj_sent = true;
@@ -1234,29 +1398,11 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
                 __syncthreads();
             }
         }
-        // (e) HJ values of every ordered agent pair for the NEXT step (safety_filter.py:192-201, 345-354): they depend only on
-        //     the state this step leaves behind, and the L2 gathers overlap this environment's copies draining to HBM. The
-        //     agent kernel of the next lsm_step consumes them (lsm_pair_kernel recomputes them if the state was edited).
-        if (kp.pairval != nullptr && R.next_filter) {
-            double* pv = kp.pairval + (size_t)ee * (N * N);
-            for (int t = tid; t < N * N; t += T) {
-                const int i = t / N, j = t - i * N;
-                if (i == j || R.done[1][i] || R.done[1][j]) continue;
-                const double2 pi = R.pos[i], pj = R.pos[j];
-                double i2, i3, j2, j3;
-                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                    const double2 vi = R.vel[N + i], vj = R.vel[N + j];
-                    i2 = vi.x; i3 = vi.y; j2 = vj.x; j3 = vj.y;
-                } else {
-                    i2 = R.air.theta[i]; i3 = R.air.spd_post[i]; j2 = R.air.theta[j]; j3 = R.air.spd_post[j];
-                }
-                pv[t] = pair_value_raw<DYN>(kp.vg, pi.x, pi.y, i2, i3, pj.x, pj.y, j2, j3);
-            }
-        }
     }
     // every bulk copy issued by this block has finished READING shared memory before the block retires
     if (tid == 0) bulk_store_wait_read<0>();
     cp_async_wait_all();
+    tl_end(kp.timeline, TL_EMIT_END);
 }
 
 }  // namespace lsm

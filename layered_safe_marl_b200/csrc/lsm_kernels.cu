@@ -34,7 +34,7 @@ namespace lsm {
 
 constexpr int kAgentBlock = 128;
 constexpr int kAgentMinB = 2;
-constexpr int kPairBlock = 256;
+constexpr int kPairBlock = kPairThreads;
 
 // experiments: LSM_AGENT_MINB=3 trades ~100-400 B of spills for 12 instead of 8 resident physics warps per SM
 static int agent_minb() {
@@ -179,20 +179,55 @@ cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void*
     return launch_one(f.pair, kp, (unsigned)blocks, kPairBlock, 0, stream, persist_ptr, persist_bytes, true);
 }
 
-cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
+// resident emit blocks per SM: what fits, minus (when the pair kernel runs beside the emit kernel) enough registers /
+// threads for kPairResident pair blocks per SM
+constexpr int kPairResident = 2;
+static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, int* out) {
+    int bps = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, f.emit, f.emit_threads, f.emit_smem);
+    if (e != cudaSuccess) return e;
+    if (bps < 1) return cudaErrorLaunchOutOfResources;
+    if (reserve_pair) {
+        cudaFuncAttributes fe, fp;
+        if ((e = cudaFuncGetAttributes(&fe, f.emit)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fp, f.pair)) != cudaSuccess) return e;
+        auto block_regs = [](int regs, int threads) { return ((regs * 32 + 255) / 256 * 256) * ((threads + 31) / 32); };
+        const int need_regs = kPairResident * block_regs(fp.numRegs, kPairBlock), need_thr = kPairResident * kPairBlock;
+        while (bps > 1 && (65536 - bps * block_regs(fe.numRegs, f.emit_threads) < need_regs || 2048 - bps * f.emit_threads < need_thr)) --bps;
+    }
+    if (const char* g = std::getenv("LSM_EMIT_BPS")) { const int v = std::atoi(g); if (v >= 1 && v < bps) bps = v; }
+    *out = bps;
+    return cudaSuccess;
+}
+
+cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, int* out) {
+    SpecFns f;
+    if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
+    return emit_blocks_per_sm(f, reserve_pair, out);
+}
+
+cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair) {
     SpecFns f;
     if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
     // persistent blocks: as many as are resident at once, each loops over environments
     static int sm_count = 0;
     if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     int bps = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, f.emit, f.emit_threads, f.emit_smem);
+    cudaError_t e = emit_blocks_per_sm(f, reserve_pair, &bps);
     if (e != cudaSuccess) return e;
-    if (bps < 1) return cudaErrorLaunchOutOfResources;
     unsigned grid = (unsigned)sm_count * (unsigned)bps;
     if (grid > (unsigned)kp.b.num_envs) grid = (unsigned)kp.b.num_envs;
     if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
     return launch_one(f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
+}
+
+cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {
+    const long long total = cells << g.ndim;
+    const unsigned blocks = (unsigned)((total + 255) / 256);
+    if (g.ndim == 4) lsm_pack_grid_kernel<4><<<blocks, 256>>>(g.values, packed, g, cells);
+    else if (g.ndim == 5) lsm_pack_grid_kernel<5><<<blocks, 256>>>(g.values, packed, g, cells);
+    else return cudaErrorInvalidValue;
+    return cudaGetLastError();
 }
 
 cudaError_t edge_list_launch(const float* adj, int32_t* counts, long long* offsets, long long* edge_index, float* edge_attr,

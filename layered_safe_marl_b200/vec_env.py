@@ -194,12 +194,25 @@ class B200GraphVecEnv:
                 a = np.ascontiguousarray(a, dtype=np.float32)
             else:
                 a = np.ascontiguousarray(a, dtype=np.int32)
-            if self._act_pinned is None or self._act_pinned.shape != a.shape or \
-                    self._act_pinned.numpy().dtype != a.dtype:
-                self._act_pinned = torch.from_numpy(a.copy()).pin_memory()
-                self._act_dev = torch.empty_like(self._act_pinned, device=self.device)
-            self._act_pinned.numpy()[...] = a
-            self._act_dev.copy_(self._act_pinned, non_blocking=True)
+            tdt = torch.float32 if a.ndim == 3 else torch.int32
+            if self._act_dev is None or tuple(self._act_dev.shape) != a.shape or self._act_dev.dtype != tdt:
+                self._act_dev = torch.empty(a.shape, dtype=tdt, device=self.device)
+                self._act_pinned = None
+            src = torch.from_numpy(a) if (a.flags.writeable and self.numpy_outputs) else None
+            if src is not None and src.is_pinned():
+                # the caller's array already lives in page-locked memory: DMA straight from it. With numpy_outputs the
+                # stream is synchronised before `step` returns, so the caller cannot overwrite it too early.
+                self._act_dev.copy_(src, non_blocking=True)
+                self._act_src_keepalive = src
+            else:
+                if self._act_pinned is None:
+                    self._act_pinned = torch.empty(a.shape, dtype=self._act_dev.dtype).pin_memory()
+                    self._act_evt = torch.cuda.Event()
+                else:
+                    self._act_evt.synchronize()      # the previous step's H2D copy has left the staging buffer
+                self._act_pinned.numpy()[...] = a
+                self._act_dev.copy_(self._act_pinned, non_blocking=True)
+                self._act_evt.record(torch.cuda.current_stream(self.device))
             t = self._act_dev
         else:
             t = actions
@@ -272,6 +285,21 @@ class B200GraphVecEnv:
     def emit_only(self):
         """Relaunch the graph-emission kernel alone (measurement hook; rewrites node_obs / adj with the same values)."""
         _lib.check(self.lib.lsm_emit_only(self._h, self._stream()), 'lsm_emit_only')
+
+    def debug_timeline(self, arm: bool = True):
+        """Diagnostics: read the per-kernel %globaltimer timeline of the launches since the last arm (dict of ns relative
+        to the first kernel's start, or None when nothing was armed), then re-arm / disarm."""
+        out = (C.c_uint64 * 7)()
+        had = getattr(self, '_tl_armed', False)
+        _lib.check(self.lib.lsm_debug_timeline(self._h, int(bool(arm)), out if had else None), 'lsm_debug_timeline')
+        self._tl_armed = bool(arm)
+        if not had:
+            return None
+        names = ('pair_start', 'pair_body_end', 'agent_start', 'agent_end', 'emit_start', 'emit_end', 'pair_end')
+        v = {k: int(out[j]) for j, k in enumerate(names)}
+        starts = [v[k] for k in ('pair_start', 'agent_start', 'emit_start') if v[k] != 2 ** 64 - 1]
+        t0 = min(starts) if starts else 0
+        return {k: (None if x in (0, 2 ** 64 - 1) else (x - t0)) for k, x in v.items()}
 
     def step_async(self, actions, num_current_episode=None):
         self._pending_actions = actions
