@@ -24,11 +24,13 @@ def needs_build() -> bool:
     return any(os.path.getmtime(p) > t for p in DEPS)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = LIB_PATH) -> str:
+    """`extra_flags` / `out_path` build an A/B variant (e.g. -DLSM_EARLY_LOADS) next to the product library; a variant
+    is selected at run time with LSM_LIB=<path> (experiments only)."""
+    if not force and not needs_build() and out_path == LIB_PATH:
         return LIB_PATH
     nvcc = os.environ.get('NVCC', 'nvcc')
-    cmd = [nvcc] + NVCC_FLAGS + (['-Xptxas', '-v'] if verbose else []) + ['-o', LIB_PATH] + SOURCES
+    cmd = [nvcc] + NVCC_FLAGS + list(extra_flags) + (['-Xptxas', '-v'] if verbose else []) + ['-o', out_path] + SOURCES
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + proc.stdout)

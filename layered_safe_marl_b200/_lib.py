@@ -67,7 +67,10 @@ def load():
     if _lib is not None:
         return _lib
     path = _build.LIB_PATH
-    if _build.needs_build():
+    alt = os.environ.get('LSM_LIB')     # experiments: an A/B build of the same sources (see _build.build)
+    if alt:
+        path = alt
+    elif _build.needs_build():
         try:
             _build.build()
         except Exception as exc:  # no nvcc on the box and no prebuilt library: fail loudly

@@ -53,6 +53,8 @@ struct lsm_handle {
     unsigned char* d_emit_rec = nullptr;
     unsigned long long* d_timeline = nullptr;   // diagnostics only (lsm_debug_timeline)
     float* d_vpacked = nullptr;          // corner-packed copy of the value grid (GridDev::packed)
+    float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
+    int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel
 };
 
 extern "C" {
@@ -171,11 +173,20 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     // the specialised pipeline emits the 'relative' node features every shipped script uses; 'global' runs the generic kernel
     h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) &&
               !(force_generic != nullptr && force_generic[0] == '1');
+    // where the next step's HJ pair values are computed (measured): in lsm_pair_kernel behind the emit kernel
+    // ("late": best or equal-best at every benchmarked size); LSM_PAIR=late|emit|front overrides (experiments)
+    h->pair_placement = 0;
+    if (const char* pp = std::getenv("LSM_PAIR")) {
+        if (!std::strcmp(pp, "late")) h->pair_placement = 0;
+        else if (!std::strcmp(pp, "emit")) h->pair_placement = 1;
+        else if (!std::strcmp(pp, "front")) h->pair_placement = 2;
+    }
     const char* fe = std::getenv("LSM_EPW");
     h->forced_epw = fe ? std::atoi(fe) : 0;
     if (h->spec) {
         h->bytes_per_env = h->geo.rec_bytes + h->geo.scratch_bytes;
-        // agent kernel: one lane per agent, 32/G envs per warp (LSM_EPW overrides for experiments)
+        // agent kernel: one lane per agent, 32/N envs per warp (LSM_EPW overrides for experiments)
+        h->epw_max = 32 / N; kp.EPW = h->epw_max;
         if (h->forced_epw >= 1 && h->forced_epw <= h->epw_max) kp.EPW = h->forced_epw;
         int wpb = h->geo.agent_block / 32;
         while (wpb > 1 && h->bytes_per_env * kp.EPW * wpb > h->smem_optin) --wpb;
@@ -253,6 +264,7 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_emit_rec) cudaFree(h->d_emit_rec);
     if (h->d_timeline) cudaFree(h->d_timeline);
     if (h->d_vpacked) cudaFree(h->d_vpacked);
+    if (h->d_grads8) cudaFree(h->d_grads8);
     delete h;
     return 0;
 }
@@ -292,14 +304,25 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     if (h->spec && std::getenv("LSM_NO_PACKED") == nullptr) {
         const char* mx = std::getenv("LSM_PACKED_MAX_MB");
         const size_t max_bytes = (size_t)(mx ? std::atoll(mx) : 2048) << 20;
-        const size_t bytes = cells * ((size_t)1 << g->ndim) * sizeof(float);
-        if (bytes <= max_bytes && cells * ((size_t)1 << g->ndim) / 4 < (size_t)0x7fffffff) {
+        size_t pcells = 1;      // n slots on periodic dims, n + 1 on the others (see lsm_pack_grid_kernel)
+        for (int k = 0; k < g->ndim; ++k) pcells *= (size_t)(g->periodic[k] ? g->shape[k] : g->shape[k] + 1);
+        const size_t bytes = pcells * ((size_t)1 << g->ndim) * sizeof(float);
+        if (bytes <= max_bytes && pcells < (size_t)0x7fffffff) {
             cudaError_t e = cudaMalloc(&h->d_vpacked, bytes);
-            if (e == cudaSuccess) e = lsm::pack_grid_launch(h->kp.vg, h->d_vpacked, (long long)cells);
+            if (e == cudaSuccess) e = lsm::pack_grid_launch(h->kp.vg, h->d_vpacked, (long long)pcells);
             if (e == cudaSuccess) e = cudaDeviceSynchronize();
             if (e != cudaSuccess) return cuda_fail(e, "lsm_set_value_grid: corner-packed table");
             h->kp.vg.packed = h->d_vpacked;
         }
+    }
+    if (h->d_grads8) { cudaFree(h->d_grads8); h->d_grads8 = nullptr; }
+    h->kp.vg.grads8 = nullptr;
+    if (h->spec && g->ndim == 5 && std::getenv("LSM_NO_PACKED") == nullptr) {
+        cudaError_t e = cudaMalloc(&h->d_grads8, cells * 8 * sizeof(float));
+        if (e == cudaSuccess) e = lsm::pad_grads_launch(g->grads, h->d_grads8, (long long)cells);
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) return cuda_fail(e, "lsm_set_value_grid: padded gradient rows");
+        h->kp.vg.grads8 = h->d_grads8;
     }
     return 0;
 }
@@ -348,13 +371,16 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     out->emit_block_threads = h->spec ? h->geo.emit_threads : 0;
     out->emit_smem_bytes_per_block = h->spec ? h->geo.emit_smem : 0;
     out->emit_regs_per_thread = h->emit_regs; out->emit_blocks_per_sm = h->emit_blocks_per_sm;
-    if (h->spec) {   // the grid lsm_step launches (room left for the pair kernel when the filter is on)
-        int bps = 0;
-        const bool pair_path = (h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg;
-        if (lsm::spec_emit_blocks_per_sm(h->kp.c.dynamics, h->kp.N, h->kp.L, pair_path, &bps) == cudaSuccess) out->emit_blocks_per_sm = bps;
+    const bool pair_path_li = h->spec && (h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg;
+    if (h->spec) {   // the emit kernel / grid lsm_step launches (room left for the pair kernel with placement "late")
+        int bps = 0, regs = 0;
+        if (lsm::spec_emit_blocks_per_sm(h->kp.c.dynamics, h->kp.N, h->kp.L, pair_path_li && h->pair_placement == 0,
+                                         pair_path_li && h->pair_placement == 1, &bps, &regs) == cudaSuccess) {
+            out->emit_blocks_per_sm = bps; out->emit_regs_per_thread = regs;
+        }
     }
     out->pair_regs_per_thread = h->pair_regs;
-    out->launches_per_step = h->spec ? (((h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg) ? 3 : 2) : 1;   // agent, emit, pair (filter on)
+    out->launches_per_step = h->spec ? ((pair_path_li && h->pair_placement != 1) ? 3 : 2) : 1;   // agent, emit [, pair]
     out->emit_record_bytes = h->spec ? h->geo.rec_bytes : 0;
     return 0;
 }
@@ -380,12 +406,12 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     kp.pairval = nullptr;
     kp.pair_late = 0;
     const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
-    const bool pair_up_front = (kp.debug & 32) != 0;   // experiments: K_a in front of the agent kernel on every step
+    const int placement = (kp.debug & 32) ? 2 : h->pair_placement;   // LSM_DEBUG 32: K_a in front of the agent kernel on every step
     if (pair_path && mode == lsm::MODE_STEP) {
         // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
-        // pair kernel launched behind the previous emit kernel; recomputed here when the state was edited in between
+        // previous launch (emit kernel / late pair kernel); recomputed here when the state was edited in between
         kp.pairval = h->d_pairval;
-        if (!h->pairval_valid || pair_up_front) {
+        if (!h->pairval_valid || placement == 2) {
             e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
             if (e != cudaSuccess) return cuda_fail(e, who);
         }
@@ -395,13 +421,18 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
                            persist, h->persist_bytes);
     if (e != cudaSuccess) return cuda_fail(e, who);
     if (h->spec) {
+        const bool was_valid = h->pairval_valid;
         h->pairval_valid = false;
         if (!(kp.debug & 1)) {
-            // K_c: graph observation (persistent blocks)
-            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes, pair_path && !pair_up_front);
+            // K_c: graph observation (persistent blocks) [+ the next step's pair values, placement 1]
+            const bool pie = pair_path && placement == 1;
+            kp.pairval = pie ? h->d_pairval : nullptr;
+            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes, pair_path && placement == 0, pie);
             if (e != cudaSuccess) return cuda_fail(e, who);
+            // a masked reset refreshes only the masked environments: the others keep what they had
+            if (pie) h->pairval_valid = env_mask == nullptr ? true : (was_valid && mode != lsm::MODE_STEP);
         }
-        if (pair_path && !pair_up_front) {
+        if (pair_path && placement == 0) {
             // K_a for the NEXT step, beside the emit kernel's drain (see lsm_pair_kernel)
             kp.pairval = h->d_pairval;
             kp.pair_late = (kp.debug & 1) ? 0 : 1;
@@ -469,9 +500,12 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     lsm::KParams kp = h->kp;
     kp.mode = lsm::MODE_OBSERVE; kp.env_mask = nullptr;
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
-    kp.pairval = nullptr; kp.pair_late = 0;
-    const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & (2 | 32));
-    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, nullptr, 0, pair_path);   // same grid as inside lsm_step
+    kp.pair_late = 0;
+    const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 2);
+    const int placement = (kp.debug & 32) ? 2 : h->pair_placement;
+    const bool pie = pair_path && placement == 1;     // the same kernel, grid and work as inside lsm_step
+    kp.pairval = pie ? h->d_pairval : nullptr;
+    cudaError_t e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, nullptr, 0, pair_path && placement == 0, pie);
     if (e != cudaSuccess) return cuda_fail(e, "lsm_emit_only");
     return 0;
 }

@@ -36,6 +36,9 @@ struct GridDev {
     // slowest; upper index = lower + 1, wrapped on periodic dims, clamped at the last node otherwise). One lookup reads
     // one 64-byte (4-D) / 128-byte (5-D) aligned chunk instead of 2^ndim scattered words. NULL = not built.
     const float* packed;
+    // 5-D grids: gradient rows padded from 5 to 8 floats (library-owned copy) so that one corner is two 16-byte loads
+    // instead of five scalar ones. NULL = not built (4-D rows are one float4 already).
+    const float* grads8;
 };
 
 // per-env shared-memory block: element offsets (in bytes from the env block base)

@@ -18,9 +18,10 @@ cudaError_t upload_magnetic_tables(const double* cos_tab, const double* sin_tab)
 cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int block_threads, int smem_bytes,
                           cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
 cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
-cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair);
-cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, int* out);
+cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair, bool pie);
+cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, bool pie, int* out, int* regs);
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells);
+cudaError_t pad_grads_launch(const float* grads, float* grads8, long long cells);
 cudaError_t edge_list_launch(const float* adj, int32_t* counts, long long* offsets, long long* edge_index, float* edge_attr,
                              long long num_graphs, int E, long long capacity, cudaStream_t stream);
 }  // namespace lsm

@@ -196,6 +196,12 @@ __device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32
             const float4 v = ldg_hint(reinterpret_cast<const float4*>(g.grads) + lin, keep);
             out[0] = out[0] + weight * (double)v.x; out[1] = out[1] + weight * (double)v.y;
             out[2] = out[2] + weight * (double)v.z; out[3] = out[3] + weight * (double)v.w;
+        } else if (ND == 5 && g.grads8 != nullptr) {
+            const float4 a = ldg_hint(reinterpret_cast<const float4*>(g.grads8) + 2 * (size_t)lin, keep);
+            const float4 b = ldg_hint(reinterpret_cast<const float4*>(g.grads8) + 2 * (size_t)lin + 1, keep);
+            out[0] = out[0] + weight * (double)a.x; out[1] = out[1] + weight * (double)a.y;
+            out[2] = out[2] + weight * (double)a.z; out[3] = out[3] + weight * (double)a.w;
+            out[ND - 1] = out[ND - 1] + weight * (double)b.x;
         } else {
 #pragma unroll
             for (int d = 0; d < ND; ++d) out[d] = out[d] + weight * (double)ldg_hint(g.grads + lin * ND + d, keep);
@@ -203,7 +209,15 @@ __device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32
     }
 }
 
+__global__ void __launch_bounds__(256) lsm_pad_grads_kernel(const float* __restrict__ grads, float* __restrict__ grads8, long long cells) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cells * 8) return;
+    const long long cell = t >> 3; const int d = (int)(t & 7);
+    grads8[t] = d < 5 ? grads[cell * 5 + d] : 0.0f;
+}
+
 struct LeanGrad {
+    static constexpr bool kRotRel = true;     // relative_state_rot, like pair_value_raw below
     template <int ND>
     __device__ __forceinline__ static void eval(const GridDev& g, const double (&rel)[ND], double (&out)[ND]) {
         Stencil32<ND> st;
@@ -214,9 +228,12 @@ struct LeanGrad {
 
 // ---------------------------------------------------------------------------------------------
 // corner-packed table (GridDev::packed): builder + lookup. The lookup reproduces stencil32_setup + stencil32_value
-// bit for bit (same positions, weights, corner order, sequential adds); positions whose lower index falls outside
-// [0, n-1] on a non-periodic dim (the declared clamp region) take the scattered path instead.
+// bit for bit (same positions, weights, corner order, sequential adds), including the declared index clamp outside
+// the box; only NaN positions take the scattered path.
 // ---------------------------------------------------------------------------------------------
+// Table extent per dim: n on periodic dims; n + 1 on the others, slot c standing for the index pair
+// (max(c - 1, 0), min(c, n - 1)) - slot 0 is the "both clamped to node 0" pair the declared out-of-box behaviour needs,
+// slot n the "both clamped to node n - 1" pair - so every finite position is served by one chunk.
 template <int ND>
 __global__ void __launch_bounds__(256) lsm_pack_grid_kernel(const float* __restrict__ values, float* __restrict__ packed,
                                                           GridDev g, long long cells) {
@@ -228,15 +245,18 @@ __global__ void __launch_bounds__(256) lsm_pack_grid_kernel(const float* __restr
 #pragma unroll
     for (int d = ND - 1; d >= 0; --d) {
         const int n = g.shape[d];
-        const int il = (int)(rem % n); rem /= n;
-        int ih = il + 1;
-        if (g.periodic[d]) { if (ih >= n) ih -= n; } else if (ih > n - 1) ih = n - 1;
+        const int ext = g.periodic[d] ? n : n + 1;
+        const int c = (int)(rem % ext); rem /= ext;
+        int il, ih;
+        if (g.periodic[d]) { il = c; ih = c + 1 >= n ? c + 1 - n : c + 1; }
+        else { il = c - 1 < 0 ? 0 : c - 1; ih = c > n - 1 ? n - 1 : c; }
         lin += (long long)(((corner >> (ND - 1 - d)) & 1) ? ih : il) * mul;
         mul *= n;
     }
     packed[t] = values[lin];
 }
 
+// reproduces stencil32_setup + stencil32_value bit for bit; false only for NaN positions
 template <int ND>
 __device__ __forceinline__ bool packed_value(const GridDev& g, const double (&x)[ND], double& out) {
     constexpr int NC = 1 << ND;
@@ -245,28 +265,29 @@ __device__ __forceinline__ bool packed_value(const GridDev& g, const double (&x)
     int cell = 0, mul = 1;
 #pragma unroll
     for (int d = ND - 1; d >= 0; --d) {
-        const double pos = div_exact(x[d] - g.lo[d], g.spacing[d], g.inv_spacing[d]);
+        double pos = div_exact(x[d] - g.lo[d], g.spacing[d], g.inv_spacing[d]);
+        if (isnan(pos)) ok = false;
+        if (!(fabs(pos) <= 1.0e9)) pos = pos < 0.0 ? -1.0e9 : 1.0e9;     // declared clamp, as in stencil32_setup
         const double fl = floor(pos);
         const double w = pos - fl;
         wlo[d] = 1.0 - w; whi[d] = w;
         const int n = g.shape[d];
-        // NaN / out-of-box positions fail these comparisons and go to the scattered path
         if (g.periodic[d]) {
-            if (!(fabs(pos) <= 1.0e9)) ok = false;
             int il = (int)fl % n; if (il < 0) il += n;
-            cell += il * mul;
+            cell += il * mul; mul *= n;
         } else {
-            if (!(fl >= 0.0 && fl <= (double)(n - 1))) ok = false;
-            cell += (int)fl * mul;
+            const int c = min(max((int)fl, -1), n - 1) + 1;
+            cell += c * mul; mul *= n + 1;
         }
-        mul *= n;
     }
     if (!ok) return false;
     const float4* src = reinterpret_cast<const float4*>(g.packed) + (size_t)cell * (NC / 4);
-    float4 q[NC / 4];
+    float v[NC];
 #pragma unroll
-    for (int k = 0; k < NC / 4; ++k) q[k] = __ldg(src + k);
-    const float* v = reinterpret_cast<const float*>(q);
+    for (int k = 0; k < NC / 4; ++k) {
+        const float4 q = __ldg(src + k);
+        v[4 * k] = q.x; v[4 * k + 1] = q.y; v[4 * k + 2] = q.z; v[4 * k + 3] = q.w;
+    }
     double acc = 0.0;
 #pragma unroll
     for (int corner = 0; corner < NC; ++corner) {
@@ -299,7 +320,7 @@ __device__ __forceinline__ double pair_value_raw(const GridDev& vg, double ex, d
     // safety_filter.py:192-201, 345-354
     constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
     double rel[ND];
-    relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+    relative_state_rot<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
     if (vg.packed != nullptr) {
         double v;
         if (packed_value<ND>(vg, rel, v)) return isnan(v) ? INFINITY : v;
@@ -331,9 +352,10 @@ __global__ void __launch_bounds__(kPairThreads) lsm_pair_kernel(const __grid_con
     if (!kp.pair_late) pdl_wait();
     tl_start(kp.timeline, TL_PAIR_START);
     const long long n = kp.b.num_envs;
-    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    // grid-stride: the late placement runs a bounded number of blocks per SM (lsm_kernels.cu) so that these fp64-heavy
+    // warps take a fixed share of the issue slots next to the emit kernel's producers
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * (N * N); t += (long long)gridDim.x * blockDim.x)
     [&] {
-        if (t >= n * (N * N)) return;
         const int env = (int)(t / (N * N)), r = (int)(t - (long long)env * (N * N));
         const int i = r / N, j = r - i * N;
         if (i == j) return;
@@ -386,9 +408,11 @@ __device__ __forceinline__ void emit_obs_row(const EmitRec<DYN, N, L>& R, const 
         o[4] = (float)P.lsin[g]; o[5] = (float)P.lcos[g]; o[6] = (float)P.lsp[g];
     } else {
         double rx, ry; rotate_into(gp.x - x, gp.y - y, R.air.cth[ai], R.air.sth[ai], rx, ry);
-        const double rh = P.lh[g] - s2;
+        // sin / cos(goal heading - theta) by the angle-difference identity over the tabulated landmark and own sin / cos
+        // (<= 1e-15 from the reference expression, like the node features)
+        const double ci = R.air.cth[ai], si = R.air.sth[ai];
         o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-        o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)P.lsp[g];
+        o[3] = (float)(P.lsin[g] * ci - P.lcos[g] * si); o[4] = (float)(P.lcos[g] * ci + P.lsin[g] * si); o[5] = (float)P.lsp[g];
     }
 }
 
@@ -549,9 +573,12 @@ __device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, 
         const double dx = x - pa.x, dy = y - pa.y;
         const double rd = sqrt(dx * dx + dy * dy);
         const double closeness = 1.0 - clipd((rd - sep) / (eng - sep), 0.0, 1.0);
-        const double dir = atan2(ry, rx);
+        // unit vector towards the other agent: (cos, sin)(atan2(ry, rx)) == (rx, ry) / |r| to ~1e-16 (reward tolerance
+        // 1e-5); atan2(0, 0) = 0 for coincident agents. Three libm calls per flagged neighbour were 31 % of this kernel's
+        // instructions in the airtaxi benchmark (profiles/r01_v7_*).
+        const double cdir = rd > 0.0 ? rx / rd : 1.0, sdir = rd > 0.0 ? ry / rd : 0.0;
         const double2 va = R.vel[(a < ai ? N : 0) + a];
-        double change = cos(dir) * (va.x - vpx) + sin(dir) * (va.y - vpy);
+        double change = cdir * (va.x - vpx) + sdir * (va.y - vpy);
         change = fabs(pymin(0.0, change));
         pc_pen += change * closeness;
     }
@@ -587,14 +614,14 @@ __device__ __noinline__ bool goal_reached_cold(double x, double y, double s2, do
 }
 
 // ---------------------------------------------------------------------------------------------
-// K_b: per-agent physics. A warp owns EPW consecutive environments, G = next_pow2(N) lanes each.
+// K_b: per-agent physics. A warp owns EPW <= 32 / N consecutive environments, N lanes each.
 // ---------------------------------------------------------------------------------------------
 template <int DYN, int N, int L, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_constant__ KParams kp) {
     using REC = EmitRec<DYN, N, L>;
     using SCR = AgentScratch<DYN, N, L>;
     constexpr int M = REC::M, E = REC::E;
-    constexpr int G = Pow2<N>::value;
+    constexpr int G = N;                          // lanes per environment: 32 / N environments per warp, no padding lanes
     constexpr int Dobs = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const lsm_config& c = kp.c;
@@ -644,6 +671,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             const double* afp = kp.b.agent_f64 + a;
             prefetch_l2(afp + LSM_AF_TIMES_REQ_A * fstride); prefetch_l2(afp + LSM_AF_TIMES_REQ_B * fstride);
             prefetch_l2(afp + LSM_AF_DISTS_GOAL_A * fstride); prefetch_l2(afp + LSM_AF_DISTS_GOAL_B * fstride);
+            if (kp.mode == MODE_STEP) {   // read late (load_motion / load_bookkeeping)
+                prefetch_l2(afp + LSM_AF_P_DIST * fstride); prefetch_l2(afp + LSM_AF_STATE_TIME * fstride);
+                prefetch_l2(afp + LSM_AF_GOAL_MIN_TIME * fstride); prefetch_l2(afp + LSM_AF_DIST_LEFT * fstride);
+                prefetch_l2(afp + LSM_AF_EP_TRAVEL_DIST * fstride); prefetch_l2(afp + LSM_AF_EP_MIN_DIST * fstride);
+                const int* aipp = kp.b.agent_i32 + a;
+                prefetch_l2(aipp + LSM_AI_NUM_COLLISIONS * fstride); prefetch_l2(aipp + LSM_AI_EP_TRAVEL_LEN * fstride);
+                prefetch_l2(aipp + LSM_AI_EP_CONFLICT * fstride); prefetch_l2(aipp + LSM_AI_EP_MULTI * fstride);
+                prefetch_l2(aipp + LSM_AI_EP_DONE * fstride);
+            }
         }
         {
             const size_t lstride = (size_t)n * M;
@@ -672,18 +708,30 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
         }
         if (agent_on) {
             x = af[LSM_AF_X * fstride]; y = af[LSM_AF_Y * fstride]; s2 = af[LSM_AF_S2 * fstride]; s3 = af[LSM_AF_S3 * fstride];
-            p_dist = af[LSM_AF_P_DIST * fstride]; state_time = af[LSM_AF_STATE_TIME * fstride];
-            min_rel = af[LSM_AF_MIN_REL_DIST * fstride]; goal_min_time = af[LSM_AF_GOAL_MIN_TIME * fstride];
-            times_req = af[(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) * fstride];
-            dists_goal = af[(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) * fstride];
-            dist_left = af[LSM_AF_DIST_LEFT * fstride]; ep_travel_dist = af[LSM_AF_EP_TRAVEL_DIST * fstride];
-            ep_min_dist = af[LSM_AF_EP_MIN_DIST * fstride]; action_diff = af[LSM_AF_ACTION_DIFF * fstride];
             reached = aip[LSM_AI_REACHED * fstride]; done = aip[LSM_AI_DONE * fstride];
             safety_filtered = aip[LSM_AI_SAFETY_FILTERED * fstride]; deconflict = aip[LSM_AI_DECONFLICT_IDX * fstride];
-            ncoll = aip[LSM_AI_NUM_COLLISIONS * fstride]; ep_len = aip[LSM_AI_EP_TRAVEL_LEN * fstride];
-            ep_conflict = aip[LSM_AI_EP_CONFLICT * fstride]; ep_multi = aip[LSM_AI_EP_MULTI * fstride];
-            ep_done = aip[LSM_AI_EP_DONE * fstride];
         }
+        // Bookkeeping state is loaded where it is first needed (L2 hits after the prefetch above) instead of being
+        // carried in registers through the filter / dynamics phase, whose register peak decides the occupancy.
+#define LSM_LOAD_MOTION()  /* before the dynamics */ \
+        if (agent_on) { p_dist = af[LSM_AF_P_DIST * fstride]; state_time = af[LSM_AF_STATE_TIME * fstride]; }
+#define LSM_LOAD_BOOKKEEPING(STEP_MODE)  /* a step always overwrites min_rel / action_diff */ \
+        if (agent_on) { \
+            if (!(STEP_MODE)) { min_rel = af[LSM_AF_MIN_REL_DIST * fstride]; action_diff = af[LSM_AF_ACTION_DIFF * fstride]; } \
+            goal_min_time = af[LSM_AF_GOAL_MIN_TIME * fstride]; \
+            times_req = af[(parity ? LSM_AF_TIMES_REQ_B : LSM_AF_TIMES_REQ_A) * fstride]; \
+            dists_goal = af[(parity ? LSM_AF_DISTS_GOAL_B : LSM_AF_DISTS_GOAL_A) * fstride]; \
+            dist_left = af[LSM_AF_DIST_LEFT * fstride]; ep_travel_dist = af[LSM_AF_EP_TRAVEL_DIST * fstride]; \
+            ep_min_dist = af[LSM_AF_EP_MIN_DIST * fstride]; \
+            ncoll = aip[LSM_AI_NUM_COLLISIONS * fstride]; ep_len = aip[LSM_AI_EP_TRAVEL_LEN * fstride]; \
+            ep_conflict = aip[LSM_AI_EP_CONFLICT * fstride]; ep_multi = aip[LSM_AI_EP_MULTI * fstride]; \
+            ep_done = aip[LSM_AI_EP_DONE * fstride]; \
+        }
+#ifdef LSM_EARLY_LOADS   /* A/B build: everything loaded up front, like the first pipeline */
+        { LSM_LOAD_MOTION() LSM_LOAD_BOOKKEEPING(false) }
+#else
+        if (kp.mode != MODE_STEP) { LSM_LOAD_MOTION() LSM_LOAD_BOOKKEEPING(false) }
+#endif
         // landmark tables of the group's environments: contiguous runs per field
         {
             const int total = nenv * M;
@@ -731,6 +779,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             }
             __syncwarp();
             double safe0 = raw0, safe1 = raw1;
+#ifndef LSM_EARLY_LOADS
+            LSM_LOAD_MOTION()
+#endif
             for (int it = 0; it < c.num_internal_step; ++it) {
                 // HJ values of (ego, other): from lsm_pair_kernel for the states this launch started with, in-kernel
                 // for later internal steps
@@ -819,7 +870,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                         if (use_filter_arg) rew -= 1.0; else rew -= 1.0 * q.sloped;
                     } else {
                         double rpx, rpy;
-                        rotate_into(x - gx, y - gy, cos(gh), sin(gh), rpx, rpy);
+                        rotate_into(x - gx, y - gy, P.lcos[goal_pre], P.lsin[goal_pre], rpx, rpy);   // tabulated cos / sin(gh)
                         const double rs[4] = { rpx, rpy, theta - gh, speed };
                         Stencil32<4> st;
                         stencil32_setup<4>(kp.tg, rs, st);
@@ -853,6 +904,9 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 s2 = s2q; s3 = s3q;
             }
             __syncwarp();
+#ifndef LSM_EARLY_LOADS
+            LSM_LOAD_BOOKKEEPING(true)
+#endif
             if (agent_on) {
                 // one pass over the other agents: min distance, collisions, episode statistics, proximity rewards.
                 // Agent a is seen after its own update if a < i (rewards) / a <= i (statistics), else before.
@@ -1128,7 +1182,10 @@ struct __align__(16) EmitShared {
     unsigned disc[2][GEO::W], keepm[N * GEO::W];
 };
 
-template <int DYN, int N, int L, int WPE, int MINB>
+// PIE ("pair in emit"): also compute the next step's HJ pair values per environment after its copies are issued - the
+// placement that wins for few agents (one launch less; the lookups of an 8-agent environment occupy half a block once).
+// For many agents the per-block chain gets long and lsm_pair_kernel behind this kernel is faster (see lsm_capi.cu).
+template <int DYN, int N, int L, int WPE, int MINB, bool PIE = false>
 __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_constant__ KParams kp) {
     using ES = EmitShared<DYN, N, L, WPE>;
     using REC = EmitRec<DYN, N, L>;
@@ -1370,20 +1427,12 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             if (GEO::NODE_BULK || adj_bulk) bulk_store_fence();
             __syncthreads();
             if (tid == 0) {
-                if (debug & 4096) {      // experiments: no eviction-priority hint on the stream
-                    if (adj_bulk && !adj_sent && !(debug & 8)) {
+                const unsigned long long stream_pol = l2_evict_first();
+                if (adj_bulk && !adj_sent && !(debug & 8)) {
 #pragma unroll 1
-                        for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u);
-                    }
-                    if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u);
-                } else {
-                    const unsigned long long stream_pol = l2_evict_first();
-                    if (adj_bulk && !adj_sent && !(debug & 8)) {
-#pragma unroll 1
-                        for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u, stream_pol);
-                    }
-                    if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
+                    for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u, stream_pol);
                 }
+                if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
                 bulk_store_commit();
             }
             adj_sent = true;
@@ -1396,6 +1445,26 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
                     for (int q = tid; q < nfl; q += T) __stcs(nbase + r0 * F + q, buf[q]);
                 }
                 __syncthreads();
+            }
+        }
+        // (e) PIE: HJ values of every ordered agent pair for the NEXT step (safety_filter.py:192-201, 345-354): they depend
+        //     only on the state this step leaves behind; the lookups overlap this environment's copies draining to HBM.
+        if constexpr (PIE) {
+            if (kp.pairval != nullptr && R.next_filter) {
+                double* pv = kp.pairval + (size_t)ee * (N * N);
+                for (int t = tid; t < N * N; t += T) {
+                    const int i = t / N, j = t - i * N;
+                    if (i == j || R.done[1][i] || R.done[1][j]) continue;
+                    const double2 pi = R.pos[i], pj = R.pos[j];
+                    double i2, i3, j2, j3;
+                    if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                        const double2 vi = R.vel[N + i], vj = R.vel[N + j];
+                        i2 = vi.x; i3 = vi.y; j2 = vj.x; j3 = vj.y;
+                    } else {
+                        i2 = R.air.theta[i]; i3 = R.air.spd_post[i]; j2 = R.air.theta[j]; j3 = R.air.spd_post[j];
+                    }
+                    pv[t] = pair_value_raw<DYN>(kp.vg, pi.x, pi.y, i2, i3, pj.x, pj.y, j2, j3);
+                }
             }
         }
     }

@@ -35,6 +35,8 @@ namespace lsm {
 constexpr int kAgentBlock = 128;
 constexpr int kAgentMinB = 2;
 constexpr int kPairBlock = kPairThreads;
+constexpr int kPairResident = 2;          // SM room the emit grid leaves for pair blocks (placement "late")
+constexpr int kPairLateBlocksPerSm = 8;   // grid bound of the late pair kernel (measured: >= 6 is best everywhere)
 
 // experiments: LSM_AGENT_MINB=3 trades ~100-400 B of spills for 12 instead of 8 resident physics warps per SM
 static int agent_minb() {
@@ -44,6 +46,7 @@ static int agent_minb() {
 
 struct SpecFns {
     const void* pair; const void* agent; const void* emit;
+    const void* emit_pie;     // emit kernel that also computes the next step's pair values (placement "emit")
     int rec_bytes, scratch_bytes, emit_smem, emit_threads;
 };
 
@@ -51,6 +54,7 @@ struct SpecFns {
 template <int WPE_, int EMINB_>
 static void cfg2_emit_variant(SpecFns* f) {
     f->emit = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_>;
+    f->emit_pie = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_, true>;
     f->emit_smem = (int)sizeof(EmitShared<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_>);
     f->emit_threads = 32 * WPE_;
 }
@@ -75,6 +79,7 @@ static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
         f->agent = agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, 3>          \
                                      : (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>; \
         f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
+        f->emit_pie = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_, true>;             \
         f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
         f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \
         f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, WPE_>);                               \
@@ -122,6 +127,7 @@ cudaError_t spec_prepare_aux(int dynamics, int N, int L, int* emit_regs, int* em
     if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
     cudaError_t e = prepare_one(f.emit, f.emit_threads, f.emit_smem, emit_regs, emit_blocks_per_sm);
     if (e != cudaSuccess) return e;
+    { int r = 0, b = 0; e = prepare_one(f.emit_pie, f.emit_threads, f.emit_smem, &r, &b); if (e != cudaSuccess) return e; }
     int bps = 0;
     return prepare_one(f.pair, kPairBlock, 0, pair_regs, &bps);
 }
@@ -175,21 +181,29 @@ cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void*
     SpecFns f;
     if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
     const long long tasks = (long long)kp.b.num_envs * kp.N * kp.N;
-    const long long blocks = (tasks + kPairBlock - 1) / kPairBlock;
+    long long blocks = (tasks + kPairBlock - 1) / kPairBlock;
+    if (kp.pair_late) {
+        // beside the emit kernel: a bounded number of resident blocks per SM, each striding over the pairs
+        static int sm_count = 0;
+        if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+        int bps = kPairLateBlocksPerSm;
+        if (const char* g = std::getenv("LSM_PAIR_BPS")) { const int v = std::atoi(g); if (v >= 1) bps = v; }
+        if (blocks > (long long)sm_count * bps) blocks = (long long)sm_count * bps;
+    }
     return launch_one(f.pair, kp, (unsigned)blocks, kPairBlock, 0, stream, persist_ptr, persist_bytes, true);
 }
 
 // resident emit blocks per SM: what fits, minus (when the pair kernel runs beside the emit kernel) enough registers /
 // threads for kPairResident pair blocks per SM
-constexpr int kPairResident = 2;
-static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, int* out) {
+static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool pie, int* out) {
     int bps = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, f.emit, f.emit_threads, f.emit_smem);
+    const void* fn = pie ? f.emit_pie : f.emit;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, f.emit_threads, f.emit_smem);
     if (e != cudaSuccess) return e;
     if (bps < 1) return cudaErrorLaunchOutOfResources;
     if (reserve_pair) {
         cudaFuncAttributes fe, fp;
-        if ((e = cudaFuncGetAttributes(&fe, f.emit)) != cudaSuccess) return e;
+        if ((e = cudaFuncGetAttributes(&fe, fn)) != cudaSuccess) return e;
         if ((e = cudaFuncGetAttributes(&fp, f.pair)) != cudaSuccess) return e;
         auto block_regs = [](int regs, int threads) { return ((regs * 32 + 255) / 256 * 256) * ((threads + 31) / 32); };
         const int need_regs = kPairResident * block_regs(fp.numRegs, kPairBlock), need_thr = kPairResident * kPairBlock;
@@ -200,25 +214,31 @@ static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, int* 
     return cudaSuccess;
 }
 
-cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, int* out) {
+cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, bool pie, int* out, int* regs) {
     SpecFns f;
     if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
-    return emit_blocks_per_sm(f, reserve_pair, out);
+    if (regs != nullptr) {
+        cudaFuncAttributes fa;
+        cudaError_t e = cudaFuncGetAttributes(&fa, pie ? f.emit_pie : f.emit);
+        if (e != cudaSuccess) return e;
+        *regs = fa.numRegs;
+    }
+    return emit_blocks_per_sm(f, reserve_pair, pie, out);
 }
 
-cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair) {
+cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair, bool pie) {
     SpecFns f;
     if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
     // persistent blocks: as many as are resident at once, each loops over environments
     static int sm_count = 0;
     if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     int bps = 0;
-    cudaError_t e = emit_blocks_per_sm(f, reserve_pair, &bps);
+    cudaError_t e = emit_blocks_per_sm(f, reserve_pair, pie, &bps);
     if (e != cudaSuccess) return e;
     unsigned grid = (unsigned)sm_count * (unsigned)bps;
     if (grid > (unsigned)kp.b.num_envs) grid = (unsigned)kp.b.num_envs;
     if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
-    return launch_one(f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
+    return launch_one(pie ? f.emit_pie : f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
 }
 
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {
@@ -227,6 +247,11 @@ cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {
     if (g.ndim == 4) lsm_pack_grid_kernel<4><<<blocks, 256>>>(g.values, packed, g, cells);
     else if (g.ndim == 5) lsm_pack_grid_kernel<5><<<blocks, 256>>>(g.values, packed, g, cells);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t pad_grads_launch(const float* grads, float* grads8, long long cells) {
+    lsm_pad_grads_kernel<<<(unsigned)((cells * 8 + 255) / 256), 256>>>(grads, grads8, cells);
     return cudaGetLastError();
 }
 

@@ -51,6 +51,25 @@ __device__ __forceinline__ void relative_state(double ex, double ey, double e2, 
     }
 }
 
+// The same relative state with the airtaxi position written as a rotation into the ego frame:
+//   d cos(phi - theta_e) = dx cos(theta_e) + dy sin(theta_e),  d sin(phi - theta_e) = dy cos(theta_e) - dx sin(theta_e)
+// (phi = atan2(dy, dx), d = |(dx, dy)|) - equal to safety_filter.py:277-284 to ~1e-16 d, one sincos instead of
+// sqrt + atan2 + cos + sin per pair. Used by the specialised pipeline; the generic kernel keeps the literal form.
+template <int DYN>
+__device__ __forceinline__ void relative_state_rot(double ex, double ey, double e2, double e3, double ox, double oy,
+                                                   double o2, double o3, double (&r)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5]) {
+    if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+        r[0] = ex - ox; r[1] = ey - oy; r[2] = e2 - o2; r[3] = e3 - o3;
+    } else {
+        const double ddx = ox - ex, ddy = oy - ey;
+        double se, ce;
+        sincos(e2, &se, &ce);
+        r[0] = ddx * ce + ddy * se;
+        r[1] = ddy * ce - ddx * se;
+        r[2] = o2 - e2; r[3] = e3; r[4] = o3;
+    }
+}
+
 template <int DYN>
 __device__ __forceinline__ double hj_value(const KParams& kp, const Curriculum& q,
                                            const double (&rel)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5], bool& in_range) {
@@ -68,6 +87,7 @@ __device__ __forceinline__ double hj_value(const KParams& kp, const Curriculum& 
 // `kv` (first minimum of the HJ value) and the smallest distance are known: gradient lookup,
 // least-restrictive bang-bang or CBF-QP, control clipping, filtered flag.
 struct ClassicGrad {
+    static constexpr bool kRotRel = false;
     template <int ND>
     __device__ __forceinline__ static void eval(const GridDev& g, const double (&rel)[ND], double (&out)[ND]) {
         Stencil<ND> st;
@@ -87,7 +107,8 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
     if (best_d > c.coordination_range) return;
     if (!kv_in_range) return;
     double rel[ND];
-    relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+    if constexpr (GRAD::kRotRel) relative_state_rot<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+    else relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
     const double uref[4] = { raw0, raw1, oraw0, oraw1 };
     double g[ND];
     GRAD::template eval<ND>(kp.vg, rel, g);
