@@ -46,7 +46,8 @@ class LsmLaunchInfo(C.Structure):
                 ('blocks_per_sm', C.c_int32), ('sm_count', C.c_int32), ('specialised', C.c_int32),
                 ('emit_block_threads', C.c_int32), ('emit_smem_bytes_per_block', C.c_int32),
                 ('emit_regs_per_thread', C.c_int32), ('emit_blocks_per_sm', C.c_int32),
-                ('pair_regs_per_thread', C.c_int32), ('launches_per_step', C.c_int32), ('emit_record_bytes', C.c_int32)]
+                ('pair_regs_per_thread', C.c_int32), ('launches_per_step', C.c_int32), ('emit_record_bytes', C.c_int32),
+                ('chunks', C.c_int32), ('pair_placement', C.c_int32)]
 
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',

@@ -1,5 +1,6 @@
 // lsm_capi.cu - the extern "C" boundary declared in include/lsm_b200.h.
 // Host-only logic: validation, shared-memory layout, lookup tables, launch geometry.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -53,6 +54,12 @@ struct lsm_handle {
     unsigned char* d_emit_rec = nullptr;
     unsigned long long* d_timeline = nullptr;   // diagnostics only (lsm_debug_timeline)
     float* d_vpacked = nullptr;          // corner-packed copy of the value grid (GridDev::packed)
+    // chunked launches: big batches are split into `chunks` env ranges on library-owned streams so that the latency-bound
+    // agent kernel of one range runs beside the HBM-bound emit kernel of another (fork / join with events, no host sync)
+    int chunks = 1;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> ev_join;
+    cudaEvent_t ev_fork = nullptr;
     float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
     int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel
 };
@@ -265,6 +272,9 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_timeline) cudaFree(h->d_timeline);
     if (h->d_vpacked) cudaFree(h->d_vpacked);
     if (h->d_grads8) cudaFree(h->d_grads8);
+    for (cudaStream_t st : h->streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     delete h;
     return 0;
 }
@@ -345,6 +355,27 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
         return fail(2, "lsm_bind_buffers: adj and node_obs must be 16-byte aligned");
     h->kp.b = *b;
     h->have_buffers = true;
+    // chunked launches for big batches (measured on B200, DESIGN.md 3: 4 ranges pay off from ~0.4 GB of observations per
+    // step - 0.8 GB: -11 %, 10.7 GB: -9 % - while a 0.1 GB step is launch-latency bound and stays on the caller's stream:
+    // +26 % with 2 ranges). LSM_CHUNKS overrides.
+    {
+        const double step_bytes = (double)b->num_envs * 4.0 * h->kp.N * h->kp.E * (double)(h->kp.F + h->kp.E);
+        int want = step_bytes >= 4.0e8 ? 4 : 1;
+        if (const char* ce = std::getenv("LSM_CHUNKS")) { const int v = std::atoi(ce); if (v >= 1 && v <= 16) want = v; }
+        if (!h->spec) want = 1;
+        h->chunks = want;
+        while ((int)h->streams.size() < (want > 1 ? want : 0)) {
+            cudaStream_t st; cudaEvent_t ev;
+            cudaError_t e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "lsm_bind_buffers: chunk streams");
+            h->streams.push_back(st); h->ev_join.push_back(ev);
+        }
+        if (want > 1 && h->ev_fork == nullptr) {
+            cudaError_t e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "lsm_bind_buffers: chunk streams");
+        }
+    }
     if (h->spec) {
         // library-owned scratch between the launches of one step
         if (h->d_pairval) { cudaFree(h->d_pairval); h->d_pairval = nullptr; }
@@ -382,6 +413,12 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     out->pair_regs_per_thread = h->pair_regs;
     out->launches_per_step = h->spec ? ((pair_path_li && h->pair_placement != 1) ? 3 : 2) : 1;   // agent, emit [, pair]
     out->emit_record_bytes = h->spec ? h->geo.rec_bytes : 0;
+    {
+        const int K = (h->spec && h->chunks > 1 && ngroups >= 4LL * h->chunks * h->warps_per_block) ? h->chunks : 1;
+        out->chunks = K;
+        out->launches_per_step *= K;
+        out->pair_placement = pair_path_li ? h->pair_placement : -1;
+    }
     return 0;
 }
 
@@ -397,49 +434,78 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     kp.mode = mode; kp.flag = flag; kp.action_idx = action_idx; kp.action_onehot = action_onehot;
     kp.env_mask = env_mask; kp.episode = (long long)episode; kp.seed = (unsigned long long)seed;
     const long long ngroups = (kp.b.num_envs + kp.EPW - 1) / kp.EPW;
-    kp.ngroups = (int)ngroups;
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
-    long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
-    if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;   // generic kernel: persistent grid
     const void* persist = (h->l2_persist && mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
-    cudaError_t e;
-    kp.pairval = nullptr;
-    kp.pair_late = 0;
     const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;   // LSM_DEBUG 32: K_a in front of the agent kernel on every step
-    if (pair_path && mode == lsm::MODE_STEP) {
-        // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
-        // previous launch (emit kernel / late pair kernel); recomputed here when the state was edited in between
-        kp.pairval = h->d_pairval;
-        if (!h->pairval_valid || placement == 2) {
-            e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
-            if (e != cudaSuccess) return cuda_fail(e, who);
+    const bool was_valid = h->pairval_valid;
+
+    // the launches of one env-group range [g0, g1) on stream `s`
+    auto launch_range = [&](long long g0, long long g1, cudaStream_t s) -> cudaError_t {
+        lsm::KParams k = kp;
+        k.grp_begin = (int)g0; k.ngroups = (int)g1;
+        k.env_begin = (int)(g0 * kp.EPW);
+        k.env_end = (int)std::min<long long>(kp.b.num_envs, g1 * kp.EPW);
+        long long blocks = (g1 - g0 + h->warps_per_block - 1) / h->warps_per_block;
+        if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;   // generic kernel: persistent grid
+        cudaError_t e;
+        k.pairval = nullptr;
+        k.pair_late = 0;
+        if (pair_path && mode == lsm::MODE_STEP) {
+            // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
+            // previous launch (emit kernel / late pair kernel); recomputed here when the state was edited in between
+            k.pairval = h->d_pairval;
+            if (!was_valid || placement == 2) {
+                e = lsm::spec_launch_pair(k, s, persist, h->persist_bytes);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        // K_b (specialised: per-agent physics) or the fused generic kernel
+        e = lsm::kernel_launch(k, h->spec, (int)blocks, h->block_threads, h->smem_per_block, s, persist, h->persist_bytes);
+        if (e != cudaSuccess) return e;
+        if (h->spec) {
+            if (!(k.debug & 1)) {
+                // K_c: graph observation (persistent blocks) [+ the next step's pair values, placement 1]
+                const bool pie = pair_path && placement == 1;
+                k.pairval = pie ? h->d_pairval : nullptr;
+                e = lsm::spec_launch_emit(k, s, persist, h->persist_bytes, pair_path && placement == 0, pie);
+                if (e != cudaSuccess) return e;
+            }
+            if (pair_path && placement == 0) {
+                // K_a for the NEXT step, beside the emit kernel's drain (see lsm_pair_kernel)
+                k.pairval = h->d_pairval;
+                k.pair_late = (k.debug & 1) ? 0 : 1;
+                e = lsm::spec_launch_pair(k, s, persist, h->persist_bytes);
+                if (e != cudaSuccess) return e;
+            }
+        }
+        return cudaSuccess;
+    };
+
+    cudaError_t e = cudaSuccess;
+    const int K = (h->spec && h->chunks > 1 && ngroups >= 4LL * h->chunks * h->warps_per_block) ? h->chunks : 1;
+    if (K == 1) {
+        e = launch_range(0, ngroups, (cudaStream_t)stream);
+        if (e != cudaSuccess) return cuda_fail(e, who);
+    } else {
+        // fork: every library stream waits for the caller's stream; join: the caller's stream waits for every range
+        if ((e = cudaEventRecord(h->ev_fork, (cudaStream_t)stream)) != cudaSuccess) return cuda_fail(e, who);
+        const long long per = ((ngroups + K - 1) / K + h->warps_per_block - 1) / h->warps_per_block * h->warps_per_block;
+        for (int q = 0; q < K; ++q) {
+            const long long g0 = std::min<long long>(ngroups, per * q), g1 = std::min<long long>(ngroups, per * (q + 1));
+            if (g0 >= g1) continue;
+            if ((e = cudaStreamWaitEvent(h->streams[q], h->ev_fork, 0)) != cudaSuccess) return cuda_fail(e, who);
+            if ((e = launch_range(g0, g1, h->streams[q])) != cudaSuccess) return cuda_fail(e, who);
+            if ((e = cudaEventRecord(h->ev_join[q], h->streams[q])) != cudaSuccess) return cuda_fail(e, who);
+            if ((e = cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join[q], 0)) != cudaSuccess) return cuda_fail(e, who);
         }
     }
-    // K_b (specialised: per-agent physics) or the fused generic kernel
-    e = lsm::kernel_launch(kp, h->spec, (int)blocks, h->block_threads, h->smem_per_block, (cudaStream_t)stream,
-                           persist, h->persist_bytes);
-    if (e != cudaSuccess) return cuda_fail(e, who);
     if (h->spec) {
-        const bool was_valid = h->pairval_valid;
         h->pairval_valid = false;
-        if (!(kp.debug & 1)) {
-            // K_c: graph observation (persistent blocks) [+ the next step's pair values, placement 1]
-            const bool pie = pair_path && placement == 1;
-            kp.pairval = pie ? h->d_pairval : nullptr;
-            e = lsm::spec_launch_emit(kp, (cudaStream_t)stream, persist, h->persist_bytes, pair_path && placement == 0, pie);
-            if (e != cudaSuccess) return cuda_fail(e, who);
-            // a masked reset refreshes only the masked environments: the others keep what they had
-            if (pie) h->pairval_valid = env_mask == nullptr ? true : (was_valid && mode != lsm::MODE_STEP);
-        }
-        if (pair_path && placement == 0) {
-            // K_a for the NEXT step, beside the emit kernel's drain (see lsm_pair_kernel)
-            kp.pairval = h->d_pairval;
-            kp.pair_late = (kp.debug & 1) ? 0 : 1;
-            e = lsm::spec_launch_pair(kp, (cudaStream_t)stream, persist, h->persist_bytes);
-            if (e != cudaSuccess) return cuda_fail(e, who);
-            h->pairval_valid = true;
-        }
+        if (pair_path && placement == 0) h->pairval_valid = true;
+        // placement 1: a masked reset refreshes only the masked environments, the others keep what they had
+        if (pair_path && placement == 1 && !(kp.debug & 1))
+            h->pairval_valid = env_mask == nullptr ? true : (was_valid && mode != lsm::MODE_STEP);
     }
     return 0;
 }
@@ -501,6 +567,7 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     kp.mode = lsm::MODE_OBSERVE; kp.env_mask = nullptr;
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
     kp.pair_late = 0;
+    kp.grp_begin = 0; kp.env_begin = 0; kp.env_end = (int)kp.b.num_envs;
     const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 2);
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;
     const bool pie = pair_path && placement == 1;     // the same kernel, grid and work as inside lsm_step

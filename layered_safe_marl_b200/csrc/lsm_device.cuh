@@ -79,7 +79,9 @@ struct KParams {
     const uint16_t* pair_tab;  // [num_pairs][2] entity pairs a < b
     const uint32_t* pair32;    // [num_pairs] the same pairs packed (a << 16) | b
     int num_pairs;
-    int ngroups;               // ceil(num_envs / EPW)
+    int ngroups;               // ceil(num_envs / EPW); with chunked launches: END of this launch's env-group range
+    int grp_begin;             // first env group of this launch (chunked multi-stream launches; 0 otherwise)
+    int env_begin, env_end;    // the same range in environments (emit / pair kernels)
     int debug;                 // LSM_DEBUG experiment switches (0 in production): 1 skip graph emission, 2 skip HJ pair lookups, 4 skip node rows, 8 skip adjacency stores
     const uint32_t* sel_tab;   // [N][W] entities whose owner agent is <= i
     // exact squared thresholds (host): lt(T) = min{t : sqrt_rn(t) >= T} so that d < T <=> d2 < lt(T);

@@ -354,7 +354,8 @@ __global__ void __launch_bounds__(kPairThreads) lsm_pair_kernel(const __grid_con
     const long long n = kp.b.num_envs;
     // grid-stride: the late placement runs a bounded number of blocks per SM (lsm_kernels.cu) so that these fp64-heavy
     // warps take a fixed share of the issue slots next to the emit kernel's producers
-    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n * (N * N); t += (long long)gridDim.x * blockDim.x)
+    for (long long t = (long long)kp.env_begin * (N * N) + (long long)blockIdx.x * blockDim.x + threadIdx.x; t < (long long)kp.env_end * (N * N);
+         t += (long long)gridDim.x * blockDim.x)
     [&] {
         const int env = (int)(t / (N * N)), r = (int)(t - (long long)env * (N * N));
         const int i = r / N, j = r - i * N;
@@ -647,7 +648,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
     pdl_wait();
     tl_start(kp.timeline, TL_AGENT_START);
 
-    for (int grp = blockIdx.x * warps_per_block + warp_in_block; grp < ngroups; grp += gridDim.x * warps_per_block) {
+    for (int grp = kp.grp_begin + blockIdx.x * warps_per_block + warp_in_block; grp < ngroups; grp += gridDim.x * warps_per_block) {
         const int env0 = grp * EPW;
         const int env = env0 + le;
         bool env_on = lane_has_env && env < n;
@@ -1244,16 +1245,17 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         for (int k = tid; k < Q; k += T) cp_async16(dst + k, src + k);
     };
     int it = 0, tiles = 0;
-    if ((int)blockIdx.x < n) prefetch(blockIdx.x, 0);
+    const int env_end = kp.env_end;                 // this launch's environment range (chunked launches)
+    if (kp.env_begin + (int)blockIdx.x < env_end) prefetch(kp.env_begin + blockIdx.x, 0);
     cp_async_commit();
-    for (int ee = blockIdx.x; ee < n; ee += gridDim.x, ++it) {
+    for (int ee = kp.env_begin + blockIdx.x; ee < env_end; ee += gridDim.x, ++it) {
         const int rb = it & 1;                         // record slot
         const int tb = NBUF == 2 ? (tiles & 1) : 0;    // tile buffer (alternates per PROCESSED environment)
         cp_async_wait_all();
         // the bulk copies that last read this iteration's tile buffers have finished reading them
         if (tid == 0) { if (NBUF == 2) bulk_store_wait_read<1>(); else bulk_store_wait_read<0>(); }
         __syncthreads();
-        if (ee + (int)gridDim.x < n) prefetch(ee + gridDim.x, rb ^ 1);
+        if (ee + (int)gridDim.x < env_end) prefetch(ee + gridDim.x, rb ^ 1);
         cp_async_commit();
         if (masked_reset && kp.env_mask[ee] == 0) continue;
         if (debug & 128) continue;   // experiments: + record load

@@ -180,8 +180,9 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
 cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
     SpecFns f;
     if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
-    const long long tasks = (long long)kp.b.num_envs * kp.N * kp.N;
+    const long long tasks = (long long)(kp.env_end - kp.env_begin) * kp.N * kp.N;
     long long blocks = (tasks + kPairBlock - 1) / kPairBlock;
+    if (blocks < 1) blocks = 1;
     if (kp.pair_late) {
         // beside the emit kernel: a bounded number of resident blocks per SM, each striding over the pairs
         static int sm_count = 0;
@@ -236,7 +237,8 @@ cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void*
     cudaError_t e = emit_blocks_per_sm(f, reserve_pair, pie, &bps);
     if (e != cudaSuccess) return e;
     unsigned grid = (unsigned)sm_count * (unsigned)bps;
-    if (grid > (unsigned)kp.b.num_envs) grid = (unsigned)kp.b.num_envs;
+    if (grid > (unsigned)(kp.env_end - kp.env_begin)) grid = (unsigned)(kp.env_end - kp.env_begin);
+    if (grid < 1) grid = 1;
     if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
     return launch_one(pie ? f.emit_pie : f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
 }

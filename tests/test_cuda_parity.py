@@ -228,3 +228,35 @@ def test_pair_value_variants_agree(shape, monkeypatch):
             assert np.array_equal(filt[t][1], ref_filt[t][1]), f"{v}: deconflicting agent differs at step {t}"
         assert np.array_equal(state['agent_values'], ref_state['agent_values']), f"{v}: states differ"
         assert np.array_equal(safe, ref_safe), f"{v}: applied controls differ"
+
+
+@pytest.mark.parametrize('shape', ['di8', 'air10'])
+def test_chunked_launches_identical(shape, monkeypatch):
+    """Big batches are split into env ranges on library-owned streams (fork / join by events). The split must not change
+    a single bit of any output or state, including ragged last ranges and auto-resets."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    kw = dict(di8=dict(num_agents=8, world_size=4), air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6))[shape]
+    args = G.default_args(use_safety_filter=True, episode_length=7, **kw)
+    n, T, episode = 333, 10, 6249
+    rng = np.random.default_rng(8)
+    acts = rng.integers(0, 25, (T, n, args.num_agents)).astype(np.int32)
+    outs = []
+    for chunks in ('1', '3', '4'):
+        monkeypatch.setenv('LSM_CHUNKS', chunks)
+        env = B200GraphVecEnv(args, num_envs=n, seed=5)
+        assert env.launch_info()['chunks'] == int(chunks)
+        env.reset(episode)
+        trace = []
+        for t in range(T):
+            o = env.step(torch.as_tensor(acts[t], device=env.device), episode)
+            trace.append([x.cpu().numpy().copy() for x in o[:6]])
+        outs.append((trace, env.get_state(), env.ep_info.cpu().numpy()))
+        env.close()
+    for trace, state, ep in outs[1:]:
+        for t in range(T):
+            for a, b in zip(trace[t], outs[0][0][t]):
+                assert np.array_equal(a, b, equal_nan=True), f"step {t}: chunked output differs"
+        for k in state:
+            assert np.array_equal(np.asarray(state[k]), np.asarray(outs[0][1][k]), equal_nan=True), f"state {k} differs"
+        assert np.array_equal(ep, outs[0][2], equal_nan=True)

@@ -14,9 +14,9 @@ done
 python bench.py --impl reference --steps 20 --warmup 3 > $O/${TAG}_bench_ref.json 2>&1
 CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --e2e-steps 3"
 $CMD > $O/${TAG}_plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file $O/${TAG}_launches.csv $CMD > $O/${TAG}_ncu1.log 2>&1
 $CMD > $O/${TAG}_plain2.log 2>&1 &&
-ncu --set full --clock-control none --import-source on -k regex:lsm_ -s 12 -c 4 -f -o $O/${TAG}_prof_cfg2 $CMD > $O/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:lsm_ -s 12 -c 6 -f -o $O/${TAG}_prof_cfg2 $CMD > $O/${TAG}_ncu2.log 2>&1
 tail -3 $O/${TAG}_pytest.log; cat $O/${TAG}_smoke.log | tail -2
 python - <<PY
 import json
