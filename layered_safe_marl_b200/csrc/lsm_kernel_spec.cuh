@@ -1,18 +1,22 @@
 // lsm_kernel_spec.cuh - the step pipeline specialised at compile time on (dynamics, N agents, L landmarks
 // per agent): constant-size records, unrolled loops, immediate-offset stores.
 //
-// One env.step is THREE launches, each at the natural parallelism of its phase (a fused single kernel
-// needs ~250 registers for the physics and then runs the store-bound graph emission at 7 warps per SM;
-// measured in profiles/r01_v3_*: 17 % issue utilisation, latency-bound):
+// One env.step is THREE launches, each at the natural parallelism of its phase (a fused single kernel needs ~250
+// registers for the physics and then runs the store-bound graph emission at 7 warps per SM; measured in
+// profiles/r01_v3_*: 17 % issue utilisation, latency-bound), in stream order
 //
-//   lsm_pair_kernel   one THREAD per ordered (env, ego, other) pair: relative state + multilinear HJ value
-//                     lookup (safety_filter.py:192-201, 345-354) -> pairval[env][ego][other] (float64, L2 resident)
-//   lsm_agent_kernel  one LANE per agent, 32/G envs per warp: action decode, argmin / gradient / bang-bang or QP,
-//                     dynamics, goal / reward / done, episode statistics, auto-reset, state write-back; leaves
-//                     a compact per-env "emit record" (positions, velocities, goal tables, pre/post flags)
-//   lsm_emit_kernel   one BLOCK (WPE warps) per env, low register count / high occupancy: radius-thresholded
-//                     distance matrix, disconnected-entity masks, adjacency and node-feature stores - the
-//                     HBM-bound part (>= 96 % of the algorithmic bytes)
+//   lsm_agent_kernel  one LANE per agent, 32/N envs per warp: action decode, argmin over the precomputed HJ pair values /
+//                     gradient / bang-bang or QP, dynamics, goal / reward / done, episode statistics, auto-reset, state
+//                     write-back; leaves a compact per-env "emit record" (positions, velocities, goal tables, pre/post flags)
+//   lsm_emit_kernel   persistent blocks of WPE warps loop over envs, low register count: radius-thresholded distance
+//                     matrix, disconnected-entity masks, adjacency and node-feature tiles in shared memory -> TMA bulk
+//                     stores - the HBM-bound part (>= 96 % of the algorithmic bytes)
+//   lsm_pair_kernel   one THREAD per ordered (env, ego, other) pair: relative state + multilinear HJ value lookup from the
+//                     corner-packed table (safety_filter.py:192-201, 345-354) -> pairval[env][ego][other] for the NEXT step;
+//                     launched behind the emit kernel without a dependency wait, so it runs beside the emit kernel's drain
+//
+// Big batches are split into env ranges on library-owned streams (lsm_capi.cu) so that the latency-bound agent kernel of
+// one range overlaps the HBM-bound emit kernel of another.
 //
 // Same decisions as the generic kernel for every thresholded quantity:
 //   * the HJ stencil uses 32-bit indices and an exactly rounded division by the grid spacing through its

@@ -4,7 +4,7 @@
 //   lsm_kernel_generic.cuh  run-time N / L fallback for every other configuration
 //   lsm_step_common.cuh     dynamics, HJ filter resolution, grid interpolation shared by both
 //
-// Specialised path: three launches per step (pair values -> per-agent physics -> graph emission), see
+// Specialised path: three launches per step (per-agent physics -> graph emission -> next step's pair values), see
 // lsm_kernel_spec.cuh. Generic path ("warp per env group", one fused launch): a warp owns EPW consecutive
 // environments, G = next power of two >= N lanes per environment; per-agent phases run one lane per
 // agent; the graph observation is built in the warp's shared-memory slice and written with all 32 lanes.
