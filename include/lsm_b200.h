@@ -137,7 +137,7 @@ typedef struct lsm_launch_info {
     int32_t launches_per_step;    /* kernels one lsm_step launches in steady state */
     int32_t emit_record_bytes;    /* per-env record handed from the agent kernel to the emit kernel */
     int32_t chunks;               /* env ranges one lsm_step is split into (library-owned streams, fork/join by events); 1 = none */
-    int32_t pair_placement;       /* next step's HJ pair values: 0 behind the emit kernel, 1 inside it, 2 in front of the agent kernel */
+    int32_t pair_placement;       /* next step's HJ pair values: 0 behind the emit kernel, 1 inside it, 2 in front of the agent kernel, 3 between the two; -1 none */
 } lsm_launch_info;
 
 typedef struct lsm_handle lsm_handle;

@@ -61,7 +61,7 @@ struct lsm_handle {
     std::vector<cudaEvent_t> ev_join;
     cudaEvent_t ev_fork = nullptr;
     float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
-    int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel
+    int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel, 3 between agent and emit kernel
 };
 
 extern "C" {
@@ -181,12 +181,15 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) &&
               !(force_generic != nullptr && force_generic[0] == '1');
     // where the next step's HJ pair values are computed (measured): in lsm_pair_kernel behind the emit kernel
-    // ("late": best or equal-best at every benchmarked size); LSM_PAIR=late|emit|front overrides (experiments)
-    h->pair_placement = 0;
+    // ("late") for the 4-D double-integrator grid; between the agent and the emit kernel ("middle") for the 5-D airtaxi
+    // grid, whose lookups are half an emit kernel's worth of work and hurt it more when they share the SMs.
+    // LSM_PAIR=late|emit|front|middle overrides (experiments)
+    h->pair_placement = cfg->dynamics == LSM_DYN_AIRTAXI ? 3 : 0;
     if (const char* pp = std::getenv("LSM_PAIR")) {
         if (!std::strcmp(pp, "late")) h->pair_placement = 0;
         else if (!std::strcmp(pp, "emit")) h->pair_placement = 1;
         else if (!std::strcmp(pp, "front")) h->pair_placement = 2;
+        else if (!std::strcmp(pp, "middle")) h->pair_placement = 3;
     }
     const char* fe = std::getenv("LSM_EPW");
     h->forced_epw = fe ? std::atoi(fe) : 0;
@@ -464,6 +467,13 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
         e = lsm::kernel_launch(k, h->spec, (int)blocks, h->block_threads, h->smem_per_block, s, persist, h->persist_bytes);
         if (e != cudaSuccess) return e;
         if (h->spec) {
+            if (pair_path && placement == 3) {
+                // K_a for the NEXT step between the agent and the emit kernel: alone on the GPU at full occupancy
+                k.pairval = h->d_pairval;
+                k.pair_late = 0;
+                e = lsm::spec_launch_pair(k, s, persist, h->persist_bytes);
+                if (e != cudaSuccess) return e;
+            }
             if (!(k.debug & 1)) {
                 // K_c: graph observation (persistent blocks) [+ the next step's pair values, placement 1]
                 const bool pie = pair_path && placement == 1;
@@ -502,7 +512,7 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     }
     if (h->spec) {
         h->pairval_valid = false;
-        if (pair_path && placement == 0) h->pairval_valid = true;
+        if (pair_path && (placement == 0 || placement == 3)) h->pairval_valid = true;
         // placement 1: a masked reset refreshes only the masked environments, the others keep what they had
         if (pair_path && placement == 1 && !(kp.debug & 1))
             h->pairval_valid = env_mask == nullptr ? true : (was_valid && mode != lsm::MODE_STEP);

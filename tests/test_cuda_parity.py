@@ -189,8 +189,8 @@ def test_onehot_actions_and_numpy_outputs():
 
 @pytest.mark.parametrize('shape', ['di8', 'air10', 'di32'])
 def test_pair_value_variants_agree(shape, monkeypatch):
-    """The next step's HJ pair values may be produced by three placements (behind the emit kernel, inside it, in front
-    of the agent kernel) and from two layouts of the value grid (corner-packed table, scattered gathers). All of them
+    """The next step's HJ pair values may be produced by four placements (behind the emit kernel, inside it, in front
+    of the agent kernel, between the two) and from two layouts of the value grid (corner-packed table, scattered gathers). All of them
     must drive the filter identically:
     same deconflicting agent, same activation mask and bit-identical states."""
     import torch
@@ -199,7 +199,7 @@ def test_pair_value_variants_agree(shape, monkeypatch):
               di32=dict(num_agents=32, world_size=4))[shape]
     args = G.default_args(use_safety_filter=True, episode_length=250, **kw)
     n, T, episode = (64, 12, 6249) if shape != 'di32' else (16, 6, 6249)
-    variants = [('late', '0', False), ('emit', '0', False), ('front', '0', False), ('late', '0', True)]
+    variants = [('late', '0', False), ('emit', '0', False), ('front', '0', False), ('middle', '0', False), ('late', '0', True)]
     results = []
     rng = np.random.default_rng(4)
     acts = rng.integers(0, 25, (T, n, args.num_agents)).astype(np.int32)
