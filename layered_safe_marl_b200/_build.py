@@ -25,7 +25,7 @@ def needs_build() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, extra_flags=(), out_path: str = LIB_PATH) -> str:
-    """`extra_flags` / `out_path` build an A/B variant (e.g. -DLSM_EARLY_LOADS) next to the product library; a variant
+    """`extra_flags` / `out_path` build an A/B variant (extra -D switches) next to the product library; a variant
     is selected at run time with LSM_LIB=<path> (experiments only)."""
     if not force and not needs_build() and out_path == LIB_PATH:
         return LIB_PATH

@@ -732,11 +732,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             ep_conflict = aip[LSM_AI_EP_CONFLICT * fstride]; ep_multi = aip[LSM_AI_EP_MULTI * fstride]; \
             ep_done = aip[LSM_AI_EP_DONE * fstride]; \
         }
-#ifdef LSM_EARLY_LOADS   /* A/B build: everything loaded up front, like the first pipeline */
-        { LSM_LOAD_MOTION() LSM_LOAD_BOOKKEEPING(false) }
-#else
         if (kp.mode != MODE_STEP) { LSM_LOAD_MOTION() LSM_LOAD_BOOKKEEPING(false) }
-#endif
         // landmark tables of the group's environments: contiguous runs per field
         {
             const int total = nenv * M;
@@ -784,9 +780,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             }
             __syncwarp();
             double safe0 = raw0, safe1 = raw1;
-#ifndef LSM_EARLY_LOADS
             LSM_LOAD_MOTION()
-#endif
             for (int it = 0; it < c.num_internal_step; ++it) {
                 // HJ values of (ego, other): from lsm_pair_kernel for the states this launch started with, in-kernel
                 // for later internal steps
@@ -909,9 +903,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 s2 = s2q; s3 = s3q;
             }
             __syncwarp();
-#ifndef LSM_EARLY_LOADS
             LSM_LOAD_BOOKKEEPING(true)
-#endif
             if (agent_on) {
                 // one pass over the other agents: min distance, collisions, episode statistics, proximity rewards.
                 // Agent a is seen after its own update if a < i (rewards) / a <= i (statistics), else before.

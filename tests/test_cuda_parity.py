@@ -260,3 +260,30 @@ def test_chunked_launches_identical(shape, monkeypatch):
         for k in state:
             assert np.array_equal(np.asarray(state[k]), np.asarray(outs[0][1][k]), equal_nan=True), f"state {k} differs"
         assert np.array_equal(ep, outs[0][2], equal_nan=True)
+
+
+def test_pinned_host_actions_are_used_in_place():
+    """Host-facing path: a page-locked one-hot array is DMA'd straight from the caller's memory, a pageable one is
+    staged; both give the same step."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    args = G.default_args(num_agents=8, use_safety_filter=True, episode_length=25, world_size=4)
+    rng = np.random.default_rng(2)
+    idx = rng.integers(0, 25, (4, 40, 8))
+    onehot = np.eye(25, dtype=np.float32)[idx]
+    pinned = torch.from_numpy(onehot.copy()).pin_memory()
+    outs = []
+    for use_pinned in (False, True):
+        env = B200GraphVecEnv(args, num_envs=40, seed=9, numpy_outputs=True)
+        env.reset(6249)
+        trace = []
+        for t in range(4):
+            a = pinned[t].numpy() if use_pinned else onehot[t]
+            o = env.step(a, 6249)
+            trace.append([np.array(x) for x in o[:6]])
+        outs.append(trace)
+        assert (getattr(env, '_act_pinned', None) is None) == use_pinned     # no staging buffer on the pinned path
+        env.close()
+    for ta, tb in zip(*outs):
+        for x, y in zip(ta, tb):
+            assert np.array_equal(x, y, equal_nan=True)
