@@ -26,11 +26,22 @@ namespace lsm {
 // host-side launch helpers (used by lsm_capi.cu)
 // ---------------------------------------------------------------------------------------------
 // (dynamics, N, L, warps per env of the emit kernel, resident emit blocks per SM the register budget targets)
+#ifndef LSM_AIR_WPE
+#define LSM_AIR_WPE 2
+#endif
+// BASELINE.json's benchmark shapes (8 / 3 / 32 double-integrator agents, 10 airtaxi agents) and the shapes the
+// reference's own scripts ship with (train.sh: 4 agents, 2 landmarks, either dynamics; eval_airtaxi.sh: 8 and 16 agents;
+// eval_double_integrator.sh: 4 agents; the 16-agent dense golden rollout)
 #define LSM_SPEC_LIST(X)                               \
     X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 4, 4)           \
     X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2, 1, 16)          \
     X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2, 4, 3)          \
-    X(LSM_DYN_AIRTAXI, 10, 2, 2, 5)
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 4, 2, 2, 8)           \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 16, 2, 4, 4)          \
+    X(LSM_DYN_AIRTAXI, 10, 2, LSM_AIR_WPE, 5)          \
+    X(LSM_DYN_AIRTAXI, 4, 2, 2, 8)                     \
+    X(LSM_DYN_AIRTAXI, 8, 2, 2, 5)                     \
+    X(LSM_DYN_AIRTAXI, 16, 2, 4, 4)
 
 constexpr int kAgentBlock = 128;
 constexpr int kAgentMinB = 2;

@@ -287,3 +287,18 @@ def test_pinned_host_actions_are_used_in_place():
     for ta, tb in zip(*outs):
         for x, y in zip(ta, tb):
             assert np.array_equal(x, y, equal_nan=True)
+
+
+@pytest.mark.parametrize('dyn,N', [('double_integrator', 4), ('double_integrator', 16), ('airtaxi', 4), ('airtaxi', 8), ('airtaxi', 16)])
+def test_oracle_batch_reference_script_shapes(dyn, N):
+    """The shapes the reference's own scripts ship with (train.sh: 4 agents; eval_airtaxi.sh: 8 / 16; eval_double_integrator.sh: 4)
+    run the specialised pipeline; same bar as the benchmark shapes."""
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    air = dyn == 'airtaxi'
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=True, episode_length=350 if air else 250,
+                          world_size=6 if air else 4)
+    probe = B200GraphVecEnv(args, num_envs=4, seed=0)
+    assert probe.launch_info()['specialised'] == 1
+    probe.close()
+    _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=air)), n=96, T=12, episode=6249, seed=13 + N,
+                         auto_reset=True, max_bad_env_fraction=0.025 if air else 0.0)
