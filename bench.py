@@ -309,9 +309,9 @@ def run_ours(a):
     cpu = None
     if not a.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        n_s = 512
+        n_s = 1024
         probe, dtp, _ = oracle_throughput(a.workload, n_s, 3, 1, cores)
-        steps_s = int(max(5, min(400, 12.0 / max(dtp / 3, 1e-6))))
+        steps_s = int(max(5, min(20000, 12.0 / max(dtp / 3, 1e-6))))      # ~12 s of CPU work on every host thread
         val, dts, _ = oracle_throughput(a.workload, n_s, steps_s, 2, cores)
         cpu = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                "sample": f"{n_s} envs x {steps_s} steps of {a.workload} ({dts:.1f} s) with the C oracle port of the "
