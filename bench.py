@@ -14,6 +14,8 @@ integrator, 8 agents, 2 landmarks per agent, HJ safety filter on with the synthe
             copied back to pinned host memory) - host<->device copies inside the timed region.
   roofline  algorithmic bytes per launch / mean kernel time vs the measured HBM copy peak.
   cpu_baseline   the C oracle (a port of the reference's Python path) on this box's host cores, bounded sample.
+  timeline_us    diagnostics: device-side (%globaltimer) window of each kernel of one flushed step, us after the first
+            block of the step (measured in a separate loop after the timed regions).
 
 `--impl reference` times the CPU oracle port alone (the reference itself is Python and does not exist
 on the GPU box); rank 0 only.
@@ -232,6 +234,19 @@ def run_ours(a):
             ee[t].record()
         torch.cuda.synchronize()
         emit_ms = float(np.mean([s.elapsed_time(e) for s, e in zip(es, ee)]))
+    # device-side timeline of one step (diagnostics, outside every timed region): %globaltimer first-block-in /
+    # last-block-out of each kernel, median over a few flushed steps
+    timeline = None
+    if li0.get('specialised', 0) and rank == 0:
+        rows = []
+        env.debug_timeline(True)
+        for t in range(min(K, 15)):
+            flush.fill_(0.0)
+            env.step(actions[W + t], episode)
+            rows.append(env.debug_timeline(True))
+        env.debug_timeline(False)
+        timeline = {k: (round(float(np.median([r[k] for r in rows if r[k] is not None])) / 1000.0, 2)
+                        if any(r[k] is not None for r in rows) else None) for k in rows[0]}
     if world > 1:
         tt = torch.tensor([total_ms, noflush_ms], dtype=torch.float64, device=device)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -334,6 +349,7 @@ def run_ours(a):
                     "steps": Ke, "ms_per_step": e2e_ms / Ke,
                     "api": "B200GraphVecEnv.step(host one-hot float32 actions) -> host numpy obs/agent_id/node_obs/adj/rewards/dones"},
             "gpu_launches": K * li.get('launches_per_step', 1),
+            "timeline_us": timeline,
             "roofline": roofline,
             "cpu_baseline": cpu,
             "episode_stats": stats}
