@@ -358,13 +358,82 @@ def run_ours(a):
         dist.destroy_process_group()
 
 
+def run_rollout(a):
+    """`--workload cfg5`: BASELINE configs[4] - rollout collection of the onpolicy GraphMPE runner (8 agents, 8192 envs
+    per GPU) with the device-resident rollout buffer: env.step writes observations / graphs / rewards straight into the
+    buffer slot (zero copy), insert() builds masks / share_obs on the device. The policy forward is NOT part of this
+    repo: actions are drawn on the device (stated in `config`). Each step lands in a different 221 MB slot of the
+    5.7 GB buffer, i.e. the outputs are larger than L2 without a flush."""
+    import torch
+    import torch.distributed as dist
+    from layered_safe_marl_b200 import B200GraphVecEnv, DeviceGraphRolloutBuffer
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    device = torch.device(f'cuda:{local_rank}'); torch.cuda.set_device(device)
+    args, flags, _, episode = build_args('cfg2')
+    n_envs = a.envs or 8192
+    T = 25
+    env = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=1234, binary_cfg=flags, env_id_base=rank * n_envs)
+    buf = DeviceGraphRolloutBuffer(env, T, use_centralized_V=True, zero_copy=True)
+    N = env.N
+    K, W = a.steps, a.warmup
+    gen = torch.Generator(device=device); gen.manual_seed(7 + rank)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    buf.warmup(num_current_episode=episode)
+
+    def collect(steps):
+        for _ in range(steps):
+            actions = torch.randint(0, 25, (n_envs, N), generator=gen, device=device, dtype=torch.int32)
+            out = env.step(actions, episode)
+            buf.insert(out, actions=actions)
+            if buf.step == 0:
+                buf.after_update()
+    collect(W)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); collect(K); e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt[0])
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
+        li = env.launch_info()
+        line = {"metric": METRIC, "value": n_envs * world * N * K / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": K,
+                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic",
+                "config": {"workload": "BASELINE configs[4] shape: rollout collection (env.step + rollout-buffer insert, zero copy) "
+                                       "8 agents x 8192 envs per B200, HJ filter on; policy forward excluded (actions drawn on device)",
+                           "envs_per_gpu": n_envs, "num_agents": N, "buffer_steps": T,
+                           "l2": "every step lands in a different 221 MB buffer slot (outputs > L2), no flush", "launch": li},
+                "clocks": clocks, "e2e": None, "gpu_launches": K * li.get('launches_per_step', 1),
+                "roofline": {"bound": "hbm", "achieved": bytes_per_step / (ms / K / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
+                             "frac": bytes_per_step / (ms / K / 1000.0) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+                             "kernel": "whole collection step (3 kernels + insert's elementwise torch ops)",
+                             "algorithmic_bytes_per_launch": bytes_per_step},
+                "cpu_baseline": None}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=200)
     ap.add_argument('--warmup', type=int, default=20)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS))
+    ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload’s)')
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -372,7 +441,11 @@ def main():
     if a.warmup < 3:
         a.warmup = 3
     if a.impl == 'reference':
+        if a.workload == 'cfg5':
+            a.workload = 'cfg2'       # the same environment; the reference arm times env.step only
         run_reference(a)
+    elif a.workload == 'cfg5':
+        run_rollout(a)
     else:
         run_ours(a)
 

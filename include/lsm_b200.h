@@ -187,6 +187,16 @@ int lsm_set_output_buffers(lsm_handle *h, float *obs, float *node_obs, float *ad
 int lsm_edge_list(lsm_handle *h, const float *adj, int64_t *edge_index, float *edge_attr, int32_t *counts,
                   int64_t *offsets, int64_t capacity, void *stream);
 
+/* Rollout-buffer bookkeeping of one step in one launch (reference GMPERunner.insert + GraphReplayBuffer.insert,
+ * onpolicy/runner/shared/graph_mpe_runner.py:437-487, onpolicy/utils/graph_buffer.py:168-250), all DEVICE pointers:
+ *   obs           float [num_envs][N][D]       the observation slot the step kernels just wrote
+ *   done          uint8 [num_envs][N]          the step's done flags
+ *   share_obs     float [num_envs][N][N*D]     <- every agent's obs of the env, concatenated (NULL: not centralised)
+ *   masks         float [num_envs][N]          <- 0 where done else 1
+ *   active_masks  float [num_envs][N]          <- like masks, but 1 for every agent of an env whose agents are all done */
+int lsm_rollout_insert(lsm_handle *h, const float *obs, const uint8_t *done, float *share_obs, float *masks,
+                       float *active_masks, void *stream);
+
 /* Tell the library that the caller edited the bound state tensors (agent_f64 / agent_i32 / env_f64) directly.
  * The specialised pipeline keeps the HJ pair values of the current state from the previous launch
  * (safety_filter.py:192-201 evaluated one step ahead); after an edit the next lsm_step recomputes them first. */

@@ -53,7 +53,7 @@ class LsmLaunchInfo(C.Structure):
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
                     'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline')
+                    'lsm_debug_timeline', 'lsm_rollout_insert')
 
 _lib = None
 
@@ -94,9 +94,10 @@ def load():
     lib.lsm_set_output_buffers.argtypes = [C.c_void_p] + [C.c_void_p] * 5
     lib.lsm_edge_list.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     lib.lsm_debug_timeline.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+    lib.lsm_rollout_insert.argtypes = [C.c_void_p] * 7
     for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
                  'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline'):
+                    'lsm_debug_timeline', 'lsm_rollout_insert'):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

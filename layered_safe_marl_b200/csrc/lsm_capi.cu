@@ -563,6 +563,18 @@ int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* e
     return 0;
 }
 
+int lsm_rollout_insert(lsm_handle* h, const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
+                       void* stream) {
+    if (h == nullptr) return fail(1, "lsm_rollout_insert: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_rollout_insert: lsm_bind_buffers has not been called");
+    if (obs == nullptr || done == nullptr || masks == nullptr || active_masks == nullptr)
+        return fail(1, "lsm_rollout_insert: obs, done, masks and active_masks must be non-null");
+    cudaError_t e = lsm::rollout_insert_launch(obs, done, share_obs, masks, active_masks, (long long)h->kp.b.num_envs, h->kp.N, h->kp.D,
+                                               (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_rollout_insert");
+    return 0;
+}
+
 int lsm_invalidate(lsm_handle* h) {
     if (h == nullptr) return fail(1, "lsm_invalidate: null handle");
     h->pairval_valid = false;

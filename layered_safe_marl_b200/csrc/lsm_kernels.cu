@@ -16,6 +16,7 @@
 #include "lsm_kernel_generic.cuh"
 #include "lsm_kernel_spec.cuh"
 #include "lsm_edges.cuh"
+#include "lsm_rollout.cuh"
 #include "lsm_host.h"
 
 #include <cstdlib>
@@ -260,6 +261,15 @@ cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {
     if (g.ndim == 4) lsm_pack_grid_kernel<4><<<blocks, 256>>>(g.values, packed, g, cells);
     else if (g.ndim == 5) lsm_pack_grid_kernel<5><<<blocks, 256>>>(g.values, packed, g, cells);
     else return cudaErrorInvalidValue;
+    return cudaGetLastError();
+}
+
+cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
+                                  long long n, int N, int D, cudaStream_t stream) {
+    const long long total = n * (long long)N * N * D;
+    long long blocks = (total + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    lsm_rollout_insert_kernel<<<(unsigned)blocks, 256, 0, stream>>>(obs, done, share_obs, masks, active_masks, n, N, D);
     return cudaGetLastError();
 }
 

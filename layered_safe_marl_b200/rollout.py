@@ -58,6 +58,12 @@ class DeviceGraphRolloutBuffer:
         self.bad_masks = torch.ones_like(self.masks)
         self.active_masks = torch.ones_like(self.masks)
         self.step = 0
+        # agent ids never change (scenario.get_id == agent index): every slot is filled once instead of on every insert
+        self.agent_id.copy_(env.agent_id.view(1, n, N, 1).expand(T + 1, n, N, 1))
+        if self.use_centralized_V:
+            self.share_agent_id.copy_(env.agent_id.view(1, n, 1, N).expand(T + 1, n, N, N))
+        else:
+            self.share_agent_id.copy_(self.agent_id)
         # zero-copy: per-step reward / done landing zones the kernels write into
         self._done_u8 = torch.zeros((n, N), dtype=torch.uint8, device=dev)
         self._bound_slot = None
@@ -92,9 +98,8 @@ class DeviceGraphRolloutBuffer:
         obs, agent_id, node_obs, adj = reset_out[:4]
         if not self.zero_copy:
             self.obs[0].copy_(obs); self.node_obs[0].copy_(node_obs); self.adj[0].copy_(adj)
-        so, sa = self._share(self.obs[0], agent_id)
+        so, _ = self._share(self.obs[0], agent_id)
         self.share_obs[0].copy_(so)
-        self.agent_id[0].copy_(agent_id); self.share_agent_id[0].copy_(sa)
         self.step = 0
         self.bind_next_slot()
         return reset_out
@@ -106,30 +111,41 @@ class DeviceGraphRolloutBuffer:
         obs, agent_id, node_obs, adj, rewards, dones = step_out[:6]
         s = self.step
         dones = dones.to(torch.bool)
-        dones_env = dones.all(dim=1)                                   # np.all(dones, axis=1)
         if rnn_states is not None:
             rnn_states = torch.where(dones[..., None, None], torch.zeros_like(rnn_states), rnn_states)
             self.rnn_states[s + 1].copy_(rnn_states)
         if rnn_states_critic is not None:
             rnn_states_critic = torch.where(dones[..., None, None], torch.zeros_like(rnn_states_critic), rnn_states_critic)
             self.rnn_states_critic[s + 1].copy_(rnn_states_critic)
-        masks = (~dones).to(torch.float32).unsqueeze(-1)               # masks[dones] = 0
-        active = masks.clone()
-        active[dones_env] = 1.0                                        # active_masks[dones_env] = 1
-        if not (self.zero_copy and self._bound_slot == s):
+        if self.zero_copy and self._bound_slot == s:
+            # the step kernels already wrote obs / node_obs / adj / rewards / done in place: masks, active masks and the
+            # centralised share_obs of slot s+1 in ONE launch (lsm_rollout_insert)
+            import ctypes as C
+            from . import _lib
+            env = self.env
+            so_ptr = C.c_void_p(self.share_obs[s + 1].data_ptr()) if self.use_centralized_V else None
+            _lib.check(env.lib.lsm_rollout_insert(env._h, C.c_void_p(self.obs[s + 1].data_ptr()), C.c_void_p(self._done_u8.data_ptr()),
+                                                  so_ptr, C.c_void_p(self.masks[s + 1].data_ptr()),
+                                                  C.c_void_p(self.active_masks[s + 1].data_ptr()), env._stream()), 'lsm_rollout_insert')
+            if not self.use_centralized_V:
+                self.share_obs[s + 1].copy_(self.obs[s + 1])
+        else:
+            dones_env = dones.all(dim=1)                                   # np.all(dones, axis=1)
+            masks = (~dones).to(torch.float32).unsqueeze(-1)               # masks[dones] = 0
+            active = masks.clone()
+            active[dones_env] = 1.0                                        # active_masks[dones_env] = 1
             self.obs[s + 1].copy_(obs); self.node_obs[s + 1].copy_(node_obs); self.adj[s + 1].copy_(adj)
             self.rewards[s].copy_(rewards.reshape(self.n_rollout_threads, self.num_agents, 1))
-        so, sa = self._share(self.obs[s + 1], agent_id)
-        self.share_obs[s + 1].copy_(so)
-        self.agent_id[s + 1].copy_(agent_id); self.share_agent_id[s + 1].copy_(sa)
+            so, _ = self._share(self.obs[s + 1], agent_id)
+            self.share_obs[s + 1].copy_(so)
+            self.masks[s + 1].copy_(masks)
+            self.active_masks[s + 1].copy_(active)
         if actions is not None:
             self.actions[s].copy_(actions.reshape(self.actions[s].shape))
         if action_log_probs is not None:
             self.action_log_probs[s].copy_(action_log_probs.reshape(self.action_log_probs[s].shape))
         if values is not None:
             self.value_preds[s].copy_(values.reshape(self.value_preds[s].shape))
-        self.masks[s + 1].copy_(masks)
-        self.active_masks[s + 1].copy_(active)
         self.step = (s + 1) % self.episode_length
         self.bind_next_slot()
 

@@ -23,6 +23,7 @@ def _fake_env(n, N, L, D, F, device='cpu'):
     e = types.SimpleNamespace()
     e.num_envs, e.N, e.E, e.D, e.F, e.device = n, N, N * (1 + L), D, F, torch.device(device)
     e.action_space = [Discrete(25) for _ in range(N)]
+    e.agent_id = torch.arange(N, dtype=torch.int32).view(1, N, 1).expand(n, N, 1).contiguous()
     return e
 
 
@@ -53,6 +54,9 @@ def test_rollout_buffer_matches_reference_insert_and_gae():
     ref['masks'] = np.ones(tuple(rb.masks.shape), dtype=np.float32)
     ref['active_masks'] = np.ones(tuple(rb.masks.shape), dtype=np.float32)
     agent_id = np.tile(np.arange(N, dtype=np.int32).reshape(1, N, 1), (n, 1, 1))
+    # agent ids are constant: the device buffer fills every slot once at construction, the reference fills slot 0 in warmup
+    ref['agent_id'][0] = agent_id
+    ref['share_agent_id'][0] = np.expand_dims(agent_id.reshape(n, -1), 1).repeat(N, axis=1)
     values = rng.normal(size=(T + 1, n, N, 1)).astype(np.float32)
     for t in range(T):
         obs = rng.normal(size=(n, N, D)).astype(np.float32)
