@@ -207,7 +207,7 @@ def run_ours(a):
     for t in range(K):
         flush.fill_(0.0)                      # L2 flush between timed iterations (not timed)
         starts[t].record()
-        env.step(actions[W + t], episode)     # pair -> agent -> emit kernels (launch_info.launches_per_step)
+        env.step(actions[W + t], episode)     # agent -> emit -> pair kernels (launch_info.launches_per_step)
         stops[t].record()
     torch.cuda.synchronize()
     t_wall = time.perf_counter() - t_wall0
