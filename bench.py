@@ -221,6 +221,26 @@ def run_ours(a):
     e1.record()
     torch.cuda.synchronize()
     noflush_ms = e0.elapsed_time(e1)
+    # no flush, but the big outputs rotate over slots whose total size exceeds L2 (what a rollout buffer does: every step
+    # writes node_obs / adj into the next slot), so they are never L2 resident while the few-MB state stays warm
+    slot_bytes = (env.node_obs.numel() + env.adj.numel()) * 4
+    n_slots = max(2, int(np.ceil(2.5 * 126e6 / slot_bytes)))
+    rot_ms = None
+    if slot_bytes * n_slots < 40e9:
+        slots = [(torch.empty_like(env.node_obs), torch.empty_like(env.adj)) for _ in range(n_slots)]
+        for t in range(min(W, 5)):
+            env.set_output_buffers(node_obs=slots[t % n_slots][0], adj=slots[t % n_slots][1])
+            env.step(actions[t], episode)
+        torch.cuda.synchronize()
+        r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0.record()
+        for t in range(K):
+            env.set_output_buffers(node_obs=slots[t % n_slots][0], adj=slots[t % n_slots][1])
+            env.step(actions[W + t], episode)
+        r1.record()
+        torch.cuda.synchronize()
+        rot_ms = r0.elapsed_time(r1)
+        del slots
     # the dominant kernel alone (graph emission: >= 96 % of the algorithmic bytes), same flush between launches
     li0 = env.launch_info()
     emit_ms = None
@@ -343,6 +363,10 @@ def run_ours(a):
                        "launch": li},
             "ms_per_step_back_to_back": noflush_ms / K,
             "value_back_to_back": total_envs * N * K / (noflush_ms / 1000.0),
+            "rotating_outputs": None if rot_ms is None else {
+                "ms_per_step": rot_ms / K, "value": n_envs * N * K / (rot_ms / 1000.0), "slots": n_slots,
+                "note": "this rank, no L2 flush: node_obs / adj of consecutive steps go to different slots (total > 2.5 x L2), "
+                        "like a rollout buffer; the few-MB state stays L2-warm as in a real run"},
             "wall_s_timed_loop": t_wall,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
