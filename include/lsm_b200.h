@@ -197,6 +197,15 @@ int lsm_edge_list(lsm_handle *h, const float *adj, int64_t *edge_index, float *e
 int lsm_rollout_insert(lsm_handle *h, const float *obs, const uint8_t *done, float *share_obs, float *masks,
                        float *active_masks, void *stream);
 
+/* The float64 sin / cos / atan2 of include/lsm_math.h (what the kernels use instead of libdevice so that they agree bit
+ * for bit with the CPU oracle), evaluated on the HOST (lsm_math_eval: a, b, out are host pointers; no GPU needed -
+ * B200GraphVecEnv.set_state tabulates the landmark heading sin / cos with it, like the on-device reset does) or on the
+ * DEVICE (lsm_math_eval_device: device pointers). op: 0 sin(a), 1 cos(a), 2 atan2(a, b), 3 / 4 the sin / cos half of the
+ * header's one-reduction sincos; b may be NULL unless op == 2. Replaces numpy's libm at multiagent/core.py:105-131,179-181,
+ * safety_filter.py:277-284, navigation_graph_safe.py:606-656, utils.py:79-349. */
+int lsm_math_eval(int op, const double *a, const double *b, double *out, int64_t n);
+int lsm_math_eval_device(int op, const double *a, const double *b, double *out, int64_t n, void *stream);
+
 /* Tell the library that the caller edited the bound state tensors (agent_f64 / agent_i32 / env_f64) directly.
  * The specialised pipeline keeps the HJ pair values of the current state from the previous launch
  * (safety_filter.py:192-201 evaluated one step ahead); after an edit the next lsm_step recomputes them first. */

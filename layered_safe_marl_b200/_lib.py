@@ -53,7 +53,7 @@ class LsmLaunchInfo(C.Structure):
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
                     'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline', 'lsm_rollout_insert')
+                    'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device')
 
 _lib = None
 
@@ -95,9 +95,11 @@ def load():
     lib.lsm_edge_list.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     lib.lsm_debug_timeline.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.lsm_rollout_insert.argtypes = [C.c_void_p] * 7
+    lib.lsm_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+    lib.lsm_math_eval_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
                  'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline', 'lsm_rollout_insert'):
+                    'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device'):
         getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib

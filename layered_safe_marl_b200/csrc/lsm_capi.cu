@@ -121,7 +121,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     for (int k = 0; k < 5; ++k) {
         const double stair = (double)k / 4.0;
         const double phase = stair * 0.5 * lsm::kPi;
-        kp.sep_ratio_tab[k] = 1.0 - std::cos(phase);
+        kp.sep_ratio_tab[k] = 1.0 - lsm_cos(phase);
     }
     // exact squared thresholds: sqrt_rn is monotone, so {t : sqrt_rn(t) >= T} is [lt(T), inf)
     {
@@ -257,7 +257,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     const double step = (2.0 * lsm::kPi - 0.0) / (double)lsm::kMagSegments;
     for (int k = 0; k < lsm::kMagSegments; ++k) {
         const double phi = (double)k * step + 0.0;
-        ctab[k] = std::cos(phi); stab[k] = std::sin(phi);
+        ctab[k] = lsm_cos(phi); stab[k] = lsm_sin(phi);
     }
     e = lsm::upload_magnetic_tables(ctab, stab);
     if (e != cudaSuccess) { lsm_destroy(h); return cuda_fail(e, "upload_magnetic_tables"); }
@@ -572,6 +572,26 @@ int lsm_rollout_insert(lsm_handle* h, const float* obs, const uint8_t* done, flo
     cudaError_t e = lsm::rollout_insert_launch(obs, done, share_obs, masks, active_masks, (long long)h->kp.b.num_envs, h->kp.N, h->kp.D,
                                                (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "lsm_rollout_insert");
+    return 0;
+}
+
+int lsm_math_eval(int op, const double* a, const double* b, double* out, int64_t n) {
+    if (a == nullptr || out == nullptr || (op == 2 && b == nullptr)) return fail(1, "lsm_math_eval: null argument");
+    if (op < 0 || op > 4) return fail(2, "lsm_math_eval: op must be 0 sin, 1 cos, 2 atan2, 3 sincos.sin, 4 sincos.cos");
+    for (int64_t k = 0; k < n; ++k) {
+        if (op == 0) out[k] = lsm_sin(a[k]);
+        else if (op == 1) out[k] = lsm_cos(a[k]);
+        else if (op == 2) out[k] = lsm_atan2(a[k], b[k]);
+        else { double s, c; lsm_sincos(a[k], &s, &c); out[k] = op == 3 ? s : c; }
+    }
+    return 0;
+}
+
+int lsm_math_eval_device(int op, const double* a, const double* b, double* out, int64_t n, void* stream) {
+    if (a == nullptr || out == nullptr || (op == 2 && b == nullptr)) return fail(1, "lsm_math_eval_device: null argument");
+    if (op < 0 || op > 4) return fail(2, "lsm_math_eval_device: bad op");
+    cudaError_t e = lsm::math_eval_launch(op, a, b, out, (long long)n, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_math_eval_device");
     return 0;
 }
 

@@ -10,6 +10,8 @@
 #include <cuda_runtime.h>
 
 #include "../../include/lsm_b200.h"
+// float64 sin / cos / sincos / atan2 shared bit for bit with the CPU oracle (no libdevice / glibc rounding freedom)
+#include "../../include/lsm_math.h"
 
 namespace lsm {
 
@@ -269,7 +271,7 @@ __device__ __forceinline__ Curriculum curriculum(const KParams& kp, double ratio
 }
 
 // utils.py:79-81
-__device__ __forceinline__ double direction_alignment_error(double h, double href) { return 0.5 - 0.5 * cos(h - href); }
+__device__ __forceinline__ double direction_alignment_error(double h, double href) { return 0.5 - 0.5 * lsm_cos(h - href); }
 
 // utils.py:104-112 with precomputed cos / sin of the reference heading
 __device__ __forceinline__ void rotate_into(double dx, double dy, double c, double s, double& ox, double& oy) {
@@ -278,7 +280,7 @@ __device__ __forceinline__ void rotate_into(double dx, double dy, double c, doub
 }
 
 template <int DYN>
-__device__ __forceinline__ double theta_of(double s2, double s3) { return DYN == LSM_DYN_DOUBLE_INTEGRATOR ? atan2(s3, s2) : s2; }
+__device__ __forceinline__ double theta_of(double s2, double s3) { return DYN == LSM_DYN_DOUBLE_INTEGRATOR ? lsm_atan2(s3, s2) : s2; }
 template <int DYN>
 __device__ __forceinline__ double speed_of(double s2, double s3) {
     return DYN == LSM_DYN_DOUBLE_INTEGRATOR ? sqrt(s2 * s2 + s3 * s3) : s3;

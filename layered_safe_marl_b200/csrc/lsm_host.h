@@ -23,6 +23,7 @@ cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pai
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells);
 cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
                                   long long n, int N, int D, cudaStream_t stream);
+cudaError_t math_eval_launch(int op, const double* a, const double* b, double* out, long long n, cudaStream_t stream);
 cudaError_t pad_grads_launch(const float* grads, float* grads8, long long cells);
 cudaError_t edge_list_launch(const float* adj, int32_t* counts, long long* offsets, long long* edge_index, float* edge_attr,
                              long long num_graphs, int E, long long capacity, cudaStream_t stream);

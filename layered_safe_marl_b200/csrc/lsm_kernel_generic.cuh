@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 min_rel = m;
                 theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vpx = s3 * ct; vpy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
                 goal_pre = goal_index(reached, ai, N, M);
                 const double gx = S.lx[goal_pre], gy = S.ly[goal_pre], gh = S.lh[goal_pre], gs = S.lsp[goal_pre];
                 // observation (pre-update goal): navigation_graph_safe.py:855-875, utils.py:114-137
@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     double rx, ry; rotate_into(gx - x, gy - y, S.cth[ai], S.sth[ai], rx, ry);
                     const double rh = gh - s2;
                     o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                    o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)gs;
+                    o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh); o[5] = (float)gs;
                 }
                 // reward_reach_goal: navigation_graph_safe.py:691-791
                 const double he = direction_alignment_error(theta, gh);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 if (reached_now) {
                     const double spr = 1.0 - sen;
                     const double pdx = gx - x, pdy = gy - y;
-                    double cte = pdx * sin(theta) - pdy * cos(theta);
+                    double cte = pdx * lsm_sin(theta) - pdy * lsm_cos(theta);
                     const double nrm = norm2(pdx, pdy);
                     cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
                     cte = clipd(cte, 0.0, 1.0);
@@ -233,23 +233,23 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 if (!done) {
                     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
                         if (!use_filter_arg) {   // utils.py:323-349
-                            const double cg = cos(gh), sg = sin(gh);
+                            const double cg = lsm_cos(gh), sg = lsm_sin(gh);
                             double rpx, rpy, rvx, rvy;
                             rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
                             const double dist = norm2(rpx, rpy);
-                            const double ang = atan2(rpy, rpx);
+                            const double ang = lsm_atan2(rpy, rpx);
                             const double ang_range = kPi / 6;
                             rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
                             const double rh = magnetic_heading(rpx, rpy, 2.0 * q.dist_thresh);
                             double ref_speed = pymax(gs, 0.1);
                             const double dr = clipd(dist / 1.5, 0.0, 1.0);
                             ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
-                            const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
+                            const double ex = rvx - ref_speed * lsm_cos(rh), ey = rvy - ref_speed * lsm_sin(rh);
                             const double err = norm2(ex, ey);
                             double pen;
-                            if (cos(ang) < cos(ang_range)) pen = err;
+                            if (lsm_cos(ang) < lsm_cos(ang_range)) pen = err;
                             else {
-                                const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
+                                const double ar = clipd((lsm_cos(ang) - lsm_cos(ang_range)) / (1.0 - lsm_cos(ang_range)), 0.0, 1.0);
                                 pen = err * (1.0 - ar) + dist * ar;
                             }
                             double hap = 3.0 * pen;
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                         if (use_filter_arg) rew -= 1.0; else rew -= 1.0 * q.sloped;
                     } else {
                         double rpx, rpy;
-                        rotate_into(x - gx, y - gy, cos(gh), sin(gh), rpx, rpy);
+                        rotate_into(x - gx, y - gy, lsm_cos(gh), lsm_sin(gh), rpx, rpy);
                         const double rs[4] = { rpx, rpy, theta - gh, speed };
                         Stencil<4> st;
                         stencil_setup<4>(kp.tg, rs, st);
@@ -307,10 +307,10 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                         if (rd < q.eng && !adone) {
                             const double rx = S.ax[a] - x, ry = S.ay[a] - y;
                             const double closeness = 1.0 - clipd((rd - q.sep) / (q.eng - q.sep), 0.0, 1.0);
-                            const double dir = atan2(ry, rx);
+                            const double dir = lsm_atan2(ry, rx);
                             const double vax = a < ai ? S.vpost_x[a] : S.vpre_x[a];
                             const double vay = a < ai ? S.vpost_y[a] : S.vpre_y[a];
-                            double change = cos(dir) * (vax - vpx) + sin(dir) * (vay - vpy);
+                            double change = lsm_cos(dir) * (vax - vpx) + lsm_sin(dir) * (vay - vpy);
                             change = fabs(pymin(0.0, change));
                             pen += change * closeness;
                             count += 1;
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
             if (agent_on) {
                 double vx, vy;
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
                 const int g = goal_index(reached, ai, N, M);
                 S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
                 S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
@@ -505,7 +505,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                         }
                     }
                     for (int l = 0; l < L - 1; ++l)
-                        S.lh[l * N + i] = atan2(S.ly[(l + 1) * N + i] - S.ly[l * N + i], S.lx[(l + 1) * N + i] - S.lx[l * N + i]);
+                        S.lh[l * N + i] = lsm_atan2(S.ly[(l + 1) * N + i] - S.ly[l * N + i], S.lx[(l + 1) * N + i] - S.lx[l * N + i]);
                     const double last_heading = S.lh[(L - 2) * N + i];
                     const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
                     if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
@@ -525,8 +525,8 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     }
                     S.lh[(L - 1) * N + i] = last_heading;
                     for (int l = 0; l < L; ++l) {
-                        S.lsin[l * N + i] = sin(S.lh[l * N + i]);
-                        S.lcos[l * N + i] = cos(S.lh[l * N + i]);
+                        S.lsin[l * N + i] = lsm_sin(S.lh[l * N + i]);
+                        S.lcos[l * N + i] = lsm_cos(S.lh[l * N + i]);
                     }
                 }
             }
@@ -540,7 +540,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
+                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; S.cth[ai] = ct; S.sth[ai] = st; }
                 S.ax[ai] = x; S.ay[ai] = y; S.as2[ai] = s2; S.as3[ai] = s3;
                 S.vpre_x[ai] = vx; S.vpre_y[ai] = vy; S.vpost_x[ai] = vx; S.vpost_y[ai] = vy;
                 S.spd_post[ai] = (DYN == LSM_DYN_DOUBLE_INTEGRATOR) ? 0.0 : s3;
@@ -556,7 +556,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
                     const double rh = S.lh[g] - s2;
                     o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                    o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
+                    o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh); o[5] = (float)S.lsp[g];
                 }
             }
             if (do_reset && sample) reset_count += 1;
@@ -585,7 +585,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 double rx, ry; rotate_into(S.lx[g] - x, S.ly[g] - y, S.cth[ai], S.sth[ai], rx, ry);
                 const double rh = S.lh[g] - s2;
                 o[0] = (float)s3; o[1] = (float)rx; o[2] = (float)ry;
-                o[3] = (float)sin(rh); o[4] = (float)cos(rh); o[5] = (float)S.lsp[g];
+                o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh); o[5] = (float)S.lsp[g];
             }
         }
 

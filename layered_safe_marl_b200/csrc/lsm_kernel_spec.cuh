@@ -499,7 +499,7 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, 
             if (lp[i].x > lp[N + i].x) { const double2 t = lp[i]; lp[i] = lp[N + i]; lp[N + i] = t; }
         }
         for (int l = 0; l < L - 1; ++l)
-            P.lh[l * N + i] = atan2(lp[(l + 1) * N + i].y - lp[l * N + i].y, lp[(l + 1) * N + i].x - lp[l * N + i].x);
+            P.lh[l * N + i] = lsm_atan2(lp[(l + 1) * N + i].y - lp[l * N + i].y, lp[(l + 1) * N + i].x - lp[l * N + i].x);
         const double last_heading = P.lh[(L - 2) * N + i];
         const double cr = use_filter_arg ? 1.0 : ratio_sloped(ratio, 0.25, 0.75);
         if (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
@@ -519,7 +519,7 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, 
         P.lh[(L - 1) * N + i] = last_heading;
     }
     for (int m = 0; m < M; ++m) {
-        const double sv = sin(P.lh[m]), cv = cos(P.lh[m]);
+        const double sv = lsm_sin(P.lh[m]), cv = lsm_cos(P.lh[m]);
         P.lsin[m] = sv; P.lcos[m] = cv;
         R.cst[m] = make_float4((float)sv, (float)cv, (float)P.lsp[m], 1.0f);
     }
@@ -532,23 +532,23 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, 
 // utils.py:323-349 (double integrator without the safety-filter argument): heading/velocity penalty
 __device__ __noinline__ double magnetic_penalty(double x, double y, double s2, double s3, double gx, double gy,
                                                double gh, double gs, double dist_thresh, double sloped) {
-    const double cg = cos(gh), sg = sin(gh);
+    const double cg = lsm_cos(gh), sg = lsm_sin(gh);
     double rpx, rpy, rvx, rvy;
     rotate_into(x - gx, y - gy, cg, sg, rpx, rpy);
     const double dist = norm2(rpx, rpy);
-    const double ang = atan2(rpy, rpx);
+    const double ang = lsm_atan2(rpy, rpx);
     const double ang_range = kPi / 6;
     rotate_into(s2 - 0.0, s3 - 0.0, cg, sg, rvx, rvy);
     const double rh = magnetic_heading(rpx, rpy, 2.0 * dist_thresh);
     double ref_speed = pymax(gs, 0.1);
     const double dr = clipd(dist / 1.5, 0.0, 1.0);
     ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
-    const double ex = rvx - ref_speed * cos(rh), ey = rvy - ref_speed * sin(rh);
+    const double ex = rvx - ref_speed * lsm_cos(rh), ey = rvy - ref_speed * lsm_sin(rh);
     const double err = norm2(ex, ey);
     double pen;
-    if (cos(ang) < cos(ang_range)) pen = err;
+    if (lsm_cos(ang) < lsm_cos(ang_range)) pen = err;
     else {
-        const double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
+        const double ar = clipd((lsm_cos(ang) - lsm_cos(ang_range)) / (1.0 - lsm_cos(ang_range)), 0.0, 1.0);
         pen = err * (1.0 - ar) + dist * ar;
     }
     double hap = 3.0 * pen;
@@ -559,7 +559,7 @@ __device__ __noinline__ double magnetic_penalty(double x, double y, double s2, d
 // navigation_graph_safe.py:700-720: heading * speed * cross-track factor of the goal reward (only on the step a goal is reached)
 __device__ __noinline__ double goal_reward_factor(double theta, double pdx, double pdy, double hpr, double sen) {
     const double spr = 1.0 - sen;
-    double cte = pdx * sin(theta) - pdy * cos(theta);
+    double cte = pdx * lsm_sin(theta) - pdy * lsm_cos(theta);
     const double nrm = norm2(pdx, pdy);
     cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
     cte = clipd(cte, 0.0, 1.0);
@@ -843,7 +843,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             if (agent_on) {
                 theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
-                else { cth = cos(s2); sth = sin(s2); vpx = s3 * cth; vpy = s3 * sth; R.air.cth[ai] = cth; R.air.sth[ai] = sth; }
+                else { cth = lsm_cos(s2); sth = lsm_sin(s2); vpx = s3 * cth; vpy = s3 * sth; R.air.cth[ai] = cth; R.air.sth[ai] = sth; }
                 goal_pre = goal_index(reached, ai, N, M);
                 const double2 gp = R.pos[N + goal_pre];
                 const double gx = gp.x, gy = gp.y, gh = P.lh[goal_pre], gs = P.lsp[goal_pre];
@@ -990,7 +990,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             if (agent_on) {
                 double vx, vy;
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
+                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
                 const int g = goal_index(reached, ai, N, M);
                 goal_obs = g;
                 R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
@@ -1054,7 +1054,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = cos(s2), st = sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
+                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
                 R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
                 R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
                 R.pos[E + ai] = g0; R.pos[E + N + ai] = g0;

@@ -273,6 +273,22 @@ cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* 
     return cudaGetLastError();
 }
 
+// include/lsm_math.h evaluated on the device (bit-identity test against the host / oracle evaluation)
+__global__ void __launch_bounds__(256) lsm_math_eval_kernel(int op, const double* __restrict__ a, const double* __restrict__ b,
+                                                          double* __restrict__ out, long long n) {
+    const long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    if (op == 0) out[k] = lsm_sin(a[k]);
+    else if (op == 1) out[k] = lsm_cos(a[k]);
+    else if (op == 2) out[k] = lsm_atan2(a[k], b[k]);
+    else { double s, c; lsm_sincos(a[k], &s, &c); out[k] = (op == 3) ? s : c; }
+}
+cudaError_t math_eval_launch(int op, const double* a, const double* b, double* out, long long n, cudaStream_t stream) {
+    if (n <= 0) return cudaSuccess;
+    lsm_math_eval_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(op, a, b, out, n);
+    return cudaGetLastError();
+}
+
 cudaError_t pad_grads_launch(const float* grads, float* grads8, long long cells) {
     lsm_pad_grads_kernel<<<(unsigned)((cells * 8 + 255) / 256), 256>>>(grads, grads8, cells);
     return cudaGetLastError();

@@ -26,7 +26,7 @@ __device__ double magnetic_heading(double px, double py, double radius) {
         by = by + cy / rmag3;
     }
     bx = bx / scale_x;
-    return atan2(by, bx);
+    return lsm_atan2(by, bx);
 }
 
 __device__ __forceinline__ int goal_index(int reached, int i, int N, int M) {   // navigation_graph_safe.py:576-582
@@ -44,9 +44,9 @@ __device__ __forceinline__ void relative_state(double ex, double ey, double e2, 
     } else {
         const double ddx = ox - ex, ddy = oy - ey;
         const double dist = sqrt(ddx * ddx + ddy * ddy);
-        const double ang = atan2(ddy, ddx);
-        r[0] = dist * cos(ang - e2);
-        r[1] = dist * sin(ang - e2);
+        const double ang = lsm_atan2(ddy, ddx);
+        r[0] = dist * lsm_cos(ang - e2);
+        r[1] = dist * lsm_sin(ang - e2);
         r[2] = o2 - e2; r[3] = e3; r[4] = o3;
     }
 }
@@ -63,7 +63,7 @@ __device__ __forceinline__ void relative_state_rot(double ex, double ey, double 
     } else {
         const double ddx = ox - ex, ddy = oy - ey;
         double se, ce;
-        sincos(e2, &se, &ce);
+        lsm_sincos(e2, &se, &ce);
         r[0] = ddx * ce + ddy * se;
         r[1] = ddy * ce - ddx * se;
         r[2] = o2 - e2; r[3] = e3; r[4] = o3;
@@ -159,8 +159,8 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
 #pragma unroll
             for (int k = 0; k < 4; ++k) u[k] = (a[k] < 0.0) ? lo[k] : hi[k];
         } else {
-            const double f0 = -rel[3] + rel[ND - 1] * cos(rel[2]);
-            const double f1 = rel[ND - 1] * sin(rel[2]);
+            const double f0 = -rel[3] + rel[ND - 1] * lsm_cos(rel[2]);
+            const double f1 = rel[ND - 1] * lsm_sin(rel[2]);
             double b = g[0] * f0 + g[1] * f1;
             b = b + c.cbf_rate * best_v;
             double pinv[4];
@@ -215,14 +215,14 @@ __device__ __forceinline__ void integrate(double& x, double& y, double& s2, doub
         double v1 = v0 + ac * dt;
         double ddx, ddy;
         if (fabs(om * dt) < 1e-3) {
-            const double T = dt, c0 = cos(th0), s0 = sin(th0), o = om;
+            const double T = dt, c0 = lsm_cos(th0), s0 = lsm_sin(th0), o = om;
             const double i0 = T, i1 = T * T / 2.0, i2 = T * T * T / 3.0, i3 = T * T * T * T / 4.0, i4 = T * T * T * T * T / 5.0;
             const double cc0 = c0, cc1 = -s0 * o, cc2 = -c0 * o * o / 2.0, cc3 = s0 * o * o * o / 6.0;
             const double sc0 = s0, sc1 = c0 * o, sc2 = -s0 * o * o / 2.0, sc3 = -c0 * o * o * o / 6.0;
             ddx = v0 * (cc0 * i0 + cc1 * i1 + cc2 * i2 + cc3 * i3) + ac * (cc0 * i1 + cc1 * i2 + cc2 * i3 + cc3 * i4);
             ddy = v0 * (sc0 * i0 + sc1 * i1 + sc2 * i2 + sc3 * i3) + ac * (sc0 * i1 + sc1 * i2 + sc2 * i3 + sc3 * i4);
         } else {
-            const double s1 = sin(th1), c1 = cos(th1), s0 = sin(th0), c0 = cos(th0);
+            const double s1 = lsm_sin(th1), c1 = lsm_cos(th1), s0 = lsm_sin(th0), c0 = lsm_cos(th0);
             ddx = (v1 * s1 - v0 * s0) / om + ac * (c1 - c0) / (om * om);
             ddy = (-(v1 * c1) + v0 * c0) / om + ac * (s1 - s0) / (om * om);
         }

@@ -169,8 +169,9 @@ def synthetic_ttr_grid(shape=TTR_GRID_SHAPE) -> HjGrid:
 
 
 def load_reference_pickle(file_name: str, target_separation_distance: float) -> HjGrid:
-    """Load a Drive-format value-function pickle (needs `hj_reachability_utils` importable for
-    unpickling, exactly like the reference). Field names: safety_filter.py:158-166."""
+    """Load a Drive-format VALUE-FUNCTION pickle (`data/*_value_function.pkl`; needs `hj_reachability_utils` importable
+    for unpickling, exactly like the reference). Field names: safety_filter.py:158-166. The time-to-reach file
+    (`data/airtaxi_ttr_function.pkl`) has a different convention - use `load_reference_ttr_pickle` for it."""
     with open(file_name, 'rb') as f:
         data = pickle.load(f)
     meta = data.grid_meta_data
@@ -179,3 +180,22 @@ def load_reference_pickle(file_name: str, target_separation_distance: float) -> 
     periodic = tuple(d in periodic_dims for d in range(len(shape)))
     return make_hj_handle(np.asarray(data.values), meta.domain_lo, meta.domain_hi, periodic,
                           data.info['separation_distance'], target_separation_distance)
+
+
+def _periodic_mask(meta, ndim: int):
+    periodic_dims = tuple(getattr(meta, 'periodic_dims', ()) or ())
+    return tuple(d in periodic_dims for d in range(ndim))
+
+
+def load_reference_ttr_pickle(file_name: str) -> HjGrid:
+    """Load a Drive-format time-to-reach pickle the way `make_world` does (reference
+    navigation_graph_safe.py:128-138): the values are used RAW (no negation, no separation shift, no gradients),
+    `ttr_max` comes from `data.ttr_max` (the reward's fallback for out-of-range states, :751-755), periodic dims
+    from the grid meta data. Needs `hj_reachability_utils` importable for unpickling, exactly like the reference."""
+    with open(file_name, 'rb') as f:
+        data = pickle.load(f)
+    meta = data.grid_meta_data
+    values = np.ascontiguousarray(np.asarray(data.values), dtype=np.float32)
+    return HjGrid(lo=np.asarray(meta.domain_lo, dtype=np.float64), hi=np.asarray(meta.domain_hi, dtype=np.float64),
+                  shape=tuple(int(s) for s in values.shape), periodic=_periodic_mask(meta, values.ndim), values=values,
+                  grads=None, separation_distance=0.0, ttr_max=float(data.ttr_max))

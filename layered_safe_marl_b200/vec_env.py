@@ -413,11 +413,24 @@ class B200GraphVecEnv:
         lm = self.landmarks
         lm[LY.LF_X].copy_(lp[..., 0]); lm[LY.LF_Y].copy_(lp[..., 1]); lm[LY.LF_HEADING].copy_(lh)
         lm[LY.LF_SPEED].copy_(t(s['landmark_speed'], torch.float64))
-        # sin / cos of the landmark headings are tabulated on the HOST (libm), like after a host-side load
-        lh_np = np.asarray(s['landmark_heading'], dtype=np.float64)
-        lm[LY.LF_SIN].copy_(t(np.sin(lh_np), torch.float64)); lm[LY.LF_COS].copy_(t(np.cos(lh_np), torch.float64))
+        # sin / cos of the landmark headings: the same float64 implementation (include/lsm_math.h) the on-device reset
+        # sampler uses, evaluated on the host, so an injected state is bit-identical to a sampled one
+        lh_np = np.ascontiguousarray(s['landmark_heading'], dtype=np.float64)
+        lm[LY.LF_SIN].copy_(t(self.math_eval(0, lh_np), torch.float64)); lm[LY.LF_COS].copy_(t(self.math_eval(1, lh_np), torch.float64))
         self.env_f64[LY.EF_CURRICULUM_RATIO].copy_(t(s['curriculum_ratio'], torch.float64))
         self.env_i32[LY.EI_CURRENT_STEP].copy_(t(s['current_step'], torch.int32))
+
+    def math_eval(self, op: int, a, b=None):
+        """include/lsm_math.h on the host (op 0 sin, 1 cos, 2 atan2(a, b)): the kernels' own float64 trigonometry."""
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        out = np.empty_like(a)
+        bp = None
+        if b is not None:
+            b = np.ascontiguousarray(b, dtype=np.float64)
+            bp = b.ctypes.data_as(C.c_void_p)
+        _lib.check(self.lib.lsm_math_eval(int(op), a.ctypes.data_as(C.c_void_p), bp, out.ctypes.data_as(C.c_void_p), a.size),
+                   'lsm_math_eval')
+        return out
 
     def get_state(self) -> dict:
         f = self.agent_f64.cpu().numpy(); i = self.agent_i32.cpu().numpy()

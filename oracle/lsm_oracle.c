@@ -11,6 +11,8 @@
  * formulation instead; agreement between the two is part of what the parity tests check.
  */
 #include "lsm_oracle.h"
+/* float64 sin / cos / atan2 shared bit for bit with the CUDA kernels (numpy's libm in the reference) */
+#include "../include/lsm_math.h"
 
 #include <math.h>
 #include <pthread.h>
@@ -143,7 +145,7 @@ void lsmo_curriculum(const lsmo_params *p, double ratio, double out[12]) {
     out[7] = p->diff_from_filtered_action_rew * stair;
     out[8] = p->hj_value_rew * stair;
     double phase = ratio_stair(ratio, 4, 0.2, 0.75) * 0.5 * PI;
-    double sep_ratio = 1.0 - cos(phase);
+    double sep_ratio = 1.0 - lsm_cos(phase);
     int use_filter_arg = (p->flags & LSMO_FLAG_USE_SAFETY_FILTER) != 0;
     int initial_phase = use_filter_arg && (p->flags & LSMO_FLAG_INITIAL_PHASE_USE_SAFETY_FILTER);
     int world_filter = use_filter_arg;
@@ -167,7 +169,7 @@ double lsmo_magnetic_heading(double px, double py, double radius) {
     double bx = 0.0, by = 0.0;
     for (int k = 0; k < NSEG; ++k) {
         double phi = (double)k * step + 0.0;
-        double c = cos(phi), s = sin(phi);
+        double c = lsm_cos(phi), s = lsm_sin(phi);
         double Ly = -radius * c, Lz = -radius * s;
         double dLy = radius * s, dLz = -radius * c;
         double rx = px - 0.0, ry = py - Ly, rz = 0.0 - Lz;
@@ -179,7 +181,7 @@ double lsmo_magnetic_heading(double px, double py, double radius) {
         by = by + cy / rmag3;
     }
     bx = bx / scale_x;
-    return atan2(by, bx);
+    return lsm_atan2(by, bx);
 }
 
 /* ------------------------------------------------------------------------------------------
@@ -205,14 +207,14 @@ typedef struct {
 } env_t;
 
 static inline double a_theta(const env_t *w, int i) {   /* core.py:97-99,179-181 */
-    return w->dyn == LSMO_DYN_DI ? atan2(w->s3[i], w->s2[i]) : w->s2[i];
+    return w->dyn == LSMO_DYN_DI ? lsm_atan2(w->s3[i], w->s2[i]) : w->s2[i];
 }
 static inline double a_speed(const env_t *w, int i) {   /* core.py:89-91,174-176 */
     return w->dyn == LSMO_DYN_DI ? sqrt(w->s2[i] * w->s2[i] + w->s3[i] * w->s3[i]) : w->s3[i];
 }
 static inline void a_vel(const env_t *w, int i, double v[2]) {   /* core.py:105-108,183-185 */
     if (w->dyn == LSMO_DYN_DI) { v[0] = w->s2[i]; v[1] = w->s3[i]; }
-    else { v[0] = w->s3[i] * cos(w->s2[i]); v[1] = w->s3[i] * sin(w->s2[i]); }
+    else { v[0] = w->s3[i] * lsm_cos(w->s2[i]); v[1] = w->s3[i] * lsm_sin(w->s2[i]); }
 }
 
 /* navigation_graph_safe.py:576-582 get_agent_current_goal (landmark index) */
@@ -223,12 +225,12 @@ static inline int current_goal(const env_t *w, int i) {
 }
 
 /* utils.py:79-81 */
-static inline double direction_alignment_error(double h, double href) { return 0.5 - 0.5 * cos(h - href); }
+static inline double direction_alignment_error(double h, double href) { return 0.5 - 0.5 * lsm_cos(h - href); }
 
 /* utils.py:104-112: rot = [[c, s], [-s, c]] applied to (q - ref) */
 static inline void rel_pos_from_reference(double qx, double qy, double rx, double ry, double heading, double out[2]) {
     double dx = qx - rx, dy = qy - ry;
-    double c = cos(heading), s = sin(heading);
+    double c = lsm_cos(heading), s = lsm_sin(heading);
     out[0] = c * dx + s * dy;
     out[1] = (-s) * dx + c * dy;
 }
@@ -277,13 +279,30 @@ static void di_relative_state(const env_t *w, int e, int o, double r[4]) {      
     r[0] = w->x[e] - w->x[o]; r[1] = w->y[e] - w->y[o];
     r[2] = w->s2[e] - w->s2[o]; r[3] = w->s3[e] - w->s3[o];
 }
+/* LITERAL (default): d cos(phi - theta_e), d sin(phi - theta_e) with phi = atan2(dy, dx), as the reference writes it.
+ * ROTATION: the same point as the rotation of (dx, dy) by theta_e,
+ *     d cos(phi - theta_e) = dx cos(theta_e) + dy sin(theta_e),   d sin(phi - theta_e) = dy cos(theta_e) - dx sin(theta_e)
+ * - equal to the literal form to ~1e-16 d; it is the form the specialised CUDA pipeline evaluates (one sincos per pair
+ * instead of sqrt + atan2 + cos + sin). tests/ select it to compare that pipeline BIT FOR BIT; the golden rollouts of
+ * the reference are checked with the literal form, and tests/test_oracle_golden.py checks that the two forms give
+ * the same discrete outputs on them. */
+static int g_rel_form = 0;
+void lsmo_set_relative_state_form(int form) { g_rel_form = form ? 1 : 0; }
+int lsmo_get_relative_state_form(void) { return g_rel_form; }
 static void at_relative_state(const env_t *w, int e, int o, double r[5]) {      /* safety_filter.py:277-284 */
     double ddx = w->x[o] - w->x[e], ddy = w->y[o] - w->y[e];
-    double dist = sqrt(ddx * ddx + ddy * ddy);
     double rel_heading = w->s2[o] - w->s2[e];
-    double ang = atan2(ddy, ddx);
-    r[0] = dist * cos(ang - w->s2[e]);
-    r[1] = dist * sin(ang - w->s2[e]);
+    if (g_rel_form == 0) {
+        double dist = sqrt(ddx * ddx + ddy * ddy);
+        double ang = lsm_atan2(ddy, ddx);
+        r[0] = dist * lsm_cos(ang - w->s2[e]);
+        r[1] = dist * lsm_sin(ang - w->s2[e]);
+    } else {
+        double se, ce;
+        lsm_sincos(w->s2[e], &se, &ce);
+        r[0] = ddx * ce + ddy * se;
+        r[1] = ddy * ce - ddx * se;
+    }
     r[2] = rel_heading; r[3] = w->s3[e]; r[4] = w->s3[o];
 }
 static double hj_value(const env_t *w, const double *rel, int *in_range) {
@@ -382,8 +401,8 @@ static void apply_safety_filter(env_t *w, double raw[][2], double safe[][2], int
                 if (rel[4] >= vmax) { memcpy(lo2, lo, sizeof lo); memcpy(hi2, hi, sizeof hi); hi2[3] = 0.0; }
                 for (int k = 0; k < 4; ++k) u[k] = (a[k] < 0.0) ? lo2[k] : hi2[k];
             } else {
-                double f0 = -rel[3] + rel[4] * cos(rel[2]);
-                double f1 = rel[4] * sin(rel[2]);
+                double f0 = -rel[3] + rel[4] * lsm_cos(rel[2]);
+                double f1 = rel[4] * lsm_sin(rel[2]);
                 double b = g[0] * f0 + g[1] * f1;
                 b = b + p->cbf_rate * best_v;
                 double pinv[4];
@@ -438,7 +457,7 @@ static void integrate_airtaxi(env_t *w, int i, const double u[2], double dt) {
     double ddx, ddy;
     if (fabs(om * dt) < 1e-3) {
         /* series in (om*dt): integral of (v0 + a t) (cos, sin)(th0 + om t) */
-        double T = dt, c0 = cos(th0), s0 = sin(th0), o = om;
+        double T = dt, c0 = lsm_cos(th0), s0 = lsm_sin(th0), o = om;
         double i0 = T, i1 = T * T / 2.0, i2 = T * T * T / 3.0, i3 = T * T * T * T / 4.0, i4 = T * T * T * T * T / 5.0;
         /* cos(th0+ot) ~ c0 - s0 o t - c0 o^2 t^2/2 + s0 o^3 t^3/6 ; sin ~ s0 + c0 o t - s0 o^2 t^2/2 - c0 o^3 t^3/6 */
         double cc0 = c0, cc1 = -s0 * o, cc2 = -c0 * o * o / 2.0, cc3 = s0 * o * o * o / 6.0;
@@ -446,7 +465,7 @@ static void integrate_airtaxi(env_t *w, int i, const double u[2], double dt) {
         ddx = v0 * (cc0 * i0 + cc1 * i1 + cc2 * i2 + cc3 * i3) + ac * (cc0 * i1 + cc1 * i2 + cc2 * i3 + cc3 * i4);
         ddy = v0 * (sc0 * i0 + sc1 * i1 + sc2 * i2 + sc3 * i3) + ac * (sc0 * i1 + sc1 * i2 + sc2 * i3 + sc3 * i4);
     } else {
-        double s1 = sin(th1), c1 = cos(th1), s0 = sin(th0), c0 = cos(th0);
+        double s1 = lsm_sin(th1), c1 = lsm_cos(th1), s0 = lsm_sin(th0), c0 = lsm_cos(th0);
         ddx = (v1 * s1 - v0 * s0) / om + ac * (c1 - c0) / (om * om);
         ddy = (-(v1 * c1) + v0 * c0) / om + ac * (s1 - s0) / (om * om);
     }
@@ -523,13 +542,13 @@ static void emit_obs(const env_t *w, int i, float *out) {
     if (w->dyn == LSMO_DYN_DI) {
         out[0] = (float)w->s2[i]; out[1] = (float)w->s3[i];
         out[2] = (float)(w->lx[g] - w->x[i]); out[3] = (float)(w->ly[g] - w->y[i]);
-        out[4] = (float)sin(w->lh[g]); out[5] = (float)cos(w->lh[g]);
+        out[4] = (float)lsm_sin(w->lh[g]); out[5] = (float)lsm_cos(w->lh[g]);
         out[6] = (float)w->ls[g];
     } else {
         double rp[2]; rel_pos_from_reference(w->lx[g], w->ly[g], w->x[i], w->y[i], w->s2[i], rp);
         double rh = w->lh[g] - w->s2[i];
         out[0] = (float)w->s3[i]; out[1] = (float)rp[0]; out[2] = (float)rp[1];
-        out[3] = (float)sin(rh); out[4] = (float)cos(rh); out[5] = (float)w->ls[g];
+        out[3] = (float)lsm_sin(rh); out[4] = (float)lsm_cos(rh); out[5] = (float)w->ls[g];
     }
 }
 /* navigation_graph_safe.py:1038-1089 + utils.py:139-255 */
@@ -566,14 +585,14 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 o[0] = (float)(w->x[e] - w->x[i]); o[1] = (float)(w->y[e] - w->y[i]);
                 o[2] = (float)(w->s2[e] - vi[0]); o[3] = (float)(w->s3[e] - vi[1]);
                 o[4] = (float)(w->lx[g] - w->x[i]); o[5] = (float)(w->ly[g] - w->y[i]);
-                o[6] = (float)sin(w->lh[g]); o[7] = (float)cos(w->lh[g]);
+                o[6] = (float)lsm_sin(w->lh[g]); o[7] = (float)lsm_cos(w->lh[g]);
                 o[8] = (float)w->ls[g]; o[9] = 0.0f;
             } else {
                 int m = e - N;
                 o[0] = (float)(w->lx[m] - w->x[i]); o[1] = (float)(w->ly[m] - w->y[i]);
                 o[2] = (float)(-vi[0]); o[3] = (float)(-vi[1]);
                 o[4] = o[0]; o[5] = o[1];
-                o[6] = (float)sin(w->lh[m]); o[7] = (float)cos(w->lh[m]);
+                o[6] = (float)lsm_sin(w->lh[m]); o[7] = (float)lsm_cos(w->lh[m]);
                 o[8] = (float)w->ls[m]; o[9] = 1.0f;
             }
         } else {
@@ -589,9 +608,9 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 rel_pos_from_reference(w->lx[g], w->ly[g], w->x[i], w->y[i], thi, rg);
                 double rgh = w->lh[g] - thi;
                 o[0] = (float)rp[0]; o[1] = (float)rp[1]; o[2] = (float)rs;
-                o[3] = (float)sin(rh); o[4] = (float)cos(rh);
+                o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh);
                 o[5] = (float)rg[0]; o[6] = (float)rg[1];
-                o[7] = (float)sin(rgh); o[8] = (float)cos(rgh);
+                o[7] = (float)lsm_sin(rgh); o[8] = (float)lsm_cos(rgh);
                 o[9] = (float)w->ls[g]; o[10] = 0.0f;
             } else {
                 int m = e - N;
@@ -599,7 +618,7 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 rel_pos_from_reference(w->lx[m], w->ly[m], w->x[i], w->y[i], thi, rp);
                 double rh = w->lh[m] - thi;
                 o[0] = (float)rp[0]; o[1] = (float)rp[1]; o[2] = (float)w->s3[i];
-                o[3] = (float)sin(rh); o[4] = (float)cos(rh);
+                o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh);
                 o[5] = o[0]; o[6] = o[1]; o[7] = o[3]; o[8] = o[4];
                 o[9] = (float)w->ls[m]; o[10] = 1.0f;
             }
@@ -640,7 +659,7 @@ static double reward_reach_goal(const env_t *w, int i) {
         double spr = 1.0 - sen;
         /* utils.py:83-89 cross_track_error */
         double pdx = w->lx[g] - w->x[i], pdy = w->ly[g] - w->y[i];
-        double cte = pdx * sin(th) - pdy * cos(th);
+        double cte = pdx * lsm_sin(th) - pdy * lsm_cos(th);
         double nrm = norm2(pdx, pdy);
         cte = fabs(cte) / (nrm > 1e-6 ? nrm : 1e-6);
         cte = clipd(cte, 0.0, 1.0);
@@ -657,19 +676,19 @@ static double reward_reach_goal(const env_t *w, int i) {
                 double rp[2], rv[2];
                 rel_pos_from_reference(w->x[i], w->y[i], w->lx[g], w->ly[g], w->lh[g], rp);
                 double dist = norm2(rp[0], rp[1]);
-                double ang = atan2(rp[1], rp[0]);
+                double ang = lsm_atan2(rp[1], rp[0]);
                 const double ang_range = PI / 6;
                 rel_pos_from_reference(w->s2[i], w->s3[i], 0.0, 0.0, w->lh[g], rv);
                 double rh = lsmo_magnetic_heading(rp[0], rp[1], 2.0 * w->cur[4]);
                 double ref_speed = pymax(w->ls[g], 0.1);
                 double dr = clipd(dist / 1.5, 0.0, 1.0);
                 ref_speed = ref_speed * (1.0 - dr) + 1.0 * dr;
-                double ex = rv[0] - ref_speed * cos(rh), ey = rv[1] - ref_speed * sin(rh);
+                double ex = rv[0] - ref_speed * lsm_cos(rh), ey = rv[1] - ref_speed * lsm_sin(rh);
                 double err = norm2(ex, ey);
                 double pen;
-                if (cos(ang) < cos(ang_range)) pen = err;
+                if (lsm_cos(ang) < lsm_cos(ang_range)) pen = err;
                 else {
-                    double ar = clipd((cos(ang) - cos(ang_range)) / (1.0 - cos(ang_range)), 0.0, 1.0);
+                    double ar = clipd((lsm_cos(ang) - lsm_cos(ang_range)) / (1.0 - lsm_cos(ang_range)), 0.0, 1.0);
                     pen = err * (1.0 - ar) + dist * ar;
                 }
                 double hap = 3.0 * pen;
@@ -713,9 +732,9 @@ static double reward(env_t *w, int i) {
             double rd = norm2(rx, ry);
             if (rd < w->cur[10] && !w->done[a]) {
                 double closeness = 1.0 - clipd((rd - w->cur[9]) / (w->cur[10] - w->cur[9]), 0.0, 1.0);
-                double dir = atan2(ry, rx);
+                double dir = lsm_atan2(ry, rx);
                 double va[2]; a_vel(w, a, va);
-                double change = cos(dir) * (va[0] - vi[0]) + sin(dir) * (va[1] - vi[1]);
+                double change = lsm_cos(dir) * (va[0] - vi[0]) + lsm_sin(dir) * (va[1] - vi[1]);
                 change = fabs(pymin(0.0, change));
                 pen += change * closeness;
                 count += 1;
@@ -873,7 +892,7 @@ static void random_scenario(env_t *w, rng_t *r) {
             if (have_prev) for (int l = 0; l < L; ++l) if (rng_uniform(r, 0.0, 1.0) < 0.5) { gx[l] = prevx[l]; gy[l] = prevy[l]; }
             if (gx[0] > gx[1]) { double tx = gx[0], ty = gy[0]; gx[0] = gx[1]; gy[0] = gy[1]; gx[1] = tx; gy[1] = ty; }
         }
-        for (int l = 0; l < L - 1; ++l) gh[l] = atan2(gy[l + 1] - gy[l], gx[l + 1] - gx[l]);
+        for (int l = 0; l < L - 1; ++l) gh[l] = lsm_atan2(gy[l + 1] - gy[l], gx[l + 1] - gx[l]);
         double last_heading = gh[L - 2];
         double cr = use_filter_arg ? 1.0 : ratio_sloped(w->ratio, 0.25, 0.75);
         if (w->dyn == LSMO_DYN_AIRTAXI) {
@@ -893,7 +912,7 @@ static void random_scenario(env_t *w, rng_t *r) {
         for (int l = 0; l < L; ++l) {
             int m = l * N + i;
             w->lx[m] = gx[l]; w->ly[m] = gy[l]; w->lh[m] = gh[l]; w->ls[m] = gs[l];
-            w->lsin[m] = sin(gh[l]); w->lcos[m] = cos(gh[l]);
+            w->lsin[m] = lsm_sin(gh[l]); w->lcos[m] = lsm_cos(gh[l]);
             prevx[l] = gx[l]; prevy[l] = gy[l];
         }
         have_prev = 1;
@@ -1136,4 +1155,10 @@ int lsmo_observe(const lsmo_params *p, const lsmo_buffers *b, int nthreads) {
     job_t j; memset(&j, 0, sizeof j);
     j.mode = 2; j.p = p; j.b = b;
     return run_jobs(&j, nthreads);
+}
+
+/* the shared math of include/lsm_math.h, exported for tests (op: 0 sin, 1 cos, 2 atan2(a, b)) */
+void lsmo_math_eval(int op, const double *a, const double *b, double *out, int64_t n) {
+    for (int64_t k = 0; k < n; ++k)
+        out[k] = op == 0 ? lsm_sin(a[k]) : (op == 1 ? lsm_cos(a[k]) : lsm_atan2(a[k], b[k]));
 }

@@ -130,6 +130,12 @@ double lsmo_interpolate(const lsmo_grid *g, const double *x, int component /* -1
 void lsmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void lsmo_curriculum(const lsmo_params *p, double ratio, double out[12]);
 double lsmo_magnetic_heading(double px, double py, double radius);
+/* include/lsm_math.h evaluated on the host (op: 0 sin, 1 cos, 2 atan2(a, b)) */
+void lsmo_math_eval(int op, const double *a, const double *b, double *out, int64_t n);
+/* airtaxi relative position (safety_filter.py:277-284): 0 = literal atan2 / cos / sin form (default), 1 = rotation
+ * form (what the specialised CUDA pipeline evaluates; differs from the literal form by ~1e-16 relative). Process-global. */
+void lsmo_set_relative_state_form(int form);
+int lsmo_get_relative_state_form(void);
 
 #ifdef __cplusplus
 }

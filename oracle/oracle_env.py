@@ -65,7 +65,7 @@ class Buffers(C.Structure):
 def build(force=False):
     if force or not os.path.exists(LIB_PATH) or \
             os.path.getmtime(LIB_PATH) < max(os.path.getmtime(os.path.join(HERE, f))
-                                             for f in ('lsm_oracle.c', 'lsm_oracle.h')):
+                                             for f in ('lsm_oracle.c', 'lsm_oracle.h', '../include/lsm_math.h')):
         subprocess.check_call(['make', '-C', HERE, '-s'])
     return LIB_PATH
 
@@ -84,7 +84,32 @@ def lib():
         _lib.lsmo_interpolate.restype = C.c_double
         _lib.lsmo_magnetic_heading.restype = C.c_double
         _lib.lsmo_magnetic_heading.argtypes = [C.c_double, C.c_double, C.c_double]
+        _lib.lsmo_math_eval.restype = None
+        _lib.lsmo_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
+        _lib.lsmo_set_relative_state_form.argtypes = [C.c_int]
+        _lib.lsmo_get_relative_state_form.restype = C.c_int
     return _lib
+
+
+def math_eval(op, a, b=None):
+    """include/lsm_math.h on the host: op 0 sin(a), 1 cos(a), 2 atan2(a, b) - the float64 trigonometry the oracle and
+    the CUDA kernels share (numpy's libm in the reference)."""
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    out = np.empty_like(a)
+    bp = None
+    if b is not None:
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        bp = b.ctypes.data_as(C.c_void_p)
+    lib().lsmo_math_eval(int(op), a.ctypes.data_as(C.c_void_p), bp, out.ctypes.data_as(C.c_void_p), a.size)
+    return out
+
+
+def set_relative_state_form(form: int):
+    """0 = the reference's literal airtaxi relative position (safety_filter.py:277-284), 1 = the rotation form the
+    specialised CUDA pipeline evaluates (see lsm_oracle.c). Process-global; returns the previous setting."""
+    prev = lib().lsmo_get_relative_state_form()
+    lib().lsmo_set_relative_state_form(int(form))
+    return prev
 
 
 def action_tables(dynamics):
@@ -236,7 +261,7 @@ class OracleEnv(object):
         self.landmarks[LF['X']][sel] = lp[..., 0]; self.landmarks[LF['Y']][sel] = lp[..., 1]
         self.landmarks[LF['HEADING']][sel] = lh
         self.landmarks[LF['SPEED']][sel] = s['landmark_speed']
-        self.landmarks[LF['SIN']][sel] = np.sin(lh); self.landmarks[LF['COS']][sel] = np.cos(lh)
+        self.landmarks[LF['SIN']][sel] = math_eval(0, lh); self.landmarks[LF['COS']][sel] = math_eval(1, lh)
         self.env_f64[0][sel] = s['curriculum_ratio']
         self.env_i32[EI['CURRENT_STEP']][sel] = s['current_step']
 

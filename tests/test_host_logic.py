@@ -204,3 +204,36 @@ def test_episode_stats_allreduce_gloo_world2():
     assert [r[1:3] for r in res] == [(0, 5), (5, 5)]
     for r in res:
         assert abs(r[3] - 4.5) < 1e-12    # mean of 0..9 over both shards
+
+
+class _FakeMeta:          # stand-ins for hj_reachability_utils' pickled containers (field names: safety_filter.py:158-166,
+    pass                  # navigation_graph_safe.py:132-138)
+
+
+class _FakeData:
+    pass
+
+
+def test_reference_pickle_loaders(tmp_path):
+    """Value-function pickles go through HjDataHandle's negate + shift + gradients; the TTR pickle is used raw with
+    ttr_max from the file (navigation_graph_safe.py:128-138, 751-755)."""
+    import pickle
+    from layered_safe_marl_b200 import hj_grid as H
+    rng = np.random.default_rng(0)
+    meta = _FakeMeta(); meta.domain_lo = [-1.0, -2.0, -np.pi, 0.03]; meta.domain_hi = [1.0, 2.0, np.pi, 0.09]
+    meta.shape = (5, 6, 8, 3); meta.periodic_dims = (2,)
+    ttr = _FakeData(); ttr.grid_meta_data = meta; ttr.values = rng.uniform(0, 50, meta.shape); ttr.ttr_max = 123.5
+    p = tmp_path / 'ttr.pkl'
+    with open(p, 'wb') as f:
+        pickle.dump(ttr, f)
+    g = H.load_reference_ttr_pickle(str(p))
+    assert g.ttr_max == 123.5 and g.grads is None and g.periodic == (False, False, True, False)
+    assert g.values.dtype == np.float32 and np.array_equal(g.values, ttr.values.astype(np.float32))   # raw: no sign flip, no shift
+    assert np.array_equal(g.lo, np.asarray(meta.domain_lo)) and g.shape == meta.shape
+    val = _FakeData(); val.grid_meta_data = meta; val.values = rng.normal(size=meta.shape); val.info = {'separation_distance': 0.5}
+    p2 = tmp_path / 'val.pkl'
+    with open(p2, 'wb') as f:
+        pickle.dump(val, f)
+    h = H.load_reference_pickle(str(p2), 0.8)
+    want = (-val.values.astype(np.float32) - np.float32(0.8 - 0.5)).astype(np.float32)
+    assert np.array_equal(h.values, want) and h.separation_distance == 0.8 and h.grads.shape == meta.shape + (4,)
