@@ -12,7 +12,9 @@ integrator, 8 agents, 2 landmarks per agent, HJ safety filter on with the synthe
   e2e       the same metric through the public API the reference's runner calls
             (B200GraphVecEnv.step with HOST one-hot actions in pinned memory, every returned array
             copied back to pinned host memory) - host<->device copies inside the timed region.
-  roofline  algorithmic bytes per launch / mean kernel time vs the measured HBM copy peak.
+  roofline  WHOLE STEP: algorithmic bytes of one env.step of the batch / mean event-timed step vs the
+            measured HBM copy peak; `dominant_kernel` = lsm_emit_kernel timed alone on its 8d OUTPUT bytes.
+  workloads the other BASELINE configs (cfg3, cfg4, cfg5) measured the same way, shorter (value, ms, whole-step frac).
   cpu_baseline   the C oracle (a port of the reference's Python path) on this box's host cores, bounded sample.
   timeline_us    diagnostics: device-side (%globaltimer) window of each kernel of one flushed step, us after the first
             block of the step (measured in a separate loop after the timed regions).
@@ -147,22 +149,74 @@ def oracle_throughput(workload, n_envs, steps, warmup, nthreads, seed=0):
 
 
 def run_reference(a):
-    """`--impl reference`: the CPU oracle port with every host thread; rank 0 only."""
+    """`--impl reference`: the CPU oracle port with every host thread; rank 0 only. Whatever --steps says, the timed
+    loop runs for at least ~5 s (a 0.05 s sample moved by +-20 %); both step counts are reported."""
     rank = int(os.environ.get('RANK', '0'))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
     n_sample = 1024
-    val, dt, params = oracle_throughput(a.workload, n_sample, a.steps, a.warmup, cores)
-    sample = f"{n_sample} envs x {a.steps} steps of {a.workload} on {cores} host threads (C oracle port of the reference's Python path)"
+    _, dtp, _ = oracle_throughput(a.workload, n_sample, 5, 2, cores)
+    steps_run = int(max(a.steps, min(50000, 5.0 / max(dtp / 5, 1e-6))))
+    val, dt, params = oracle_throughput(a.workload, n_sample, steps_run, a.warmup, cores)
+    sample = (f"{n_sample} envs x {steps_run} steps ({dt:.1f} s; --steps asked for {a.steps}) of {a.workload} on {cores} host threads "
+              f"(C oracle port of the reference's Python path)")
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": 1000.0 * dt / a.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "steps_run": steps_run, "warmup": a.warmup, "ms_per_step": 1000.0 * dt / steps_run, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": WORKLOAD_DESC[a.workload], "sample_envs": n_sample},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def measure_brief(workload, device, rank, world, steps, warmup, flush):
+    """One of the other BASELINE configs, measured like the headline one (flushed CUDA-event timing per step, max over
+    ranks) but shorter: -> {value, ms_per_step, ms_per_step_back_to_back, whole_step_frac, ...}."""
+    import torch
+    import torch.distributed as dist
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    args, flags, n_envs, episode = build_args(workload)
+    env = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=1234, binary_cfg=flags, env_id_base=rank * n_envs)
+    N = env.N
+    gen = torch.Generator(device=device); gen.manual_seed(77 + rank)
+    actions = torch.randint(0, 25, (warmup + steps, n_envs, N), generator=gen, device=device, dtype=torch.int32)
+    env.reset(episode)
+    for t in range(warmup):
+        env.step(actions[t], episode)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    for t in range(steps):
+        flush.fill_(0.0)
+        starts[t].record(); env.step(actions[warmup + t], episode); stops[t].record()
+    torch.cuda.synchronize()
+    total_ms = float(sum(s.elapsed_time(e) for s, e in zip(starts, stops)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for t in range(steps):
+        env.step(actions[warmup + t], episode)
+    e1.record(); torch.cuda.synchronize()
+    b2b_ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([total_ms, b2b_ms], dtype=torch.float64, device=device)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms, b2b_ms = float(tt[0]), float(tt[1])
+    peak, _ = measured_peak()
+    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
+    li = env.launch_info()
+    out = {"workload": WORKLOAD_DESC[workload], "envs_per_gpu": n_envs, "num_agents": N, "steps": steps,
+           "value": n_envs * world * N * steps / (total_ms / 1000.0), "unit": UNIT, "ms_per_step": total_ms / steps,
+           "ms_per_step_back_to_back": b2b_ms / steps, "algorithmic_bytes_per_step": bytes_per_step,
+           "whole_step_frac": bytes_per_step / (total_ms / steps / 1000.0) / 1e9 / peak,
+           "launches_per_step": li.get('launches_per_step', 1), "chunks": li.get('chunks', 1)}
+    env.close()
+    del env, actions
+    torch.cuda.empty_cache()
+    return out
 
 
 def run_ours(a):
@@ -280,7 +334,7 @@ def run_ours(a):
     # ---- e2e: host one-hot actions in, every returned array back to pinned host memory --------------
     Ke = max(3, min(K, a.e2e_steps))
     env_h = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=4321, binary_cfg=flags,
-                            env_id_base=rank * n_envs, numpy_outputs=True)
+                            env_id_base=rank * n_envs, numpy_outputs=True, numa_bind=True)
     env_h.reset(episode)
     rng = np.random.default_rng(99 + rank)
     onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + 2, n_envs, N))]).pin_memory()
@@ -305,40 +359,72 @@ def run_ours(a):
     e2e_value = total_envs * N * Ke / (e2e_ms / 1000.0)
     clocks = sampler.stop() if rank == 0 else None
     h2d = n_envs * N * 25 * 4
-    d2h = n_envs * (N * D * 4 + N * 4 + N * env.E * F * 4 + N * env.E * env.E * 4 + N * 4 + N)
+    dense_adj_bytes = n_envs * N * env.E * env.E * 4
+    small = n_envs * (N * D * 4 + N * env.E * F * 4 + N * 4 + N)          # obs, node_obs, rewards, dones
+    compact = env_h._compact is not None
+    if compact:
+        # the adjacency crosses PCIe as one thresholded E x E matrix per env + per-observer keep masks
+        d2h = small + n_envs * (env.E * env.E * 4 + N * ((env.E + 31) // 32) * 4)
+    else:
+        d2h = small + dense_adj_bytes
+    e2e_host = {"adjacency": ("compact over PCIe (1 E x E matrix + N keep masks per env), expanded to the dense (n,N,E,E) float32 "
+                              f"array on the host by {env_h.host_threads} threads with non-temporal stores "
+                              "(lsm_expand_adjacency_host), chunked so that the expansion overlaps the DMA of the later chunks")
+                             if compact else "dense over PCIe",
+                "host_bytes_written_per_step": d2h + (dense_adj_bytes if compact else 0),
+                "host_threads": env_h.host_threads}
+    env_h.close()
+    del env_h
+
+    # ---- the other BASELINE configs, same method, shorter (every rank takes part: max over ranks inside) -------------
+    extra = None
+    if a.workload == 'cfg2' and not a.no_extra_workloads:
+        extra = {}
+        env.close()
+        torch.cuda.empty_cache()
+        for w, ks in (('cfg3', 40), ('cfg4', 20)):
+            extra[w] = measure_brief(w, device, rank, world, ks, 5, flush)
+        extra['cfg5'] = measure_rollout(device, rank, world, 8192, 50, 25)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant (only) kernel -------------------------------------------------
-    li_spec = env.launch_info().get('specialised', 1)
+    # ---- roofline: the WHOLE STEP on SURVEY 8d's algorithmic bytes; the dominant kernel as a sub-key ----------------
+    li_spec = li0.get('specialised', 1)
     peak, peak_src = measured_peak()
     bytes_per_step = algorithmic_bytes_per_env_step(N, L, D, F) * n_envs
-    step_frac = bytes_per_step / (float(step_ms.mean()) / 1000.0) / 1e9 / peak
-    if emit_ms is not None:
-        # dominant kernel = lsm_emit_kernel: its algorithmic bytes are node_obs + adj written + the emit record read
-        bytes_per_launch = n_envs * (4 * N * env.E * (F + env.E)) + n_envs * li0.get('emit_record_bytes', 0)
-        mean_kernel_s = emit_ms / 1000.0
-    else:
-        bytes_per_launch = bytes_per_step
-        mean_kernel_s = float(step_ms.mean()) / 1000.0
-    achieved = bytes_per_launch / mean_kernel_s / 1e9
+    step_s = float(step_ms.mean()) / 1000.0
+    achieved = bytes_per_step / step_s / 1e9
     traffic = None
-    tp = os.path.join(REPO, 'profiles', 'traffic_r01.json')
+    tp = os.path.join(REPO, 'profiles', 'traffic_r02.json')
+    if not os.path.exists(tp):
+        tp = os.path.join(REPO, 'profiles', 'traffic_r01.json')
     if os.path.exists(tp):
         try:
             with open(tp) as f:
                 traffic = json.load(f).get(a.workload)
         except Exception:
             traffic = None
+    dominant = None
+    if emit_ms is not None:
+        # lsm_emit_kernel alone on ITS 8d bytes: node_obs + adj written (the per-env record it reads is an implementation
+        # intermediate and is not counted)
+        out_bytes = n_envs * (4 * N * env.E * (F + env.E))
+        dominant = {"kernel": "lsm_emit_kernel<dyn,N,L> (graph emission), timed alone with the same L2 flush",
+                    "algorithmic_bytes_per_launch": out_bytes, "mean_launch_ms": emit_ms,
+                    "achieved": out_bytes / (emit_ms / 1000.0) / 1e9, "frac": out_bytes / (emit_ms / 1000.0) / 1e9 / peak,
+                    "traffic": traffic,
+                    "note": "traffic = ncu dram bytes of this kernel per launch (profiles/traffic_r0*.json). When the step's "
+                            "output fits the 126 MB L2 (cfg2: 107 MB) about half of it is still dirty in L2 when the kernel "
+                            "ends, so traffic / algorithmic ~ 0.5 there; at cfg3 / cfg4 (outputs >> L2) it is ~1.0"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
-                "kernel": "lsm_emit_kernel<dyn,N,L> (graph emission; timed alone with the same L2 flush)" if li_spec else "lsm_generic_kernel<dyn>",
-                "algorithmic_bytes_per_launch": bytes_per_launch, "mean_launch_ms": mean_kernel_s * 1000.0,
-                "whole_step": {"frac": step_frac, "algorithmic_bytes": bytes_per_step, "mean_ms": float(step_ms.mean()),
-                               "median_ms": float(np.median(step_ms)), "launches": li0.get('launches_per_step', 1)}}
+                "traffic": None, "peak_source": peak_src,
+                "kernel": ("whole step = lsm_agent_kernel + lsm_emit_kernel + lsm_pair_kernel" if li_spec else "lsm_generic_kernel<dyn>"),
+                "algorithmic_bytes_per_launch": bytes_per_step, "mean_launch_ms": step_s * 1000.0,
+                "median_ms": float(np.median(step_ms)), "launches": li0.get('launches_per_step', 1),
+                "dominant_kernel": dominant}
 
     # ---- CPU baseline (bounded sample) ----------------------------------------------------------
     cpu = None
@@ -353,7 +439,7 @@ def run_ours(a):
                          f"reference's Python path on {cores} host threads; the Python reference itself measured "
                          f"1.0e3 agent-steps/s on 8 cores (BASELINE.md)"}
 
-    li = env.launch_info()
+    li = li0
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": total_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
@@ -371,44 +457,34 @@ def run_ours(a):
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": Ke, "ms_per_step": e2e_ms / Ke,
-                    "api": "B200GraphVecEnv.step(host one-hot float32 actions) -> host numpy obs/agent_id/node_obs/adj/rewards/dones"},
+                    "api": "B200GraphVecEnv.step(host one-hot float32 actions) -> host numpy obs/agent_id/node_obs/adj/rewards/dones",
+                    "host_side": e2e_host},
             "gpu_launches": K * li.get('launches_per_step', 1),
             "timeline_us": timeline,
             "roofline": roofline,
             "cpu_baseline": cpu,
+            "workloads": extra,
             "episode_stats": stats}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_rollout(a):
-    """`--workload cfg5`: BASELINE configs[4] - rollout collection of the onpolicy GraphMPE runner (8 agents, 8192 envs
-    per GPU) with the device-resident rollout buffer: env.step writes observations / graphs / rewards straight into the
-    buffer slot (zero copy), insert() builds masks / share_obs on the device. The policy forward is NOT part of this
-    repo: actions are drawn on the device (stated in `config`). Each step lands in a different 221 MB slot of the
-    5.7 GB buffer, i.e. the outputs are larger than L2 without a flush."""
+def measure_rollout(device, rank, world, n_envs, K, W):
+    """BASELINE configs[4] shape - rollout collection of the onpolicy GraphMPE runner (8 agents, 8192 envs per GPU) with
+    the device-resident rollout buffer: env.step writes observations / graphs / rewards straight into the buffer slot
+    (zero copy), insert() builds masks / share_obs on the device. The policy forward is NOT part of this repo: actions
+    are drawn on the device (stated in `config`). Each step lands in a different 221 MB slot of the 5.7 GB buffer, i.e.
+    the outputs are larger than L2 without a flush."""
     import torch
     import torch.distributed as dist
     from layered_safe_marl_b200 import B200GraphVecEnv, DeviceGraphRolloutBuffer
-    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    if world > 1:
-        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
-    device = torch.device(f'cuda:{local_rank}'); torch.cuda.set_device(device)
     args, flags, _, episode = build_args('cfg2')
-    n_envs = a.envs or 8192
     T = 25
     env = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=1234, binary_cfg=flags, env_id_base=rank * n_envs)
     buf = DeviceGraphRolloutBuffer(env, T, use_centralized_V=True, zero_copy=True)
     N = env.N
-    K, W = a.steps, a.warmup
     gen = torch.Generator(device=device); gen.manual_seed(7 + rank)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     buf.warmup(num_current_episode=episode)
 
     def collect(steps):
@@ -428,23 +504,51 @@ def run_rollout(a):
     ms = e0.elapsed_time(e1)
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt[0])
+    peak, peak_src = measured_peak()
+    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
+    li = env.launch_info()
+    out = {"workload": "BASELINE configs[4] shape: rollout collection (env.step + rollout-buffer insert, zero copy) "
+                       "8 agents x 8192 envs per B200, HJ filter on; policy forward excluded (actions drawn on device)",
+           "envs_per_gpu": n_envs, "num_agents": N, "buffer_steps": T, "steps": K,
+           "value": n_envs * world * N * K / (ms / 1000.0), "unit": UNIT, "ms_per_step": ms / K,
+           "algorithmic_bytes_per_step": bytes_per_step, "whole_step_frac": bytes_per_step / (ms / K / 1000.0) / 1e9 / peak,
+           "peak_source": peak_src, "launch": li,
+           "l2": "every step lands in a different 221 MB buffer slot (outputs > L2), no flush"}
+    env.close()
+    del buf, env
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_rollout(a):
+    """`--workload cfg5` as the headline line (see measure_rollout)."""
+    import torch
+    import torch.distributed as dist
+    world = int(os.environ.get('WORLD_SIZE', '1')); rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1:
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group('nccl', device_id=torch.device(f'cuda:{local_rank}'))
+    device = torch.device(f'cuda:{local_rank}'); torch.cuda.set_device(device)
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    r = measure_rollout(device, rank, world, a.envs or 8192, a.steps, a.warmup)
     clocks = sampler.stop() if rank == 0 else None
     if rank == 0:
-        peak, peak_src = measured_peak()
-        bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
-        li = env.launch_info()
-        line = {"metric": METRIC, "value": n_envs * world * N * K / (ms / 1000.0), "unit": UNIT, "n_gpus": world, "steps": K,
-                "warmup": W, "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        peak, _ = measured_peak()
+        li = r['launch']
+        line = {"metric": METRIC, "value": r['value'], "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": r['ms_per_step'], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic",
-                "config": {"workload": "BASELINE configs[4] shape: rollout collection (env.step + rollout-buffer insert, zero copy) "
-                                       "8 agents x 8192 envs per B200, HJ filter on; policy forward excluded (actions drawn on device)",
-                           "envs_per_gpu": n_envs, "num_agents": N, "buffer_steps": T,
-                           "l2": "every step lands in a different 221 MB buffer slot (outputs > L2), no flush", "launch": li},
-                "clocks": clocks, "e2e": None, "gpu_launches": K * li.get('launches_per_step', 1),
-                "roofline": {"bound": "hbm", "achieved": bytes_per_step / (ms / K / 1000.0) / 1e9, "peak": peak, "unit": "GB/s",
-                             "frac": bytes_per_step / (ms / K / 1000.0) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
-                             "kernel": "whole collection step (3 kernels + insert's elementwise torch ops)",
-                             "algorithmic_bytes_per_launch": bytes_per_step},
+                "config": {"workload": r['workload'], "envs_per_gpu": r['envs_per_gpu'], "num_agents": r['num_agents'],
+                           "buffer_steps": r['buffer_steps'], "l2": r['l2'], "launch": li},
+                "clocks": clocks, "e2e": None, "gpu_launches": a.steps * (li.get('launches_per_step', 1) + 1),
+                "roofline": {"bound": "hbm", "achieved": r['whole_step_frac'] * peak, "peak": peak, "unit": "GB/s",
+                             "frac": r['whole_step_frac'], "traffic": None, "peak_source": r['peak_source'],
+                             "kernel": "whole collection step (3 kernels + lsm_rollout_insert)",
+                             "algorithmic_bytes_per_launch": r['algorithmic_bytes_per_step']},
                 "cpu_baseline": None}
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -461,6 +565,7 @@ def main():
     ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload’s)')
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extra-workloads', action='store_true', help='skip the cfg3 / cfg4 / cfg5 sub-blocks of the default line')
     a = ap.parse_args()
     if a.warmup < 3:
         a.warmup = 3

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LSM_ABI_VERSION 2
+#define LSM_ABI_VERSION 3
 
 enum { LSM_DYN_DOUBLE_INTEGRATOR = 0, LSM_DYN_AIRTAXI = 1 };
 
@@ -77,6 +77,16 @@ enum {
     LSM_EP_NUM_REACHED_GOAL_MEAN, LSM_EP_CONFLICT_PERCENTAGE, LSM_EP_MIN_DISTANCE_MEAN,
     LSM_EP_MIN_DISTANCE_MIN, LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE, LSM_EP_COUNT
 };
+
+/* terminal-step snapshot of the fields info_callback reads (navigation_graph_safe.py:386-450), written ONLY for an
+ * environment that auto-resets in this step, before the reset overwrites its state: graphworker returns the terminal
+ * step's infos and only appends the episode summary (onpolicy/envs/env_wrappers.py:861-874).
+ * term_f64[field][env][agent], term_i32[field][env][agent], term_env_f64[env] = curriculum ratio of the finished episode */
+enum {
+    LSM_TF_X = 0, LSM_TF_Y, LSM_TF_MIN_REL_DIST, LSM_TF_DIST_LEFT, LSM_TF_TIMES_REQ_NEW, LSM_TF_TIMES_REQ_OLD,
+    LSM_TF_DISTS_GOAL_NEW, LSM_TF_DISTS_GOAL_OLD, LSM_TF_GOAL_MIN_TIME, LSM_TF_COUNT
+};
+enum { LSM_TI_NUM_COLLISIONS = 0, LSM_TI_SAFETY_FILTERED, LSM_TI_COUNT };
 
 #define LSM_MAX_AGENTS 32
 #define LSM_MAX_LANDMARKS 128
@@ -125,7 +135,24 @@ typedef struct lsm_buffers {
     double *safe_action;          /* [num_envs][N][2]  control applied in the last internal step */
     double *ep_info;              /* [num_envs][LSM_EP_COUNT]  summary written when an env resets */
     float *reward_individual;     /* [num_envs][N] or NULL: pre-sum reward when LSM_FLAG_SHARED_REWARD */
+    /* terminal-step info snapshot of auto-resetting envs (all three NULL = not recorded) */
+    double *term_f64;             /* [LSM_TF_COUNT][num_envs][N] */
+    int32_t *term_i32;            /* [LSM_TI_COUNT][num_envs][N] */
+    double *term_env_f64;         /* [num_envs] */
 } lsm_buffers;
+
+/* Launch-shape choices a caller may override (lsm_set_tuning, right after lsm_create; 0 / -1 = automatic). These are
+ * the product's only knobs; ablation switches live in the LSM_EXPERIMENTS build (liblsm_b200_exp.so), not here. */
+typedef struct lsm_tuning {
+    int32_t chunks;               /* env ranges one step is split into on library-owned streams (1..16); 0 = automatic
+                                     (4 from 0.4 GB of observations per step, else 1) */
+    int32_t pair_placement;       /* where the next step's HJ pair values are computed: 0 behind the emit kernel,
+                                     2 in front of the agent kernel, 3 between agent and emit kernel; -1 = automatic
+                                     (0 for the 4-D grid, 3 for the 5-D grid) */
+    int32_t packed_grid;          /* 1 corner-packed value table (one aligned chunk per lookup), 0 scattered gathers;
+                                     -1 = automatic (packed when the table fits 2 GiB) */
+    int32_t _reserved;
+} lsm_tuning;
 
 typedef struct lsm_launch_info {
     int32_t grid_blocks, block_threads, warps_per_block, envs_per_warp;
@@ -149,6 +176,7 @@ int lsm_create(const lsm_config *cfg, lsm_handle **out);
 int lsm_destroy(lsm_handle *h);
 int lsm_set_value_grid(lsm_handle *h, const lsm_grid_desc *g);
 int lsm_set_ttr_grid(lsm_handle *h, const lsm_grid_desc *g);
+int lsm_set_tuning(lsm_handle *h, const lsm_tuning *t);
 int lsm_bind_buffers(lsm_handle *h, const lsm_buffers *b);
 int lsm_get_launch_info(lsm_handle *h, lsm_launch_info *out);
 
@@ -174,6 +202,24 @@ int lsm_observe(lsm_handle *h, void *stream);
  * env_wrappers.py:985-996, and .copy() in GraphReplayBuffer.insert, graph_buffer.py:223-228).
  * node_obs and adj must be 16-byte aligned. */
 int lsm_set_output_buffers(lsm_handle *h, float *obs, float *node_obs, float *adj, float *reward, uint8_t *done);
+
+/* Compact adjacency for HOST-facing callers (GraphSubprocVecEnv.step_wait returns host arrays,
+ * onpolicy/envs/env_wrappers.py:983-996): the N observer matrices of one environment are ONE radius-thresholded E x E
+ * distance matrix with observer-specific rows / columns zeroed (navigation_graph_safe.py:974-992). With both pointers
+ * non-NULL the step kernels write, instead of the dense adj output,
+ *   adj_base  DEVICE float    [num_envs][E][E]     thresholded distances, unmasked
+ *   adj_keep  DEVICE uint32   [num_envs][N][W]     W = ceil(E / 32): bit e of observer i's words = entity e is connected
+ * so that 1/N of the adjacency bytes cross PCIe; lsm_expand_adjacency_host rebuilds the dense array byte for byte.
+ * Both NULL restores the dense output. Specialised (dynamics, N, L) configurations only (returns 6 otherwise). */
+int lsm_set_compact_adjacency(lsm_handle *h, float *adj_base, uint32_t *adj_keep);
+
+/* HOST function (no GPU work): adj[e][i][a][b] = keep_i[a] && keep_i[b] ? base[e][a][b] : 0 for e in [0, num_envs),
+ * written by `threads` worker threads (<= 0: one per online core, at most 16) of a pool the library keeps, with
+ * non-temporal stores (cached_stores == 0: the array is larger than the host's caches and is written once) or ordinary
+ * stores (cached_stores != 0: the consumer reads it right away and it fits the last-level cache). All pointers are HOST pointers; adj must be 16-byte aligned (4-byte when E*E % 4 != 0). Pure data movement - every float is
+ * either copied or zero. */
+int lsm_expand_adjacency_host(const float *adj_base, const uint32_t *adj_keep, float *adj, int64_t num_envs,
+                              int32_t num_agents, int32_t num_entities, int32_t threads, int32_t cached_stores);
 
 /* Compacted COO edge list of the adjacency output in the order the reference's GNN builds on every forward
  * (TransformerConvNet.process_adj, onpolicy/algorithms/utils/gnn.py:376-407): graphs = num_envs * N, row-major

@@ -12,7 +12,8 @@
  * Algorithms: the classic fdlibm / msun kernels (Sun Microsystems 1993, freely redistributable): argument
  * reduction by Cody-Waite with a three-part pi/2 (exact for |x| < 2^20 * pi/2; headings here stay below ~1e2 rad),
  * degree-13 / degree-14 minimax polynomials on [-pi/4, pi/4], atan by four-interval reduction + degree-11
- * polynomial in x^2. Error < 1 ulp for sin / cos, < 2 ulp for atan2 (checked against the host libm in
+ * polynomial in x^2 (the reduction is applied to numerator and denominator, so atan2 needs one division). Error < 1 ulp for
+ * sin / cos, < 2 ulp for atan2 (checked against the host libm in
  * tests/test_lsm_math.py). Beyond the
  * Cody-Waite range the reduction falls back to a plain (inaccurate but deterministic) floor-based one; NaN / inf
  * give NaN.
@@ -23,10 +24,16 @@
 #include <stdint.h>
 #include <string.h>
 
+/* LSM_MATH_FN: small helpers, inlined. LSM_MATH_API: the four public functions. In device code they are NOT inlined:
+ * the per-agent kernel calls them from ~40 sites and is bound by instruction fetch, so one shared copy of each is faster
+ * than 40 inlined reductions + polynomials (the arithmetic - and therefore every result bit - is the same either way). */
 #if defined(__CUDACC__)
-#define LSM_MATH_FN __host__ __device__ inline
+#define LSM_MATH_FN __host__ __device__ __forceinline__
+#define LSM_MATH_API __host__ __device__ __noinline__ inline
+#define LSM_MATH_HAS_INL 1
 #else
 #define LSM_MATH_FN static inline
+#define LSM_MATH_API static inline
 #endif
 
 LSM_MATH_FN int64_t lsm_m_bits(double x) {
@@ -69,7 +76,11 @@ LSM_MATH_FN double lsm_m_kcos(double x, double y) {
     return w + (((1.0 - w) - hz) + (z * r - x * y));
 }
 
-/* Cody-Waite reduction for pi/4 < |x| < 2^20 * pi/2: x = n * pi/2 + (y0 + y1); returns n mod 4 */
+/* Cody-Waite reduction for |x| < 2^20 * pi/2: x = n * pi/2 + (y0 + y1); returns n mod 4.
+ * Written for a SIMT machine: straight-line selects instead of branches wherever lanes of one warp would disagree
+ * (quadrant, "no reduction needed", interval of atan) - a divergent branch executes both sides one after the other,
+ * two independent polynomial chains interleave. Only the never / rarely taken paths (cancellation near a multiple of
+ * pi/2, non-finite and out-of-range arguments) are branches. */
 LSM_MATH_FN int lsm_m_rem_medium(double x, int32_t ix, double* y0, double* y1) {
     const double invpio2 = 6.36619772367581382433e-01,
                  pio2_1 = 1.57079632673412561417e+00, pio2_1t = 6.07710050650619224932e-11,
@@ -105,63 +116,51 @@ LSM_MATH_FN int lsm_m_rem_medium(double x, int32_t ix, double* y0, double* y1) {
 /* x = n * pi/2 + (y0 + y1), |y0 + y1| <= pi/4 (+ a little); returns n mod 4 */
 LSM_MATH_FN int lsm_m_rem_pio2(double x, double* y0, double* y1) {
     const int32_t ix = lsm_m_hi(x) & 0x7fffffff;
-    if (ix <= 0x3fe921fb) { *y0 = x; *y1 = 0.0; return 0; }            /* |x| ~<= pi/4 */
-    if (ix < 0x413921fb) return lsm_m_rem_medium(x, ix, y0, y1);        /* |x| < 2^20 * pi/2 */
-    if (ix >= 0x7ff00000) { *y0 = x - x; *y1 = 0.0; return 0; }        /* inf / NaN -> NaN */
-    {   /* out of contract (|x| >= 1.6e6 rad): deterministic, not accurate */
-        const double twopi = 6.283185307179586;
-        const double big = 6755399441055744.0;
-        const double q = x / twopi;
-        double r = 0.0;
-        if (lsm_m_abs(q) < 2251799813685248.0) r = x - ((q + big) - big) * twopi;
-        {
-            const int32_t ir = lsm_m_hi(r) & 0x7fffffff;
-            if (ir <= 0x3fe921fb) { *y0 = r; *y1 = 0.0; return 0; }
-            return lsm_m_rem_medium(r, ir, y0, y1);
+    double xr = x;
+    int32_t ir = ix;
+    if (ix >= 0x413921fb) {                                             /* never taken in contract */
+        if (ix >= 0x7ff00000) { *y0 = x - x; *y1 = 0.0; return 0; }    /* inf / NaN -> NaN */
+        {   /* |x| >= 2^20 * pi/2 ~ 1.6e6 rad: deterministic, not accurate */
+            const double twopi = 6.283185307179586;
+            const double big = 6755399441055744.0;
+            const double q = x / twopi;
+            xr = 0.0;
+            if (lsm_m_abs(q) < 2251799813685248.0) xr = x - ((q + big) - big) * twopi;
+            ir = lsm_m_hi(xr) & 0x7fffffff;
         }
     }
-}
-
-LSM_MATH_FN double lsm_sin(double x) {
-    double y0, y1;
-    const int32_t ix = lsm_m_hi(x) & 0x7fffffff;
-    if (ix < 0x3e500000) return x;                                      /* |x| < 2^-26 */
-    switch (lsm_m_rem_pio2(x, &y0, &y1)) {
-        case 0: return lsm_m_ksin(y0, y1);
-        case 1: return lsm_m_kcos(y0, y1);
-        case 2: return -lsm_m_ksin(y0, y1);
-        default: return -lsm_m_kcos(y0, y1);
+    {
+        double h, t;
+        const int n = lsm_m_rem_medium(xr, ir, &h, &t);
+        const int small = ir <= 0x3fe921fb;                             /* |x| ~<= pi/4: no reduction (select, not a branch) */
+        *y0 = small ? xr : h;
+        *y1 = small ? 0.0 : t;
+        return small ? 0 : n;
     }
 }
 
-LSM_MATH_FN double lsm_cos(double x) {
-    double y0, y1;
-    switch (lsm_m_rem_pio2(x, &y0, &y1)) {
-        case 0: return lsm_m_kcos(y0, y1);
-        case 1: return -lsm_m_ksin(y0, y1);
-        case 2: return -lsm_m_kcos(y0, y1);
-        default: return lsm_m_ksin(y0, y1);
-    }
-}
-
-/* exactly lsm_sin(x) and lsm_cos(x), one argument reduction */
-LSM_MATH_FN void lsm_sincos(double x, double* s, double* c) {
+/* exactly lsm_sin(x) and lsm_cos(x), one argument reduction; both kernels are always evaluated (independent chains) */
+LSM_MATH_FN void lsm_sincos_inl(double x, double* s, double* c) {
     double y0, y1;
     const int32_t ix = lsm_m_hi(x) & 0x7fffffff;
     const int n = lsm_m_rem_pio2(x, &y0, &y1);
     const double ks = lsm_m_ksin(y0, y1), kc = lsm_m_kcos(y0, y1);
-    double sv, cv;
-    switch (n) {
-        case 0: sv = ks; cv = kc; break;
-        case 1: sv = kc; cv = -ks; break;
-        case 2: sv = -ks; cv = -kc; break;
-        default: sv = -kc; cv = ks; break;
-    }
-    if (ix < 0x3e500000) sv = x;
+    const double a = (n & 1) ? kc : ks;                                 /* n: 0 (s, c)  1 (c, -s)  2 (-s, -c)  3 (-c, s) */
+    const double b = (n & 1) ? ks : kc;
+    double sv = (n & 2) ? -a : a;
+    const double cv = ((n + 1) & 2) ? -b : b;
+    if (ix < 0x3e500000) sv = x;                                        /* |x| < 2^-26 */
     *s = sv; *c = cv;
 }
+LSM_MATH_FN double lsm_sin_inl(double x) { double s, c; lsm_sincos_inl(x, &s, &c); return s; }
+LSM_MATH_FN double lsm_cos_inl(double x) { double s, c; lsm_sincos_inl(x, &s, &c); return c; }
 
-LSM_MATH_FN double lsm_atan(double x) {
+/* atan(a / b) for finite a >= 0, b > 0 with ONE division: the four-interval reduction of fdlibm's atan applied to the
+ * quotient before it is formed,
+ *     t < 7/16: a / b      [7/16, 11/16): (2a - b) / (2b + a)      [11/16, 19/16): (a - b) / (a + b)
+ *     [19/16, 39/16): (a - 1.5 b) / (b + 1.5 a)      >= 39/16: -b / a
+ * then atan(t) = atanhi[id] + atan(reduced) with the degree-11 polynomial in the reduced argument squared. */
+LSM_MATH_FN double lsm_m_atan_ratio(double a, double b) {
     const double hi0 = 4.63647609000806093515e-01, hi1 = 7.85398163397448278999e-01, hi2 = 9.82793723247329054082e-01,
                  hi3 = 1.57079632679489655800e+00;
     const double lo0 = 2.26987774529616870924e-17, lo1 = 3.06161699786838301793e-17, lo2 = 1.39033110312309984516e-17,
@@ -170,51 +169,38 @@ LSM_MATH_FN double lsm_atan(double x) {
                  a3 = -1.11111104054623557880e-01, a4 = 9.09088713343650656196e-02, a5 = -7.69187620504482999495e-02,
                  a6 = 6.66107313738753120669e-02, a7 = -5.83357013379057348645e-02, a8 = 4.97687799461593236017e-02,
                  a9 = -3.65315727442169155270e-02, a10 = 1.62858201153657823623e-02;
-    const int32_t hx = lsm_m_hi(x), ix = hx & 0x7fffffff;
-    double ahi = 0.0, alo = 0.0;
-    int id;
-    if (ix >= 0x44100000) {                                             /* |x| >= 2^66 or NaN */
-        if (x != x) return x + x;
-        return hx > 0 ? hi3 + lo3 : -hi3 - lo3;
-    }
-    if (ix < 0x3fdc0000) {                                              /* |x| < 0.4375 */
-        if (ix < 0x3e400000) return x;                                  /* |x| < 2^-27 */
-        id = -1;
-    } else {
-        x = lsm_m_abs(x);
-        if (ix < 0x3ff30000) {                                          /* |x| < 1.1875 */
-            if (ix < 0x3fe60000) { id = 0; ahi = hi0; alo = lo0; x = (2.0 * x - 1.0) / (2.0 + x); }
-            else { id = 1; ahi = hi1; alo = lo1; x = (x - 1.0) / (x + 1.0); }
-        } else {
-            if (ix < 0x40038000) { id = 2; ahi = hi2; alo = lo2; x = (x - 1.5) / (1.0 + 1.5 * x); }
-            else { id = 3; ahi = hi3; alo = lo3; x = -1.0 / x; }
-        }
-    }
+    /* interval of t = a / b by comparing a with multiples of b (the intervals overlap in validity, so the last-bit
+       position of a boundary does not matter) */
+    const int g0 = a >= 0.4375 * b, g1 = a >= 0.6875 * b, g2 = a >= 1.1875 * b, g3 = a >= 2.4375 * b;
+    double num = a, den = b, ahi = 0.0, alo = 0.0;
+    if (g0) { num = (a + a) - b; den = (b + b) + a; ahi = hi0; alo = lo0; }
+    if (g1) { num = a - b; den = a + b; ahi = hi1; alo = lo1; }
+    if (g2) { num = a - 1.5 * b; den = b + 1.5 * a; ahi = hi2; alo = lo2; }
+    if (g3) { num = -b; den = a; ahi = hi3; alo = lo3; }
     {
+        const double x = num / den;
         const double z = x * x;
         const double w = z * z;
         const double s1 = z * (a0 + w * (a2 + w * (a4 + w * (a6 + w * (a8 + w * a10)))));
         const double s2 = w * (a1 + w * (a3 + w * (a5 + w * (a7 + w * a9))));
-        if (id < 0) return x - x * (s1 + s2);
-        {
-            const double zz = ahi - ((x * (s1 + s2) - alo) - x);
-            return hx < 0 ? -zz : zz;
-        }
+        const double p = x * (s1 + s2);
+        const double r_small = x - p;
+        const double r_big = ahi - ((p - alo) - x);
+        return g0 ? r_big : r_small;
     }
 }
 
-LSM_MATH_FN double lsm_atan2(double y, double x) {
+LSM_MATH_FN double lsm_atan2_inl(double y, double x) {
     const double pi = 3.1415926535897931160e+00, pi_lo = 1.2246467991473531772e-16;
     const double pi_o_2 = 1.5707963267948965580e+00, pi_o_4 = 7.8539816339744827900e-01;
     const int64_t bx = lsm_m_bits(x), by = lsm_m_bits(y);
     const int32_t hx = (int32_t)(bx >> 32), hy = (int32_t)(by >> 32);
     const int32_t ix = hx & 0x7fffffff, iy = hy & 0x7fffffff;
     const uint32_t lx = (uint32_t)bx, ly = (uint32_t)by;
-    int m;
+    int m = ((hy >> 31) & 1) | ((hx >> 30) & 2);                        /* 2 * sign(x) + sign(y) */
     double z;
+    /* special operands first (uniformly not taken on real data) */
     if (x != x || y != y) return x + y;
-    if (x == 1.0) return lsm_atan(y);
-    m = ((hy >> 31) & 1) | ((hx >> 30) & 2);                            /* 2 * sign(x) + sign(y) */
     if ((iy | (int32_t)ly) == 0) {                                      /* y = +-0 */
         switch (m) { case 0: case 1: return y; case 2: return pi; default: return -pi; }
     }
@@ -229,15 +215,32 @@ LSM_MATH_FN double lsm_atan2(double y, double x) {
     {
         const int32_t k = (iy - ix) >> 20;
         if (k > 60) { z = pi_o_2 + 0.5 * pi_lo; m &= 1; }               /* |y / x| > 2^60 */
-        else if (hx < 0 && k < -60) z = 0.0;                            /* |y| / x < -2^60 */
-        else z = lsm_atan(lsm_m_abs(y / x));
+        else if (k < -60) z = hx < 0 ? 0.0 : lsm_m_abs(y) / lsm_m_abs(x);   /* tiny quotient: atan(t) = t */
+        else z = lsm_m_atan_ratio(lsm_m_abs(y), lsm_m_abs(x));
     }
-    switch (m) {
-        case 0: return z;
-        case 1: return -z;
-        case 2: return pi - (z - pi_lo);
-        default: return (z - pi_lo) - pi;
+    {
+        const double zn = (m & 2) ? pi - (z - pi_lo) : z;               /* x < 0: reflect */
+        return (m & 1) ? -zn : zn;                                      /* y < 0: (z - pi_lo) - pi == -(pi - (z - pi_lo)) */
     }
 }
+
+/* the public functions: one shared (not inlined) copy each in device code; `*_inl` above are the same arithmetic,
+ * force-inlined, for the two or three call sites on the per-agent kernel's critical path */
+#if defined(LSM_MATH_AB_LIBDEVICE) && defined(__CUDA_ARCH__)
+/* A/B timing build only (never the product, breaks bit-identity with the oracle): CUDA's own libdevice functions */
+#define lsm_sin sin
+#define lsm_cos cos
+#define lsm_sincos sincos
+#define lsm_atan2 atan2
+#define lsm_sin_inl sin
+#define lsm_cos_inl cos
+#define lsm_sincos_inl sincos
+#define lsm_atan2_inl atan2
+#else
+LSM_MATH_API double lsm_sin(double x) { return lsm_sin_inl(x); }
+LSM_MATH_API double lsm_cos(double x) { return lsm_cos_inl(x); }
+LSM_MATH_API void lsm_sincos(double x, double* s, double* c) { lsm_sincos_inl(x, s, c); }
+LSM_MATH_API double lsm_atan2(double y, double x) { return lsm_atan2_inl(y, x); }
+#endif
 
 #endif /* LSM_MATH_H */

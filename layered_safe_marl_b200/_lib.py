@@ -37,7 +37,12 @@ class LsmBuffers(C.Structure):
                 ('env_f64', C.c_void_p), ('env_i32', C.c_void_p),
                 ('obs', C.c_void_p), ('node_obs', C.c_void_p), ('adj', C.c_void_p),
                 ('reward', C.c_void_p), ('done', C.c_void_p), ('safe_action', C.c_void_p),
-                ('ep_info', C.c_void_p), ('reward_individual', C.c_void_p)]
+                ('ep_info', C.c_void_p), ('reward_individual', C.c_void_p),
+                ('term_f64', C.c_void_p), ('term_i32', C.c_void_p), ('term_env_f64', C.c_void_p)]
+
+
+class LsmTuning(C.Structure):
+    _fields_ = [('chunks', C.c_int32), ('pair_placement', C.c_int32), ('packed_grid', C.c_int32), ('_reserved', C.c_int32)]
 
 
 class LsmLaunchInfo(C.Structure):
@@ -53,7 +58,8 @@ class LsmLaunchInfo(C.Structure):
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
                     'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device')
+                    'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device', 'lsm_set_tuning',
+                    'lsm_set_compact_adjacency', 'lsm_expand_adjacency_host')
 
 _lib = None
 
@@ -95,12 +101,14 @@ def load():
     lib.lsm_edge_list.argtypes = [C.c_void_p] * 6 + [C.c_int64, C.c_void_p]
     lib.lsm_debug_timeline.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
     lib.lsm_rollout_insert.argtypes = [C.c_void_p] * 7
+    lib.lsm_set_tuning.argtypes = [C.c_void_p, C.POINTER(LsmTuning)]
+    lib.lsm_set_compact_adjacency.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.lsm_expand_adjacency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
     lib.lsm_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
     lib.lsm_math_eval_device.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
-    for name in ('lsm_create', 'lsm_destroy', 'lsm_set_value_grid', 'lsm_set_ttr_grid', 'lsm_bind_buffers',
-                 'lsm_get_launch_info', 'lsm_step', 'lsm_reset', 'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
-                    'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device'):
-        getattr(lib, name).restype = C.c_int
+    for name in EXPORTED_SYMBOLS:
+        if name not in ('lsm_abi_version', 'lsm_last_error'):
+            getattr(lib, name).restype = C.c_int
     _lib = lib
     return lib
 

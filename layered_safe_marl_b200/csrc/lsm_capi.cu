@@ -5,7 +5,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <emmintrin.h>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "lsm_host.h"
@@ -22,6 +27,66 @@ int cuda_fail(cudaError_t e, const char* what) {
 
 int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 int align_up(int v, int a) { return (v + a - 1) / a * a; }
+
+// every entry point that touches the device runs on the handle's device and restores the caller's current device
+struct DeviceGuard {
+    int prev = -1; bool switched = false;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard() { if (switched) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// host-side worker pool of lsm_expand_adjacency_host: persistent threads, one job (a function over [0, parts)) at a time
+// ---------------------------------------------------------------------------------------------------------------
+class HostPool {
+public:
+    static HostPool& get() { static HostPool p; return p; }
+    template <class F> void run(int parts, F&& fn) {
+        std::unique_lock<std::mutex> api(api_mu_);                 // one job at a time
+        while ((int)threads_.size() < parts - 1) threads_.emplace_back([this] { loop(); });
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            job_ = [&fn](int part) { fn(part); };
+            parts_ = parts; next_ = 1; pending_ = parts - 1;
+        }
+        cv_.notify_all();
+        fn(0);                                                     // the caller takes part 0
+        std::unique_lock<std::mutex> lk(mu_);
+        done_cv_.wait(lk, [this] { return pending_ == 0; });
+        parts_ = 0; next_ = 0; job_ = nullptr;
+    }
+private:
+    HostPool() = default;
+    ~HostPool() {
+        { std::lock_guard<std::mutex> lk(mu_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    void loop() {
+        for (;;) {
+            int part;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this] { return stop_ || next_ < parts_; });
+                if (stop_) return;
+                part = next_++;
+            }
+            job_(part);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                if (--pending_ == 0) done_cv_.notify_all();
+            }
+        }
+    }
+    std::mutex api_mu_, mu_;
+    std::condition_variable cv_, done_cv_;
+    std::vector<std::thread> threads_;
+    std::function<void(int)> job_;
+    int parts_ = 0, next_ = 0, pending_ = 0;
+    bool stop_ = false;
+};
 
 }  // namespace
 
@@ -61,6 +126,7 @@ struct lsm_handle {
     std::vector<cudaEvent_t> ev_join;
     cudaEvent_t ev_fork = nullptr;
     float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
+    lsm_tuning tuning = { 0, -1, -1, 0 };   // lsm_set_tuning (0 / -1 = automatic)
     int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel, 3 between agent and emit kernel
 };
 
@@ -99,7 +165,9 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     // An L2 persisting set-aside for the HJ grid is OFF by default: carving 32 MB out of the 126 MB L2 slowed the
     // step's 107 MB store stream by 25-35 % on B200 (plain 16-byte stores of the adjacency bytes: 22.6 -> 16.8 us;
     // whole cfg2 step 52.5 -> 47.9 us), while the 3-24 MB grids stay L2-resident on their own. LSM_L2_PERSIST=1 opts in.
+#ifdef LSM_EXPERIMENTS
     h->l2_persist = std::getenv("LSM_L2_PERSIST") != nullptr;
+#endif
     if (prop.persistingL2CacheMaxSize > 0 && h->l2_persist) {
         size_t want = (size_t)prop.persistingL2CacheMaxSize;
         if (want > ((size_t)32 << 20)) want = (size_t)32 << 20;
@@ -176,23 +244,25 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.bytes_per_env = align_up(off, 16);
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    const char* force_generic = std::getenv("LSM_FORCE_GENERIC");
     // the specialised pipeline emits the 'relative' node features every shipped script uses; 'global' runs the generic kernel
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) &&
-              !(force_generic != nullptr && force_generic[0] == '1');
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL);
+#ifdef LSM_EXPERIMENTS
+    { const char* force_generic = std::getenv("LSM_FORCE_GENERIC"); if (force_generic != nullptr && force_generic[0] == '1') h->spec = false; }
+#endif
     // where the next step's HJ pair values are computed (measured): in lsm_pair_kernel behind the emit kernel
     // ("late") for the 4-D double-integrator grid; between the agent and the emit kernel ("middle") for the 5-D airtaxi
     // grid, whose lookups are half an emit kernel's worth of work and hurt it more when they share the SMs.
-    // LSM_PAIR=late|emit|front|middle overrides (experiments)
+    // lsm_set_tuning overrides.
     h->pair_placement = cfg->dynamics == LSM_DYN_AIRTAXI ? 3 : 0;
+#ifdef LSM_EXPERIMENTS
     if (const char* pp = std::getenv("LSM_PAIR")) {
         if (!std::strcmp(pp, "late")) h->pair_placement = 0;
         else if (!std::strcmp(pp, "emit")) h->pair_placement = 1;
         else if (!std::strcmp(pp, "front")) h->pair_placement = 2;
         else if (!std::strcmp(pp, "middle")) h->pair_placement = 3;
     }
-    const char* fe = std::getenv("LSM_EPW");
-    h->forced_epw = fe ? std::atoi(fe) : 0;
+    { const char* fe = std::getenv("LSM_EPW"); h->forced_epw = fe ? std::atoi(fe) : 0; }
+#endif
     if (h->spec) {
         h->bytes_per_env = h->geo.rec_bytes + h->geo.scratch_bytes;
         // agent kernel: one lane per agent, 32/N envs per warp (LSM_EPW overrides for experiments)
@@ -267,6 +337,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
 
 int lsm_destroy(lsm_handle* h) {
     if (h == nullptr) return 0;
+    DeviceGuard guard(h->device);
     if (h->d_pair_tab) cudaFree(h->d_pair_tab);
     if (h->d_sel_tab) cudaFree(h->d_sel_tab);
     if (h->d_pair32) cudaFree(h->d_pair32);
@@ -310,13 +381,14 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     for (int k = 0; k < g->ndim; ++k) cells *= (size_t)g->shape[k];
     h->persist_bytes = cells * sizeof(float);
     if (h->persist_bytes > h->max_window) h->persist_bytes = h->max_window;
-    // corner-packed copy for the pair kernel (one aligned chunk per lookup). LSM_NO_PACKED=1 keeps the scattered gathers;
-    // tables larger than LSM_PACKED_MAX_MB (default 2048) are not built.
+    // corner-packed copy for the pair kernel (one aligned chunk per lookup); lsm_tuning.packed_grid = 0 keeps the scattered
+    // gathers; tables larger than 2 GiB are not built.
+    DeviceGuard guard(h->device);
+    const bool want_packed = h->tuning.packed_grid != 0;
     if (h->d_vpacked) { cudaFree(h->d_vpacked); h->d_vpacked = nullptr; }
     h->kp.vg.packed = nullptr;
-    if (h->spec && std::getenv("LSM_NO_PACKED") == nullptr) {
-        const char* mx = std::getenv("LSM_PACKED_MAX_MB");
-        const size_t max_bytes = (size_t)(mx ? std::atoll(mx) : 2048) << 20;
+    if (h->spec && want_packed) {
+        const size_t max_bytes = (size_t)2048 << 20;
         size_t pcells = 1;      // n slots on periodic dims, n + 1 on the others (see lsm_pack_grid_kernel)
         for (int k = 0; k < g->ndim; ++k) pcells *= (size_t)(g->periodic[k] ? g->shape[k] : g->shape[k] + 1);
         const size_t bytes = pcells * ((size_t)1 << g->ndim) * sizeof(float);
@@ -330,7 +402,7 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     }
     if (h->d_grads8) { cudaFree(h->d_grads8); h->d_grads8 = nullptr; }
     h->kp.vg.grads8 = nullptr;
-    if (h->spec && g->ndim == 5 && std::getenv("LSM_NO_PACKED") == nullptr) {
+    if (h->spec && g->ndim == 5 && want_packed) {
         cudaError_t e = cudaMalloc(&h->d_grads8, cells * 8 * sizeof(float));
         if (e == cudaSuccess) e = lsm::pad_grads_launch(g->grads, h->d_grads8, (long long)cells);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
@@ -342,9 +414,26 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
 
 int lsm_set_ttr_grid(lsm_handle* h, const lsm_grid_desc* g) {
     if (h == nullptr) return fail(1, "lsm_set_ttr_grid: null handle");
+    DeviceGuard guard(h->device);
     int rc = fill_grid(g, &h->kp.tg, 4, false, "lsm_set_ttr_grid");
     if (rc) return rc;
     h->kp.has_tg = 1;
+    return 0;
+}
+
+int lsm_set_tuning(lsm_handle* h, const lsm_tuning* t) {
+    if (h == nullptr || t == nullptr) return fail(1, "lsm_set_tuning: null argument");
+    if (t->chunks < 0 || t->chunks > 16) return fail(2, "lsm_set_tuning: chunks must be 0 (automatic) or 1..16");
+    if (t->pair_placement != -1 && t->pair_placement != 0 && t->pair_placement != 2 && t->pair_placement != 3) {
+#ifdef LSM_EXPERIMENTS
+        if (t->pair_placement != 1)
+#endif
+        return fail(2, "lsm_set_tuning: pair_placement must be -1 (automatic), 0 (behind the emit kernel), 2 (in front of the agent kernel) or 3 (between them)");
+    }
+    if (t->packed_grid < -1 || t->packed_grid > 1) return fail(2, "lsm_set_tuning: packed_grid must be -1, 0 or 1");
+    if (h->have_buffers || h->kp.has_vg) return fail(5, "lsm_set_tuning: call it right after lsm_create (before lsm_set_value_grid / lsm_bind_buffers)");
+    h->tuning = *t;
+    if (t->pair_placement >= 0) h->pair_placement = t->pair_placement;
     return 0;
 }
 
@@ -356,15 +445,19 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
     for (const void* p : ptrs) if (p == nullptr) return fail(2, "lsm_bind_buffers: every buffer pointer must be non-null");
     if (((uintptr_t)b->adj & 15u) || ((uintptr_t)b->node_obs & 15u))
         return fail(2, "lsm_bind_buffers: adj and node_obs must be 16-byte aligned");
+    if ((b->term_f64 != nullptr) != (b->term_i32 != nullptr) || (b->term_f64 != nullptr) != (b->term_env_f64 != nullptr))
+        return fail(2, "lsm_bind_buffers: term_f64, term_i32 and term_env_f64 must be all set or all NULL");
+    DeviceGuard guard(h->device);
     h->kp.b = *b;
+    h->kp.adj_base = nullptr; h->kp.adj_keep = nullptr;
     h->have_buffers = true;
     // chunked launches for big batches (measured on B200, DESIGN.md 3: 4 ranges pay off from ~0.4 GB of observations per
     // step - 0.8 GB: -11 %, 10.7 GB: -9 % - while a 0.1 GB step is launch-latency bound and stays on the caller's stream:
-    // +26 % with 2 ranges). LSM_CHUNKS overrides.
+    // +26 % with 2 ranges). lsm_tuning.chunks overrides.
     {
         const double step_bytes = (double)b->num_envs * 4.0 * h->kp.N * h->kp.E * (double)(h->kp.F + h->kp.E);
         int want = step_bytes >= 4.0e8 ? 4 : 1;
-        if (const char* ce = std::getenv("LSM_CHUNKS")) { const int v = std::atoi(ce); if (v >= 1 && v <= 16) want = v; }
+        if (h->tuning.chunks >= 1 && h->tuning.chunks <= 16) want = h->tuning.chunks;
         if (!h->spec) want = 1;
         h->chunks = want;
         while ((int)h->streams.size() < (want > 1 ? want : 0)) {
@@ -395,6 +488,7 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
 
 int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     if (h == nullptr || out == nullptr) return fail(1, "lsm_get_launch_info: null argument");
+    DeviceGuard guard(h->device);
     const long long ngroups = h->have_buffers ? (h->kp.b.num_envs + h->kp.EPW - 1) / h->kp.EPW : 0;
     long long blocks = (ngroups + h->warps_per_block - 1) / h->warps_per_block;
     if (!h->spec && blocks > h->grid_cap) blocks = h->grid_cap;
@@ -437,7 +531,12 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     kp.mode = mode; kp.flag = flag; kp.action_idx = action_idx; kp.action_onehot = action_onehot;
     kp.env_mask = env_mask; kp.episode = (long long)episode; kp.seed = (unsigned long long)seed;
     const long long ngroups = (kp.b.num_envs + kp.EPW - 1) / kp.EPW;
+    DeviceGuard guard(h->device);
+#ifdef LSM_EXPERIMENTS
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
+#else
+    kp.debug = 0;
+#endif
     const void* persist = (h->l2_persist && mode == lsm::MODE_STEP && h->kp.has_vg && needs_vg) ? (const void*)h->kp.vg.values : nullptr;
     const bool pair_path = h->spec && (c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg && !(kp.debug & 2);
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;   // LSM_DEBUG 32: K_a in front of the agent kernel on every step
@@ -548,6 +647,71 @@ int lsm_set_output_buffers(lsm_handle* h, float* obs, float* node_obs, float* ad
     return 0;
 }
 
+int lsm_set_compact_adjacency(lsm_handle* h, float* adj_base, uint32_t* adj_keep) {
+    if (h == nullptr) return fail(1, "lsm_set_compact_adjacency: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_set_compact_adjacency: lsm_bind_buffers has not been called");
+    if ((adj_base == nullptr) != (adj_keep == nullptr)) return fail(2, "lsm_set_compact_adjacency: pass both pointers or neither");
+    if (adj_base != nullptr && !h->spec)
+        return fail(6, "lsm_set_compact_adjacency: this configuration runs the fused generic kernel (dense adjacency only)");
+    if ((uintptr_t)adj_base & 15u) return fail(2, "lsm_set_compact_adjacency: adj_base must be 16-byte aligned");
+    h->kp.adj_base = adj_base; h->kp.adj_keep = adj_keep;
+    return 0;
+}
+
+int lsm_expand_adjacency_host(const float* adj_base, const uint32_t* adj_keep, float* adj, int64_t num_envs, int32_t N, int32_t E,
+                              int32_t threads, int32_t cached_stores) {
+    if (adj_base == nullptr || adj_keep == nullptr || adj == nullptr) return fail(1, "lsm_expand_adjacency_host: null argument");
+    if (num_envs < 0 || N < 1 || N > LSM_MAX_AGENTS || E < N || E > LSM_MAX_AGENTS + LSM_MAX_LANDMARKS)
+        return fail(2, "lsm_expand_adjacency_host: bad sizes");
+    if (((uintptr_t)adj & 3u) || (((E * E) % 4) == 0 && ((uintptr_t)adj & 15u)))
+        return fail(2, "lsm_expand_adjacency_host: adj must be 16-byte aligned (4-byte when E*E is not a multiple of 4)");
+    if (num_envs == 0) return 0;
+    int T = threads;
+    if (T <= 0) { T = (int)std::thread::hardware_concurrency(); if (T < 1) T = 1; if (T > 16) T = 16; }
+    if ((int64_t)T > num_envs) T = (int)num_envs;
+    const int W = (E + 31) / 32, EE = E * E;
+    const bool vec = (EE % 4) == 0;          // every observer matrix starts 16-byte aligned
+    auto work = [&](int part) {
+        const int64_t e0 = num_envs * part / T, e1 = num_envs * (part + 1) / T;
+        alignas(16) float row[LSM_MAX_AGENTS + LSM_MAX_LANDMARKS + 4];
+        for (int64_t e = e0; e < e1; ++e) {
+            const float* base = adj_base + e * EE;
+            for (int i = 0; i < N; ++i) {
+                const uint32_t* keep = adj_keep + (e * N + i) * W;
+                float* dst = adj + (e * N + i) * EE;
+                if (vec && (E % 4) == 0) {
+                    // rows are 16-byte multiples: build the row mask once per observer, stream the rows
+                    alignas(16) uint32_t cm[LSM_MAX_AGENTS + LSM_MAX_LANDMARKS + 4];
+                    for (int b = 0; b < E; ++b) cm[b] = ((keep[b >> 5] >> (b & 31)) & 1u) ? 0xffffffffu : 0u;
+                    for (int a = 0; a < E; ++a) {
+                        const bool ka = (keep[a >> 5] >> (a & 31)) & 1u;
+                        const __m128i am = _mm_set1_epi32(ka ? -1 : 0);
+                        for (int b = 0; b < E; b += 4) {
+                            const __m128i v = _mm_loadu_si128((const __m128i*)(base + a * E + b));
+                            const __m128i m = _mm_and_si128(_mm_load_si128((const __m128i*)(cm + b)), am);
+                            if (cached_stores) _mm_store_si128((__m128i*)(dst + a * E + b), _mm_and_si128(v, m));
+                            else _mm_stream_si128((__m128i*)(dst + a * E + b), _mm_and_si128(v, m));
+                        }
+                    }
+                } else {
+                    for (int a = 0; a < E; ++a) {
+                        const bool ka = (keep[a >> 5] >> (a & 31)) & 1u;
+                        for (int b = 0; b < E; ++b) {
+                            const bool kb = (keep[b >> 5] >> (b & 31)) & 1u;
+                            row[b] = (ka && kb) ? base[a * E + b] : 0.0f;
+                        }
+                        std::memcpy(dst + a * E, row, sizeof(float) * E);
+                    }
+                }
+            }
+        }
+        _mm_sfence();
+    };
+    if (T == 1) work(0);
+    else HostPool::get().run(T, work);
+    return 0;
+}
+
 int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* edge_attr, int32_t* counts, int64_t* offsets,
                   int64_t capacity, void* stream) {
     if (h == nullptr) return fail(1, "lsm_edge_list: null handle");
@@ -555,6 +719,7 @@ int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* e
     if (edge_index == nullptr || edge_attr == nullptr || counts == nullptr || offsets == nullptr)
         return fail(1, "lsm_edge_list: null output");
     if (capacity < 1) return fail(2, "lsm_edge_list: capacity must be >= 1");
+    DeviceGuard guard(h->device);
     const float* a = adj ? adj : h->kp.b.adj;
     const long long graphs = (long long)h->kp.b.num_envs * h->kp.N;
     cudaError_t e = lsm::edge_list_launch(a, counts, (long long*)offsets, (long long*)edge_index, edge_attr, graphs, h->kp.E,
@@ -569,6 +734,7 @@ int lsm_rollout_insert(lsm_handle* h, const float* obs, const uint8_t* done, flo
     if (!h->have_buffers) return fail(5, "lsm_rollout_insert: lsm_bind_buffers has not been called");
     if (obs == nullptr || done == nullptr || masks == nullptr || active_masks == nullptr)
         return fail(1, "lsm_rollout_insert: obs, done, masks and active_masks must be non-null");
+    DeviceGuard guard(h->device);
     cudaError_t e = lsm::rollout_insert_launch(obs, done, share_obs, masks, active_masks, (long long)h->kp.b.num_envs, h->kp.N, h->kp.D,
                                                (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "lsm_rollout_insert");
@@ -607,7 +773,12 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     if (!h->spec) return fail(6, "lsm_emit_only: this configuration runs the fused generic kernel (no separate emission launch)");
     lsm::KParams kp = h->kp;
     kp.mode = lsm::MODE_OBSERVE; kp.env_mask = nullptr;
+    DeviceGuard guard(h->device);
+#ifdef LSM_EXPERIMENTS
     { const char* dbg = std::getenv("LSM_DEBUG"); kp.debug = dbg ? std::atoi(dbg) : 0; }
+#else
+    kp.debug = 0;
+#endif
     kp.pair_late = 0;
     kp.grp_begin = 0; kp.env_begin = 0; kp.env_end = (int)kp.b.num_envs;
     const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 2);
@@ -621,6 +792,7 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
 
 int lsm_debug_timeline(lsm_handle* h, int arm, uint64_t* out_ns) {
     if (h == nullptr) return fail(1, "lsm_debug_timeline: null handle");
+    DeviceGuard guard(h->device);
     cudaError_t e;
     if (out_ns != nullptr && h->d_timeline != nullptr) {
         if ((e = cudaDeviceSynchronize()) != cudaSuccess) return cuda_fail(e, "lsm_debug_timeline");

@@ -97,6 +97,8 @@ struct KParams {
     double* pairval;           // [num_envs][N][N] raw HJ value of (ego, other) from lsm_pair_kernel; NULL = compute in-kernel
     unsigned char* emit_rec;   // [num_envs][sizeof(EmitRec)] per-env record consumed by lsm_emit_kernel
     int pair_late;             // lsm_pair_kernel launched BEHIND the emit kernel of the same step (runs beside its drain)
+    float* adj_base;           // compact adjacency (lsm_set_compact_adjacency): [num_envs][E][E], NULL = dense adj output
+    unsigned* adj_keep;        //                                             [num_envs][N][W]
     unsigned long long* timeline;   // diagnostics (lsm_debug_timeline), NULL in production: globaltimer min-start / max-end per kernel
 };
 
@@ -287,12 +289,12 @@ __device__ __forceinline__ double speed_of(double s2, double s3) {
 }
 
 // navigation_graph_safe.py:606-656
+// `he` = direction_alignment_error(theta, goal heading), computed once by the caller (the reward needs it too)
 template <int DYN>
-__device__ __forceinline__ bool goal_reached(double x, double y, double theta, double speed, double gx, double gy,
-                                             double gh, double gs, const Curriculum& q) {
+__device__ __forceinline__ bool goal_reached_he(double x, double y, double he, double speed, double gx, double gy,
+                                                double gs, const Curriculum& q) {
     const double dx = x - gx, dy = y - gy;
     const double dist = sqrt(dx * dx + dy * dy);
-    const double he = direction_alignment_error(theta, gh);
     const double ve = fabs(speed - gs);
     bool cond;
     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
@@ -308,6 +310,11 @@ __device__ __forceinline__ bool goal_reached(double x, double y, double theta, d
         }
     } else cond = he < q.heading_thresh;
     return dist < q.dist_thresh && cond && ve < q.speed_thresh;
+}
+template <int DYN>
+__device__ __forceinline__ bool goal_reached(double x, double y, double theta, double speed, double gx, double gy,
+                                             double gh, double gs, const Curriculum& q) {
+    return goal_reached_he<DYN>(x, y, direction_alignment_error(theta, gh), speed, gx, gy, gs, q);
 }
 
 // single-constraint QP (declared semantics; replaces cvxpy/OSQP at safety_filter.py:286-308,364-376)

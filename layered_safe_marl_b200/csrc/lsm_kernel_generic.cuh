@@ -443,6 +443,12 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
                 out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
             }
+            if (do_reset && kp.mode == MODE_STEP && kp.b.term_f64 != nullptr) {
+                if (agent_on)
+                    term_snapshot(kp.b, (size_t)env * N + ai, (size_t)kp.b.num_envs * N, x, y, min_rel, dist_left, times_req, times_old,
+                                  dists_goal, dists_old, goal_min_time, ncoll, safety_filtered);
+                if (ai == 0) kp.b.term_env_f64[env] = ratio;
+            }
             if (do_reset) {
                 current_step = 0;
                 ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);

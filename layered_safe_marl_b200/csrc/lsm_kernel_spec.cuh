@@ -519,7 +519,8 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, 
         P.lh[(L - 1) * N + i] = last_heading;
     }
     for (int m = 0; m < M; ++m) {
-        const double sv = lsm_sin(P.lh[m]), cv = lsm_cos(P.lh[m]);
+        double sv, cv;
+        lsm_sincos(P.lh[m], &sv, &cv);
         P.lsin[m] = sv; P.lcos[m] = cv;
         R.cst[m] = make_float4((float)sv, (float)cv, (float)P.lsp[m], 1.0f);
     }
@@ -781,6 +782,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             __syncwarp();
             double safe0 = raw0, safe1 = raw1;
             LSM_LOAD_MOTION()
+            // airtaxi: sin / cos of the own heading, evaluated once per internal step and shared by the filter's relative
+            // frame (before the dynamics), the integration and the velocity / observation frame (after it)
+            double hsc[2] = { 0.0, 1.0 };
+            if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) { if (agent_on) lsm_sincos_inl(s2, &hsc[0], &hsc[1]); }
             for (int it = 0; it < c.num_internal_step; ++it) {
                 // HJ values of (ego, other): from lsm_pair_kernel for the states this launch started with, in-kernel
                 // for later internal steps
@@ -819,7 +824,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                             const double best_d = (best_d2 >= kp.r2_gt) ? INFINITY : 0.0;
                             const double2 po = R.pos[kv];
                             filter_resolve<DYN, LeanGrad>(kp, best_d, best_v, !isinf(best_v), x, y, s2, s3, po.x, po.y, P.as2[kv], P.as3[kv],
-                                                raw0, raw1, P.rawx[kv], P.rawy[kv], safe0, safe1, filt);
+                                                raw0, raw1, P.rawx[kv], P.rawy[kv], safe0, safe1, filt, hsc[0], hsc[1]);
                         }
                     }
                     deconflict = dec; safety_filtered = filt;
@@ -828,7 +833,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 if (agent_on) {
                     const double d0 = raw0 - safe0, d1 = raw1 - safe1;
                     action_diff = sqrt(d0 * d0 + d1 * d1);
-                    if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time);
+                    if (!done) integrate<DYN>(x, y, s2, s3, safe0, safe1, c.dt, p_dist, state_time,
+                                              DYN != LSM_DYN_DOUBLE_INTEGRATOR ? hsc : nullptr);
                     R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
                 }
                 __syncwarp();
@@ -841,21 +847,23 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             double cth = 1.0, sth = 0.0;
             bool reached_now = false;
             if (agent_on) {
-                theta = theta_of<DYN>(s2, s3); speed = speed_of<DYN>(s2, s3);
-                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vpx = s2; vpy = s3; }
-                else { cth = lsm_cos(s2); sth = lsm_sin(s2); vpx = s3 * cth; vpy = s3 * sth; R.air.cth[ai] = cth; R.air.sth[ai] = sth; }
+                // the two / three trigonometric evaluations on this kernel's critical path are the force-inlined flavours
+                // of the shared implementation (same arithmetic as lsm_atan2 / lsm_cos / lsm_sincos, include/lsm_math.h)
+                speed = speed_of<DYN>(s2, s3);
+                if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { theta = lsm_atan2_inl(s3, s2); vpx = s2; vpy = s3; }
+                else { theta = s2; sth = hsc[0]; cth = hsc[1]; vpx = s3 * cth; vpy = s3 * sth; R.air.cth[ai] = cth; R.air.sth[ai] = sth; }   // hsc = lsm_sincos(s2)
                 goal_pre = goal_index(reached, ai, N, M);
                 const double2 gp = R.pos[N + goal_pre];
                 const double gx = gp.x, gy = gp.y, gh = P.lh[goal_pre], gs = P.lsp[goal_pre];
                 emit_obs_row<DYN, N, L>(R, P, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
                 // reward_reach_goal: navigation_graph_safe.py:691-791
-                const double he = direction_alignment_error(theta, gh);
+                const double he = 0.5 - 0.5 * lsm_cos_inl(theta - gh);     // direction_alignment_error, utils.py:79-81
                 const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
                 const double se = fabs(speed - gs);
                 const double sen = clipd(se / q.speed_thresh, 0.0, 1.0);
                 double cra = ratio_sloped(ratio, 0.25, 0.75);
                 if (use_filter_arg) cra = 1.0;
-                reached_now = goal_reached<DYN>(x, y, theta, speed, gx, gy, gh, gs, q);
+                reached_now = goal_reached_he<DYN>(x, y, he, speed, gx, gy, gs, q);
                 if (reached_now) {
                     const double pr = goal_reward_factor(theta, gx - x, gy - y, hpr, sen);
                     double goal_rew;
@@ -990,7 +998,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             if (agent_on) {
                 double vx, vy;
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
+                else { double ct, st; lsm_sincos(s2, &st, &ct); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
                 const int g = goal_index(reached, ai, N, M);
                 goal_obs = g;
                 R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
@@ -1037,6 +1045,15 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
                 out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
             }
+            if (do_reset && kp.mode == MODE_STEP && kp.b.term_f64 != nullptr) {
+                // `parity` already names the slot this step's values go to; last step's are still in the other one
+                if (agent_on)
+                    term_snapshot(kp.b, (size_t)env * N + ai, fstride, x, y, min_rel, dist_left, times_req,
+                                  af[(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) * fstride], dists_goal,
+                                  af[(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) * fstride], goal_min_time, ncoll,
+                                  safety_filtered);
+                if (ai == 0) kp.b.term_env_f64[env] = ratio;
+            }
             if (do_reset) {
                 current_step = 0;
                 ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
@@ -1054,7 +1071,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
-                else { const double ct = lsm_cos(s2), st = lsm_sin(s2); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
+                else { double ct, st; lsm_sincos(s2, &st, &ct); vx = s3 * ct; vy = s3 * st; R.air.cth[ai] = ct; R.air.sth[ai] = st; }
                 R.pos[ai] = make_double2(x, y); P.as2[ai] = s2; P.as3[ai] = s3;
                 R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
                 R.pos[E + ai] = g0; R.pos[E + N + ai] = g0;
@@ -1194,14 +1211,21 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ES& S = *reinterpret_cast<ES*>(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int n = (int)kp.b.num_envs;
     const double r2_lt = kp.r2_lt;
+    // ablation switches exist only in the LSM_EXPERIMENTS build (liblsm_b200_exp.so); the product kernel has none
+#ifdef LSM_EXPERIMENTS
     const int debug = kp.debug;
+    const int n = (int)kp.b.num_envs;
+#define LSM_DBG(bit) ((debug & (bit)) != 0)
+#else
+#define LSM_DBG(bit) false
+#endif
     // the dependents (normally lsm_pair_kernel, which does not wait at its top) are released only once the agent kernel
     // this launch depends on is complete and flushed
     pdl_wait();
     pdl_launch_dependents();
     tl_start(kp.timeline, TL_EMIT_START);
+#ifdef LSM_EXPERIMENTS
     if (debug & 64) return;          // experiments: launch + block dispatch floor
     if (debug & 512) {               // experiments: every bulk copy of this block back to back, nothing else
         if (tid == 0) {
@@ -1233,7 +1257,13 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         }
         return;
     }
+#endif
     const bool masked_reset = kp.mode == MODE_RESET && kp.env_mask != nullptr;
+    // compact adjacency (host-facing callers, lsm_set_compact_adjacency): ONE thresholded E x E matrix per environment +
+    // the per-observer keep masks instead of the N masked copies - 1/N of the adjacency bytes cross PCIe and the host
+    // expands them (lsm_expand_adjacency_host)
+    const bool compact = kp.adj_base != nullptr;
+    const int warp = tid >> 5;
 
     auto prefetch = [&](int env, int slot) {
         const int4* src = reinterpret_cast<const int4*>(kp.emit_rec + (size_t)env * sizeof(REC));
@@ -1248,16 +1278,18 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         const int rb = it & 1;                         // record slot
         const int tb = NBUF == 2 ? (tiles & 1) : 0;    // tile buffer (alternates per PROCESSED environment)
         cp_async_wait_all();
-        // the bulk copies that last read this iteration's tile buffers have finished reading them
-        if (tid == 0) { if (NBUF == 2) bulk_store_wait_read<1>(); else bulk_store_wait_read<0>(); }
+        // the bulk copies that last read this iteration's tile buffers have finished reading them (bulk groups are per
+        // thread: lane 0 of every warp issues a share of the copies and commits exactly one group per environment)
+        if (lane == 0) { if (NBUF == 2) bulk_store_wait_read<1>(); else bulk_store_wait_read<0>(); }
         __syncthreads();
         if (ee + (int)gridDim.x < env_end) prefetch(ee + gridDim.x, rb ^ 1);
         cp_async_commit();
         if (masked_reset && kp.env_mask[ee] == 0) continue;
-        if (debug & 128) continue;   // experiments: + record load
+        if (LSM_DBG(128)) continue;   // experiments: + record load
         ++tiles;
         const REC& R = S.rec[rb];
         float* const dthr = S.dthr[tb];
+#ifdef LSM_EXPERIMENTS
         if (debug & 256) {           // experiments: the bulk copies alone (whatever the tiles hold), no compute
             if (tid == 0) {
                 if (GEO::ADJ_BULK) for (int i = 0; i < N; ++i) bulk_store(kp.b.adj + ((size_t)ee * N + i) * EE, dthr, (unsigned)EE * 4u);
@@ -1266,6 +1298,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             continue;
         }
+#endif
         // (a) thresholded distance matrix: d2 in float64 against the exact squared radius; the stored float32 value is
         //     d2f * rsqrt(d2f). Thread a (one per entity) walks the circular distances d = 1 .. E/2 to entity a + d
         //     (for even E the last distance only needs a < E/2), so every unordered pair is visited once.
@@ -1320,10 +1353,18 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             __syncthreads();
         }
+        if (compact) {
+            unsigned* kdst = kp.adj_keep + (size_t)ee * (N * W);
+            for (int k = tid; k < N * W; k += T) kdst[k] = any_disc != 0u ? S.keepm[k] : 0xffffffffu;
+            if (!GEO::ADJ_BULK) {
+                float* bdst = kp.adj_base + (size_t)ee * EE;
+                for (int idx = tid; idx < EE; idx += T) __stcs(bdst + idx, dthr[idx]);
+            }
+        }
         // (d) adjacency
         float* abase = kp.b.adj + (size_t)ee * (N * EE);
-        const bool adj_bulk = GEO::ADJ_BULK && any_change == 0u && !(debug & 16);
-        if (!(debug & 8)) {
+        const bool adj_bulk = GEO::ADJ_BULK && any_change == 0u && !LSM_DBG(16) && !compact;
+        if (!LSM_DBG(8) && !compact) {
             if (adj_bulk) {
                 // every observer sees the same matrix: mask it once in place; thread 0 sends it N times below
                 if (any_disc != 0u) {
@@ -1416,25 +1457,29 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             const int nb = NBUF == 2 ? tb : 0;
             if (c > 0) {
                 // the previous chunk's copy has finished reading the buffer this chunk is written to
-                if (tid == 0) bulk_store_wait_read<0>();
+                if (lane == 0 && warp == WPE - 1) bulk_store_wait_read<0>();
                 __syncthreads();
             }
             float* buf = S.nodes[nb];
-            if (!(debug & 4))
+            if (!LSM_DBG(4))
                 for (int r = tid; r < nrows; r += T) node_row(r0 + r, buf + r * F);
-            if (GEO::NODE_BULK || adj_bulk) bulk_store_fence();
+            if (GEO::NODE_BULK || adj_bulk || compact) bulk_store_fence();
             __syncthreads();
-            if (tid == 0) {
+            if (lane == 0) {
+                // the copies of one environment are issued by lane 0 of EVERY warp (observer i by warp i mod WPE, the node
+                // chunk by the last warp) instead of by one thread while the other 127 wait at the next barrier
                 const unsigned long long stream_pol = l2_evict_first();
-                if (adj_bulk && !adj_sent && !(debug & 8)) {
+                if (adj_bulk && !adj_sent && !LSM_DBG(8)) {
 #pragma unroll 1
-                    for (int i = 0; i < N; ++i) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u, stream_pol);
+                    for (int i = warp; i < N; i += WPE) bulk_store(abase + i * EE, dthr, (unsigned)EE * 4u, stream_pol);
                 }
-                if (GEO::NODE_BULK && !(debug & 4)) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
+                if (compact && GEO::ADJ_BULK && !adj_sent && warp == 0)
+                    bulk_store(kp.adj_base + (size_t)ee * EE, dthr, (unsigned)EE * 4u, stream_pol);
+                if (GEO::NODE_BULK && !LSM_DBG(4) && warp == WPE - 1) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
                 bulk_store_commit();
             }
             adj_sent = true;
-            if (!GEO::NODE_BULK && !(debug & 4)) {
+            if (!GEO::NODE_BULK && !LSM_DBG(4)) {
                 const int nfl = nrows * F;
                 if (F % 2 == 0 && (ROWS * F) % 2 == 0) {
                     for (int q = tid; q < nfl / 2; q += T)
@@ -1467,9 +1512,10 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         }
     }
     // every bulk copy issued by this block has finished READING shared memory before the block retires
-    if (tid == 0) bulk_store_wait_read<0>();
+    if (lane == 0) bulk_store_wait_read<0>();
     cp_async_wait_all();
     tl_end(kp.timeline, TL_EMIT_END);
+#undef LSM_DBG
 }
 
 }  // namespace lsm

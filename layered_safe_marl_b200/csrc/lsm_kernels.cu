@@ -50,11 +50,17 @@ constexpr int kPairBlock = kPairThreads;
 constexpr int kPairResident = 2;          // SM room the emit grid leaves for pair blocks (placement "late")
 constexpr int kPairLateBlocksPerSm = 8;   // grid bound of the late pair kernel (measured: >= 6 is best everywhere)
 
-// experiments: LSM_AGENT_MINB=3 trades ~100-400 B of spills for 12 instead of 8 resident physics warps per SM
+// The product library (liblsm_b200.so) has ONE instantiation per kernel and configuration and reads no environment
+// variable. Alternative kernel shapes and ablation switches are compiled only with -DLSM_EXPERIMENTS
+// (liblsm_b200_exp.so, `_build.build_experiments()`; selected by the tools with LSM_LIB=<path>).
+#ifdef LSM_EXPERIMENTS
+// LSM_AGENT_MINB=3 trades ~100-400 B of spills for 12 instead of 8 resident physics warps per SM
 static int agent_minb() {
     static const int v = [] { const char* e = std::getenv("LSM_AGENT_MINB"); return e ? std::atoi(e) : 0; }();
     return v;
 }
+static int env_int(const char* name, int dflt) { const char* e = std::getenv(name); return e ? std::atoi(e) : dflt; }
+#endif
 
 struct SpecFns {
     const void* pair; const void* agent; const void* emit;
@@ -62,7 +68,8 @@ struct SpecFns {
     int rec_bytes, scratch_bytes, emit_smem, emit_threads;
 };
 
-// experiments: LSM_WPE=2|4 selects an alternative emit-kernel shape for the cfg2 specialisation
+#ifdef LSM_EXPERIMENTS
+// LSM_WPE=2|4 selects an alternative emit-kernel shape for the cfg2 specialisation
 template <int WPE_, int EMINB_>
 static void cfg2_emit_variant(SpecFns* f) {
     f->emit = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_>;
@@ -71,27 +78,37 @@ static void cfg2_emit_variant(SpecFns* f) {
     f->emit_threads = 32 * WPE_;
 }
 
+#endif
+
 static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f);
 static bool spec_fns(int dynamics, int N, int L, SpecFns* f) {
     if (!spec_fns_base(dynamics, N, L, f)) return false;
+#ifdef LSM_EXPERIMENTS
     if (dynamics == LSM_DYN_DOUBLE_INTEGRATOR && N == 8 && L == 2) {
-        const char* e = std::getenv("LSM_WPE");
-        const int w = e ? std::atoi(e) : 0;
+        const int w = env_int("LSM_WPE", 0);
         if (w == 1) cfg2_emit_variant<1, 8>(f);
         if (w == 2) cfg2_emit_variant<2, 8>(f);
         if (w == 24) cfg2_emit_variant<2, 4>(f);    // two warps per block at half the occupancy target
     }
+#endif
     return true;
 }
 
+#ifdef LSM_EXPERIMENTS
+#define LSM_AGENT_FN(DYN_, N_, L_) (agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, 3> \
+                                                      : (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>)
+#define LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_) ((const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_, true>)
+#else
+#define LSM_AGENT_FN(DYN_, N_, L_) ((const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>)
+#define LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_) nullptr   /* "pair values inside the emit kernel": experiments only */
+#endif
 static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
 #define X(DYN_, N_, L_, WPE_, EMINB_)                                                             \
     if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
         f->pair = (const void*)lsm_pair_kernel<DYN_, N_>;                                         \
-        f->agent = agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, 3>          \
-                                     : (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>; \
+        f->agent = LSM_AGENT_FN(DYN_, N_, L_);                                                    \
         f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
-        f->emit_pie = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_, true>;             \
+        f->emit_pie = LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_);                                \
         f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
         f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \
         f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, WPE_>);                               \
@@ -139,7 +156,7 @@ cudaError_t spec_prepare_aux(int dynamics, int N, int L, int* emit_regs, int* em
     if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
     cudaError_t e = prepare_one(f.emit, f.emit_threads, f.emit_smem, emit_regs, emit_blocks_per_sm);
     if (e != cudaSuccess) return e;
-    { int r = 0, b = 0; e = prepare_one(f.emit_pie, f.emit_threads, f.emit_smem, &r, &b); if (e != cudaSuccess) return e; }
+    if (f.emit_pie != nullptr) { int r = 0, b = 0; e = prepare_one(f.emit_pie, f.emit_threads, f.emit_smem, &r, &b); if (e != cudaSuccess) return e; }
     int bps = 0;
     return prepare_one(f.pair, kPairBlock, 0, pair_regs, &bps);
 }
@@ -159,7 +176,11 @@ static cudaError_t launch_one(const void* fn, const KParams& kp, unsigned grid_b
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     int nattr = 0;
+#ifdef LSM_EXPERIMENTS
     static const bool no_pdl = std::getenv("LSM_NO_PDL") != nullptr;
+#else
+    constexpr bool no_pdl = false;
+#endif
     if (pdl && !no_pdl) {
         attr[nattr].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         attr[nattr].val.programmaticStreamSerializationAllowed = 1;
@@ -200,7 +221,9 @@ cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void*
         static int sm_count = 0;
         if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
         int bps = kPairLateBlocksPerSm;
-        if (const char* g = std::getenv("LSM_PAIR_BPS")) { const int v = std::atoi(g); if (v >= 1) bps = v; }
+#ifdef LSM_EXPERIMENTS
+        { const int v = env_int("LSM_PAIR_BPS", 0); if (v >= 1) bps = v; }
+#endif
         if (blocks > (long long)sm_count * bps) blocks = (long long)sm_count * bps;
     }
     return launch_one(f.pair, kp, (unsigned)blocks, kPairBlock, 0, stream, persist_ptr, persist_bytes, true);
@@ -210,7 +233,7 @@ cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void*
 // threads for kPairResident pair blocks per SM
 static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool pie, int* out) {
     int bps = 0;
-    const void* fn = pie ? f.emit_pie : f.emit;
+    const void* fn = (pie && f.emit_pie != nullptr) ? f.emit_pie : f.emit;
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, f.emit_threads, f.emit_smem);
     if (e != cudaSuccess) return e;
     if (bps < 1) return cudaErrorLaunchOutOfResources;
@@ -222,7 +245,9 @@ static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool 
         const int need_regs = kPairResident * block_regs(fp.numRegs, kPairBlock), need_thr = kPairResident * kPairBlock;
         while (bps > 1 && (65536 - bps * block_regs(fe.numRegs, f.emit_threads) < need_regs || 2048 - bps * f.emit_threads < need_thr)) --bps;
     }
-    if (const char* g = std::getenv("LSM_EMIT_BPS")) { const int v = std::atoi(g); if (v >= 1 && v < bps) bps = v; }
+#ifdef LSM_EXPERIMENTS
+    { const int v = env_int("LSM_EMIT_BPS", 0); if (v >= 1 && v < bps) bps = v; }
+#endif
     *out = bps;
     return cudaSuccess;
 }
@@ -232,7 +257,7 @@ cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pai
     if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
     if (regs != nullptr) {
         cudaFuncAttributes fa;
-        cudaError_t e = cudaFuncGetAttributes(&fa, pie ? f.emit_pie : f.emit);
+        cudaError_t e = cudaFuncGetAttributes(&fa, (pie && f.emit_pie != nullptr) ? f.emit_pie : f.emit);
         if (e != cudaSuccess) return e;
         *regs = fa.numRegs;
     }
@@ -251,7 +276,10 @@ cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void*
     unsigned grid = (unsigned)sm_count * (unsigned)bps;
     if (grid > (unsigned)(kp.env_end - kp.env_begin)) grid = (unsigned)(kp.env_end - kp.env_begin);
     if (grid < 1) grid = 1;
-    if (const char* g = std::getenv("LSM_EMIT_GRID")) { const unsigned v = (unsigned)std::atoi(g); if (v >= 1 && v < grid) grid = v; }
+#ifdef LSM_EXPERIMENTS
+    { const unsigned v = (unsigned)env_int("LSM_EMIT_GRID", 0); if (v >= 1 && v < grid) grid = v; }
+#endif
+    if (pie && f.emit_pie == nullptr) return cudaErrorInvalidValue;
     return launch_one(pie ? f.emit_pie : f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
 }
 

@@ -45,8 +45,10 @@ __device__ __forceinline__ void relative_state(double ex, double ey, double e2, 
         const double ddx = ox - ex, ddy = oy - ey;
         const double dist = sqrt(ddx * ddx + ddy * ddy);
         const double ang = lsm_atan2(ddy, ddx);
-        r[0] = dist * lsm_cos(ang - e2);
-        r[1] = dist * lsm_sin(ang - e2);
+        double sa, ca;
+        lsm_sincos(ang - e2, &sa, &ca);          // exactly lsm_cos / lsm_sin of the same argument, one reduction
+        r[0] = dist * ca;
+        r[1] = dist * sa;
         r[2] = o2 - e2; r[3] = e3; r[4] = o3;
     }
 }
@@ -55,19 +57,26 @@ __device__ __forceinline__ void relative_state(double ex, double ey, double e2, 
 //   d cos(phi - theta_e) = dx cos(theta_e) + dy sin(theta_e),  d sin(phi - theta_e) = dy cos(theta_e) - dx sin(theta_e)
 // (phi = atan2(dy, dx), d = |(dx, dy)|) - equal to safety_filter.py:277-284 to ~1e-16 d, one sincos instead of
 // sqrt + atan2 + cos + sin per pair. Used by the specialised pipeline; the generic kernel keeps the literal form.
+// (se, ce) = lsm_sincos(e2), passed in by callers that already have them (airtaxi only; ignored for the double integrator)
 template <int DYN>
-__device__ __forceinline__ void relative_state_rot(double ex, double ey, double e2, double e3, double ox, double oy,
-                                                   double o2, double o3, double (&r)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5]) {
+__device__ __forceinline__ void relative_state_rot_sc(double ex, double ey, double e2, double e3, double ox, double oy,
+                                                      double o2, double o3, double se, double ce,
+                                                      double (&r)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5]) {
     if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
         r[0] = ex - ox; r[1] = ey - oy; r[2] = e2 - o2; r[3] = e3 - o3;
     } else {
         const double ddx = ox - ex, ddy = oy - ey;
-        double se, ce;
-        lsm_sincos(e2, &se, &ce);
         r[0] = ddx * ce + ddy * se;
         r[1] = ddy * ce - ddx * se;
         r[2] = o2 - e2; r[3] = e3; r[4] = o3;
     }
+}
+template <int DYN>
+__device__ __forceinline__ void relative_state_rot(double ex, double ey, double e2, double e3, double ox, double oy,
+                                                   double o2, double o3, double (&r)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5]) {
+    double se = 0.0, ce = 1.0;
+    if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) lsm_sincos(e2, &se, &ce);
+    relative_state_rot_sc<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, se, ce, r);
 }
 
 template <int DYN>
@@ -101,13 +110,14 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
                                                double ex, double ey, double e2, double e3,
                                                double ox, double oy, double o2, double o3,
                                                double raw0, double raw1, double oraw0, double oraw1,
-                                               double& safe0, double& safe1, int& filtered) {
+                                               double& safe0, double& safe1, int& filtered,
+                                               double se = 0.0, double ce = 1.0 /* kRotRel: lsm_sincos(e2) of the caller */) {
     constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
     const lsm_config& c = kp.c;
     if (best_d > c.coordination_range) return;
     if (!kv_in_range) return;
     double rel[ND];
-    if constexpr (GRAD::kRotRel) relative_state_rot<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
+    if constexpr (GRAD::kRotRel) relative_state_rot_sc<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, se, ce, rel);
     else relative_state<DYN>(ex, ey, e2, e3, ox, oy, o2, o3, rel);
     const double uref[4] = { raw0, raw1, oraw0, oraw1 };
     double g[ND];
@@ -159,8 +169,10 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
 #pragma unroll
             for (int k = 0; k < 4; ++k) u[k] = (a[k] < 0.0) ? lo[k] : hi[k];
         } else {
-            const double f0 = -rel[3] + rel[ND - 1] * lsm_cos(rel[2]);
-            const double f1 = rel[ND - 1] * lsm_sin(rel[2]);
+            double s2r, c2r;
+            lsm_sincos(rel[2], &s2r, &c2r);
+            const double f0 = -rel[3] + rel[ND - 1] * c2r;
+            const double f1 = rel[ND - 1] * s2r;
             double b = g[0] * f0 + g[1] * f1;
             b = b + c.cbf_rate * best_v;
             double pinv[4];
@@ -193,10 +205,27 @@ __device__ __forceinline__ void filter_resolve(const KParams& kp, double best_d,
     safe0 = u[0]; safe1 = u[1];
 }
 
+// Terminal-step snapshot of what info_callback reads (navigation_graph_safe.py:386-450) for an environment that is
+// about to auto-reset: graphworker returns the terminal step's infos (env_wrappers.py:861-874), the reset below would
+// overwrite them.
+__device__ __forceinline__ void term_snapshot(const lsm_buffers& b, size_t a, size_t fstride, double x, double y, double min_rel,
+                                              double dist_left, double times_new, double times_old, double dists_new,
+                                              double dists_old, double goal_min_time, int ncoll, int safety_filtered) {
+    double* tf = b.term_f64 + a;
+    tf[LSM_TF_X * fstride] = x; tf[LSM_TF_Y * fstride] = y; tf[LSM_TF_MIN_REL_DIST * fstride] = min_rel;
+    tf[LSM_TF_DIST_LEFT * fstride] = dist_left; tf[LSM_TF_TIMES_REQ_NEW * fstride] = times_new;
+    tf[LSM_TF_TIMES_REQ_OLD * fstride] = times_old; tf[LSM_TF_DISTS_GOAL_NEW * fstride] = dists_new;
+    tf[LSM_TF_DISTS_GOAL_OLD * fstride] = dists_old; tf[LSM_TF_GOAL_MIN_TIME * fstride] = goal_min_time;
+    int* ti = b.term_i32 + a;
+    ti[LSM_TI_NUM_COLLISIONS * fstride] = ncoll; ti[LSM_TI_SAFETY_FILTERED * fstride] = safety_filtered;
+}
+
 // core.py:191-210 / :110-131, closed-form over one dt
+// airtaxi, `sc` != nullptr: sc[0..1] = lsm_sincos(theta before the step) from the caller; on return sc[0..1] =
+// lsm_sincos(theta after the step) - the per-agent kernel needs both anyway (filter frame before, velocity after).
 template <int DYN>
 __device__ __forceinline__ void integrate(double& x, double& y, double& s2, double& s3, double u0, double u1, double dt,
-                                          double& p_dist, double& state_time) {
+                                          double& p_dist, double& state_time, double* sc = nullptr) {
     if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
         double vx = s2, vy = s3;
         x = x + vx * dt + 0.5 * u0 * dt * dt;
@@ -214,15 +243,19 @@ __device__ __forceinline__ void integrate(double& x, double& y, double& s2, doub
         const double th1 = th0 + om * dt;
         double v1 = v0 + ac * dt;
         double ddx, ddy;
-        if (fabs(om * dt) < 1e-3) {
-            const double T = dt, c0 = lsm_cos(th0), s0 = lsm_sin(th0), o = om;
+        double s0, c0, s1 = 0.0, c1 = 1.0;
+        if (sc != nullptr) { s0 = sc[0]; c0 = sc[1]; } else lsm_sincos(th0, &s0, &c0);
+        const bool small = fabs(om * dt) < 1e-3;
+        if (sc != nullptr || !small) lsm_sincos(th1, &s1, &c1);
+        if (sc != nullptr) { sc[0] = s1; sc[1] = c1; }
+        if (small) {
+            const double T = dt, o = om;
             const double i0 = T, i1 = T * T / 2.0, i2 = T * T * T / 3.0, i3 = T * T * T * T / 4.0, i4 = T * T * T * T * T / 5.0;
             const double cc0 = c0, cc1 = -s0 * o, cc2 = -c0 * o * o / 2.0, cc3 = s0 * o * o * o / 6.0;
             const double sc0 = s0, sc1 = c0 * o, sc2 = -s0 * o * o / 2.0, sc3 = -c0 * o * o * o / 6.0;
             ddx = v0 * (cc0 * i0 + cc1 * i1 + cc2 * i2 + cc3 * i3) + ac * (cc0 * i1 + cc1 * i2 + cc2 * i3 + cc3 * i4);
             ddy = v0 * (sc0 * i0 + sc1 * i1 + sc2 * i2 + sc3 * i3) + ac * (sc0 * i1 + sc1 * i2 + sc2 * i3 + sc3 * i4);
         } else {
-            const double s1 = lsm_sin(th1), c1 = lsm_cos(th1), s0 = lsm_sin(th0), c0 = lsm_cos(th0);
             ddx = (v1 * s1 - v0 * s0) / om + ac * (c1 - c0) / (om * om);
             ddy = (-(v1 * c1) + v0 * c0) / om + ac * (s1 - s0) / (om * om);
         }

@@ -72,6 +72,31 @@ def compute_agent_infos(agent_f64: np.ndarray, agent_i32: np.ndarray, env_i32: n
     return out
 
 
+def apply_terminal_snapshot(agent_f64, agent_i32, env_i32, ratio, term_f64, term_i32, term_ratio):
+    """For the envs that auto-reset in this step the device state already belongs to the NEW episode, while the
+    reference's graphworker returns the TERMINAL step's info dicts and only appends the episode summary
+    (onpolicy/envs/env_wrappers.py:861-874). The kernels snapshot the fields `info_callback` reads just before the
+    reset (include/lsm_b200.h LSM_TF_* / LSM_TI_*); this puts them back, in place, for those envs (host copies)."""
+    jr = env_i32[LY.EI_JUST_RESET].astype(bool)
+    if not jr.any():
+        return ratio
+    f, i = agent_f64, agent_i32
+    par = env_i32[LY.EI_PARITY].astype(bool)
+    for dst, src in ((LY.AF_X, LY.TF_X), (LY.AF_Y, LY.TF_Y), (LY.AF_MIN_REL_DIST, LY.TF_MIN_REL_DIST),
+                     (LY.AF_DIST_LEFT, LY.TF_DIST_LEFT), (LY.AF_GOAL_MIN_TIME, LY.TF_GOAL_MIN_TIME)):
+        f[dst][jr] = term_f64[src][jr]
+    new_b, new_a = jr & par, jr & ~par          # the slot `parity` names holds the newest values
+    for slot_a, slot_b, t_new, t_old in ((LY.AF_TIMES_REQ_A, LY.AF_TIMES_REQ_B, LY.TF_TIMES_REQ_NEW, LY.TF_TIMES_REQ_OLD),
+                                         (LY.AF_DISTS_GOAL_A, LY.AF_DISTS_GOAL_B, LY.TF_DISTS_GOAL_NEW, LY.TF_DISTS_GOAL_OLD)):
+        f[slot_b][new_b] = term_f64[t_new][new_b]; f[slot_a][new_b] = term_f64[t_old][new_b]
+        f[slot_a][new_a] = term_f64[t_new][new_a]; f[slot_b][new_a] = term_f64[t_old][new_a]
+    i[LY.AI_NUM_COLLISIONS][jr] = term_i32[LY.TI_NUM_COLLISIONS][jr]
+    i[LY.AI_SAFETY_FILTERED][jr] = term_i32[LY.TI_SAFETY_FILTERED][jr]
+    ratio = np.array(ratio, dtype=np.float64, copy=True)
+    ratio[jr] = term_ratio[jr]
+    return ratio
+
+
 def separation_distance_of(params, ratio: np.ndarray) -> np.ndarray:
     """scenario.separation_distance from the per-env curriculum ratio (navigation_graph_safe.py:349-363)."""
     from .config import FLAG_SEPARATION_DISTANCE_CURRICULUM
@@ -112,6 +137,9 @@ class LazyInfos:
             af = env.agent_f64.cpu().numpy()
             ai = env.agent_i32.cpu().numpy()
             ratio = env.env_f64[LY.EF_CURRICULUM_RATIO].cpu().numpy()
+            if h['env_i32'][LY.EI_JUST_RESET].any():
+                ratio = apply_terminal_snapshot(af, ai, h['env_i32'], ratio, env.term_f64.cpu().numpy(),
+                                                env.term_i32.cpu().numpy(), env.term_env_f64.cpu().numpy())
             rew = (env.reward_individual if env.reward_individual is not None else env.reward).cpu().numpy()
             h['agent'] = compute_agent_infos(af, ai, h['env_i32'], rew, separation_distance_of(env.params, ratio))
         self._host = h

@@ -38,6 +38,13 @@ EF_COUNT = 1
 EI_CURRENT_STEP, EI_RESET_COUNT, EI_PARITY, EI_JUST_RESET = range(4)
 EI_COUNT = 4
 
+# terminal-step info snapshot of auto-resetting envs (include/lsm_b200.h LSM_TF_* / LSM_TI_*)
+(TF_X, TF_Y, TF_MIN_REL_DIST, TF_DIST_LEFT, TF_TIMES_REQ_NEW, TF_TIMES_REQ_OLD, TF_DISTS_GOAL_NEW, TF_DISTS_GOAL_OLD,
+ TF_GOAL_MIN_TIME) = range(9)
+TF_COUNT = 9
+TI_NUM_COLLISIONS, TI_SAFETY_FILTERED = range(2)
+TI_COUNT = 2
+
 # episode summary (environment.py:1065-1073), in this order
 EP_INFO_KEYS = ('travel_time_mean', 'travel_distance_mean', 'done_percentage', 'num_reached_goal_mean',
                 'conflict_percentage', 'min_distance_mean', 'min_distance_min',

@@ -19,6 +19,7 @@ to get host numpy arrays like the reference returns).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional
 
 import numpy as np
@@ -52,6 +53,34 @@ def make_config_struct(p: ScenarioParams) -> _lib.LsmConfig:
     return c
 
 
+def _bind_to_gpu_numa_node(device) -> Optional[int]:
+    """Pin this process (and the host worker threads it creates later) to the CPUs of the NUMA node the GPU hangs off, so
+    that pinned staging buffers are allocated node-local (first touch) and the adjacency expander writes local memory.
+    A no-op on single-node hosts / when sysfs has no answer. Returns the node or None."""
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id if hasattr(torch.cuda.get_device_properties(device), 'pci_bus_id') else None
+        if bus is None:
+            import subprocess
+            bus = subprocess.check_output(['nvidia-smi', '--query-gpu=pci.bus_id', '--format=csv,noheader', '-i',
+                                           str(device.index)], text=True).strip()
+        bus = bus.lower()
+        if len(bus.split(':')[0]) == 8:
+            bus = bus[4:]
+        node = int(open(f'/sys/bus/pci/devices/{bus}/numa_node').read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f'/sys/devices/system/node/node{node}/cpulist').read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 class _DeviceGrid:
     """An HjGrid uploaded to the GPU + its C descriptor."""
 
@@ -78,12 +107,26 @@ class B200GraphVecEnv:
     def __init__(self, args, num_envs: Optional[int] = None, device='cuda:0', seed: int = 0,
                  value_grid: Optional[HjGrid] = None, ttr_grid: Optional[HjGrid] = None,
                  binary_cfg=RewardBinaryConfig, weight_cfg=RewardWeightConfig, env_id_base: int = 0,
-                 numpy_outputs: bool = False, auto_reset: bool = True):
+                 numpy_outputs: bool = False, auto_reset: bool = True, tuning: Optional[dict] = None,
+                 host_threads: Optional[int] = None, numa_bind: bool = False):
         if not torch.cuda.is_available():
             raise RuntimeError("B200GraphVecEnv needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()   # raises if the sm_100a library is missing
         self.device = torch.device(device)
-        torch.cuda.set_device(self.device)
+        if self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
+        if numa_bind:
+            _bind_to_gpu_numa_node(self.device)
+        self._dev_ctx = torch.cuda.device(self.device)
+        self._dev_ctx.__enter__()      # lsm_create adopts the current device; restored at the end of __init__
+        try:
+            self._init(args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
+                       auto_reset, tuning, host_threads)
+        finally:
+            self._dev_ctx.__exit__(None, None, None)
+
+    def _init(self, args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
+              auto_reset, tuning, host_threads):
         self.params = scenario_params_from_args(args, binary_cfg=binary_cfg, weight_cfg=weight_cfg)
         p = self.params
         self.num_envs = int(num_envs if num_envs is not None else args.n_rollout_threads)
@@ -116,6 +159,14 @@ class B200GraphVecEnv:
         self._cfg = cfg
         self._h = C.c_void_p()
         _lib.check(self.lib.lsm_create(C.byref(cfg), C.byref(self._h)), 'lsm_create')
+        if tuning:
+            # launch-shape overrides (include/lsm_b200.h lsm_tuning): chunks, pair_placement, packed_grid
+            unknown = set(tuning) - {'chunks', 'pair_placement', 'packed_grid'}
+            if unknown:
+                raise ValueError(f"unknown tuning keys {sorted(unknown)}")
+            t = _lib.LsmTuning(int(tuning.get('chunks', 0)), int(tuning.get('pair_placement', -1)),
+                               int(tuning.get('packed_grid', -1)), 0)
+            _lib.check(self.lib.lsm_set_tuning(self._h, C.byref(t)), 'lsm_set_tuning')
 
         # --- grids (HjDataHandle / TTR loading); synthetic when none is given
         needs_vg = bool(p.flags & (FLAG_USE_SAFETY_FILTER | FLAG_HJ_VALUE))
@@ -156,6 +207,10 @@ class B200GraphVecEnv:
         self.reward_individual = None
         if p.flags & FLAG_SHARED_REWARD:
             self.reward_individual = torch.zeros((n, N), dtype=f32, device=dev)
+        # terminal-step snapshot of the info fields of auto-resetting envs (written only on a reset, read by LazyInfos)
+        self.term_f64 = torch.zeros((LY.TF_COUNT, n, N), dtype=f64, device=dev)
+        self.term_i32 = torch.zeros((LY.TI_COUNT, n, N), dtype=i32, device=dev)
+        self.term_env_f64 = torch.zeros((n,), dtype=f64, device=dev)
         # agent ids are constant (scenario.get_id -> global_id == agent index)
         self.agent_id = torch.arange(N, dtype=torch.int32, device=dev).view(1, N, 1).expand(n, N, 1).contiguous()
         self._agent_id_np = None
@@ -163,7 +218,7 @@ class B200GraphVecEnv:
         b.num_envs = n
         b.env_id_base = self.env_id_base
         for name in ('agent_f64', 'agent_i32', 'landmarks', 'env_f64', 'env_i32', 'obs', 'node_obs', 'adj',
-                     'reward', 'done', 'safe_action', 'ep_info'):
+                     'reward', 'done', 'safe_action', 'ep_info', 'term_f64', 'term_i32', 'term_env_f64'):
             setattr(b, name, getattr(self, name).data_ptr())
         b.reward_individual = self.reward_individual.data_ptr() if self.reward_individual is not None else None
         self._buffers = b
@@ -175,6 +230,28 @@ class B200GraphVecEnv:
         self._pending_episode = None
         self._host_out = None
         self.closed = False
+        # host-facing path (numpy_outputs): the adjacency crosses PCIe as ONE thresholded E x E matrix per env + the
+        # per-observer keep masks and is expanded on the host (lsm_set_compact_adjacency / lsm_expand_adjacency_host)
+        self._compact = None
+        self.host_cached_stores = False
+        self.host_profile = None      # set to {} to accumulate wall-clock seconds of the host-side phases of _outputs
+        if host_threads is None:
+            local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
+            host_threads = max(1, min(8, (os.cpu_count() or 1) // local_world))
+        self.host_threads = int(host_threads)
+        if self.numpy_outputs and self.launch_info()['specialised'] == 1:
+            Wm = (E + 31) // 32
+            cpt = {'base': torch.zeros((n, E, E), dtype=f32, device=dev),
+                   'keep': torch.zeros((n, N, Wm), dtype=i32, device=dev)}
+            cpt['base_h'] = torch.empty((n, E, E), dtype=f32).pin_memory()
+            cpt['keep_h'] = torch.empty((n, N, Wm), dtype=i32).pin_memory()
+            cpt['adj_h'] = torch.zeros((n, N, E, E), dtype=f32)     # zero-fill = first touch of every page
+            chunks = 1 if n < 256 else 4
+            cpt['bounds'] = [(n * c // chunks, n * (c + 1) // chunks) for c in range(chunks)]
+            cpt['events'] = [torch.cuda.Event() for _ in range(chunks)]
+            _lib.check(self.lib.lsm_set_compact_adjacency(self._h, C.c_void_p(cpt['base'].data_ptr()),
+                                                          C.c_void_p(cpt['keep'].data_ptr())), 'lsm_set_compact_adjacency')
+            self._compact = cpt
 
     # ------------------------------------------------------------------------------------------
     def launch_info(self) -> dict:
@@ -241,7 +318,19 @@ class B200GraphVecEnv:
             if self._host_out is None:
                 self._host_out = {}
             res = []
+            cpt = self._compact
+            stream = torch.cuda.current_stream(self.device)
+            if cpt is not None:
+                # adjacency first: compact matrices + keep masks in env chunks, an event behind each chunk, so that the
+                # host expansion of chunk c runs while the DMA engine is still moving the later chunks and node_obs
+                for (lo, hi), ev in zip(cpt['bounds'], cpt['events']):
+                    cpt['base_h'][lo:hi].copy_(cpt['base'][lo:hi], non_blocking=True)
+                    cpt['keep_h'][lo:hi].copy_(cpt['keep'][lo:hi], non_blocking=True)
+                    ev.record(stream)
             for t in outs:
+                if cpt is not None and t is self.adj:
+                    res.append(cpt['adj_h'])
+                    continue
                 key = t.data_ptr()
                 if t is self.agent_id:
                     if self._agent_id_np is None:
@@ -254,7 +343,26 @@ class B200GraphVecEnv:
                     self._host_out[key] = hb
                 hb.copy_(t, non_blocking=True)
                 res.append(hb)
-            torch.cuda.current_stream(self.device).synchronize()
+            prof = self.host_profile
+            if prof is not None:
+                import time
+                t0 = time.perf_counter()
+            if cpt is not None:
+                E, N = self.E, self.N
+                for (lo, hi), ev in zip(cpt['bounds'], cpt['events']):
+                    ev.synchronize()
+                    if prof is not None:
+                        t1 = time.perf_counter(); prof['wait_chunk'] = prof.get('wait_chunk', 0.0) + (t1 - t0)
+                    _lib.check(self.lib.lsm_expand_adjacency_host(
+                        C.c_void_p(cpt['base_h'][lo:hi].data_ptr()), C.c_void_p(cpt['keep_h'][lo:hi].data_ptr()),
+                        C.c_void_p(cpt['adj_h'][lo:hi].data_ptr()), hi - lo, N, E, self.host_threads, int(self.host_cached_stores)),
+                        'lsm_expand_adjacency_host')
+                    if prof is not None:
+                        t0 = time.perf_counter(); prof['expand'] = prof.get('expand', 0.0) + (t0 - t1)
+            stream.synchronize()
+            if prof is not None:
+                prof['final_sync'] = prof.get('final_sync', 0.0) + (time.perf_counter() - t0)
+                prof['calls'] = prof.get('calls', 0) + 1
             return [r if isinstance(r, np.ndarray) else r.numpy() for r in res]
         if copy:
             return [t.clone() for t in outs]
@@ -358,6 +466,8 @@ class B200GraphVecEnv:
         """(edge_index (2, nnz) int64, edge_attr (nnz, 1) float32) of `adj` (default: the last step's adjacency) in
         the order of the reference's TransformerConvNet.process_adj (gnn.py:376-407) for the (num_envs*N, E, E)
         batch the runner feeds the policy - without materialising adj.nonzero(). One host sync (reads nnz)."""
+        if adj is None and self._compact is not None:
+            raise RuntimeError("numpy_outputs=True keeps the adjacency compact on the device; pass adj= explicitly")
         a = self.adj if adj is None else adj
         assert a.is_cuda and a.dtype == torch.float32 and a.is_contiguous() and a.numel() == self.n * self.N * self.E * self.E
         graphs = self.n * self.N

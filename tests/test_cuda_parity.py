@@ -232,29 +232,24 @@ def test_onehot_actions_and_numpy_outputs():
 
 
 @pytest.mark.parametrize('shape', ['di8', 'air10', 'di32'])
-def test_pair_value_variants_agree(shape, monkeypatch):
-    """The next step's HJ pair values may be produced by four placements (behind the emit kernel, inside it, in front
-    of the agent kernel, between the two) and from two layouts of the value grid (corner-packed table, scattered gathers). All of them
-    must drive the filter identically:
-    same deconflicting agent, same activation mask and bit-identical states."""
+def test_pair_value_variants_agree(shape):
+    """The next step's HJ pair values may be produced at three places of the pipeline (behind the emit kernel, in front
+    of the agent kernel, between the two; lsm_tuning.pair_placement) and from two layouts of the value grid (corner-packed
+    table, scattered gathers; lsm_tuning.packed_grid). All of them must drive the filter identically: same deconflicting
+    agent, same activation mask and bit-identical states."""
     import torch
     from layered_safe_marl_b200 import B200GraphVecEnv
     kw = dict(di8=dict(num_agents=8, world_size=4), air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6),
               di32=dict(num_agents=32, world_size=4))[shape]
     args = G.default_args(use_safety_filter=True, episode_length=250, **kw)
     n, T, episode = (64, 12, 6249) if shape != 'di32' else (16, 6, 6249)
-    variants = [('late', '0', False), ('emit', '0', False), ('front', '0', False), ('middle', '0', False), ('late', '0', True)]
+    variants = [dict(pair_placement=0), dict(pair_placement=2), dict(pair_placement=3), dict(pair_placement=0, packed_grid=0)]
     results = []
     rng = np.random.default_rng(4)
     acts = rng.integers(0, 25, (T, n, args.num_agents)).astype(np.int32)
-    for placement, debug, no_packed in variants:
-        monkeypatch.setenv('LSM_PAIR', placement)
-        monkeypatch.setenv('LSM_DEBUG', debug)
-        if no_packed:
-            monkeypatch.setenv('LSM_NO_PACKED', '1')
-        else:
-            monkeypatch.delenv('LSM_NO_PACKED', raising=False)
-        env = B200GraphVecEnv(args, num_envs=n, seed=21)
+    for tuning in variants:
+        env = B200GraphVecEnv(args, num_envs=n, seed=21, tuning=tuning)
+        assert env.launch_info()['pair_placement'] == tuning['pair_placement']
         env.reset(episode)
         filt = []
         for t in range(T):
@@ -263,7 +258,6 @@ def test_pair_value_variants_agree(shape, monkeypatch):
             filt.append((s['safety_filtered'].copy(), s['deconflicting_agent_index'].copy()))
         results.append((env.get_state(), filt, env.safe_action.cpu().numpy()))
         env.close()
-    monkeypatch.setenv('LSM_DEBUG', '0')
     ref_state, ref_filt, ref_safe = results[0]
     assert sum(int(f[0].sum()) for f in ref_filt) > 0, "no filter activation in this rollout: the test would be vacuous"
     for (state, filt, safe), v in zip(results[1:], variants[1:]):
@@ -275,9 +269,9 @@ def test_pair_value_variants_agree(shape, monkeypatch):
 
 
 @pytest.mark.parametrize('shape', ['di8', 'air10'])
-def test_chunked_launches_identical(shape, monkeypatch):
-    """Big batches are split into env ranges on library-owned streams (fork / join by events). The split must not change
-    a single bit of any output or state, including ragged last ranges and auto-resets."""
+def test_chunked_launches_identical(shape):
+    """Big batches are split into env ranges on library-owned streams (fork / join by events; lsm_tuning.chunks). The
+    split must not change a single bit of any output or state, including ragged last ranges and auto-resets."""
     import torch
     from layered_safe_marl_b200 import B200GraphVecEnv
     kw = dict(di8=dict(num_agents=8, world_size=4), air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6))[shape]
@@ -286,10 +280,9 @@ def test_chunked_launches_identical(shape, monkeypatch):
     rng = np.random.default_rng(8)
     acts = rng.integers(0, 25, (T, n, args.num_agents)).astype(np.int32)
     outs = []
-    for chunks in ('1', '3', '4'):
-        monkeypatch.setenv('LSM_CHUNKS', chunks)
-        env = B200GraphVecEnv(args, num_envs=n, seed=5)
-        assert env.launch_info()['chunks'] == int(chunks)
+    for chunks in (1, 3, 4):
+        env = B200GraphVecEnv(args, num_envs=n, seed=5, tuning=dict(chunks=chunks))
+        assert env.launch_info()['chunks'] == chunks
         env.reset(episode)
         trace = []
         for t in range(T):
@@ -304,6 +297,82 @@ def test_chunked_launches_identical(shape, monkeypatch):
         for k in state:
             assert np.array_equal(np.asarray(state[k]), np.asarray(outs[0][1][k]), equal_nan=True), f"state {k} differs"
         assert np.array_equal(ep, outs[0][2], equal_nan=True)
+
+
+@pytest.mark.parametrize('shape', ['di8', 'air10', 'di3'])
+def test_host_outputs_compact_adjacency_is_byte_identical(shape):
+    """Host-facing path (numpy_outputs=True, what the unmodified runner consumes): the adjacency crosses PCIe as one
+    thresholded E x E matrix per env + per-observer keep masks and is expanded on the host. Every returned array must be
+    byte-identical to the device-resident env's dense outputs - with goals reached (disconnected landmarks), agents done
+    and auto-resets in the rollout, and with the D2H copy chunked (n >= 256)."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    kw = dict(di8=dict(num_agents=8, world_size=2, use_safety_filter=True),
+              air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6, use_safety_filter=True),
+              di3=dict(num_agents=3, world_size=2, use_safety_filter=False))[shape]
+    args = G.default_args(episode_length=12, **kw)
+    n, T, episode = 300, 30, 6249
+    dev_env = B200GraphVecEnv(args, num_envs=n, seed=3)
+    host_env = B200GraphVecEnv(args, num_envs=n, seed=3, numpy_outputs=True)
+    assert host_env._compact is not None and len(host_env._compact['bounds']) == 4
+    o1, o2 = dev_env.reset(episode), host_env.reset(episode)
+    for a, b in zip(o1[:4], o2[:4]):
+        assert np.array_equal(a.cpu().numpy().view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
+    rng = np.random.default_rng(1)
+    saw_disconnected = False
+    for t in range(T):
+        idx = rng.integers(0, 25, (n, args.num_agents)).astype(np.int32)
+        o1 = dev_env.step(torch.as_tensor(idx, device=dev_env.device), episode)
+        o2 = host_env.step(idx, episode)
+        for k, (a, b) in enumerate(zip(o1[:6], o2[:6])):
+            assert np.array_equal(a.cpu().numpy().view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), f"step {t} output {k}"
+        st = dev_env.get_state()
+        saw_disconnected |= bool((st['reached_goal'] > 0).any())
+    assert saw_disconnected or shape == 'air10', "no goal was reached: the keep masks were never exercised"
+
+
+def test_infos_on_an_auto_reset_step_are_the_terminal_steps():
+    """graphworker returns the TERMINAL step's per-agent info dicts and appends the episode summary
+    (onpolicy/envs/env_wrappers.py:861-874); the device state of such an env already belongs to the new episode. The
+    kernels snapshot the info fields before the reset; LazyInfos must return them. Checked against the oracle stepped
+    WITHOUT auto-reset from the same pre-step state."""
+    import torch
+    import oracle_env as O
+    from layered_safe_marl_b200 import B200GraphVecEnv, config as cfg, infos as I, layout as LY
+    args = G.default_args(num_agents=4, use_safety_filter=True, episode_length=5, world_size=2)
+    flags = G.BinaryFlags({})
+    params = cfg.scenario_params_from_args(args, binary_cfg=flags)
+    vg, tg = G.value_grid_for(params)
+    n, episode = 64, 6249
+    env = B200GraphVecEnv(args, num_envs=n, seed=17, binary_cfg=flags)
+    env.reset(episode)
+    rng = np.random.default_rng(5)
+    checked = 0
+    for t in range(12):
+        pre = env.get_state()
+        idx = rng.integers(0, 25, (n, 4)).astype(np.int32)
+        out = env.step(torch.as_tensor(idx, device=env.device), episode)
+        infos = out[6]
+        jr = infos.just_reset()
+        if not jr.any():
+            continue
+        ora = O.OracleEnv(params.asdict(), n, value_grid=vg, ttr_grid=tg, seed=17, nthreads=4)
+        ora.set_state(pre)
+        ora.step(idx, episode=episode, auto_reset=False)
+        want = I.compute_agent_infos(ora.agent_f64, ora.agent_i32, ora.env_i32, ora.reward,
+                                     I.separation_distance_of(params, ora.env_f64[LY.EF_CURRICULUM_RATIO]))
+        for e in np.nonzero(jr)[0]:
+            got = infos[int(e)]
+            assert len(got) == 5 and 'done_percentage' in got[4]          # N agent dicts + the episode summary
+            for i in range(4):
+                for k in I.AGENT_INFO_KEYS:
+                    if k == 'individual_reward':
+                        G.assert_close(got[i][k], want[k][e, i], f'{k}')
+                    else:
+                        assert np.array_equal(np.asarray(got[i][k]), np.asarray(want[k][e, i]), equal_nan=True), \
+                            f"t={t} env {e} agent {i} info['{k}']: got {got[i][k]!r} want {want[k][e, i]!r}"
+            checked += 1
+    assert checked >= 10, "episode_length=5 must produce auto-resets in 12 steps"
 
 
 def test_pinned_host_actions_are_used_in_place():

@@ -78,6 +78,9 @@ def test_layout_matches_public_and_oracle_headers():
     for k, v in ai.items():
         if k != 'COUNT':
             assert getattr(LY, 'AI_' + k) == v
+    for pre in ('TF_', 'TI_'):
+        for k, v in _enum_values(pub, 'LSM_' + pre).items():
+            assert getattr(LY, pre + k) == v
     import oracle_env as O
     assert O.AF_COUNT == LY.AF_COUNT and O.AI_COUNT == LY.AI_COUNT and O.AF['DIST_LEFT'] == LY.AF_DIST_LEFT
 
@@ -93,7 +96,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for sym in declared:
         assert getattr(lib, sym) is not None
     lib.lsm_abi_version.restype = ctypes.c_int
-    assert lib.lsm_abi_version() == 2
+    assert lib.lsm_abi_version() == 3
     # struct sizes must agree with the header (checked via the oracle's identical layout of lsm_config)
     import oracle_env as O
     assert ctypes.sizeof(_lib.LsmConfig) == ctypes.sizeof(O.Params)
@@ -237,3 +240,29 @@ def test_reference_pickle_loaders(tmp_path):
     h = H.load_reference_pickle(str(p2), 0.8)
     want = (-val.values.astype(np.float32) - np.float32(0.8 - 0.5)).astype(np.float32)
     assert np.array_equal(h.values, want) and h.separation_distance == 0.8 and h.grads.shape == meta.shape + (4,)
+
+
+@pytest.mark.parametrize('N,L', [(8, 2), (3, 2), (10, 2), (32, 2)])
+def test_expand_adjacency_host_matches_numpy(N, L):
+    """lsm_expand_adjacency_host (a HOST function of the product library: the e2e path ships one thresholded E x E matrix
+    per env + per-observer keep masks over PCIe and rebuilds the reference's (n, N, E, E) array on the host) against
+    the definition adj[e, i, a, b] = keep_i[a] & keep_i[b] ? base[e, a, b] : 0, byte for byte, for row widths that take
+    the vector path (E % 4 == 0) and the scalar one."""
+    from layered_safe_marl_b200 import _lib
+    lib = _lib.load()
+    E = N * (1 + L); W = (E + 31) // 32
+    rng = np.random.default_rng(N)
+    n = 37
+    base = rng.uniform(0, 4, (n, E, E)).astype(np.float32)
+    base[rng.uniform(size=base.shape) < 0.3] = 0.0
+    keep_bits = rng.uniform(size=(n, N, E)) < 0.8
+    keep_bits[0] = True
+    keep = np.zeros((n, N, W), dtype=np.uint32)
+    for e in range(E):
+        keep[..., e >> 5] |= (keep_bits[..., e].astype(np.uint32) << np.uint32(e & 31))
+    want = np.where(keep_bits[:, :, :, None] & keep_bits[:, :, None, :], base[:, None], np.float32(0.0)).astype(np.float32)
+    for threads, cached in ((1, 0), (3, 0), (0, 0), (4, 1)):
+        out = np.full((n, N, E, E), np.nan, dtype=np.float32)
+        _lib.check(lib.lsm_expand_adjacency_host(base.ctypes.data_as(ctypes.c_void_p), keep.ctypes.data_as(ctypes.c_void_p),
+                                                 out.ctypes.data_as(ctypes.c_void_p), n, N, E, threads, cached), 'expand')
+        assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), f"threads={threads} cached={cached}"

@@ -115,3 +115,49 @@ def test_rollout(name):
         # episode summary reported by the next reset (environment.py:1046-1074)
         env.reset(episode=meta['episode'], sample=False)
         G.assert_close(env.ep_info[0], z['ep_info'], f'{name} ep_info')
+
+
+@pytest.mark.parametrize('name', [c for c in CASES if c.startswith('at')])
+def test_rollout_rotation_form(name):
+    """The airtaxi relative position in its ROTATION form (what the specialised CUDA pipeline evaluates, selected in the
+    oracle with set_relative_state_form(1)) reproduces the reference's golden rollouts under the same bar as the literal
+    form of safety_filter.py:277-284 - discrete outputs included."""
+    z, meta, args, flags, params = G.load_case(name)
+    prev = O.set_relative_state_form(1)
+    try:
+        env, ties = rollout_with_tie_policy(lambda: make_oracle(params), z, meta, name,
+                                            lambda e, a: e.step(a, episode=meta['episode'], auto_reset=False))
+    finally:
+        O.set_relative_state_form(prev)
+    if ties:
+        print(f"{name} (rotation form): roundoff ties at {ties}")
+
+
+def test_relative_state_forms_agree_on_a_batch():
+    """Literal vs rotation form on 256 seeded airtaxi environments x 25 steps (BASELINE config 3 shape): every
+    divergence in a discrete output is counted and printed; the continuous states agree to 1e-9."""
+    args = G.default_args(dynamics_type='airtaxi', num_agents=10, use_safety_filter=True, episode_length=350, world_size=6)
+    from layered_safe_marl_b200 import config as cfg
+    flags = G.BinaryFlags(dict(POTENTIAL_CONFLICT=True))
+    params = cfg.scenario_params_from_args(args, binary_cfg=flags)
+    vg, tg = G.value_grid_for(params)
+    n, T, episode = 256, 25, 6249
+    envs = [O.OracleEnv(params.asdict(), n, value_grid=vg, ttr_grid=tg, seed=2, nthreads=8) for _ in range(2)]
+    rng = np.random.default_rng(9)
+    acts = rng.integers(0, 25, (T, n, params.num_agents)).astype(np.int32)
+    for form, env in enumerate(envs):
+        prev = O.set_relative_state_form(form)
+        try:
+            env.reset(episode=episode, sample=True)
+            for t in range(T):
+                env.step(acts[t], episode=episode, auto_reset=True)
+        finally:
+            O.set_relative_state_form(prev)
+    a, b = envs[0].get_state(), envs[1].get_state()
+    diverged = np.zeros(n, dtype=bool)
+    for k in ('reached_goal', 'done', 'safety_filtered', 'deconflicting_agent_index', 'num_agent_collisions'):
+        diverged |= (np.asarray(a[k]) != np.asarray(b[k])).reshape(n, -1).any(axis=1)
+    print(f"literal vs rotation form: {int(diverged.sum())} of {n} envs differ in a discrete output after {T} steps")
+    assert diverged.sum() <= 2, "the two forms differ by ~1e-16: a divergence needs a state within roundoff of a threshold"
+    ok = ~diverged
+    G.assert_close(np.asarray(b['agent_values'])[ok], np.asarray(a['agent_values'])[ok], 'states', rtol=1e-9, atol=1e-12)

@@ -16,9 +16,9 @@ cases = [('di8', dict(num_agents=8, world_size=4), 4096), ('air10', dict(dynamic
 for name, kw, n in cases:
     args = G.default_args(use_safety_filter=True, episode_length=30, **kw)
     digests = {}
-    for placement, chunks in (('front', '1'), ('late', '1'), ('middle', '1'), ('emit', '1'), ('late', '4'), ('middle', '4')):
-        os.environ['LSM_PAIR'] = placement; os.environ['LSM_CHUNKS'] = chunks
-        env = B200GraphVecEnv(args, num_envs=n, seed=17)
+    # pair_placement: 2 front, 0 late, 3 middle (lsm_tuning); chunks: env ranges on library-owned streams
+    for placement, chunks in ((2, 1), (0, 1), (3, 1), (0, 4), (3, 4)):
+        env = B200GraphVecEnv(args, num_envs=n, seed=17, tuning=dict(pair_placement=placement, chunks=chunks))
         gen = torch.Generator(device=env.device); gen.manual_seed(5)
         env.reset(6249)
         h = hashlib.sha256()
