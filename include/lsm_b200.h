@@ -233,6 +233,18 @@ int lsm_expand_adjacency_host(const float *adj_base, const uint32_t *adj_keep, f
 int lsm_edge_list(lsm_handle *h, const float *adj, int64_t *edge_index, float *edge_attr, int32_t *counts,
                   int64_t *offsets, int64_t capacity, void *stream);
 
+/* Fused edge output: from now on every lsm_step / lsm_reset / lsm_observe ALSO writes the COO list of
+ * the step's adjacency, in the same order and layout as lsm_edge_list, straight from the emission kernel (row masks by
+ * ballot, ranks by popcount, per-graph start offsets from a counting pre-pass over the per-env records) - the dense
+ * tensor is not read back, and with dense_adj == 0 it is not written at all (the 4*N*E*E term of SURVEY 8d disappears;
+ * per edge 20 bytes are written instead, which pays when the mean degree is below ~E/5). Nothing is synchronised:
+ * offsets[graphs] holds nnz ON THE DEVICE; entries past `capacity` are dropped. All four pointers NULL switches it
+ * off. Specialised (dynamics, N, L) configurations only (returns 6 otherwise).
+ *   edge_index DEVICE int64 [2][capacity], edge_attr DEVICE float [capacity], counts DEVICE int32 [graphs],
+ *   offsets DEVICE int64 [graphs + 1]                                         graphs = num_envs * N */
+int lsm_set_edge_output(lsm_handle *h, int64_t *edge_index, float *edge_attr, int32_t *counts, int64_t *offsets,
+                        int64_t capacity, int dense_adj);
+
 /* Rollout-buffer bookkeeping of one step in one launch (reference GMPERunner.insert + GraphReplayBuffer.insert,
  * onpolicy/runner/shared/graph_mpe_runner.py:437-487, onpolicy/utils/graph_buffer.py:168-250), all DEVICE pointers:
  *   obs           float [num_envs][N][D]       the observation slot the step kernels just wrote

@@ -126,6 +126,11 @@ struct lsm_handle {
     std::vector<cudaEvent_t> ev_join;
     cudaEvent_t ev_fork = nullptr;
     float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
+    // fused COO edge output (lsm_set_edge_output): library-owned scratch + per-range "counts done" events
+    long long* d_edge_local = nullptr;
+    long long* d_edge_totals = nullptr;
+    unsigned* d_edge_tickets = nullptr;
+    std::vector<cudaEvent_t> ev_count;
     lsm_tuning tuning = { 0, -1, -1, 0 };   // lsm_set_tuning (0 / -1 = automatic)
     int pair_placement = 0;             // 0 late (lsm_pair_kernel behind the emit kernel), 1 inside the emit kernel, 2 in front of the agent kernel, 3 between agent and emit kernel
 };
@@ -346,6 +351,10 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_timeline) cudaFree(h->d_timeline);
     if (h->d_vpacked) cudaFree(h->d_vpacked);
     if (h->d_grads8) cudaFree(h->d_grads8);
+    if (h->d_edge_local) cudaFree(h->d_edge_local);
+    if (h->d_edge_totals) cudaFree(h->d_edge_totals);
+    if (h->d_edge_tickets) cudaFree(h->d_edge_tickets);
+    for (cudaEvent_t ev : h->ev_count) cudaEventDestroy(ev);
     for (cudaStream_t st : h->streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -450,6 +459,7 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
     DeviceGuard guard(h->device);
     h->kp.b = *b;
     h->kp.adj_base = nullptr; h->kp.adj_keep = nullptr;
+    h->kp.edge_index = nullptr;
     h->have_buffers = true;
     // chunked launches for big batches (measured on B200, DESIGN.md 3: 4 ranges pay off from ~0.4 GB of observations per
     // step - 0.8 GB: -11 %, 10.7 GB: -9 % - while a 0.1 GB step is launch-latency bound and stays on the caller's stream:
@@ -472,6 +482,9 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
             if (e != cudaSuccess) return cuda_fail(e, "lsm_bind_buffers: chunk streams");
         }
     }
+    if (h->d_edge_local) { cudaFree(h->d_edge_local); h->d_edge_local = nullptr; }     // sized by num_envs: re-made on demand
+    if (h->d_edge_totals) { cudaFree(h->d_edge_totals); h->d_edge_totals = nullptr; }
+    if (h->d_edge_tickets) { cudaFree(h->d_edge_tickets); h->d_edge_tickets = nullptr; }
     if (h->spec) {
         // library-owned scratch between the launches of one step
         if (h->d_pairval) { cudaFree(h->d_pairval); h->d_pairval = nullptr; }
@@ -542,9 +555,11 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;   // LSM_DEBUG 32: K_a in front of the agent kernel on every step
     const bool was_valid = h->pairval_valid;
 
-    // the launches of one env-group range [g0, g1) on stream `s`
-    auto launch_range = [&](long long g0, long long g1, cudaStream_t s) -> cudaError_t {
+    const bool edges = h->spec && kp.edge_index != nullptr;
+    // the launches of one env-group range [g0, g1) on stream `s` (range `q` of `nq`)
+    auto launch_range = [&](long long g0, long long g1, cudaStream_t s, int q, int nq) -> cudaError_t {
         lsm::KParams k = kp;
+        k.edge_range = q; k.edge_num_ranges = nq;
         k.grp_begin = (int)g0; k.ngroups = (int)g1;
         k.env_begin = (int)(g0 * kp.EPW);
         k.env_end = (int)std::min<long long>(kp.b.num_envs, g1 * kp.EPW);
@@ -573,6 +588,18 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
                 e = lsm::spec_launch_pair(k, s, persist, h->persist_bytes);
                 if (e != cudaSuccess) return e;
             }
+            if (edges) {
+                // fused COO output: where every graph's edges start (counts + prefix inside this range); the emit kernel of
+                // a later range also needs the totals of the earlier ones -> ordered by events, never by spinning
+                k.pairval = nullptr;
+                e = lsm::spec_launch_edge_count(k, s);
+                if (e != cudaSuccess) return e;
+                if (nq > 1) {
+                    if ((e = cudaEventRecord(h->ev_count[q], s)) != cudaSuccess) return e;
+                    for (int r = 0; r < q; ++r)
+                        if ((e = cudaStreamWaitEvent(s, h->ev_count[r], 0)) != cudaSuccess) return e;
+                }
+            }
             if (!(k.debug & 1)) {
                 // K_c: graph observation (persistent blocks) [+ the next step's pair values, placement 1]
                 const bool pie = pair_path && placement == 1;
@@ -594,7 +621,7 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     cudaError_t e = cudaSuccess;
     const int K = (h->spec && h->chunks > 1 && ngroups >= 4LL * h->chunks * h->warps_per_block) ? h->chunks : 1;
     if (K == 1) {
-        e = launch_range(0, ngroups, (cudaStream_t)stream);
+        e = launch_range(0, ngroups, (cudaStream_t)stream, 0, 1);
         if (e != cudaSuccess) return cuda_fail(e, who);
     } else {
         // fork: every library stream waits for the caller's stream; join: the caller's stream waits for every range
@@ -604,7 +631,7 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
             const long long g0 = std::min<long long>(ngroups, per * q), g1 = std::min<long long>(ngroups, per * (q + 1));
             if (g0 >= g1) continue;
             if ((e = cudaStreamWaitEvent(h->streams[q], h->ev_fork, 0)) != cudaSuccess) return cuda_fail(e, who);
-            if ((e = launch_range(g0, g1, h->streams[q])) != cudaSuccess) return cuda_fail(e, who);
+            if ((e = launch_range(g0, g1, h->streams[q], q, K)) != cudaSuccess) return cuda_fail(e, who);
             if ((e = cudaEventRecord(h->ev_join[q], h->streams[q])) != cudaSuccess) return cuda_fail(e, who);
             if ((e = cudaStreamWaitEvent((cudaStream_t)stream, h->ev_join[q], 0)) != cudaSuccess) return cuda_fail(e, who);
         }
@@ -712,6 +739,38 @@ int lsm_expand_adjacency_host(const float* adj_base, const uint32_t* adj_keep, f
     return 0;
 }
 
+int lsm_set_edge_output(lsm_handle* h, int64_t* edge_index, float* edge_attr, int32_t* counts, int64_t* offsets, int64_t capacity,
+                        int dense_adj) {
+    if (h == nullptr) return fail(1, "lsm_set_edge_output: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_set_edge_output: lsm_bind_buffers has not been called");
+    if (edge_index == nullptr && edge_attr == nullptr && counts == nullptr && offsets == nullptr) { h->kp.edge_index = nullptr; return 0; }
+    if (edge_index == nullptr || edge_attr == nullptr || counts == nullptr || offsets == nullptr)
+        return fail(2, "lsm_set_edge_output: pass all four arrays, or all NULL to switch the edge output off");
+    if (capacity < 1) return fail(2, "lsm_set_edge_output: capacity must be >= 1");
+    if (!h->spec) return fail(6, "lsm_set_edge_output: this configuration runs the fused generic kernel (use lsm_edge_list on the dense adjacency)");
+    if (h->kp.adj_base != nullptr && dense_adj) return fail(2, "lsm_set_edge_output: dense_adj is not available together with the compact adjacency");
+    DeviceGuard guard(h->device);
+    cudaError_t e = cudaSuccess;
+    const size_t graphs = (size_t)h->kp.b.num_envs * (size_t)h->kp.N;
+    if (h->d_edge_local == nullptr) {
+        e = cudaMalloc(&h->d_edge_local, graphs * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_edge_totals, 16 * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_edge_tickets, 16 * sizeof(unsigned));
+        if (e == cudaSuccess) e = cudaMemset(h->d_edge_totals, 0, 16 * sizeof(long long));
+        if (e == cudaSuccess) e = cudaMemset(h->d_edge_tickets, 0, 16 * sizeof(unsigned));
+        if (e != cudaSuccess) return cuda_fail(e, "lsm_set_edge_output: scratch allocation");
+    }
+    while ((int)h->ev_count.size() < 16) {
+        cudaEvent_t ev;
+        if ((e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) != cudaSuccess) return cuda_fail(e, "lsm_set_edge_output: events");
+        h->ev_count.push_back(ev);
+    }
+    h->kp.edge_index = (long long*)edge_index; h->kp.edge_attr = edge_attr; h->kp.edge_counts = counts;
+    h->kp.edge_offsets = (long long*)offsets; h->kp.edge_capacity = (long long)capacity; h->kp.edge_dense = dense_adj ? 1 : 0;
+    h->kp.edge_local = h->d_edge_local; h->kp.edge_range_totals = h->d_edge_totals; h->kp.edge_tickets = h->d_edge_tickets;
+    return 0;
+}
+
 int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* edge_attr, int32_t* counts, int64_t* offsets,
                   int64_t capacity, void* stream) {
     if (h == nullptr) return fail(1, "lsm_edge_list: null handle");
@@ -781,6 +840,8 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
 #endif
     kp.pair_late = 0;
     kp.grp_begin = 0; kp.env_begin = 0; kp.env_end = (int)kp.b.num_envs;
+    if (kp.edge_index != nullptr && h->chunks > 1) kp.edge_index = nullptr;   // the per-range prefixes of a chunked step do not describe one launch
+    kp.edge_range = 0; kp.edge_num_ranges = 1;
     const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 2);
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;
     const bool pie = pair_path && placement == 1;     // the same kernel, grid and work as inside lsm_step

@@ -99,6 +99,17 @@ struct KParams {
     int pair_late;             // lsm_pair_kernel launched BEHIND the emit kernel of the same step (runs beside its drain)
     float* adj_base;           // compact adjacency (lsm_set_compact_adjacency): [num_envs][E][E], NULL = dense adj output
     unsigned* adj_keep;        //                                             [num_envs][N][W]
+    // fused COO edge output (lsm_set_edge_output); edge_index == nullptr = off
+    long long* edge_index;          // [2][edge_capacity]: row 0 = graph * E + row, row 1 = graph * E + col
+    float* edge_attr;               // [edge_capacity]
+    int* edge_counts;               // [num_envs * N] non-zeros per graph
+    long long* edge_offsets;        // [num_envs * N + 1] global exclusive prefix, [graphs] = nnz
+    long long edge_capacity;
+    long long* edge_local;          // library scratch [num_envs * N]: exclusive prefix inside this launch's env range
+    long long* edge_range_totals;   // library scratch [16]: edges of every env range of the step
+    unsigned* edge_tickets;         // library scratch [16]: block tickets of lsm_edge_count_kernel
+    int edge_range, edge_num_ranges;
+    int edge_dense;                 // 1: the dense adjacency is written as well
     unsigned long long* timeline;   // diagnostics (lsm_debug_timeline), NULL in production: globaltimer min-start / max-end per kernel
 };
 

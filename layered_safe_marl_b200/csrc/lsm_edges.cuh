@@ -7,7 +7,10 @@
 //     edge_attr  = adj[graph, row, col]                  (nnz, 1) float32
 // with B = num_envs * N graphs (the runner concatenates the agent axis into the batch, graph_mpe_runner.py:398-410).
 //
-// Three launches, all HBM / L2 streaming integer work (no tensor cores):
+// Two ways to get it. (1) lsm_set_edge_output: the step pipeline itself writes the list (lsm_edge_count_kernel<DYN,N,L>
+// below + the edge section of lsm_emit_kernel), the dense adjacency becomes optional and nothing is read back.
+// (2) lsm_edge_list: a post-pass over ANY dense adjacency tensor (a rollout-buffer slot, a user tensor) -
+// three launches, all HBM / L2 streaming integer work (no tensor cores):
 //   lsm_edge_count_kernel   one warp per graph: popcount of the non-zero entries -> counts[g]
 //   lsm_edge_scan_kernel    one block: exclusive prefix sum of counts -> offsets[g], offsets[B] = nnz
 //   lsm_edge_fill_kernel    one warp per graph: row-major walk in chunks of 32 entries, ballot + prefix popcount
@@ -87,6 +90,118 @@ __global__ void __launch_bounds__(256) lsm_edge_fill_kernel(const float* __restr
             }
         }
         pos += __popc(m);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Fused edge output (lsm_set_edge_output): the emit kernel itself writes the COO list, so the dense adjacency need not
+// exist. It needs to know where each graph's edges start BEFORE it writes the first one; this kernel provides that.
+//
+//   lsm_edge_count_kernel<DYN,N,L>   one WARP per environment, reading the per-env emit record the agent kernel left:
+//       the same exact float64 radius test and the same disconnected-entity masks as the emit kernel ->
+//       counts[graph] for the N observer graphs of the env. The LAST block to finish (ticket counter) turns the counts of
+//       this launch's env range into an exclusive prefix (edge_local) and the range total - no spinning, no second launch.
+//   The emit kernel adds the totals of the earlier env ranges of the step (chunked launches: ordered by stream events).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int kEdgeCountWarps = 4;
+
+template <int DYN, int N, int L>
+__global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(const __grid_constant__ KParams kp) {
+    using REC = EmitRec<DYN, N, L>;
+    constexpr int E = REC::E, W = REC::W;
+    __shared__ unsigned s_rowmask[kEdgeCountWarps][E * W];
+    __shared__ unsigned s_keep[kEdgeCountWarps][N * W];
+    __shared__ long long s_part[32 * kEdgeCountWarps];
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double r2_lt = kp.r2_lt;
+    pdl_launch_dependents();
+    pdl_wait();
+    const bool masked_reset = kp.mode == MODE_RESET && kp.env_mask != nullptr;
+    for (int ee = kp.env_begin + blockIdx.x * kEdgeCountWarps + warp; ee < kp.env_end; ee += gridDim.x * kEdgeCountWarps) {
+        if (masked_reset && kp.env_mask[ee] == 0) continue;          // keeps the counts of its last emission
+        const REC& R = *reinterpret_cast<const REC*>(kp.emit_rec + (size_t)ee * sizeof(REC));
+        unsigned* rowmask = s_rowmask[warp];
+        unsigned* keep = s_keep[warp];
+        // keep masks of the N observers (same expression as the emit kernel)
+        unsigned dpre[W], dpost[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int e = w * 32 + lane;
+            bool pre = false, post = false;
+            if (e < N) { pre = R.done[0][e] != 0; post = R.done[1][e] != 0; }
+            else if (e < E) {
+                const int m = e - N, order = m / N, owner = m - order * N;
+                pre = R.reached[0][owner] > order; post = R.reached[1][owner] > order;
+            }
+            dpre[w] = __ballot_sync(0xffffffffu, pre); dpost[w] = __ballot_sync(0xffffffffu, post);
+        }
+        for (int k = lane; k < N * W; k += 32) {
+            const int w = k % W;
+            const unsigned sel = kp.sel_tab[k];
+            unsigned pr = 0u, po = 0u;
+#pragma unroll
+            for (int q = 0; q < W; ++q) if (q == w) { pr = dpre[q]; po = dpost[q]; }
+            keep[k] = ~((po & sel) | (pr & ~sel));
+        }
+        // non-zero pattern of the thresholded distance matrix: d2 in float64 against the exact squared radius
+        double2 pb[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) pb[w] = (w * 32 + lane) < E ? R.pos[w * 32 + lane] : make_double2(0.0, 0.0);
+        for (int a = 0; a < E; ++a) {
+            const double2 pa = R.pos[a];
+#pragma unroll
+            for (int w = 0; w < W; ++w) {
+                const double dx = pa.x - pb[w].x, dy = pa.y - pb[w].y;
+                const double d2 = dx * dx + dy * dy;
+                const unsigned m = __ballot_sync(0xffffffffu, (w * 32 + lane) < E && d2 < r2_lt && d2 > 0.0);
+                if (lane == 0) rowmask[a * W + w] = m;
+            }
+        }
+        __syncwarp();
+        for (int i = 0; i < N; ++i) {
+            int c = 0;
+            for (int a = lane; a < E; a += 32) {
+                if ((keep[i * W + (a >> 5)] >> (a & 31)) & 1u) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) c += __popc(rowmask[a * W + w] & keep[i * W + w]);
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) kp.edge_counts[(size_t)ee * N + i] = c;
+        }
+        __syncwarp();
+    }
+    // last block: exclusive prefix of this range's counts
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned t = atomicAdd(kp.edge_tickets + kp.edge_range, 1u);
+        s_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    {
+        constexpr int T = 32 * kEdgeCountWarps;
+        const long long g0 = (long long)kp.env_begin * N, g1 = (long long)kp.env_end * N;
+        const long long per = (g1 - g0 + T - 1) / T;
+        const long long lo = g0 + (long long)tid * per, hi = (lo + per) < g1 ? (lo + per) : g1;
+        const volatile int* cnt = kp.edge_counts;
+        long long s = 0;
+        for (long long k = lo; k < hi; ++k) s += cnt[k];
+        s_part[tid] = s;
+        __syncthreads();
+        for (int o = 1; o < T; o <<= 1) {
+            const long long v = (tid >= o) ? s_part[tid - o] : 0;
+            __syncthreads();
+            s_part[tid] += v;
+            __syncthreads();
+        }
+        long long run = s_part[tid] - s;
+        for (long long k = lo; k < hi; ++k) { kp.edge_local[k] = run; run += cnt[k]; }
+        if (tid == T - 1) { kp.edge_range_totals[kp.edge_range] = s_part[T - 1]; kp.edge_tickets[kp.edge_range] = 0u; }
     }
 }
 

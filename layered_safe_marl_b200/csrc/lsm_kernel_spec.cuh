@@ -1194,6 +1194,11 @@ struct __align__(16) EmitShared {
     alignas(16) float dthr[GEO::NBUF][GEO::EE];              // radius-thresholded distance matrix (float32, what adj stores)
     alignas(16) float nodes[GEO::NBUF][GEO::CR * GEO::F];    // node-row chunk
     unsigned disc[2][GEO::W], keepm[N * GEO::W];
+    // fused COO edge output: non-zero bit mask of every row of the thresholded matrix, exclusive row offsets per observer
+    unsigned rowmask[GEO::E * GEO::W];
+    unsigned short rowoff[N * GEO::E];      // <= E * (E - 1) = 18 240 for the largest configuration
+    long long gbase[N];
+    long long range_base;
 };
 
 // PIE ("pair in emit"): also compute the next step's HJ pair values per environment after its copies are issued - the
@@ -1264,6 +1269,16 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
     // expands them (lsm_expand_adjacency_host)
     const bool compact = kp.adj_base != nullptr;
     const int warp = tid >> 5;
+    // fused COO edge list in process_adj order (gnn.py:376-407); the dense adjacency becomes optional
+    const bool edges = kp.edge_index != nullptr;
+    const bool dense = !compact && (!edges || kp.edge_dense != 0);
+    if (edges && tid == 0) {
+        long long b = 0;
+        for (int r = 0; r < kp.edge_range; ++r) b += kp.edge_range_totals[r];
+        S.range_base = b;
+        if (blockIdx.x == 0 && kp.edge_range == kp.edge_num_ranges - 1)
+            kp.edge_offsets[(size_t)kp.b.num_envs * N] = b + kp.edge_range_totals[kp.edge_range];     // nnz of the step
+    }
 
     auto prefetch = [&](int env, int slot) {
         const int4* src = reinterpret_cast<const int4*>(kp.emit_rec + (size_t)env * sizeof(REC));
@@ -1284,7 +1299,8 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         __syncthreads();
         if (ee + (int)gridDim.x < env_end) prefetch(ee + gridDim.x, rb ^ 1);
         cp_async_commit();
-        if (masked_reset && kp.env_mask[ee] == 0) continue;
+        // (with the fused edge list every env is re-emitted: a masked reset shifts the offsets of all later graphs)
+        if (masked_reset && kp.env_mask[ee] == 0 && !edges) continue;
         if (LSM_DBG(128)) continue;   // experiments: + record load
         ++tiles;
         const REC& R = S.rec[rb];
@@ -1345,11 +1361,79 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             any_change |= (bpre ^ bpost); any_disc |= bpost;
         }
         __syncthreads();
-        if (any_disc != 0u) {
+        if (any_disc != 0u || edges) {
             for (int k = tid; k < N * W; k += T) {
                 const int w = k % W;
                 const unsigned sel = kp.sel_tab[k];
                 S.keepm[k] = ~((S.disc[1][w] & sel) | (S.disc[0][w] & ~sel));
+            }
+            __syncthreads();
+        }
+        if (edges) {
+            // (e1) non-zero bit mask of every row (one ballot per 32 columns)
+            for (int a = warp; a < E; a += WPE) {
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const int b2 = w * 32 + lane;
+                    const unsigned m = __ballot_sync(0xffffffffu, b2 < E && dthr[a * E + b2] != 0.0f);
+                    if (lane == 0) S.rowmask[a * W + w] = m;
+                }
+            }
+            __syncthreads();
+            // (e2) edges of row a as observer i sees it, then the exclusive prefix over the rows of each observer
+            for (int k = tid; k < N * E; k += T) {
+                const int i = k / E, a = k - i * E;
+                int cnt = 0;
+                if ((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) cnt += __popc(S.rowmask[a * W + w] & S.keepm[i * W + w]);
+                }
+                S.rowoff[k] = (unsigned short)cnt;
+            }
+            __syncthreads();
+            for (int i = warp; i < N; i += WPE) {
+                int running = 0;
+                for (int c0 = 0; c0 < E; c0 += 32) {
+                    const int a = c0 + lane;
+                    const int v = a < E ? S.rowoff[i * E + a] : 0;
+                    int incl = v;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+                    if (a < E) S.rowoff[i * E + a] = (unsigned short)(running + incl - v);
+                    running += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) {
+                    // lsm_edge_count_kernel left the prefix inside this launch's env range; the caller gets the global one
+                    const long long gb = S.range_base + kp.edge_local[(size_t)ee * N + i];
+                    S.gbase[i] = gb;
+                    kp.edge_offsets[(size_t)ee * N + i] = gb;
+                }
+            }
+            __syncthreads();
+            // (e3) fill: one warp per (observer, row); lane = column inside a 32-column word, rank by popcount
+            {
+                long long* const src = kp.edge_index;
+                long long* const dst = kp.edge_index + kp.edge_capacity;
+                const long long cap = kp.edge_capacity;
+                const unsigned lt = (1u << lane) - 1u;
+                for (int r = warp; r < N * E; r += WPE) {
+                    const int i = r / E, a = r - i * E;
+                    if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
+                    const long long node0 = ((long long)ee * N + i) * E;
+                    long long p0 = S.gbase[i] + S.rowoff[r];
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
+                        if ((m >> lane) & 1u) {
+                            const long long p = p0 + __popc(m & lt);
+                            if (p < cap) {
+                                const int b2 = w * 32 + lane;
+                                src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                            }
+                        }
+                        p0 += __popc(m);
+                    }
+                }
             }
             __syncthreads();
         }
@@ -1363,8 +1447,8 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         }
         // (d) adjacency
         float* abase = kp.b.adj + (size_t)ee * (N * EE);
-        const bool adj_bulk = GEO::ADJ_BULK && any_change == 0u && !LSM_DBG(16) && !compact;
-        if (!LSM_DBG(8) && !compact) {
+        const bool adj_bulk = GEO::ADJ_BULK && any_change == 0u && !LSM_DBG(16) && dense;
+        if (!LSM_DBG(8) && dense) {
             if (adj_bulk) {
                 // every observer sees the same matrix: mask it once in place; thread 0 sends it N times below
                 if (any_disc != 0u) {

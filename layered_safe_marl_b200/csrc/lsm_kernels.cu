@@ -65,6 +65,7 @@ static int env_int(const char* name, int dflt) { const char* e = std::getenv(nam
 struct SpecFns {
     const void* pair; const void* agent; const void* emit;
     const void* emit_pie;     // emit kernel that also computes the next step's pair values (placement "emit")
+    const void* edge_count;   // per-graph edge counts + range prefix for the fused COO output
     int rec_bytes, scratch_bytes, emit_smem, emit_threads;
 };
 
@@ -109,6 +110,7 @@ static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
         f->agent = LSM_AGENT_FN(DYN_, N_, L_);                                                    \
         f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
         f->emit_pie = LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_);                                \
+        f->edge_count = (const void*)lsm_edge_count_kernel<DYN_, N_, L_>;                         \
         f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
         f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \
         f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, WPE_>);                               \
@@ -281,6 +283,18 @@ cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void*
 #endif
     if (pie && f.emit_pie == nullptr) return cudaErrorInvalidValue;
     return launch_one(pie ? f.emit_pie : f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
+}
+
+cudaError_t spec_launch_edge_count(const KParams& kp, cudaStream_t stream) {
+    SpecFns f;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    static int sm_count = 0;
+    if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
+    const long long envs = kp.env_end - kp.env_begin;
+    long long blocks = (envs + kEdgeCountWarps - 1) / kEdgeCountWarps;
+    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    if (blocks < 1) blocks = 1;
+    return launch_one(f.edge_count, kp, (unsigned)blocks, 32 * kEdgeCountWarps, 0, stream, nullptr, 0, true);
 }
 
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {

@@ -178,8 +178,67 @@ class DeviceGraphRolloutBuffer:
                     r = r * self.bad_masks[step + 1] + (1 - self.bad_masks[step + 1]) * self.value_preds[step]
                 self.returns[step] = r
 
+    def runner_view(self):
+        """Adapter for an UNMODIFIED `GMPERunner.collect` (graph_mpe_runner.py:398-415), which evaluates
+        `np.concatenate(self.buffer.<field>[step])` for nine fields to flatten (n, N, ...) into (n*N, ...). On the
+        returned view that expression yields the reshaped DEVICE tensor (a view of the buffer, no host round trip);
+        the reference policy passes tensors through `check()` unchanged (onpolicy/algorithms/utils/util.py:15-17)."""
+        return _RunnerView(self)
+
     @staticmethod
     def one_hot_actions(actions, n_actions: int = 25):
         """np.eye(n)[actions] of GMPERunner.collect (graph_mpe_runner.py:431-433), on device. The simulator also
         accepts the integer indices directly, which skips this tensor altogether."""
         return torch.nn.functional.one_hot(actions.reshape(actions.shape[0], actions.shape[1]).long(), n_actions).to(torch.float32)
+
+
+class _ConcatSlot:
+    """`buffer.<field>[step]` of a runner view: np.concatenate(slot) -> tensor.reshape(n*N, ...) via NEP 18."""
+
+    def __init__(self, tensor):
+        self._t = tensor
+
+    # np.concatenate's dispatcher iterates its first argument looking for objects that implement
+    # __array_function__; one sentinel is enough and keeps the call O(1) in the number of environments
+    def __len__(self):
+        return 1
+
+    def __iter__(self):
+        yield self
+
+    def __getitem__(self, k):
+        if k == 0:
+            return self
+        raise IndexError(k)
+
+    def __array_function__(self, func, types, args, kwargs):
+        import numpy as np
+        if func is np.concatenate and len(args) >= 1 and args[0] is self and not kwargs.get('axis'):
+            t = self._t
+            return t.reshape((t.shape[0] * t.shape[1],) + tuple(t.shape[2:]))
+        return NotImplemented
+
+    @property
+    def tensor(self):
+        return self._t
+
+
+class _FieldView:
+    def __init__(self, tensor):
+        self._t = tensor
+
+    def __getitem__(self, step):
+        return _ConcatSlot(self._t[step])
+
+
+class _RunnerView:
+    _FIELDS = ('share_obs', 'obs', 'node_obs', 'adj', 'agent_id', 'share_agent_id', 'rnn_states', 'rnn_states_critic', 'masks',
+               'available_actions', 'active_masks')
+
+    def __init__(self, buf):
+        self._buf = buf
+
+    def __getattr__(self, name):
+        if name in _RunnerView._FIELDS:
+            return _FieldView(getattr(self._buf, name))
+        return getattr(self._buf, name)

@@ -310,6 +310,12 @@ class B200GraphVecEnv:
 
     def _outputs(self, with_step: bool, copy: bool):
         outs = [self.obs, self.agent_id, self.node_obs, self.adj]
+        if not getattr(self, '_edge_dense', True) and not self.numpy_outputs:
+            # edge output without the dense adjacency: nothing was written there
+            res = [self.obs, self.agent_id, self.node_obs, None]
+            if with_step:
+                res += [self.reward, self.done.view(torch.bool)]
+            return [t.clone() if (copy and t is not None) else t for t in res]
         if with_step:
             outs += [self.reward, self.done.view(torch.bool)]
         if self.numpy_outputs:
@@ -486,6 +492,41 @@ class B200GraphVecEnv:
         if nnz > self._edge_cap:
             raise RuntimeError(f"edge list needs {nnz} entries, capacity is {self._edge_cap}")
         return self._edge_index[:, :nnz], self._edge_attr[:nnz].unsqueeze(1)
+
+    def enable_edge_output(self, capacity: Optional[int] = None, dense_adj: bool = True):
+        """From now on every step / reset / observe also writes the COO edge list of its adjacency - the
+        `(edge_index, edge_attr)` the reference's GNN derives with `process_adj` on every forward (gnn.py:376-407, 545-564)
+        - straight from the emission kernel: no post-pass over the dense tensor, and with `dense_adj=False` the dense
+        adjacency is not written at all (`step` then returns None in its place). No host synchronisation: read the result
+        with `edges()` (syncs once to size the views) or use `edge_index` / `edge_attr` / `edge_offsets` directly
+        (`edge_offsets[-1]` = nnz on the device). `capacity` defaults to the worst case N * E * (E - 1) per env."""
+        graphs = self.n * self.N
+        cap = int(capacity) if capacity is not None else graphs * self.E * (self.E - 1)
+        self.edge_index = torch.zeros((2, cap), dtype=torch.int64, device=self.device)
+        self.edge_attr = torch.zeros((cap,), dtype=torch.float32, device=self.device)
+        self.edge_counts = torch.zeros((graphs,), dtype=torch.int32, device=self.device)
+        self.edge_offsets = torch.zeros((graphs + 1,), dtype=torch.int64, device=self.device)
+        self.edge_capacity = cap
+        self._edge_dense = bool(dense_adj)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lsm_set_edge_output(self._h, C.c_void_p(self.edge_index.data_ptr()), C.c_void_p(self.edge_attr.data_ptr()),
+                                                    C.c_void_p(self.edge_counts.data_ptr()), C.c_void_p(self.edge_offsets.data_ptr()),
+                                                    cap, int(bool(dense_adj))), 'lsm_set_edge_output')
+
+    def disable_edge_output(self):
+        _lib.check(self.lib.lsm_set_edge_output(self._h, None, None, None, None, 0, 1), 'lsm_set_edge_output')
+        self.edge_index = self.edge_attr = self.edge_counts = self.edge_offsets = None
+        self._edge_dense = True
+
+    def edges(self):
+        """(edge_index (2, nnz) int64, edge_attr (nnz, 1) float32) of the last step, as `process_adj` would return them
+        for the (num_envs * N, E, E) batch. One host sync (reads nnz to size the views)."""
+        if getattr(self, 'edge_index', None) is None:
+            raise RuntimeError("call enable_edge_output() first")
+        nnz = int(self.edge_offsets[-1].item())
+        if nnz > self.edge_capacity:
+            raise RuntimeError(f"edge list needs {nnz} entries, capacity is {self.edge_capacity}")
+        return self.edge_index[:, :nnz], self.edge_attr[:nnz].unsqueeze(1)
 
     def invalidate(self):
         """Call after writing the state tensors (agent_f64, agent_i32, env_f64, landmarks) directly."""

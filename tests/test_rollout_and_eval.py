@@ -27,63 +27,94 @@ def _fake_env(n, N, L, D, F, device='cpu'):
     return e
 
 
-def _ref_insert(buf, step, obs, agent_id, node_obs, adj, rewards, dones, n, N):
-    """numpy restatement of GMPERunner.insert (graph_mpe_runner.py:444-487) + GraphReplayBuffer.insert
-    (graph_buffer.py:223-251) for the fields the environment produces."""
-    dones_env = np.all(dones, axis=1)
-    masks = np.ones((n, N, 1), dtype=np.float32)
-    masks[dones] = 0.0
-    active = np.ones((n, N, 1), dtype=np.float32)
-    active[dones] = 0.0
-    active[dones_env] = 1.0
-    share_obs = np.expand_dims(obs.reshape(n, -1), 1).repeat(N, axis=1)
-    share_agent_id = np.expand_dims(agent_id.reshape(n, -1), 1).repeat(N, axis=1)
-    buf['share_obs'][step + 1] = share_obs; buf['obs'][step + 1] = obs; buf['node_obs'][step + 1] = node_obs
-    buf['adj'][step + 1] = adj; buf['agent_id'][step + 1] = agent_id; buf['share_agent_id'][step + 1] = share_agent_id
-    buf['rewards'][step] = rewards; buf['masks'][step + 1] = masks; buf['active_masks'][step + 1] = active
+ROLLOUT_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux', 'rollout_buffer.npz')
 
 
-def test_rollout_buffer_matches_reference_insert_and_gae():
-    n, N, L, D, F, T = 5, 3, 2, 7, 10, 6
-    E = N * (1 + L)
-    env = _fake_env(n, N, L, D, F)
-    rb = DeviceGraphRolloutBuffer(env, episode_length=T, gamma=0.97, gae_lambda=0.9)
-    rng = np.random.default_rng(0)
-    ref = {k: np.zeros(tuple(getattr(rb, k).shape), dtype=np.float32 if getattr(rb, k).dtype == torch.float32 else np.int32)
-           for k in ('share_obs', 'obs', 'node_obs', 'adj', 'agent_id', 'share_agent_id', 'rewards')}
-    ref['masks'] = np.ones(tuple(rb.masks.shape), dtype=np.float32)
-    ref['active_masks'] = np.ones(tuple(rb.masks.shape), dtype=np.float32)
-    agent_id = np.tile(np.arange(N, dtype=np.int32).reshape(1, N, 1), (n, 1, 1))
-    # agent ids are constant: the device buffer fills every slot once at construction, the reference fills slot 0 in warmup
-    ref['agent_id'][0] = agent_id
-    ref['share_agent_id'][0] = np.expand_dims(agent_id.reshape(n, -1), 1).repeat(N, axis=1)
-    values = rng.normal(size=(T + 1, n, N, 1)).astype(np.float32)
+def _drive(rb, z, n, N, T, p):
+    """One pass of T inserts with the fixture's inputs, then compute_returns - what GMPERunner.run does per episode."""
     for t in range(T):
-        obs = rng.normal(size=(n, N, D)).astype(np.float32)
-        node_obs = rng.normal(size=(n, N, E, F)).astype(np.float32)
-        adj = rng.random(size=(n, N, E, E)).astype(np.float32)
-        rewards = rng.normal(size=(n, N, 1)).astype(np.float32)
-        dones = rng.random((n, N)) < 0.3
-        if t == 2:
-            dones[1] = True            # a whole env done: active_masks back to one
-        _ref_insert(ref, t, obs, agent_id, node_obs, adj, rewards, dones, n, N)
-        rb.insert((torch.from_numpy(obs), torch.from_numpy(agent_id), torch.from_numpy(node_obs), torch.from_numpy(adj),
-                   torch.from_numpy(rewards[..., 0]), torch.from_numpy(dones), None), values=torch.from_numpy(values[t]))
-    for k, v in ref.items():
-        np.testing.assert_array_equal(getattr(rb, k).numpy(), v, err_msg=k)
-    # GAE, graph_buffer.py:340-360 (no value normaliser)
-    vp = values.copy(); ret = np.zeros_like(vp); gae = 0
-    for step in reversed(range(T)):
-        delta = ref['rewards'][step] + 0.97 * vp[step + 1] * ref['masks'][step + 1] - vp[step]
-        gae = delta + 0.97 * 0.9 * ref['masks'][step + 1] * gae
-        ret[step] = gae + vp[step]
-    rb.compute_returns(torch.from_numpy(values[T]))
-    np.testing.assert_allclose(rb.returns.numpy()[:T], ret[:T], rtol=1e-6, atol=1e-6)
-    assert rb.step == 0                      # wrapped around after T inserts
-    rb.after_update()
-    np.testing.assert_array_equal(rb.obs[0].numpy(), rb.obs[-1].numpy())
-    oh = DeviceGraphRolloutBuffer.one_hot_actions(torch.from_numpy(rng.integers(0, 25, (n, N, 1))))
+        k = p * T + t
+        g = lambda name: torch.from_numpy(z['in_' + name][k])
+        rb.insert((g('obs'), torch.from_numpy(z['in_agent_id']), g('node_obs'), g('adj'), g('rewards')[..., 0], g('dones'), None),
+                  values=g('values'), actions=g('actions'), action_log_probs=g('action_log_probs'),
+                  rnn_states=g('rnn_states'), rnn_states_critic=g('rnn_states_critic'))
+    rb.compute_returns(torch.from_numpy(z['in_next_values'][p]))
+
+
+@pytest.mark.parametrize('use_gae', [True, False])
+@pytest.mark.parametrize('proper', [False, True])
+@pytest.mark.parametrize('centralized', [True, False])
+def test_rollout_buffer_matches_the_reference_buffer(use_gae, proper, centralized):
+    """DeviceGraphRolloutBuffer against the UNMODIFIED reference: GMPERunner.insert (graph_mpe_runner.py:444-487) +
+    GraphReplayBuffer.insert / compute_returns / after_update (graph_buffer.py:168-373) run on seeded inputs by
+    oracle/gen_rollout_golden.py (fixture tests/golden/aux/rollout_buffer.npz): two passes over the buffer, whole envs
+    done, GAE and discounted returns, with and without use_proper_time_limits, centralised and decentralised critic
+    inputs. Every stored array must be identical; the returns (a float32 recursion) to 1e-6."""
+    z = np.load(ROLLOUT_GOLDEN)
+    n, N, L, D, F, T = (int(v) for v in z['meta'])
+    env = _fake_env(n, N, L, D, F)
+    rb = DeviceGraphRolloutBuffer(env, episode_length=T, gamma=0.97, gae_lambda=0.9, use_gae=use_gae,
+                                  use_proper_time_limits=proper, use_centralized_V=centralized, hidden_size=8)
+    tag = f"gae{int(use_gae)}_ptl{int(proper)}_cv{int(centralized)}"
+    obs0 = torch.from_numpy(z['in_obs0'])
+    rb.warmup(reset_out=(obs0, torch.from_numpy(z['in_agent_id']), torch.zeros_like(rb.node_obs[0]), torch.zeros_like(rb.adj[0])))
+    rb.bad_masks.copy_(torch.from_numpy(z['in_bad_masks']))
+    for p in range(2):
+        _drive(rb, z, n, N, T, p)
+        assert rb.step == 0                      # wrapped around after T inserts
+        for key in z.files:
+            pre = f"{tag}_pass{p}_"
+            if not key.startswith(pre) or '_after_' in key:
+                continue
+            name = key[len(pre):]
+            got, want = getattr(rb, name).numpy(), z[key]
+            if name in ('returns', 'value_preds'):
+                np.testing.assert_allclose(got, want, rtol=1e-6, atol=1e-6, err_msg=key)
+            else:
+                np.testing.assert_array_equal(got, want, err_msg=key)
+        rb.after_update()
+        for name in ('share_obs', 'obs', 'masks', 'active_masks', 'rnn_states'):
+            np.testing.assert_array_equal(getattr(rb, name)[0].numpy(), z[f"{tag}_pass{p}_after_{name}0"], err_msg=name)
+    oh = DeviceGraphRolloutBuffer.one_hot_actions(torch.from_numpy(z['in_actions'][0].astype(np.int64)))
     assert oh.shape == (n, N, 25) and float(oh.sum()) == n * N
+    assert np.array_equal(oh.numpy(), np.squeeze(np.eye(25)[z['in_actions'][0].astype(np.int64)], 2).astype(np.float32))   # graph_mpe_runner.py:431-433
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/onpolicy'), reason="the reference tree only exists in the build container")
+def test_rollout_golden_fixture_is_reproducible_from_the_reference(tmp_path):
+    """Regenerate the fixture from /root/reference and compare with the committed one (build container only)."""
+    import subprocess
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(repo, 'oracle', 'gen_rollout_golden.py')).read().replace(
+        "os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'aux', 'rollout_buffer.npz')", repr(str(tmp_path / 'r.npz'))).replace(
+        "os.makedirs(os.path.join(os.path.dirname(HERE), 'tests', 'golden', 'aux'), exist_ok=True)", "pass").replace(
+        "HERE = os.path.dirname(os.path.abspath(__file__))", f"HERE = {os.path.join(repo, 'oracle')!r}")
+    script = tmp_path / 'gen.py'
+    script.write_text(src)
+    subprocess.check_call([sys.executable, str(script)], stdout=subprocess.DEVNULL)
+    a, b = np.load(ROLLOUT_GOLDEN), np.load(tmp_path / 'r.npz')
+    assert sorted(a.files) == sorted(b.files)
+    for k in a.files:
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+
+
+def test_runner_view_feeds_an_unmodified_collect():
+    """GMPERunner.collect (graph_mpe_runner.py:398-415) reads `np.concatenate(self.buffer.<field>[step])`. The view
+    returned by DeviceGraphRolloutBuffer.runner_view() answers that call with the (n*N, ...) reshape of the DEVICE tensor
+    (NumPy's __array_function__ protocol): no host concatenation, no copy - and the same values numpy would produce."""
+    n, N, L, D, F, T = 4, 3, 2, 7, 10, 3
+    env = _fake_env(n, N, L, D, F)
+    rb = DeviceGraphRolloutBuffer(env, episode_length=T)
+    g = torch.Generator().manual_seed(0)
+    for name in ('share_obs', 'obs', 'node_obs', 'adj', 'rnn_states', 'rnn_states_critic', 'masks'):
+        getattr(rb, name).copy_(torch.rand(getattr(rb, name).shape, generator=g))
+    view = rb.runner_view()
+    for step in (0, 2):
+        for name in ('share_obs', 'obs', 'node_obs', 'adj', 'agent_id', 'share_agent_id', 'rnn_states', 'rnn_states_critic', 'masks'):
+            got = np.concatenate(getattr(view, name)[step])          # exactly the expression the runner evaluates
+            assert torch.is_tensor(got) and got.data_ptr() == getattr(rb, name)[step].data_ptr()     # a view, not a copy
+            want = np.concatenate(getattr(rb, name)[step].numpy())
+            assert tuple(got.shape) == want.shape and np.array_equal(got.numpy(), want)
 
 
 @pytest.mark.parametrize('name,N', [('circular', 6), ('two_vehicle_conflict', 2), ('three_vehicle_conflict', 3)])
@@ -188,6 +219,52 @@ def _process_adj(adj):
     batch = edge_index[:, 0] * num_nodes
     edge_index = torch.stack([batch + edge_index[:, 1], batch + edge_index[:, 2]], dim=0)
     return edge_index, edge_attr.unsqueeze(1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('N,dyn,world,chunks', [(8, 'double_integrator', 4, 1), (8, 'double_integrator', 10, 3), (3, 'double_integrator', 6, 1),
+                                                 (10, 'airtaxi', 6, 1), (10, 'airtaxi', 14, 4), (32, 'double_integrator', 4, 1),
+                                                 (32, 'double_integrator', 16, 2)])
+def test_fused_edge_output_matches_process_adj(N, dyn, world, chunks):
+    """N2, fused: the emission kernel writes (edge_index, edge_attr) itself (lsm_set_edge_output). Bit-exact against the
+    reference's process_adj (gnn.py:376-407) applied to the dense adjacency of a twin env, at the cfg2 / cfg3 / cfg4
+    shapes, dense and sparse worlds, chunked launches (per-range prefixes joined by events), goals reached and
+    auto-resets; then with dense_adj=False (no dense tensor written at all) against the same twin."""
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    n = 61 if N == 32 else 203
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=(N != 3), episode_length=9, world_size=world)
+    twin = B200GraphVecEnv(args, num_envs=n, seed=5)
+    env = B200GraphVecEnv(args, num_envs=n, seed=5, tuning=dict(chunks=chunks))
+    assert env.launch_info()['chunks'] == chunks
+    env.enable_edge_output(dense_adj=True)
+    sparse = B200GraphVecEnv(args, num_envs=n, seed=5, tuning=dict(chunks=chunks))
+    sparse.enable_edge_output(dense_adj=False)
+    sparse.adj.fill_(-7.0)
+    episode = 6249
+    o0, o1, o2 = twin.reset(episode), env.reset(episode), sparse.reset(episode)
+
+    def check(tag):
+        ri, ra = _process_adj(twin.adj.reshape(-1, twin.E, twin.E))
+        for e, name in ((env, 'dense+edges'), (sparse, 'edges only')):
+            ei, ea = e.edges()
+            assert ei.dtype == torch.int64 and ea.dtype == torch.float32
+            assert ei.shape == ri.shape, f"{tag} {name}: nnz {ei.shape[1]} vs {ri.shape[1]}"
+            assert torch.equal(ei, ri) and torch.equal(ea, ra), f"{tag} {name}"
+            cnt = (twin.adj.reshape(-1, twin.E * twin.E) != 0).sum(dim=1).to(torch.int32)
+            assert torch.equal(e.edge_counts, cnt), f"{tag} {name}: per-graph counts"
+            assert torch.equal(e.edge_offsets[:-1], torch.cumsum(cnt.long(), 0) - cnt.long()), f"{tag} {name}: offsets"
+        assert torch.equal(env.adj, twin.adj) and torch.equal(env.node_obs, twin.node_obs), f"{tag}: dense outputs changed"
+        assert torch.equal(sparse.node_obs, twin.node_obs)
+        assert bool((sparse.adj == -7.0).all()), f"{tag}: dense_adj=False must not touch the dense tensor"
+
+    check('reset')
+    gen = torch.Generator(device='cpu'); gen.manual_seed(2)
+    for t in range(12):                                   # crosses an auto-reset
+        a = torch.randint(0, 25, (n, N), generator=gen, dtype=torch.int32).to(env.device)
+        twin.step(a, episode); env.step(a, episode)
+        out = sparse.step(a, episode)
+        assert out[3] is None
+        check(f't={t}')
 
 
 @pytest.mark.gpu
