@@ -245,6 +245,16 @@ int lsm_edge_list(lsm_handle *h, const float *adj, int64_t *edge_index, float *e
 int lsm_set_edge_output(lsm_handle *h, int64_t *edge_index, float *edge_attr, int32_t *counts, int64_t *offsets,
                         int64_t capacity, int dense_adj);
 
+/* The renderer's world graph: SafeAamScenario.update_graph, navigation_graph_safe.py:996-1015, as
+ * MultiAgentGraphEnv.step would compute it at the top of the NEXT step (environment.py:964-965) from the bound state:
+ * one graph per environment over its E entities, entities that are disconnected (agent done / landmark already reached)
+ * removed, an edge wherever 0 < d <= max_edge_dist (INCLUSIVE radius, unlike the policy-facing adjacency), row-major.
+ *   edge_index  DEVICE int64 [2][capacity]: row 0 = entity row, row 1 = entity col (indices inside the environment)
+ *   edge_weight DEVICE double [capacity]    the distance (world.edge_weight)
+ *   counts      DEVICE int32 [num_envs], offsets DEVICE int64 [num_envs + 1] (offsets[num_envs] = nnz) */
+int lsm_world_graph(lsm_handle *h, int64_t *edge_index, double *edge_weight, int32_t *counts, int64_t *offsets,
+                    int64_t capacity, void *stream);
+
 /* Rollout-buffer bookkeeping of one step in one launch (reference GMPERunner.insert + GraphReplayBuffer.insert,
  * onpolicy/runner/shared/graph_mpe_runner.py:437-487, onpolicy/utils/graph_buffer.py:168-250), all DEVICE pointers:
  *   obs           float [num_envs][N][D]       the observation slot the step kernels just wrote

@@ -127,8 +127,10 @@ struct lsm_handle {
     cudaEvent_t ev_fork = nullptr;
     float* d_grads8 = nullptr;           // padded 5-D gradient rows (GridDev::grads8)
     // fused COO edge output (lsm_set_edge_output): library-owned scratch + per-range "counts done" events
-    long long* d_edge_local = nullptr;
+    int* d_edge_local = nullptr;
     long long* d_edge_totals = nullptr;
+    long long* d_edge_block = nullptr;      // [2][edge_block_cap]: totals, then bases
+    size_t edge_block_cap = 0;
     unsigned* d_edge_tickets = nullptr;
     std::vector<cudaEvent_t> ev_count;
     lsm_tuning tuning = { 0, -1, -1, 0 };   // lsm_set_tuning (0 / -1 = automatic)
@@ -354,6 +356,7 @@ int lsm_destroy(lsm_handle* h) {
     if (h->d_edge_local) cudaFree(h->d_edge_local);
     if (h->d_edge_totals) cudaFree(h->d_edge_totals);
     if (h->d_edge_tickets) cudaFree(h->d_edge_tickets);
+    if (h->d_edge_block) cudaFree(h->d_edge_block);
     for (cudaEvent_t ev : h->ev_count) cudaEventDestroy(ev);
     for (cudaStream_t st : h->streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : h->ev_join) cudaEventDestroy(ev);
@@ -485,6 +488,7 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
     if (h->d_edge_local) { cudaFree(h->d_edge_local); h->d_edge_local = nullptr; }     // sized by num_envs: re-made on demand
     if (h->d_edge_totals) { cudaFree(h->d_edge_totals); h->d_edge_totals = nullptr; }
     if (h->d_edge_tickets) { cudaFree(h->d_edge_tickets); h->d_edge_tickets = nullptr; }
+    if (h->d_edge_block) { cudaFree(h->d_edge_block); h->d_edge_block = nullptr; }
     if (h->spec) {
         // library-owned scratch between the launches of one step
         if (h->d_pairval) { cudaFree(h->d_pairval); h->d_pairval = nullptr; }
@@ -560,6 +564,12 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     auto launch_range = [&](long long g0, long long g1, cudaStream_t s, int q, int nq) -> cudaError_t {
         lsm::KParams k = kp;
         k.edge_range = q; k.edge_num_ranges = nq;
+        if (edges) {
+            // count blocks take contiguous runs of environments; every range owns a slice of the block arrays
+            const long long per_range_envs = (long long)kp.EPW * (((ngroups + nq - 1) / nq + h->warps_per_block - 1) / h->warps_per_block * h->warps_per_block);
+            k.edge_envs_per_block = lsm::edge_count_envs_per_block(nq > 1 ? per_range_envs : kp.b.num_envs);
+            k.edge_block_ofs = (int)(q * ((per_range_envs + k.edge_envs_per_block - 1) / k.edge_envs_per_block + 1));
+        }
         k.grp_begin = (int)g0; k.ngroups = (int)g1;
         k.env_begin = (int)(g0 * kp.EPW);
         k.env_end = (int)std::min<long long>(kp.b.num_envs, g1 * kp.EPW);
@@ -753,7 +763,10 @@ int lsm_set_edge_output(lsm_handle* h, int64_t* edge_index, float* edge_attr, in
     cudaError_t e = cudaSuccess;
     const size_t graphs = (size_t)h->kp.b.num_envs * (size_t)h->kp.N;
     if (h->d_edge_local == nullptr) {
-        e = cudaMalloc(&h->d_edge_local, graphs * sizeof(long long));
+        // count blocks of one step: <= num_envs / 4 + one per env range
+        h->edge_block_cap = (size_t)h->kp.b.num_envs / 4 + 64;
+        e = cudaMalloc(&h->d_edge_local, graphs * sizeof(int));
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_edge_block, 2 * h->edge_block_cap * sizeof(long long));
         if (e == cudaSuccess) e = cudaMalloc(&h->d_edge_totals, 16 * sizeof(long long));
         if (e == cudaSuccess) e = cudaMalloc(&h->d_edge_tickets, 16 * sizeof(unsigned));
         if (e == cudaSuccess) e = cudaMemset(h->d_edge_totals, 0, 16 * sizeof(long long));
@@ -768,6 +781,7 @@ int lsm_set_edge_output(lsm_handle* h, int64_t* edge_index, float* edge_attr, in
     h->kp.edge_index = (long long*)edge_index; h->kp.edge_attr = edge_attr; h->kp.edge_counts = counts;
     h->kp.edge_offsets = (long long*)offsets; h->kp.edge_capacity = (long long)capacity; h->kp.edge_dense = dense_adj ? 1 : 0;
     h->kp.edge_local = h->d_edge_local; h->kp.edge_range_totals = h->d_edge_totals; h->kp.edge_tickets = h->d_edge_tickets;
+    h->kp.edge_block_totals = h->d_edge_block; h->kp.edge_block_base = h->d_edge_block + h->edge_block_cap;
     return 0;
 }
 
@@ -784,6 +798,20 @@ int lsm_edge_list(lsm_handle* h, const float* adj, int64_t* edge_index, float* e
     cudaError_t e = lsm::edge_list_launch(a, counts, (long long*)offsets, (long long*)edge_index, edge_attr, graphs, h->kp.E,
                                           (long long)capacity, (cudaStream_t)stream);
     if (e != cudaSuccess) return cuda_fail(e, "lsm_edge_list");
+    return 0;
+}
+
+int lsm_world_graph(lsm_handle* h, int64_t* edge_index, double* edge_weight, int32_t* counts, int64_t* offsets, int64_t capacity,
+                    void* stream) {
+    if (h == nullptr) return fail(1, "lsm_world_graph: null handle");
+    if (!h->have_buffers) return fail(5, "lsm_world_graph: lsm_bind_buffers has not been called");
+    if (edge_index == nullptr || edge_weight == nullptr || counts == nullptr || offsets == nullptr)
+        return fail(1, "lsm_world_graph: null output");
+    if (capacity < 1) return fail(2, "lsm_world_graph: capacity must be >= 1");
+    DeviceGuard guard(h->device);
+    cudaError_t e = lsm::world_graph_launch(h->kp, counts, (long long*)offsets, (long long*)edge_index, edge_weight, (long long)capacity,
+                                            (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_world_graph");
     return 0;
 }
 
@@ -842,6 +870,7 @@ int lsm_emit_only(lsm_handle* h, void* stream) {
     kp.grp_begin = 0; kp.env_begin = 0; kp.env_end = (int)kp.b.num_envs;
     if (kp.edge_index != nullptr && h->chunks > 1) kp.edge_index = nullptr;   // the per-range prefixes of a chunked step do not describe one launch
     kp.edge_range = 0; kp.edge_num_ranges = 1;
+    kp.edge_envs_per_block = lsm::edge_count_envs_per_block(kp.b.num_envs); kp.edge_block_ofs = 0;
     const bool pair_path = (kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && kp.has_vg && !(kp.debug & 2);
     const int placement = (kp.debug & 32) ? 2 : h->pair_placement;
     const bool pie = pair_path && placement == 1;     // the same kernel, grid and work as inside lsm_step

@@ -105,7 +105,11 @@ struct KParams {
     int* edge_counts;               // [num_envs * N] non-zeros per graph
     long long* edge_offsets;        // [num_envs * N + 1] global exclusive prefix, [graphs] = nnz
     long long edge_capacity;
-    long long* edge_local;          // library scratch [num_envs * N]: exclusive prefix inside this launch's env range
+    int* edge_local;                // library scratch [num_envs * N]: exclusive prefix inside the count block's env run
+    long long* edge_block_totals;   // library scratch: edges of every count block / their exclusive prefix inside the range
+    long long* edge_block_base;
+    int edge_block_ofs;             // first entry of this launch's range in the two arrays above
+    int edge_envs_per_block;        // environments per count block (contiguous run)
     long long* edge_range_totals;   // library scratch [16]: edges of every env range of the step
     unsigned* edge_tickets;         // library scratch [16]: block tickets of lsm_edge_count_kernel
     int edge_range, edge_num_ranges;

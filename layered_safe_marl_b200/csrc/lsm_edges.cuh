@@ -104,22 +104,49 @@ __global__ void __launch_bounds__(256) lsm_edge_fill_kernel(const float* __restr
 //   The emit kernel adds the totals of the earlier env ranges of the step (chunked launches: ordered by stream events).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int kEdgeCountWarps = 4;
+constexpr int kEdgeMaxEnvsPerBlock = 32;     // <= 32 envs x 32 agents = 1 024 graph counts per block in shared memory
+
+// block-wide exclusive scan of one value per thread (T = 32 * kEdgeCountWarps threads); returns the exclusive prefix,
+// *total = sum over the block. `s_w` is scratch of kEdgeCountWarps + 1 entries.
+__device__ __forceinline__ long long edge_block_exscan(long long v, long long* s_w, long long* total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const long long t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    __syncthreads();                       // s_w may still be read from the previous call
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    long long base = 0, sum = 0;
+#pragma unroll
+    for (int w = 0; w < kEdgeCountWarps; ++w) { if (w < warp) base += s_w[w]; sum += s_w[w]; }
+    *total = sum;
+    return base + incl - v;
+}
 
 template <int DYN, int N, int L>
 __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(const __grid_constant__ KParams kp) {
     using REC = EmitRec<DYN, N, L>;
     constexpr int E = REC::E, W = REC::W;
+    constexpr int T = 32 * kEdgeCountWarps;
     __shared__ unsigned s_rowmask[kEdgeCountWarps][E * W];
     __shared__ unsigned s_keep[kEdgeCountWarps][N * W];
-    __shared__ long long s_part[32 * kEdgeCountWarps];
+    __shared__ int s_cnt[kEdgeMaxEnvsPerBlock * N];
+    __shared__ long long s_w[kEdgeCountWarps + 1];
     __shared__ bool s_last;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double r2_lt = kp.r2_lt;
     pdl_launch_dependents();
     pdl_wait();
     const bool masked_reset = kp.mode == MODE_RESET && kp.env_mask != nullptr;
-    for (int ee = kp.env_begin + blockIdx.x * kEdgeCountWarps + warp; ee < kp.env_end; ee += gridDim.x * kEdgeCountWarps) {
-        if (masked_reset && kp.env_mask[ee] == 0) continue;          // keeps the counts of its last emission
+    // this block's CONTIGUOUS run of environments (so that its graph counts are one contiguous run of the prefix)
+    const int c = kp.edge_envs_per_block;
+    const int e0 = kp.env_begin + blockIdx.x * c;
+    const int e1 = (e0 + c) < kp.env_end ? (e0 + c) : kp.env_end;
+    for (int ee = e0 + warp; ee < e1; ee += kEdgeCountWarps) {
+        if (masked_reset && kp.env_mask[ee] == 0) {                  // state unchanged: the counts of its last emission
+            for (int i = lane; i < N; i += 32) s_cnt[(ee - e0) * N + i] = kp.edge_counts[(size_t)ee * N + i];
+            continue;
+        }
         const REC& R = *reinterpret_cast<const REC*>(kp.emit_rec + (size_t)ee * sizeof(REC));
         unsigned* rowmask = s_rowmask[warp];
         unsigned* keep = s_keep[warp];
@@ -160,20 +187,33 @@ __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(co
         }
         __syncwarp();
         for (int i = 0; i < N; ++i) {
-            int c = 0;
+            int cn = 0;
             for (int a = lane; a < E; a += 32) {
                 if ((keep[i * W + (a >> 5)] >> (a & 31)) & 1u) {
 #pragma unroll
-                    for (int w = 0; w < W; ++w) c += __popc(rowmask[a * W + w] & keep[i * W + w]);
+                    for (int w = 0; w < W; ++w) cn += __popc(rowmask[a * W + w] & keep[i * W + w]);
                 }
             }
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-            if (lane == 0) kp.edge_counts[(size_t)ee * N + i] = c;
+            for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
+            if (lane == 0) { kp.edge_counts[(size_t)ee * N + i] = cn; s_cnt[(ee - e0) * N + i] = cn; }
         }
         __syncwarp();
     }
-    // last block: exclusive prefix of this range's counts
+    __syncthreads();
+    // exclusive prefix inside the block's run (each thread takes a few consecutive counts), block total
+    {
+        const int m = (e1 > e0 ? (e1 - e0) : 0) * N;
+        const int per = (m + T - 1) / T;
+        const int lo = tid * per, hi = (lo + per) < m ? (lo + per) : m;
+        long long sum = 0;
+        for (int k = lo; k < hi; ++k) sum += s_cnt[k];
+        long long total;
+        long long run = edge_block_exscan(sum, s_w, &total);
+        for (int k = lo; k < hi; ++k) { kp.edge_local[(size_t)e0 * N + k] = (int)run; run += s_cnt[k]; }
+        if (tid == 0) kp.edge_block_totals[kp.edge_block_ofs + blockIdx.x] = total;
+    }
+    // last block of this launch: prefix over the block totals -> base of every block, total of the range
     __threadfence();
     __syncthreads();
     if (tid == 0) {
@@ -184,25 +224,79 @@ __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(co
     if (!s_last) return;
     __threadfence();
     {
-        constexpr int T = 32 * kEdgeCountWarps;
-        const long long g0 = (long long)kp.env_begin * N, g1 = (long long)kp.env_end * N;
-        const long long per = (g1 - g0 + T - 1) / T;
-        const long long lo = g0 + (long long)tid * per, hi = (lo + per) < g1 ? (lo + per) : g1;
-        const volatile int* cnt = kp.edge_counts;
-        long long s = 0;
-        for (long long k = lo; k < hi; ++k) s += cnt[k];
-        s_part[tid] = s;
-        __syncthreads();
-        for (int o = 1; o < T; o <<= 1) {
-            const long long v = (tid >= o) ? s_part[tid - o] : 0;
-            __syncthreads();
-            s_part[tid] += v;
-            __syncthreads();
+        const volatile long long* tot = kp.edge_block_totals + kp.edge_block_ofs;
+        long long* base = kp.edge_block_base + kp.edge_block_ofs;
+        const int G = (int)gridDim.x;
+        long long running = 0;
+        for (int t0 = 0; t0 < G; t0 += 8 * T) {
+            long long v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const int k = t0 + j * T + tid; v[j] = k < G ? tot[k] : 0; }   // all loads in flight
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                long long total;
+                const long long ex = edge_block_exscan(v[j], s_w, &total);
+                const int k = t0 + j * T + tid;
+                if (k < G) base[k] = running + ex;
+                running += total;
+            }
         }
-        long long run = s_part[tid] - s;
-        for (long long k = lo; k < hi; ++k) { kp.edge_local[k] = run; run += cnt[k]; }
-        if (tid == T - 1) { kp.edge_range_totals[kp.edge_range] = s_part[T - 1]; kp.edge_tickets[kp.edge_range] = 0u; }
+        if (tid == 0) { kp.edge_range_totals[kp.edge_range] = running; kp.edge_tickets[kp.edge_range] = 0u; }
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// World graph of the renderer: `SafeAamScenario.update_graph` (navigation_graph_safe.py:996-1015),
+// called at the top of every env.step (environment.py:964-965) on the distance matrix the previous step left behind -
+// i.e. after graph_observation zeroed, IN PLACE, the rows / columns of every disconnected entity (:974-992, quirk Q1):
+//     connect = (dists <= max_edge_dist) & (dists > 0)  ->  scipy COO (row-major)  ->  world.edge_list (2, nnz),
+//     world.edge_weight = dists[row, col] (float64)
+// ONE graph per environment, radius test INCLUSIVE (quirk Q7; the policy-facing adjacency is strict). Computed from the
+// bound state: one warp per environment, pass 0 counts, pass 1 fills (offsets from lsm_edge_scan_kernel in between).
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) lsm_world_graph_kernel(const __grid_constant__ KParams kp, int pass, int32_t* __restrict__ counts,
+                                                             const long long* __restrict__ offsets, long long* __restrict__ edge_index,
+                                                             double* __restrict__ edge_weight, long long capacity) {
+    const long long n = kp.b.num_envs;
+    const long long env = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (env >= n) return;
+    const int lane = threadIdx.x & 31;
+    const int N = kp.N, M = kp.M, E = kp.E;
+    const size_t fs = (size_t)n * N, ls = (size_t)n * M;
+    auto pos = [&](int e, double& x, double& y, bool& disc) {
+        if (e < N) {
+            x = kp.b.agent_f64[LSM_AF_X * fs + env * N + e]; y = kp.b.agent_f64[LSM_AF_Y * fs + env * N + e];
+            disc = kp.b.agent_i32[LSM_AI_DONE * fs + env * N + e] != 0;
+        } else {
+            const int m = e - N, order = m / N, owner = m - order * N;
+            x = kp.b.landmarks[LSM_LF_X * ls + env * M + m]; y = kp.b.landmarks[LSM_LF_Y * ls + env * M + m];
+            disc = kp.b.agent_i32[LSM_AI_REACHED * fs + env * N + owner] > order;
+        }
+    };
+    long long p = pass ? offsets[env] : 0;
+    int total = 0;
+    for (int a = 0; a < E; ++a) {
+        double ax, ay; bool adisc;
+        pos(a, ax, ay, adisc);
+        for (int b0 = 0; b0 < E; b0 += 32) {
+            const int b = b0 + lane;
+            bool on = false; double d2 = 0.0;
+            if (b < E && !adisc) {
+                double bx, by; bool bdisc;
+                pos(b, bx, by, bdisc);
+                const double dx = ax - bx, dy = ay - by;
+                d2 = dx * dx + dy * dy;
+                on = !bdisc && d2 < kp.r2_gt && d2 > 0.0;        // d <= R  <=>  d2 < min{t : sqrt(t) > R}
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, on);
+            if (pass && on) {
+                const long long q = p + __popc(m & ((1u << lane) - 1u));
+                if (q < capacity) { edge_index[q] = a; edge_index[capacity + q] = b; edge_weight[q] = sqrt(d2); }
+            }
+            p += __popc(m); total += __popc(m);
+        }
+    }
+    if (!pass && lane == 0) counts[env] = total;
 }
 
 }  // namespace lsm

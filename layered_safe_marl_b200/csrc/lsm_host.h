@@ -20,7 +20,10 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
 cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes);
 cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair, bool pie);
 cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, bool pie, int* out, int* regs);
+int edge_count_envs_per_block(long long envs);
 cudaError_t spec_launch_edge_count(const KParams& kp, cudaStream_t stream);
+cudaError_t world_graph_launch(const KParams& kp, int32_t* counts, long long* offsets, long long* edge_index, double* edge_weight,
+                               long long capacity, cudaStream_t stream);
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells);
 cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
                                   long long n, int N, int D, cudaStream_t stream);

@@ -1403,35 +1403,63 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
                     running += __shfl_sync(0xffffffffu, incl, 31);
                 }
                 if (lane == 0) {
-                    // lsm_edge_count_kernel left the prefix inside this launch's env range; the caller gets the global one
-                    const long long gb = S.range_base + kp.edge_local[(size_t)ee * N + i];
+                    // lsm_edge_count_kernel left: prefix inside its block's env run + base of that block inside the range
+                    const long long gb = S.range_base + kp.edge_block_base[kp.edge_block_ofs + (ee - kp.env_begin) / kp.edge_envs_per_block] +
+                                         kp.edge_local[(size_t)ee * N + i];
                     S.gbase[i] = gb;
                     kp.edge_offsets[(size_t)ee * N + i] = gb;
                 }
             }
             __syncthreads();
-            // (e3) fill: one warp per (observer, row); lane = column inside a 32-column word, rank by popcount
+            // (e3) fill. Dense graphs (mean degree > 8): one warp per (observer, row), lane = column inside a 32-column word,
+            //      rank by popcount - coalesced stores. Sparse graphs: one LANE per (observer, row) walking the few set bits
+            //      of its row (a warp per row would spend ~40 instructions on a row that holds two edges).
             {
                 long long* const src = kp.edge_index;
                 long long* const dst = kp.edge_index + kp.edge_capacity;
                 const long long cap = kp.edge_capacity;
                 const unsigned lt = (1u << lane) - 1u;
-                for (int r = warp; r < N * E; r += WPE) {
-                    const int i = r / E, a = r - i * E;
-                    if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
-                    const long long node0 = ((long long)ee * N + i) * E;
-                    long long p0 = S.gbase[i] + S.rowoff[r];
+                // total edges of the env = last observer's end; mean degree decides the strategy (block-uniform)
+                int env_edges = 0;
+                for (int i = 0; i < N; ++i) env_edges += S.rowoff[i * E + E - 1];          // lower bound is enough for the choice
+                if (env_edges > 8 * N * E) {
+                    for (int r = warp; r < N * E; r += WPE) {
+                        const int i = r / E, a = r - i * E;
+                        if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
+                        const long long node0 = ((long long)ee * N + i) * E;
+                        long long p0 = S.gbase[i] + S.rowoff[r];
 #pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
-                        if ((m >> lane) & 1u) {
-                            const long long p = p0 + __popc(m & lt);
-                            if (p < cap) {
-                                const int b2 = w * 32 + lane;
-                                src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                        for (int w = 0; w < W; ++w) {
+                            const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
+                            if ((m >> lane) & 1u) {
+                                const long long p = p0 + __popc(m & lt);
+                                if (p < cap) {
+                                    const int b2 = w * 32 + lane;
+                                    src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                                }
+                            }
+                            p0 += __popc(m);
+                        }
+                    }
+                } else {
+                    for (int r = tid; r < N * E; r += T) {
+                        const int i = r / E, a = r - i * E;
+                        if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
+                        const long long node0 = ((long long)ee * N + i) * E;
+                        long long p = S.gbase[i] + S.rowoff[r];
+#pragma unroll
+                        for (int w = 0; w < W; ++w) {
+                            unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
+                            while (m != 0u) {
+                                const int bit = __ffs(m) - 1;
+                                m &= m - 1u;
+                                if (p < cap) {
+                                    const int b2 = w * 32 + bit;
+                                    src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                                }
+                                ++p;
                             }
                         }
-                        p0 += __popc(m);
                     }
                 }
             }

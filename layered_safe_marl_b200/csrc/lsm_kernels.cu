@@ -285,16 +285,31 @@ cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void*
     return launch_one(pie ? f.emit_pie : f.emit, kp, grid, f.emit_threads, f.emit_smem, stream, persist_ptr, persist_bytes, true);
 }
 
+int edge_count_envs_per_block(long long envs) {
+    // contiguous env runs per block: at least one env per warp, at most ~2048 blocks, at most kEdgeMaxEnvsPerBlock
+    long long c = (envs + 2047) / 2048;
+    if (c < kEdgeCountWarps) c = kEdgeCountWarps;
+    if (c > kEdgeMaxEnvsPerBlock) c = kEdgeMaxEnvsPerBlock;
+    return (int)c;
+}
+
 cudaError_t spec_launch_edge_count(const KParams& kp, cudaStream_t stream) {
     SpecFns f;
     if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
-    static int sm_count = 0;
-    if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
     const long long envs = kp.env_end - kp.env_begin;
-    long long blocks = (envs + kEdgeCountWarps - 1) / kEdgeCountWarps;
-    if (blocks > (long long)sm_count * 8) blocks = (long long)sm_count * 8;
+    long long blocks = (envs + kp.edge_envs_per_block - 1) / kp.edge_envs_per_block;
     if (blocks < 1) blocks = 1;
     return launch_one(f.edge_count, kp, (unsigned)blocks, 32 * kEdgeCountWarps, 0, stream, nullptr, 0, true);
+}
+
+cudaError_t world_graph_launch(const KParams& kp, int32_t* counts, long long* offsets, long long* edge_index, double* edge_weight,
+                               long long capacity, cudaStream_t stream) {
+    const int wpb = 4;
+    const unsigned blocks = (unsigned)((kp.b.num_envs + wpb - 1) / wpb);
+    lsm_world_graph_kernel<<<blocks, wpb * 32, 0, stream>>>(kp, 0, counts, offsets, edge_index, edge_weight, capacity);
+    lsm_edge_scan_kernel<<<1, 1024, 0, stream>>>(counts, offsets, kp.b.num_envs);
+    lsm_world_graph_kernel<<<blocks, wpb * 32, 0, stream>>>(kp, 1, counts, offsets, edge_index, edge_weight, capacity);
+    return cudaGetLastError();
 }
 
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {

@@ -528,6 +528,22 @@ class B200GraphVecEnv:
             raise RuntimeError(f"edge list needs {nnz} entries, capacity is {self.edge_capacity}")
         return self.edge_index[:, :nnz], self.edge_attr[:nnz].unsqueeze(1)
 
+    def world_graph(self):
+        """The renderer's per-environment graph (`world.edge_list`, `world.edge_weight` of SafeAamScenario.update_graph,
+        navigation_graph_safe.py:996-1015; inclusive radius, disconnected entities removed) for the current state.
+        -> (edge_list (2, nnz) int64 with entity indices, edge_weight (nnz,) float64, offsets (num_envs + 1,) int64):
+        env e owns the columns offsets[e] : offsets[e + 1]. One host sync."""
+        n, E = self.n, self.E
+        cap = n * E * (E - 1)
+        ei = torch.empty((2, cap), dtype=torch.int64, device=self.device)
+        ew = torch.empty((cap,), dtype=torch.float64, device=self.device)
+        cnt = torch.empty((n,), dtype=torch.int32, device=self.device)
+        off = torch.empty((n + 1,), dtype=torch.int64, device=self.device)
+        _lib.check(self.lib.lsm_world_graph(self._h, C.c_void_p(ei.data_ptr()), C.c_void_p(ew.data_ptr()), C.c_void_p(cnt.data_ptr()),
+                                            C.c_void_p(off.data_ptr()), cap, self._stream()), 'lsm_world_graph')
+        nnz = int(off[-1].item())
+        return ei[:, :nnz], ew[:nnz], off
+
     def invalidate(self):
         """Call after writing the state tensors (agent_f64, agent_i32, env_f64, landmarks) directly."""
         _lib.check(self.lib.lsm_invalidate(self._h), 'lsm_invalidate')

@@ -291,3 +291,35 @@ def test_edge_list_matches_process_adj(N, dyn):
     z = torch.zeros_like(env.adj)
     ei, ea = env.edge_list(z)
     assert ei.shape == (2, 0) and ea.shape == (0, 1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('tag', ['di4', 'at4', 'boundary'])
+def test_world_graph_matches_reference_update_graph(tag):
+    """Row a16: lsm_world_graph against world.edge_list / world.edge_weight recorded from the unmodified reference's
+    update_graph (navigation_graph_safe.py:996-1015; fixture + generator oracle/gen_world_graph_golden.py): every
+    recorded step of a rollout is loaded as one environment of a batch. Integer indices and float64 weights bit-exact;
+    the inclusive radius (an entity exactly 4.0 away IS connected, one ulp farther is not) is part of the fixture."""
+    import json
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux', 'world_graph.npz'))
+    meta = json.loads(str(z['meta']))[tag]
+    steps = meta['steps']
+    args = G.default_args(num_landmarks=2, use_safety_filter=False, **meta['args'])
+    env = B200GraphVecEnv(args, num_envs=steps, seed=0)
+    env.reset(0)
+    s = env.get_state()
+    for k in ('agent_values', 'done', 'reached_goal', 'landmark_pos', 'landmark_heading', 'landmark_speed'):
+        s[k] = z[f'{tag}__{k}']
+    env.set_state(s)
+    ei, ew, off = env.world_graph()
+    ei, ew, off = ei.cpu().numpy(), ew.cpu().numpy(), off.cpu().numpy()
+    lens = z[f'{tag}__edge_list_len']
+    assert np.array_equal(np.diff(off), lens), "edges per environment"
+    assert np.array_equal(ei, z[f'{tag}__edge_list'])
+    assert np.array_equal(ew, z[f'{tag}__edge_weight'])
+    if tag == 'boundary':
+        pairs = set(map(tuple, ei.T.tolist()))
+        assert (0, 1) in pairs and (1, 0) in pairs and (0, 2) not in pairs
+    else:
+        assert lens.min() < lens.max()          # disconnected entities changed the graph along the rollout
