@@ -251,8 +251,8 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.bytes_per_env = align_up(off, 16);
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    // the specialised pipeline emits the 'relative' node features every shipped script uses; 'global' runs the generic kernel
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL);
+    // both node-feature types ('relative', which every shipped script uses, and 'global') run the specialised pipeline
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo);
 #ifdef LSM_EXPERIMENTS
     { const char* force_generic = std::getenv("LSM_FORCE_GENERIC"); if (force_generic != nullptr && force_generic[0] == '1') h->spec = false; }
 #endif

@@ -1517,7 +1517,10 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
         }
         // (c) node features: one thread per (observer, entity) row, assembled row-major in shared memory
-        float* nbase = kp.b.node_obs + (size_t)ee * (ROWS * F);
+        // graph_feat_type 'global' (navigation_graph_safe.py:1017-1036): 7-wide observer-independent rows [vel, pos, goal, type]
+        const bool gfeat = (kp.c.flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) != 0;
+        const int Fr = gfeat ? 7 : F;
+        float* nbase = kp.b.node_obs + (size_t)ee * (ROWS * Fr);
         auto node_row = [&](int r, float* o) {
             const int i = r / E, e = r - i * E;
             const double2 pi = R.pos[i], vi = R.vel[N + i];
@@ -1526,7 +1529,14 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             const int vidx = is_agent ? sel + e : 2 * N;
             const int gidx = is_agent ? E + sel + e : e;
             const int cidx = is_agent ? M + sel + e : e - N;
-            if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+            if (gfeat) {
+                // an agent's goal is its FIRST landmark (optimal_match_index = arange, navigation_graph_safe.py:179), a
+                // landmark's goal is itself; velocities are world-frame (landmarks: zero)
+                const double2 pe = R.pos[e], ve = R.vel[vidx], ge = is_agent ? R.pos[N + e] : pe;
+                o[0] = (float)ve.x; o[1] = (float)ve.y; o[2] = (float)pe.x; o[3] = (float)pe.y;
+                o[4] = (float)ge.x; o[5] = (float)ge.y; o[6] = is_agent ? 0.0f : 1.0f;
+                (void)gidx; (void)cidx; (void)pi; (void)vi;
+            } else if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
                 // utils.py:201-255: [p_e - p_i, v_e - v_i, goal_e - p_i, sin gh, cos gh, gspeed, type]
                 const double2 pe = R.pos[e], ve = R.vel[vidx], ge = R.pos[gidx];
                 const float4 cc = R.cst[cidx];
@@ -1574,7 +1584,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             float* buf = S.nodes[nb];
             if (!LSM_DBG(4))
-                for (int r = tid; r < nrows; r += T) node_row(r0 + r, buf + r * F);
+                for (int r = tid; r < nrows; r += T) node_row(r0 + r, buf + r * Fr);
             if (GEO::NODE_BULK || adj_bulk || compact) bulk_store_fence();
             __syncthreads();
             if (lane == 0) {
@@ -1587,17 +1597,17 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
                 }
                 if (compact && GEO::ADJ_BULK && !adj_sent && warp == 0)
                     bulk_store(kp.adj_base + (size_t)ee * EE, dthr, (unsigned)EE * 4u, stream_pol);
-                if (GEO::NODE_BULK && !LSM_DBG(4) && warp == WPE - 1) bulk_store(nbase + r0 * F, buf, (unsigned)(nrows * F) * 4u, stream_pol);
+                if (GEO::NODE_BULK && !LSM_DBG(4) && warp == WPE - 1) bulk_store(nbase + r0 * Fr, buf, (unsigned)(nrows * Fr) * 4u, stream_pol);
                 bulk_store_commit();
             }
             adj_sent = true;
             if (!GEO::NODE_BULK && !LSM_DBG(4)) {
-                const int nfl = nrows * F;
-                if (F % 2 == 0 && (ROWS * F) % 2 == 0) {
+                const int nfl = nrows * Fr;
+                if (Fr % 2 == 0 && (ROWS * Fr) % 2 == 0) {
                     for (int q = tid; q < nfl / 2; q += T)
-                        __stcs(reinterpret_cast<float2*>(nbase + r0 * F) + q, reinterpret_cast<const float2*>(buf)[q]);
+                        __stcs(reinterpret_cast<float2*>(nbase + r0 * Fr) + q, reinterpret_cast<const float2*>(buf)[q]);
                 } else {
-                    for (int q = tid; q < nfl; q += T) __stcs(nbase + r0 * F + q, buf[q]);
+                    for (int q = tid; q < nfl; q += T) __stcs(nbase + r0 * Fr + q, buf[q]);
                 }
                 __syncthreads();
             }

@@ -415,3 +415,17 @@ def test_oracle_batch_reference_script_shapes(dyn, N):
     probe.close()
     _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=air)), n=96, T=12, episode=6249, seed=13 + N,
                          auto_reset=True)
+
+
+@pytest.mark.parametrize('dyn,N', [('double_integrator', 8), ('airtaxi', 4)])
+def test_oracle_batch_global_features_run_the_specialised_pipeline(dyn, N):
+    """graph_feat_type='global' (navigation_graph_safe.py:1017-1036: 7-wide observer-independent node rows) on the
+    specialised three-kernel pipeline, against the oracle on a seeded batch with goals reached and auto-resets."""
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    air = dyn == 'airtaxi'
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=True, episode_length=9, world_size=6 if air else 3,
+                          graph_feat_type='global')
+    probe = B200GraphVecEnv(args, num_envs=4, seed=0)
+    assert probe.launch_info()['specialised'] == 1 and probe.F == 7
+    probe.close()
+    _compare_with_oracle(args, G.BinaryFlags({}), n=200, T=14, episode=6249, seed=31, auto_reset=True)

@@ -323,3 +323,20 @@ def test_world_graph_matches_reference_update_graph(tag):
         assert (0, 1) in pairs and (1, 0) in pairs and (0, 2) not in pairs
     else:
         assert lens.min() < lens.max()          # disconnected entities changed the graph along the rollout
+
+
+@pytest.mark.parametrize('tag,name,kw', [('circular', 'circular', dict(num_agents=6, dynamics_type='double_integrator', world_size=4.0)),
+                                         ('circular_at', 'circular', dict(num_agents=5, dynamics_type='airtaxi', world_size=6.0)),
+                                         ('two_vehicle_conflict', 'two_vehicle_conflict', {}),
+                                         ('three_vehicle_conflict', 'three_vehicle_conflict', {})])
+def test_eval_scenarios_match_the_reference_scenario_class(tag, name, kw):
+    """N4: the injectable initial states of eval_scenarios.py against what the reference's own scenario class builds
+    (fixture recorded by oracle/gen_eval_scenarios_golden.py from navigation_graph_safe_eval.py through the import stubs):
+    agent states and the first goal of every agent - position, heading, speed."""
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux', 'eval_scenarios.npz'))
+    s = ES.build(name, **kw)
+    N = z[f'{tag}__agent_values'].shape[0]
+    np.testing.assert_allclose(s['agent_values'][0], z[f'{tag}__agent_values'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s['landmark_pos'][0, :N], z[f'{tag}__goal0_pos'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s['landmark_heading'][0, :N], z[f'{tag}__goal0_heading'], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(s['landmark_speed'][0, :N], z[f'{tag}__goal0_speed'], rtol=0, atol=1e-12)
