@@ -334,7 +334,7 @@ def run_ours(a):
     # ---- e2e: host one-hot actions in, every returned array back to pinned host memory --------------
     Ke = max(3, min(K, a.e2e_steps))
     env_h = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=4321, binary_cfg=flags,
-                            env_id_base=rank * n_envs, numpy_outputs=True, numa_bind=True)
+                            env_id_base=rank * n_envs, numpy_outputs=True, numa_bind=a.numa_bind)
     env_h.reset(episode)
     rng = np.random.default_rng(99 + rank)
     onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + 2, n_envs, N))]).pin_memory()
@@ -565,6 +565,7 @@ def main():
     ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload’s)')
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--numa-bind', action='store_true', help='e2e: pin the process to the CPUs of the NUMA node of its GPU')
     ap.add_argument('--no-extra-workloads', action='store_true', help='skip the cfg3 / cfg4 / cfg5 sub-blocks of the default line')
     a = ap.parse_args()
     if a.warmup < 3:

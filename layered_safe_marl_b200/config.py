@@ -166,9 +166,33 @@ class ScenarioParams:
         return asdict(self)
 
 
+# Dynamics limits the kernels carry as COMPILED-IN constants (csrc/lsm_step_common.cuh integrate<> / filter_resolve<>,
+# vec_env.action_tables): the reference reads them from its editable config classes (multiagent/config.py:3-60,
+# core.py:84-160, safety_filter.py:205-215,380-392). Editing the mirrors above without rebuilding the kernels would give a
+# silently inconsistent simulator, so construction checks them.
+_COMPILED_LIMITS = {
+    'AirTaxiConfig': dict(V_MIN=60 * 0.514444 * 0.001, V_MAX=175 * 0.514444 * 0.001, ACCEL_MIN=-0.001, ACCEL_MAX=0.002,
+                          ANGULAR_RATE_MAX=0.1, MOTION_PRIM_ACCEL_OPTIONS=5, MOTION_PRIM_ANGRATE_OPTIONS=5),
+    'DoubleIntegratorConfig': dict(VX_MIN=-0.5, VX_MAX=0.5, VY_MIN=-0.5, VY_MAX=0.5, ACCELX_MIN=-0.5, ACCELX_MAX=0.5,
+                                   ACCELY_MIN=-0.5, ACCELY_MAX=0.5, ACCELX_OPTIONS=5, ACCELY_OPTIONS=5),
+}
+
+
+def assert_compiled_limits():
+    """Raise if a dynamics limit of the config classes differs from the constant compiled into the CUDA kernels."""
+    for cls in (AirTaxiConfig, DoubleIntegratorConfig):
+        for name, want in _COMPILED_LIMITS[cls.__name__].items():
+            have = getattr(cls, name)
+            if have != want:
+                raise ValueError(f"{cls.__name__}.{name} = {have!r} differs from the value compiled into the kernels ({want!r}): "
+                                 f"the dynamics limits are compile-time constants of csrc/lsm_step_common.cuh - change them "
+                                 f"there and rebuild")
+
+
 def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
                               weight_cfg=RewardWeightConfig) -> ScenarioParams:
     """Build ScenarioParams from the same argparse Namespace `make_world` consumes."""
+    assert_compiled_limits()
     dyn_name = args.dynamics_type
     if dyn_name == 'double_integrator':
         dyn, cfg = DYN_DOUBLE_INTEGRATOR, DoubleIntegratorConfig

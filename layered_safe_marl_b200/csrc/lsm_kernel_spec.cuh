@@ -1201,6 +1201,110 @@ struct __align__(16) EmitShared {
     long long range_base;
 };
 
+// Fused COO edge output of one environment: kept OUT OF LINE so that its registers do not count against
+// the occupancy of the dense path (69 -> 91 registers per thread when inlined, one resident block per SM fewer).
+template <int DYN, int N, int L, int WPE>
+__device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KParams& kp, int ee, const float* dthr) {
+    using GEO = EmitGeom<DYN, N, L>;
+    constexpr int E = GEO::E, W = GEO::W;
+    constexpr int T = 32 * WPE;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // (e1) non-zero bit mask of every row (one ballot per 32 columns)
+    for (int a = warp; a < E; a += WPE) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            const int b2 = w * 32 + lane;
+            const unsigned m = __ballot_sync(0xffffffffu, b2 < E && dthr[a * E + b2] != 0.0f);
+            if (lane == 0) S.rowmask[a * W + w] = m;
+        }
+    }
+    __syncthreads();
+    // (e2) edges of row a as observer i sees it, then the exclusive prefix over the rows of each observer
+    for (int k = tid; k < N * E; k += T) {
+        const int i = k / E, a = k - i * E;
+        int cnt = 0;
+        if ((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) {
+#pragma unroll
+            for (int w = 0; w < W; ++w) cnt += __popc(S.rowmask[a * W + w] & S.keepm[i * W + w]);
+        }
+        S.rowoff[k] = (unsigned short)cnt;
+    }
+    __syncthreads();
+    for (int i = warp; i < N; i += WPE) {
+        int running = 0;
+        for (int c0 = 0; c0 < E; c0 += 32) {
+            const int a = c0 + lane;
+            const int v = a < E ? S.rowoff[i * E + a] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
+            if (a < E) S.rowoff[i * E + a] = (unsigned short)(running + incl - v);
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) {
+            // lsm_edge_count_kernel left: prefix inside its block's env run + base of that block inside the range
+            const long long gb = S.range_base + kp.edge_block_base[kp.edge_block_ofs + (ee - kp.env_begin) / kp.edge_envs_per_block] +
+                                 kp.edge_local[(size_t)ee * N + i];
+            S.gbase[i] = gb;
+            kp.edge_offsets[(size_t)ee * N + i] = gb;
+        }
+    }
+    __syncthreads();
+    // (e3) fill. Dense graphs (mean degree > 8): one warp per (observer, row), lane = column inside a 32-column word,
+    //      rank by popcount - coalesced stores. Sparse graphs: one LANE per (observer, row) walking the few set bits
+    //      of its row (a warp per row would spend ~40 instructions on a row that holds two edges).
+    {
+        long long* const src = kp.edge_index;
+        long long* const dst = kp.edge_index + kp.edge_capacity;
+        const long long cap = kp.edge_capacity;
+        const unsigned lt = (1u << lane) - 1u;
+        // total edges of the env = last observer's end; mean degree decides the strategy (block-uniform)
+        int env_edges = 0;
+        for (int i = 0; i < N; ++i) env_edges += S.rowoff[i * E + E - 1];          // lower bound is enough for the choice
+        if (env_edges > 8 * N * E) {
+            for (int r = warp; r < N * E; r += WPE) {
+                const int i = r / E, a = r - i * E;
+                if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
+                const long long node0 = ((long long)ee * N + i) * E;
+                long long p0 = S.gbase[i] + S.rowoff[r];
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
+                    if ((m >> lane) & 1u) {
+                        const long long p = p0 + __popc(m & lt);
+                        if (p < cap) {
+                            const int b2 = w * 32 + lane;
+                            src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                        }
+                    }
+                    p0 += __popc(m);
+                }
+            }
+        } else {
+            for (int r = tid; r < N * E; r += T) {
+                const int i = r / E, a = r - i * E;
+                if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
+                const long long node0 = ((long long)ee * N + i) * E;
+                long long p = S.gbase[i] + S.rowoff[r];
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
+                    while (m != 0u) {
+                        const int bit = __ffs(m) - 1;
+                        m &= m - 1u;
+                        if (p < cap) {
+                            const int b2 = w * 32 + bit;
+                            src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
+                        }
+                        ++p;
+                    }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    }
+
 // PIE ("pair in emit"): also compute the next step's HJ pair values per environment after its copies are issued - the
 // placement that wins for few agents (one launch less; the lookups of an 8-agent environment occupy half a block once).
 // For many agents the per-block chain gets long and lsm_pair_kernel behind this kernel is faster (see lsm_capi.cu).
@@ -1369,102 +1473,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             __syncthreads();
         }
-        if (edges) {
-            // (e1) non-zero bit mask of every row (one ballot per 32 columns)
-            for (int a = warp; a < E; a += WPE) {
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    const int b2 = w * 32 + lane;
-                    const unsigned m = __ballot_sync(0xffffffffu, b2 < E && dthr[a * E + b2] != 0.0f);
-                    if (lane == 0) S.rowmask[a * W + w] = m;
-                }
-            }
-            __syncthreads();
-            // (e2) edges of row a as observer i sees it, then the exclusive prefix over the rows of each observer
-            for (int k = tid; k < N * E; k += T) {
-                const int i = k / E, a = k - i * E;
-                int cnt = 0;
-                if ((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) cnt += __popc(S.rowmask[a * W + w] & S.keepm[i * W + w]);
-                }
-                S.rowoff[k] = (unsigned short)cnt;
-            }
-            __syncthreads();
-            for (int i = warp; i < N; i += WPE) {
-                int running = 0;
-                for (int c0 = 0; c0 < E; c0 += 32) {
-                    const int a = c0 + lane;
-                    const int v = a < E ? S.rowoff[i * E + a] : 0;
-                    int incl = v;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) { const int t2 = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t2; }
-                    if (a < E) S.rowoff[i * E + a] = (unsigned short)(running + incl - v);
-                    running += __shfl_sync(0xffffffffu, incl, 31);
-                }
-                if (lane == 0) {
-                    // lsm_edge_count_kernel left: prefix inside its block's env run + base of that block inside the range
-                    const long long gb = S.range_base + kp.edge_block_base[kp.edge_block_ofs + (ee - kp.env_begin) / kp.edge_envs_per_block] +
-                                         kp.edge_local[(size_t)ee * N + i];
-                    S.gbase[i] = gb;
-                    kp.edge_offsets[(size_t)ee * N + i] = gb;
-                }
-            }
-            __syncthreads();
-            // (e3) fill. Dense graphs (mean degree > 8): one warp per (observer, row), lane = column inside a 32-column word,
-            //      rank by popcount - coalesced stores. Sparse graphs: one LANE per (observer, row) walking the few set bits
-            //      of its row (a warp per row would spend ~40 instructions on a row that holds two edges).
-            {
-                long long* const src = kp.edge_index;
-                long long* const dst = kp.edge_index + kp.edge_capacity;
-                const long long cap = kp.edge_capacity;
-                const unsigned lt = (1u << lane) - 1u;
-                // total edges of the env = last observer's end; mean degree decides the strategy (block-uniform)
-                int env_edges = 0;
-                for (int i = 0; i < N; ++i) env_edges += S.rowoff[i * E + E - 1];          // lower bound is enough for the choice
-                if (env_edges > 8 * N * E) {
-                    for (int r = warp; r < N * E; r += WPE) {
-                        const int i = r / E, a = r - i * E;
-                        if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
-                        const long long node0 = ((long long)ee * N + i) * E;
-                        long long p0 = S.gbase[i] + S.rowoff[r];
-#pragma unroll
-                        for (int w = 0; w < W; ++w) {
-                            const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
-                            if ((m >> lane) & 1u) {
-                                const long long p = p0 + __popc(m & lt);
-                                if (p < cap) {
-                                    const int b2 = w * 32 + lane;
-                                    src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
-                                }
-                            }
-                            p0 += __popc(m);
-                        }
-                    }
-                } else {
-                    for (int r = tid; r < N * E; r += T) {
-                        const int i = r / E, a = r - i * E;
-                        if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
-                        const long long node0 = ((long long)ee * N + i) * E;
-                        long long p = S.gbase[i] + S.rowoff[r];
-#pragma unroll
-                        for (int w = 0; w < W; ++w) {
-                            unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
-                            while (m != 0u) {
-                                const int bit = __ffs(m) - 1;
-                                m &= m - 1u;
-                                if (p < cap) {
-                                    const int b2 = w * 32 + bit;
-                                    src[p] = node0 + a; dst[p] = node0 + b2; kp.edge_attr[p] = dthr[a * E + b2];
-                                }
-                                ++p;
-                            }
-                        }
-                    }
-                }
-            }
-            __syncthreads();
-        }
+        if (edges) emit_edges<DYN, N, L, WPE>(S, kp, ee, dthr);
         if (compact) {
             unsigned* kdst = kp.adj_keep + (size_t)ee * (N * W);
             for (int k = tid; k < N * W; k += T) kdst[k] = any_disc != 0u ? S.keepm[k] : 0xffffffffu;

@@ -236,6 +236,14 @@ cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void*
 static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool pie, int* out) {
     int bps = 0;
     const void* fn = (pie && f.emit_pie != nullptr) ? f.emit_pie : f.emit;
+#ifndef LSM_EXPERIMENTS
+    // the answer depends only on (kernel, reserve_pair): asked once per process, not on every launch (two occupancy /
+    // attribute queries cost more host time than the launch itself)
+    struct Memo { const void* fn; bool reserve; int bps; };
+    static thread_local Memo memo[32];
+    static thread_local int memo_n = 0;
+    for (int k = 0; k < memo_n; ++k) if (memo[k].fn == fn && memo[k].reserve == reserve_pair) { *out = memo[k].bps; return cudaSuccess; }
+#endif
     cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bps, fn, f.emit_threads, f.emit_smem);
     if (e != cudaSuccess) return e;
     if (bps < 1) return cudaErrorLaunchOutOfResources;
@@ -249,6 +257,8 @@ static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool 
     }
 #ifdef LSM_EXPERIMENTS
     { const int v = env_int("LSM_EMIT_BPS", 0); if (v >= 1 && v < bps) bps = v; }
+#else
+    if (memo_n < 32) { memo[memo_n].fn = fn; memo[memo_n].reserve = reserve_pair; memo[memo_n].bps = bps; ++memo_n; }
 #endif
     *out = bps;
     return cudaSuccess;

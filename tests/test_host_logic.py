@@ -266,3 +266,13 @@ def test_expand_adjacency_host_matches_numpy(N, L):
         _lib.check(lib.lsm_expand_adjacency_host(base.ctypes.data_as(ctypes.c_void_p), keep.ctypes.data_as(ctypes.c_void_p),
                                                  out.ctypes.data_as(ctypes.c_void_p), n, N, E, threads, cached), 'expand')
         assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), f"threads={threads} cached={cached}"
+
+
+def test_edited_dynamics_limits_are_refused(monkeypatch):
+    """The acceleration / speed / turn-rate limits are compile-time constants of the kernels; a config class edited
+    without a rebuild must fail loudly instead of simulating something else than it says."""
+    args = G.default_args(num_agents=3)
+    cfg.scenario_params_from_args(args, binary_cfg=G.BinaryFlags({}))
+    monkeypatch.setattr(cfg.DoubleIntegratorConfig, 'ACCELX_MAX', 0.75)
+    with pytest.raises(ValueError, match='compiled into the kernels'):
+        cfg.scenario_params_from_args(args, binary_cfg=G.BinaryFlags({}))
