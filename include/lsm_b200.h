@@ -51,8 +51,12 @@ enum {
     LSM_FLAG_USE_SAFETY_FILTER = 1 << 6,   /* the --use_safety_filter argument */
     LSM_FLAG_SHARED_REWARD = 1 << 7,       /* --collaborative */
     LSM_FLAG_USE_MASKING = 1 << 8,         /* --use_masking (required, reference quirk Q9) */
-    LSM_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9    /* --graph_feat_type global: 7-wide observer-independent node features
+    LSM_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9,   /* --graph_feat_type global: 7-wide observer-independent node features
                                               (navigation_graph_safe.py:1017-1036); default is 'relative' */
+    LSM_FLAG_INTERP_FLOAT32 = 1 << 10      /* grid interpolation (hj_reachability Grid.interpolate: safety_filter.py:195,245,
+                                              348,418, core.py:463, navigation_graph_safe.py:751) in float32 - position,
+                                              weights and corner sum - as jax computes it without jax_enable_x64 (the
+                                              reference never enables it); default: the same formula in float64 */
 };
 
 /* state layout: agent_f64[field][env][agent], agent_i32[field][env][agent],

@@ -94,6 +94,7 @@ FLAG_USE_SAFETY_FILTER = 1 << 6   # the --use_safety_filter ARGUMENT (not the pe
 FLAG_SHARED_REWARD = 1 << 7       # --collaborative
 FLAG_USE_MASKING = 1 << 8         # --use_masking
 FLAG_GRAPH_FEAT_GLOBAL = 1 << 9   # --graph_feat_type global
+FLAG_INTERP_FLOAT32 = 1 << 10     # grid interpolation in float32 (jax without x64) instead of float64; args.interp_float32
 
 
 def reward_flags_from(binary_cfg=RewardBinaryConfig) -> int:
@@ -224,6 +225,9 @@ def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
         flags |= FLAG_SHARED_REWARD
     if graph_feat_type == 'global':
         flags |= FLAG_GRAPH_FEAT_GLOBAL
+    # not a reference argument: which DECLARED arithmetic of hj_reachability's Grid.interpolate to reproduce
+    if bool(getattr(args, 'interp_float32', False)):
+        flags |= FLAG_INTERP_FLOAT32
     num_total_episode = int(args.num_env_steps) // int(args.episode_length) // int(args.n_rollout_threads)
     return ScenarioParams(
         dynamics=dyn,

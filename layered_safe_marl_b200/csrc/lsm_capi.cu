@@ -251,8 +251,10 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.bytes_per_env = align_up(off, 16);
     h->smem_optin = (int)prop.sharedMemPerBlockOptin;
 
-    // both node-feature types ('relative', which every shipped script uses, and 'global') run the specialised pipeline
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo);
+    // both node-feature types ('relative', which every shipped script uses, and 'global') run the specialised pipeline; the
+    // float32 interpolation arithmetic (LSM_FLAG_INTERP_FLOAT32, a parity mode) lives in the generic kernel only, so that
+    // the specialised kernels carry none of its code
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_INTERP_FLOAT32);
 #ifdef LSM_EXPERIMENTS
     { const char* force_generic = std::getenv("LSM_FORCE_GENERIC"); if (force_generic != nullptr && force_generic[0] == '1') h->spec = false; }
 #endif
@@ -365,7 +367,7 @@ int lsm_destroy(lsm_handle* h) {
     return 0;
 }
 
-static int fill_grid(const lsm_grid_desc* g, lsm::GridDev* d, int want_ndim, bool need_grads, const char* who) {
+static int fill_grid(const lsm_grid_desc* g, lsm::GridDev* d, int want_ndim, bool need_grads, const char* who, bool f32) {
     if (g == nullptr || g->values == nullptr) return fail(1, std::string(who) + ": null grid");
     if (g->ndim != want_ndim) return fail(2, std::string(who) + ": wrong grid dimensionality");
     if (need_grads && g->grads == nullptr) return fail(2, std::string(who) + ": gradient array required");
@@ -380,13 +382,14 @@ static int fill_grid(const lsm_grid_desc* g, lsm::GridDev* d, int want_ndim, boo
     }
     d->separation_distance = g->separation_distance; d->ttr_max = g->ttr_max;
     d->values = g->values; d->grads = g->grads;
+    d->f32 = f32 ? 1 : 0;
     return 0;
 }
 
 int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     if (h == nullptr) return fail(1, "lsm_set_value_grid: null handle");
     const int want = h->kp.c.dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
-    int rc = fill_grid(g, &h->kp.vg, want, true, "lsm_set_value_grid");
+    int rc = fill_grid(g, &h->kp.vg, want, true, "lsm_set_value_grid", (h->kp.c.flags & LSM_FLAG_INTERP_FLOAT32) != 0);
     if (rc) return rc;
     h->kp.has_vg = 1;
     size_t cells = 1;
@@ -396,7 +399,7 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     // corner-packed copy for the pair kernel (one aligned chunk per lookup); lsm_tuning.packed_grid = 0 keeps the scattered
     // gathers; tables larger than 2 GiB are not built.
     DeviceGuard guard(h->device);
-    const bool want_packed = h->tuning.packed_grid != 0;
+    const bool want_packed = h->tuning.packed_grid != 0 && !(h->kp.c.flags & LSM_FLAG_INTERP_FLOAT32);
     if (h->d_vpacked) { cudaFree(h->d_vpacked); h->d_vpacked = nullptr; }
     h->kp.vg.packed = nullptr;
     if (h->spec && want_packed) {
@@ -427,7 +430,7 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
 int lsm_set_ttr_grid(lsm_handle* h, const lsm_grid_desc* g) {
     if (h == nullptr) return fail(1, "lsm_set_ttr_grid: null handle");
     DeviceGuard guard(h->device);
-    int rc = fill_grid(g, &h->kp.tg, 4, false, "lsm_set_ttr_grid");
+    int rc = fill_grid(g, &h->kp.tg, 4, false, "lsm_set_ttr_grid", (h->kp.c.flags & LSM_FLAG_INTERP_FLOAT32) != 0);
     if (rc) return rc;
     h->kp.has_tg = 1;
     return 0;

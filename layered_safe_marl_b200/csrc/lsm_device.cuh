@@ -41,6 +41,8 @@ struct GridDev {
     // 5-D grids: gradient rows padded from 5 to 8 floats (library-owned copy) so that one corner is two 16-byte loads
     // instead of five scalar ones. NULL = not built (4-D rows are one float4 already).
     const float* grads8;
+    // LSM_FLAG_INTERP_FLOAT32: positions, weights and the corner sum in float32 (what jax computes without x64); 0 = float64
+    int f32;
 };
 
 // per-env shared-memory block: element offsets (in bytes from the env block base)
@@ -242,6 +244,84 @@ __device__ __forceinline__ void stencil_grad(const GridDev& g, const Stencil<ND>
             for (int d = 0; d < ND; ++d) out[d] = out[d] + weight * (double)__ldg(g.grads + lin * ND + d);
         }
     }
+}
+
+// Declared FLOAT32 interpolation (LSM_FLAG_INTERP_FLOAT32; the reference never enables jax_enable_x64, so the real
+// hj_reachability.Grid.interpolate runs in float32): state, domain_lo and spacing rounded to float32, position / floor /
+// weights / weight products / corner sum all float32, same corner order and index handling as the float64 mode, no FMA.
+// One out-of-line function for values (ncomp == 0 -> out[0]) and gradient rows (ncomp == ND); scattered gathers - this
+// mode exists for parity with the real library's arithmetic, not for speed. Returns false for a NaN position.
+template <int ND>
+__device__ __noinline__ bool interp_f32(const GridDev& g, const double* x, int ncomp, double* out) {
+    float wlo[ND], whi[ND];
+    int lo[ND], hi[ND];
+    int mul = 1;
+    bool ok = true;
+#pragma unroll
+    for (int d = ND - 1; d >= 0; --d) {
+        float pos = ((float)x[d] - (float)g.lo[d]) / (float)g.spacing[d];
+        if (isnan(pos)) ok = false;
+        pos = fminf(fmaxf(pos, -1.0e9f), 1.0e9f);
+        const float fl = floorf(pos);
+        const float w = pos - fl;
+        wlo[d] = 1.0f - w; whi[d] = w;
+        const int n = g.shape[d];
+        int il = (int)fl, ih = il + 1;
+        if (g.periodic[d]) {
+            il %= n; if (il < 0) il += n;
+            ih %= n; if (ih < 0) ih += n;
+        } else {
+            il = min(max(il, 0), n - 1);
+            ih = min(max(ih, 0), n - 1);
+        }
+        lo[d] = il * mul; hi[d] = ih * mul;
+        mul *= n;
+    }
+    if (!ok) return false;
+    float acc[ND];
+#pragma unroll
+    for (int c = 0; c < ND; ++c) acc[c] = 0.0f;
+#pragma unroll
+    for (int corner = 0; corner < (1 << ND); ++corner) {
+        float weight = 0.0f; int lin = 0;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            const int bit = (corner >> (ND - 1 - d)) & 1;
+            const float wd = bit ? whi[d] : wlo[d];
+            weight = (d == 0) ? wd : weight * wd;
+            lin += bit ? hi[d] : lo[d];
+        }
+        if (ncomp == 0) acc[0] = acc[0] + weight * __ldg(g.values + lin);
+        else {
+#pragma unroll
+            for (int c = 0; c < ND; ++c) acc[c] = acc[c] + weight * __ldg(g.grads + (size_t)lin * ND + c);
+        }
+    }
+    if (ncomp == 0) out[0] = (double)acc[0];
+    else {
+#pragma unroll
+        for (int c = 0; c < ND; ++c) out[c] = (double)acc[c];
+    }
+    return true;
+}
+
+// Call-site wrappers: private copies go through the out-of-line function, so the CALLER's `x` / `out` arrays never have
+// their address taken (that would move them from registers to local memory on the float64 path as well).
+template <int ND>
+__device__ __forceinline__ double interp_f32_value(const GridDev& g, const double (&x)[ND]) {
+    double xin[ND], v;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) xin[d] = x[d];
+    return interp_f32<ND>(g, xin, 0, &v) ? v : NAN;
+}
+template <int ND>
+__device__ __forceinline__ void interp_f32_grad(const GridDev& g, const double (&x)[ND], double (&out)[ND]) {
+    double xin[ND], o[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) xin[d] = x[d];
+    const bool ok = interp_f32<ND>(g, xin, ND, o);
+#pragma unroll
+    for (int d = 0; d < ND; ++d) out[d] = ok ? o[d] : NAN;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                         Stencil<4> st;
                         stencil_setup<4>(kp.tg, rs, st);
                         double ttr = st.valid ? stencil_value<4>(kp.tg, st) : NAN;
+                        if (kp.tg.f32) ttr = interp_f32_value<4>(kp.tg, rs);
                         if (isnan(ttr)) ttr = kp.tg.ttr_max;
                         rew -= 0.04 * ttr;
                         rew -= sen * cra;

@@ -83,6 +83,12 @@ template <int DYN>
 __device__ __forceinline__ double hj_value(const KParams& kp, const Curriculum& q,
                                            const double (&rel)[DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5], bool& in_range) {
     constexpr int ND = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 4 : 5;
+    if (kp.vg.f32) {
+        const double v32 = interp_f32_value<ND>(kp.vg, rel);
+        if (isnan(v32)) { in_range = false; return INFINITY; }
+        in_range = true;
+        return v32 - (q.sep - kp.vg.separation_distance);
+    }
     Stencil<ND> st;
     stencil_setup<ND>(kp.vg, rel, st);
     if (!st.valid) { in_range = false; return INFINITY; }
@@ -99,6 +105,7 @@ struct ClassicGrad {
     static constexpr bool kRotRel = false;
     template <int ND>
     __device__ __forceinline__ static void eval(const GridDev& g, const double (&rel)[ND], double (&out)[ND]) {
+        if (g.f32) { interp_f32_grad<ND>(g, rel, out); return; }
         Stencil<ND> st;
         stencil_setup<ND>(g, rel, st);
         stencil_grad<ND>(g, st, out);

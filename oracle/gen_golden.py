@@ -107,8 +107,9 @@ def observe_now(env):
 
 
 def run_case(name, args_kw, flags, episode, T, seed, greedy_agents=(), injections=(), post=None):
-    args = H.make_args(**args_kw)
-    env = H.make_env(args, seed=seed, **flags)
+    interp_float32 = bool(args_kw.get('interp_float32', False))     # not a reference argument: selects the stub's arithmetic
+    args = H.make_args(**{k: v for k, v in args_kw.items() if k != 'interp_float32'})
+    env = H.make_env(args, seed=seed, interp_float32=interp_float32, **flags)
     sc = H.scenario_of(env)
     N = args.num_agents
     env.reset(episode)
@@ -216,6 +217,15 @@ CASES = [
          episode=3000, T=30, seed=12, greedy_agents=(0, 1), injections=(('near_goal', 0, 0.45, 1), ('near_goal', 1, 0.40, 0, 0.05))),
     dict(name='at4_global_feat', args_kw=dict(AT, num_agents=4, episode_length=30, graph_feat_type='global'), flags={},
          episode=0, T=12, seed=13, greedy_agents=(0,), injections=(('near_goal', 0, 0.5, 1),)),
+    # the second declared interpolation arithmetic (float32, jax default dtype): same scenarios as di8_filter / at10_filter_pc
+    dict(name='di8_filter_f32', args_kw=dict(DI, num_agents=8, use_safety_filter=True, world_size=2, episode_length=250,
+                                             interp_float32=True),
+         flags={}, episode=6249, T=30, seed=3, greedy_agents=(0, 1, 2, 3),
+         injections=(('near_goal', 0, 0.5, 1), ('pair', 4, 5, 0.9, 0.45), ('pair', 6, 7, 1.6, 0.3))),
+    dict(name='at10_filter_pc_f32', args_kw=dict(AT, num_agents=10, use_safety_filter=True, episode_length=350, interp_float32=True),
+         flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=36, seed=10, greedy_agents=(0, 1, 2, 3, 4),
+         injections=(('near_goal', 0, 0.6, 1), ('near_goal', 1, 0.7, 0, 0.05), ('pair', 5, 6, 2.0, 0.08),
+                     ('pair', 7, 8, 3.5, 0.06))),
     dict(name='at6_allflags', args_kw=dict(AT, num_agents=6, use_safety_filter=True, world_size=3, episode_length=350),
          flags=ALL_FLAGS, episode=4000, T=30, seed=11, greedy_agents=(0, 1),
          injections=(('near_goal', 0, 0.5, 1), ('pair', 2, 3, 1.5, 0.085), ('pair', 4, 5, 2.5, 0.035))),

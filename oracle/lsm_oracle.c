@@ -80,7 +80,51 @@ static double rng_uniform(rng_t *r, double lo, double hi) { return lo + (hi - lo
  * Grid interpolation - declared semantics of oracle/ref_stubs/hj_reachability (Grid.interpolate);
  * call sites multiagent/safety_filter.py:195,245,348,418, core.py:463, navigation_graph_safe.py:751.
  * ---------------------------------------------------------------------------------------- */
+/* LSMO_FLAG_INTERP_FLOAT32 (set from the params at every entry point): position, floor, weights, weight products and the
+ * corner sum in float32 - what jax computes without jax_enable_x64, which the reference never enables - instead of the
+ * same formula in float64. Same corner order, same index clamping / wrapping. */
+static int g_interp_f32 = 0;
+void lsmo_set_interp_float32(int on) { g_interp_f32 = on ? 1 : 0; }      /* unit tests of lsmo_interpolate */
+
+static double interpolate_f32(const lsmo_grid *g, const double *x, int component) {
+    int nd = g->ndim;
+    int64_t idx[2][5];
+    float w[2][5];
+    for (int d = 0; d < nd; ++d) {
+        double n = (double)g->shape[d];
+        double spacing = g->periodic[d] ? (g->hi[d] - g->lo[d]) / n : (g->hi[d] - g->lo[d]) / (n - 1.0);
+        float pos = ((float)x[d] - (float)g->lo[d]) / (float)spacing;
+        if (isnan(pos)) return NAN;
+        pos = fminf(fmaxf(pos, -1.0e9f), 1.0e9f);
+        float fl = floorf(pos);
+        float whi = pos - fl;
+        w[0][d] = 1.0f - whi; w[1][d] = whi;
+        int64_t il = (int64_t)fl, ih = il + 1, s = g->shape[d];
+        if (g->periodic[d]) {
+            il %= s; if (il < 0) il += s;
+            ih %= s; if (ih < 0) ih += s;
+        } else {
+            il = il < 0 ? 0 : (il > s - 1 ? s - 1 : il);
+            ih = ih < 0 ? 0 : (ih > s - 1 ? s - 1 : ih);
+        }
+        idx[0][d] = il; idx[1][d] = ih;
+    }
+    float acc = 0.0f;
+    for (int corner = 0; corner < (1 << nd); ++corner) {
+        float weight = 0.0f; int64_t lin = 0;
+        for (int d = 0; d < nd; ++d) {
+            int bit = (corner >> (nd - 1 - d)) & 1;
+            weight = (d == 0) ? w[bit][d] : weight * w[bit][d];
+            lin = lin * g->shape[d] + idx[bit][d];
+        }
+        float v = (component < 0) ? g->values[lin] : g->grads[lin * nd + component];
+        acc = acc + weight * v;
+    }
+    return (double)acc;
+}
+
 double lsmo_interpolate(const lsmo_grid *g, const double *x, int component) {
+    if (g_interp_f32) return interpolate_f32(g, x, component);
     int nd = g->ndim;
     int64_t idx[2][5];
     double w[2][5];
@@ -1134,6 +1178,7 @@ static int run_jobs(job_t *proto, int nthreads) {
 
 int lsmo_step(const lsmo_params *p, const lsmo_grid *vg, const lsmo_grid *tg, const lsmo_buffers *b,
               const int32_t *action_idx, int64_t episode, uint64_t seed, int auto_reset, int nthreads) {
+    g_interp_f32 = (p->flags & LSMO_FLAG_INTERP_FLOAT32) != 0;
     if (check(p)) return 1;
     job_t j; memset(&j, 0, sizeof j);
     j.mode = 0; j.p = p; j.vg = vg; j.tg = tg; j.b = b; j.action_idx = action_idx;
@@ -1143,6 +1188,7 @@ int lsmo_step(const lsmo_params *p, const lsmo_grid *vg, const lsmo_grid *tg, co
 
 int lsmo_reset(const lsmo_params *p, const lsmo_grid *vg, const lsmo_grid *tg, const lsmo_buffers *b,
                const uint8_t *env_mask, int64_t episode, uint64_t seed, int sample, int nthreads) {
+    g_interp_f32 = (p->flags & LSMO_FLAG_INTERP_FLOAT32) != 0;
     if (check(p)) return 1;
     job_t j; memset(&j, 0, sizeof j);
     j.mode = 1; j.p = p; j.vg = vg; j.tg = tg; j.b = b; j.env_mask = env_mask;
@@ -1151,6 +1197,7 @@ int lsmo_reset(const lsmo_params *p, const lsmo_grid *vg, const lsmo_grid *tg, c
 }
 
 int lsmo_observe(const lsmo_params *p, const lsmo_buffers *b, int nthreads) {
+    g_interp_f32 = (p->flags & LSMO_FLAG_INTERP_FLOAT32) != 0;
     if (check(p)) return 1;
     job_t j; memset(&j, 0, sizeof j);
     j.mode = 2; j.p = p; j.b = b;

@@ -35,7 +35,8 @@ enum {
     LSMO_FLAG_USE_SAFETY_FILTER = 1 << 6,
     LSMO_FLAG_SHARED_REWARD = 1 << 7,
     LSMO_FLAG_USE_MASKING = 1 << 8,
-    LSMO_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9    /* --graph_feat_type global (navigation_graph_safe.py:1017-1036) */
+    LSMO_FLAG_GRAPH_FEAT_GLOBAL = 1 << 9,   /* --graph_feat_type global (navigation_graph_safe.py:1017-1036) */
+    LSMO_FLAG_INTERP_FLOAT32 = 1 << 10      /* Grid.interpolate in float32 (jax default dtype) instead of float64 */
 };
 
 /* per-agent float64 fields: agent_f64[field][env][agent] */
@@ -127,6 +128,7 @@ int lsmo_observe(const lsmo_params *p, const lsmo_buffers *b, int nthreads);
 
 /* helpers exported for unit tests */
 double lsmo_interpolate(const lsmo_grid *g, const double *x, int component /* -1: values */);
+void lsmo_set_interp_float32(int on);   /* arithmetic of lsmo_interpolate when called directly (the entry points set it from params.flags) */
 void lsmo_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]);
 void lsmo_curriculum(const lsmo_params *p, double ratio, double out[12]);
 double lsmo_magnetic_heading(double px, double py, double radius);

@@ -87,6 +87,8 @@ def lib():
         _lib.lsmo_math_eval.restype = None
         _lib.lsmo_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]
         _lib.lsmo_set_relative_state_form.argtypes = [C.c_int]
+        _lib.lsmo_set_interp_float32.argtypes = [C.c_int]
+        _lib.lsmo_set_interp_float32.restype = None
         _lib.lsmo_get_relative_state_form.restype = C.c_int
     return _lib
 

@@ -83,10 +83,12 @@ BINARY_FLAGS = ('SAFETY_VIOLATION', 'HJ_VALUE', 'POTENTIAL_CONFLICT', 'SEPARATIO
                 'INITIAL_PHASE_USE_SAFETY_FILTER', 'DIFF_FROM_FILTERED_ACTION')
 
 
-def make_env(args, seed=0, **binary_flags):
+def make_env(args, seed=0, interp_float32=False, **binary_flags):
     """GraphMPEEnv(args) with the RewardBinaryConfig switches set the way the reference README says
     to set them (edit the class attributes), then env.seed(seed) (scripts/train_mpe.py:38)."""
     setup_reference()
+    import hj_reachability
+    hj_reachability.FLOAT32_INTERPOLATION = bool(interp_float32)      # which declared Grid.interpolate arithmetic the stub runs
     import multiagent.config as C
     for k in BINARY_FLAGS:
         setattr(C.RewardBinaryConfig, k, bool(binary_flags.get(k, False)))

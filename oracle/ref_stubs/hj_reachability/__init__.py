@@ -28,6 +28,11 @@ DECLARED SEMANTICS (parity unpinned against the real library):
 """
 import numpy as np
 
+# Second declared mode (oracle/ref_harness.make_env(interp_float32=True)): the same formula with state, domain_lo and
+# spacing rounded to float32 and every operation - position, floor, weights, weight products, corner sum - in float32,
+# which is what jax computes without jax_enable_x64 (the reference never enables it). Grid data are float32 either way.
+FLOAT32_INTERPOLATION = False
+
 
 class _Box(object):
     def __init__(self, lo, hi):
@@ -69,6 +74,8 @@ class Grid(object):
 
     def interpolate(self, values, state):
         values = np.asarray(values)
+        if FLOAT32_INTERPOLATION:
+            return self._interpolate_f32(values, state)
         state = np.asarray(state, dtype=np.float64)
         assert state.shape == (self.ndim,)
         position = (state - self.lo) / self.spacings
@@ -96,6 +103,35 @@ class Grid(object):
                 index.append(int(idx[bit][d]))
             out = out + weight * np.asarray(values[tuple(index)], dtype=np.float64)
         return out if out.shape else np.float64(out)
+
+    def _interpolate_f32(self, values, state):
+        f32 = np.float32
+        state = np.asarray(state, dtype=np.float64).astype(f32)
+        assert state.shape == (self.ndim,)
+        position = (state - self.lo.astype(f32)) / self.spacings.astype(f32)
+        assert position.dtype == f32
+        if np.any(np.isnan(position)):
+            return np.full(values.shape[self.ndim:], np.nan)
+        position = np.minimum(np.maximum(position, f32(-1.0e9)), f32(1.0e9))
+        i_lo = np.floor(position)
+        w_hi = position - i_lo
+        w_lo = f32(1.0) - w_hi
+        i_lo = i_lo.astype(np.int64)
+        i_hi = i_lo + 1
+        shape = np.asarray(self.shape, dtype=np.int64)
+        idx = [np.where(self.periodic, np.mod(ind, shape), np.clip(ind, 0, shape - 1)) for ind in (i_lo, i_hi)]
+        w = (w_lo, w_hi)
+        out = np.zeros(values.shape[self.ndim:], dtype=f32)
+        for corner in range(1 << self.ndim):
+            weight = None
+            index = []
+            for d in range(self.ndim):
+                bit = (corner >> (self.ndim - 1 - d)) & 1
+                wd = w[bit][d]
+                weight = wd if weight is None else f32(weight * wd)
+                index.append(int(idx[bit][d]))
+            out = (out + f32(weight) * np.asarray(values[tuple(index)], dtype=f32)).astype(f32)
+        return out if out.shape else f32(out)
 
     def grad_values(self, values, upwind_scheme=None):
         values = np.asarray(values, dtype=np.float64)

@@ -429,3 +429,14 @@ def test_oracle_batch_global_features_run_the_specialised_pipeline(dyn, N):
     assert probe.launch_info()['specialised'] == 1 and probe.F == 7
     probe.close()
     _compare_with_oracle(args, G.BinaryFlags({}), n=200, T=14, episode=6249, seed=31, auto_reset=True)
+
+
+@pytest.mark.parametrize('dyn,N', [('double_integrator', 8), ('airtaxi', 10), ('airtaxi', 6)])
+def test_oracle_batch_float32_interpolation(dyn, N):
+    """LSM_FLAG_INTERP_FLOAT32 (args.interp_float32): the float32 arithmetic of Grid.interpolate (a parity mode; it runs on
+    the generic fused kernel for every shape) - same zero-tolerance bar against the oracle."""
+    air = dyn == 'airtaxi'
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=True, episode_length=12, world_size=6 if air else 3,
+                          interp_float32=True)
+    _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=air, HJ_VALUE=(N == 6))), n=160, T=16, episode=6249, seed=41,
+                         auto_reset=True)

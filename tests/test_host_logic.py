@@ -144,6 +144,38 @@ def test_oracle_interpolation_matches_stub():
             assert gd == float(grid.interpolate(a.grads, x)[d])
 
 
+def test_oracle_float32_interpolation_matches_stub_bit_for_bit():
+    """The second declared arithmetic of Grid.interpolate (LSM_FLAG_INTERP_FLOAT32: position, weights, products and the
+    corner sum in float32, as jax computes without x64): C oracle == numpy stub exactly, and it is NOT the float64 mode."""
+    import oracle_env as O
+    sys.path.insert(0, os.path.join(REPO, 'oracle', 'ref_stubs'))
+    import hj_reachability as hj
+    a = hj_grid.synthetic_airtaxi_grid(shape=(7, 7, 8, 3, 3))
+    grid = hj.Grid(a.lo, a.hi, a.shape, (2,))
+    s, keep = O.make_grid(a)
+    rng = np.random.default_rng(1)
+    differ = 0
+    O.lib().lsmo_set_interp_float32(1)
+    hj.FLOAT32_INTERPOLATION = True
+    try:
+        for _ in range(200):
+            x = rng.uniform(a.lo - 1.0, a.hi + 1.0)
+            x[2] = rng.uniform(-10, 10)
+            xc = (ctypes.c_double * 5)(*x)
+            got = O.lib().lsmo_interpolate(ctypes.byref(s), xc, ctypes.c_int(-1))
+            want = grid.interpolate(a.values, x)
+            assert isinstance(want, np.float32) and got == float(want)
+            for d in range(5):
+                assert O.lib().lsmo_interpolate(ctypes.byref(s), xc, ctypes.c_int(d)) == float(grid.interpolate(a.grads, x)[d])
+            hj.FLOAT32_INTERPOLATION = False
+            differ += float(grid.interpolate(a.values, x)) != got
+            hj.FLOAT32_INTERPOLATION = True
+    finally:
+        O.lib().lsmo_set_interp_float32(0)
+        hj.FLOAT32_INTERPOLATION = False
+    assert differ > 150          # the float64 mode gives a different number almost everywhere
+
+
 @pytest.mark.parametrize('name', ['di3_nofilter_goals', 'di8_filter_allflags', 'at10_filter_pc', 'di4_collab_conflict'])
 def test_lazy_infos_reproduce_reference_info_dicts(name):
     """infos.compute_agent_infos from (previous, current) golden state == the reference's info dicts."""
