@@ -25,6 +25,7 @@ on the GPU box); rank 0 only.
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -238,32 +239,51 @@ def run_ours(a):
     if a.envs:
         n_envs = a.envs
     env = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=1234, binary_cfg=flags,
-                          env_id_base=rank * n_envs)
+                          env_id_base=rank * n_envs, tuning=dict(use_graph=a.use_graph))
     N, L, D, F = env.N, env.L, env.D, env.F
     K, W = a.steps, a.warmup
     gen = torch.Generator(device=device); gen.manual_seed(1234 + rank)
     actions = torch.randint(0, 25, (W + K, n_envs, N), generator=gen, device=device, dtype=torch.int32)
     flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=device)   # 256 MiB > 126 MB L2
+    # --use-graph 1 only: the step reads its actions from ONE device buffer (as a policy loop with a static output tensor
+    # would leave them) - with unchanged pointers the library replays the step's launches from a CUDA graph
+    act = torch.empty((n_envs, N), dtype=torch.int32, device=device) if a.use_graph == 1 else None
+
+    def step_actions(t):
+        if act is None:
+            return actions[t]
+        act.copy_(actions[t])
+        return act
 
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()      # sampled every 20 ms over warm-up + timed loops + e2e (the GPU is busy throughout)
     env.reset(episode)
     for t in range(W):
-        env.step(actions[t], episode)
+        env.step(step_actions(t), episode)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(K)]
     torch.cuda.synchronize()
+    # Every timed step is bracketed by its own pair of events, so a host hiccup between "start recorded" and "kernels
+    # enqueued" would be billed to the device. Keep the host out of the measurement: no garbage collection inside the
+    # loop, and an untimed lead-in (a few more L2 flushes, ~1 ms of GPU work) so that the launches of the first timed
+    # steps are already queued when the GPU reaches them - as they are for every later step, the host being ~2.5 x
+    # faster per iteration than the GPU.
+    gc.collect(); gc.disable()
+    for _ in range(12):
+        flush.fill_(0.0)
     t_wall0 = time.perf_counter()
     for t in range(K):
+        x = step_actions(W + t)               # this step's actions (not timed: resident in HBM when the step starts)
         flush.fill_(0.0)                      # L2 flush between timed iterations (not timed)
         starts[t].record()
-        env.step(actions[W + t], episode)     # agent -> emit -> pair kernels (launch_info.launches_per_step)
+        env.step(x, episode)                  # agent -> emit -> pair kernels (launch_info.launches_per_step)
         stops[t].record()
     torch.cuda.synchronize()
+    gc.enable()
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
@@ -271,7 +291,7 @@ def run_ours(a):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for t in range(K):
-        env.step(actions[W + t], episode)
+        env.step(step_actions(W + t), episode)
     e1.record()
     torch.cuda.synchronize()
     noflush_ms = e0.elapsed_time(e1)
@@ -367,9 +387,9 @@ def run_ours(a):
         d2h = small + n_envs * (env.E * env.E * 4 + N * ((env.E + 31) // 32) * 4)
     else:
         d2h = small + dense_adj_bytes
-    e2e_host = {"adjacency": ("compact over PCIe (1 E x E matrix + N keep masks per env), expanded to the dense (n,N,E,E) float32 "
-                              f"array on the host by {env_h.host_threads} threads with non-temporal stores "
-                              "(lsm_expand_adjacency_host), chunked so that the expansion overlaps the DMA of the later chunks")
+    e2e_host = {"adjacency": ("compact over PCIe (1 E x E matrix + N keep masks per env) in env ranges, each range expanded to the dense "
+                              f"(n,N,E,E) float32 array by {env_h.host_threads} host threads with non-temporal stores as it lands, while "
+                              "the DMA engine moves the later ranges and node_obs; the whole step is one C-ABI call (lsm_step_host)")
                              if compact else "dense over PCIe",
                 "host_bytes_written_per_step": d2h + (dense_adj_bytes if compact else 0),
                 "host_threads": env_h.host_threads}
@@ -566,6 +586,8 @@ def main():
     ap.add_argument('--e2e-steps', type=int, default=20)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--numa-bind', action='store_true', help='e2e: pin the process to the CPUs of the NUMA node of its GPU')
+    ap.add_argument('--use-graph', type=int, default=-1, choices=[-1, 0, 1],
+                    help='lsm_tuning.use_graph of the device-timed env: -1 automatic (= plain launches), 0 plain launches, 1 graph replay from a static action buffer')
     ap.add_argument('--no-extra-workloads', action='store_true', help='skip the cfg3 / cfg4 / cfg5 sub-blocks of the default line')
     a = ap.parse_args()
     if a.warmup < 3:

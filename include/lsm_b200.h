@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LSM_ABI_VERSION 3
+#define LSM_ABI_VERSION 4
 
 enum { LSM_DYN_DOUBLE_INTEGRATOR = 0, LSM_DYN_AIRTAXI = 1 };
 
@@ -155,7 +155,11 @@ typedef struct lsm_tuning {
                                      (0 for the 4-D grid, 3 for the 5-D grid) */
     int32_t packed_grid;          /* 1 corner-packed value table (one aligned chunk per lookup), 0 scattered gathers;
                                      -1 = automatic (packed when the table fits 2 GiB) */
-    int32_t _reserved;
+    int32_t use_graph;            /* 1 replay a step's launches from a CUDA graph once the same parameter block repeats (one
+                                     graph launch instead of 2-3 kernel launches: less host time per step and no host-side
+                                     gap between the kernels of one step; ~1 us more device time per step on B200), 0 plain
+                                     launches; -1 = automatic (plain launches). Single-range steps of the specialised
+                                     pipeline only */
 } lsm_tuning;
 
 typedef struct lsm_launch_info {
@@ -169,6 +173,8 @@ typedef struct lsm_launch_info {
     int32_t emit_record_bytes;    /* per-env record handed from the agent kernel to the emit kernel */
     int32_t chunks;               /* env ranges one lsm_step is split into (library-owned streams, fork/join by events); 1 = none */
     int32_t pair_placement;       /* next step's HJ pair values: 0 behind the emit kernel, 1 inside it, 2 in front of the agent kernel, 3 between the two; -1 none */
+    int32_t graph_replays;        /* lsm_step calls served by a CUDA-graph launch so far (lsm_tuning.use_graph), saturating */
+    int32_t graph_captures;       /* captures / in-place updates of that graph so far */
 } lsm_launch_info;
 
 typedef struct lsm_handle lsm_handle;
@@ -224,6 +230,36 @@ int lsm_set_compact_adjacency(lsm_handle *h, float *adj_base, uint32_t *adj_keep
  * either copied or zero. */
 int lsm_expand_adjacency_host(const float *adj_base, const uint32_t *adj_keep, float *adj, int64_t num_envs,
                               int32_t num_agents, int32_t num_entities, int32_t threads, int32_t cached_stores);
+
+/* HOST buffers of one reference-facing step (GraphSubprocVecEnv.step_wait returns host arrays,
+ * onpolicy/envs/env_wrappers.py:983-996). Every pointer is a HOST pointer; page-locked memory makes the copies true DMA.
+ * NULL = that array is not fetched (adj and the two staging arrays are required). */
+typedef struct lsm_host_io {
+    float *obs;               /* [num_envs][N][D]        */
+    float *node_obs;          /* [num_envs][N][E][F]     (F = 7 with graph_feat_type='global') */
+    float *adj;               /* [num_envs][N][E][E]     dense, rebuilt on the host; pageable memory is fine */
+    float *reward;            /* [num_envs][N]           */
+    uint8_t *done;            /* [num_envs][N]           */
+    float *adj_base_staging;  /* [num_envs][E][E]        landing area of the compact adjacency (page-locked) */
+    uint32_t *adj_keep_staging; /* [num_envs][N][W]      W = ceil(E / 32) */
+    int32_t threads;          /* host worker threads of the expansion (<= 0: one per online core, at most 16) */
+    int32_t chunks;           /* env ranges the adjacency crosses PCIe in (<= 0: automatic) */
+    int32_t cached_stores;    /* see lsm_expand_adjacency_host */
+    int32_t reserved;
+} lsm_host_io;
+
+/* Device -> host of the CURRENT outputs with the compact adjacency active (lsm_set_compact_adjacency): the thresholded
+ * matrices + keep masks leave first in `chunks` env ranges, the library's host threads expand each range into io->adj as
+ * it lands while the DMA engine is still moving the later ranges and node_obs / obs / reward / done. Returns when every
+ * host array is complete (the stream's work up to this call has finished). */
+int lsm_fetch_host(lsm_handle *h, const lsm_host_io *io, void *stream);
+
+/* The whole reference-facing step with HOST buffers in ONE call - what a host-language binding of
+ * GraphSubprocVecEnv.step(actions) (env_wrappers.py:951-996, 103-110) calls: actions host -> device (exactly one of the
+ * two HOST action arrays: int32 [num_envs][N] indices or float32 [num_envs][N][25] one-hot rows; page-locked memory is
+ * DMA'd in place, pageable memory is staged), lsm_step, lsm_fetch_host. */
+int lsm_step_host(lsm_handle *h, const int32_t *action_idx_host, const float *action_onehot_host, int64_t episode,
+                  uint64_t seed, int auto_reset, const lsm_host_io *io, void *stream);
 
 /* Compacted COO edge list of the adjacency output in the order the reference's GNN builds on every forward
  * (TransformerConvNet.process_adj, onpolicy/algorithms/utils/gnn.py:376-407): graphs = num_envs * N, row-major

@@ -42,7 +42,7 @@ class LsmBuffers(C.Structure):
 
 
 class LsmTuning(C.Structure):
-    _fields_ = [('chunks', C.c_int32), ('pair_placement', C.c_int32), ('packed_grid', C.c_int32), ('_reserved', C.c_int32)]
+    _fields_ = [('chunks', C.c_int32), ('pair_placement', C.c_int32), ('packed_grid', C.c_int32), ('use_graph', C.c_int32)]
 
 
 class LsmLaunchInfo(C.Structure):
@@ -52,14 +52,21 @@ class LsmLaunchInfo(C.Structure):
                 ('emit_block_threads', C.c_int32), ('emit_smem_bytes_per_block', C.c_int32),
                 ('emit_regs_per_thread', C.c_int32), ('emit_blocks_per_sm', C.c_int32),
                 ('pair_regs_per_thread', C.c_int32), ('launches_per_step', C.c_int32), ('emit_record_bytes', C.c_int32),
-                ('chunks', C.c_int32), ('pair_placement', C.c_int32)]
+                ('chunks', C.c_int32), ('pair_placement', C.c_int32), ('graph_replays', C.c_int32),
+                ('graph_captures', C.c_int32)]
+
+
+class LsmHostIo(C.Structure):
+    _fields_ = [('obs', C.c_void_p), ('node_obs', C.c_void_p), ('adj', C.c_void_p), ('reward', C.c_void_p),
+                ('done', C.c_void_p), ('adj_base_staging', C.c_void_p), ('adj_keep_staging', C.c_void_p),
+                ('threads', C.c_int32), ('chunks', C.c_int32), ('cached_stores', C.c_int32), ('_reserved', C.c_int32)]
 
 
 EXPORTED_SYMBOLS = ('lsm_abi_version', 'lsm_last_error', 'lsm_create', 'lsm_destroy', 'lsm_set_value_grid',
                     'lsm_set_ttr_grid', 'lsm_bind_buffers', 'lsm_get_launch_info', 'lsm_step', 'lsm_reset',
                     'lsm_observe', 'lsm_emit_only', 'lsm_invalidate', 'lsm_set_output_buffers', 'lsm_edge_list',
                     'lsm_debug_timeline', 'lsm_rollout_insert', 'lsm_math_eval', 'lsm_math_eval_device', 'lsm_set_tuning',
-                    'lsm_set_compact_adjacency', 'lsm_expand_adjacency_host', 'lsm_set_edge_output', 'lsm_world_graph')
+                    'lsm_set_compact_adjacency', 'lsm_expand_adjacency_host', 'lsm_set_edge_output', 'lsm_world_graph', 'lsm_fetch_host', 'lsm_step_host')
 
 _lib = None
 
@@ -104,6 +111,8 @@ def load():
     lib.lsm_set_tuning.argtypes = [C.c_void_p, C.POINTER(LsmTuning)]
     lib.lsm_set_compact_adjacency.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.lsm_expand_adjacency_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    lib.lsm_fetch_host.argtypes = [C.c_void_p, C.POINTER(LsmHostIo), C.c_void_p]
+    lib.lsm_step_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_uint64, C.c_int, C.POINTER(LsmHostIo), C.c_void_p]
     lib.lsm_set_edge_output.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int]
     lib.lsm_world_graph.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
     lib.lsm_math_eval.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64]

@@ -108,7 +108,7 @@ class B200GraphVecEnv:
                  value_grid: Optional[HjGrid] = None, ttr_grid: Optional[HjGrid] = None,
                  binary_cfg=RewardBinaryConfig, weight_cfg=RewardWeightConfig, env_id_base: int = 0,
                  numpy_outputs: bool = False, auto_reset: bool = True, tuning: Optional[dict] = None,
-                 host_threads: Optional[int] = None, numa_bind: bool = False):
+                 host_threads: Optional[int] = None, numa_bind: bool = False, host_chunks: Optional[int] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("B200GraphVecEnv needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()   # raises if the sm_100a library is missing
@@ -121,12 +121,12 @@ class B200GraphVecEnv:
         self._dev_ctx.__enter__()      # lsm_create adopts the current device; restored at the end of __init__
         try:
             self._init(args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
-                       auto_reset, tuning, host_threads)
+                       auto_reset, tuning, host_threads, host_chunks)
         finally:
             self._dev_ctx.__exit__(None, None, None)
 
     def _init(self, args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
-              auto_reset, tuning, host_threads):
+              auto_reset, tuning, host_threads, host_chunks=None):
         self.params = scenario_params_from_args(args, binary_cfg=binary_cfg, weight_cfg=weight_cfg)
         p = self.params
         self.num_envs = int(num_envs if num_envs is not None else args.n_rollout_threads)
@@ -160,12 +160,12 @@ class B200GraphVecEnv:
         self._h = C.c_void_p()
         _lib.check(self.lib.lsm_create(C.byref(cfg), C.byref(self._h)), 'lsm_create')
         if tuning:
-            # launch-shape overrides (include/lsm_b200.h lsm_tuning): chunks, pair_placement, packed_grid
-            unknown = set(tuning) - {'chunks', 'pair_placement', 'packed_grid'}
+            # launch-shape overrides (include/lsm_b200.h lsm_tuning): chunks, pair_placement, packed_grid, use_graph
+            unknown = set(tuning) - {'chunks', 'pair_placement', 'packed_grid', 'use_graph'}
             if unknown:
                 raise ValueError(f"unknown tuning keys {sorted(unknown)}")
             t = _lib.LsmTuning(int(tuning.get('chunks', 0)), int(tuning.get('pair_placement', -1)),
-                               int(tuning.get('packed_grid', -1)), 0)
+                               int(tuning.get('packed_grid', -1)), int(tuning.get('use_graph', -1)))
             _lib.check(self.lib.lsm_set_tuning(self._h, C.byref(t)), 'lsm_set_tuning')
 
         # --- grids (HjDataHandle / TTR loading); synthetic when none is given
@@ -237,8 +237,13 @@ class B200GraphVecEnv:
         self.host_profile = None      # set to {} to accumulate wall-clock seconds of the host-side phases of _outputs
         if host_threads is None:
             local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))
-            host_threads = max(1, min(8, (os.cpu_count() or 1) // local_world))
+            try:
+                cores = len(os.sched_getaffinity(0))
+            except AttributeError:
+                cores = os.cpu_count() or 1
+            host_threads = max(1, min(16, cores // local_world))
         self.host_threads = int(host_threads)
+        self.host_chunks = int(host_chunks) if host_chunks else 0
         if self.numpy_outputs and self.launch_info()['specialised'] == 1:
             Wm = (E + 31) // 32
             cpt = {'base': torch.zeros((n, E, E), dtype=f32, device=dev),
@@ -246,12 +251,36 @@ class B200GraphVecEnv:
             cpt['base_h'] = torch.empty((n, E, E), dtype=f32).pin_memory()
             cpt['keep_h'] = torch.empty((n, N, Wm), dtype=i32).pin_memory()
             cpt['adj_h'] = torch.zeros((n, N, E, E), dtype=f32)     # zero-fill = first touch of every page
-            chunks = 1 if n < 256 else 4
-            cpt['bounds'] = [(n * c // chunks, n * (c + 1) // chunks) for c in range(chunks)]
-            cpt['events'] = [torch.cuda.Event() for _ in range(chunks)]
+            Fr = self.F
+            cpt['obs_h'] = torch.zeros((n, N, self.D), dtype=f32).pin_memory()
+            cpt['node_h'] = torch.zeros((n, N, E, Fr), dtype=f32).pin_memory()
+            cpt['reward_h'] = torch.zeros((n, N), dtype=f32).pin_memory()
+            cpt['done_h'] = torch.zeros((n, N), dtype=torch.uint8).pin_memory()
             _lib.check(self.lib.lsm_set_compact_adjacency(self._h, C.c_void_p(cpt['base'].data_ptr()),
                                                           C.c_void_p(cpt['keep'].data_ptr())), 'lsm_set_compact_adjacency')
             self._compact = cpt
+
+    def _host_io(self, with_step: bool):
+        cpt = self._compact
+        io = _lib.LsmHostIo()
+        io.obs = cpt['obs_h'].data_ptr(); io.node_obs = cpt['node_h'].data_ptr(); io.adj = cpt['adj_h'].data_ptr()
+        io.reward = cpt['reward_h'].data_ptr() if with_step else None
+        io.done = cpt['done_h'].data_ptr() if with_step else None
+        io.adj_base_staging = cpt['base_h'].data_ptr(); io.adj_keep_staging = cpt['keep_h'].data_ptr()
+        io.threads = self.host_threads; io.chunks = self.host_chunks; io.cached_stores = int(self.host_cached_stores)
+        return io
+
+    def _host_results(self, with_step: bool):
+        cpt = self._compact
+        if self._agent_id_np is None:
+            self._agent_id_np = self.agent_id.cpu().numpy()
+        node = cpt['node_h'].numpy()
+        if node.shape != tuple(self.node_obs.shape):
+            node = node.reshape(tuple(self.node_obs.shape))
+        res = [cpt['obs_h'].numpy(), self._agent_id_np, node, cpt['adj_h'].numpy()]
+        if with_step:
+            res += [cpt['reward_h'].numpy(), cpt['done_h'].numpy().view(np.bool_)]
+        return res
 
     # ------------------------------------------------------------------------------------------
     def launch_info(self) -> dict:
@@ -321,22 +350,19 @@ class B200GraphVecEnv:
         if self.numpy_outputs:
             # host arrays like the reference returns (float64 there; float32 here - every consumer casts).
             # Staged through pinned buffers that are reused every step: valid until the next step/reset.
-            if self._host_out is None:
-                self._host_out = {}
-            res = []
             cpt = self._compact
             stream = torch.cuda.current_stream(self.device)
             if cpt is not None:
-                # adjacency first: compact matrices + keep masks in env chunks, an event behind each chunk, so that the
-                # host expansion of chunk c runs while the DMA engine is still moving the later chunks and node_obs
-                for (lo, hi), ev in zip(cpt['bounds'], cpt['events']):
-                    cpt['base_h'][lo:hi].copy_(cpt['base'][lo:hi], non_blocking=True)
-                    cpt['keep_h'][lo:hi].copy_(cpt['keep'][lo:hi], non_blocking=True)
-                    ev.record(stream)
+                # compact adjacency over PCIe, expanded by the library's host threads while the later ranges and node_obs
+                # are still in flight (lsm_fetch_host); returns when every host array is complete
+                io = self._host_io(with_step)
+                _lib.check(self.lib.lsm_fetch_host(self._h, C.byref(io), self._stream()), 'lsm_fetch_host')
+                return self._host_results(with_step)
+            # generic-kernel configurations: dense adjacency straight into pinned buffers
+            if self._host_out is None:
+                self._host_out = {}
+            res = []
             for t in outs:
-                if cpt is not None and t is self.adj:
-                    res.append(cpt['adj_h'])
-                    continue
                 key = t.data_ptr()
                 if t is self.agent_id:
                     if self._agent_id_np is None:
@@ -349,26 +375,7 @@ class B200GraphVecEnv:
                     self._host_out[key] = hb
                 hb.copy_(t, non_blocking=True)
                 res.append(hb)
-            prof = self.host_profile
-            if prof is not None:
-                import time
-                t0 = time.perf_counter()
-            if cpt is not None:
-                E, N = self.E, self.N
-                for (lo, hi), ev in zip(cpt['bounds'], cpt['events']):
-                    ev.synchronize()
-                    if prof is not None:
-                        t1 = time.perf_counter(); prof['wait_chunk'] = prof.get('wait_chunk', 0.0) + (t1 - t0)
-                    _lib.check(self.lib.lsm_expand_adjacency_host(
-                        C.c_void_p(cpt['base_h'][lo:hi].data_ptr()), C.c_void_p(cpt['keep_h'][lo:hi].data_ptr()),
-                        C.c_void_p(cpt['adj_h'][lo:hi].data_ptr()), hi - lo, N, E, self.host_threads, int(self.host_cached_stores)),
-                        'lsm_expand_adjacency_host')
-                    if prof is not None:
-                        t0 = time.perf_counter(); prof['expand'] = prof.get('expand', 0.0) + (t0 - t1)
             stream.synchronize()
-            if prof is not None:
-                prof['final_sync'] = prof.get('final_sync', 0.0) + (time.perf_counter() - t0)
-                prof['calls'] = prof.get('calls', 0) + 1
             return [r if isinstance(r, np.ndarray) else r.numpy() for r in res]
         if copy:
             return [t.clone() for t in outs]
@@ -422,9 +429,23 @@ class B200GraphVecEnv:
     def step_wait(self, copy: bool = False):
         actions, episode = self._pending_actions, self._pending_episode
         self._pending_actions = None
+        ep = 0 if episode is None else int(episode)
+        if self._compact is not None and not torch.is_tensor(actions):
+            # host actions in, host arrays out: the whole step is ONE C-ABI call (lsm_step_host)
+            a = np.asarray(actions)
+            a = np.ascontiguousarray(a, dtype=np.float32 if a.ndim == 3 else np.int32)
+            want = (self.n, self.N, LY.NUM_ACTIONS) if a.ndim == 3 else (self.n, self.N)
+            assert a.shape == want, f"actions must be {(self.n, self.N)} indices or {(self.n, self.N, LY.NUM_ACTIONS)} one-hot"
+            self._step_id += 1
+            io = self._host_io(True)
+            ptr = C.c_void_p(a.ctypes.data)
+            _lib.check(self.lib.lsm_step_host(self._h, None if a.ndim == 3 else ptr, ptr if a.ndim == 3 else None, ep,
+                                              self.seed, int(self.auto_reset), C.byref(io), self._stream()), 'lsm_step_host')
+            obs, agent_id, node_obs, adj, rewards, dones = self._host_results(True)
+            infos = LazyInfos(self, self._step_id, reset_only=False)
+            return obs, agent_id, node_obs, adj, rewards, dones, infos
         idx_ptr, onehot_ptr = self._stage_actions(actions)
         self._step_id += 1
-        ep = 0 if episode is None else int(episode)
         _lib.check(self.lib.lsm_step(self._h, idx_ptr, onehot_ptr, ep, self.seed, int(self.auto_reset),
                                      self._stream()), 'lsm_step')
         obs, agent_id, node_obs, adj, rewards, dones = self._outputs(True, copy)

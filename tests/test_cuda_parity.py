@@ -313,8 +313,9 @@ def test_host_outputs_compact_adjacency_is_byte_identical(shape):
     args = G.default_args(episode_length=12, **kw)
     n, T, episode = 300, 30, 6249
     dev_env = B200GraphVecEnv(args, num_envs=n, seed=3)
-    host_env = B200GraphVecEnv(args, num_envs=n, seed=3, numpy_outputs=True)
-    assert host_env._compact is not None and len(host_env._compact['bounds']) == 4
+    # uneven env ranges and thread shares on purpose (300 envs in 7 ranges, 3 host threads)
+    host_env = B200GraphVecEnv(args, num_envs=n, seed=3, numpy_outputs=True, host_chunks=7, host_threads=3)
+    assert host_env._compact is not None
     o1, o2 = dev_env.reset(episode), host_env.reset(episode)
     for a, b in zip(o1[:4], o2[:4]):
         assert np.array_equal(a.cpu().numpy().view(np.uint8), np.ascontiguousarray(b).view(np.uint8))
@@ -323,7 +324,14 @@ def test_host_outputs_compact_adjacency_is_byte_identical(shape):
     for t in range(T):
         idx = rng.integers(0, 25, (n, args.num_agents)).astype(np.int32)
         o1 = dev_env.step(torch.as_tensor(idx, device=dev_env.device), episode)
-        o2 = host_env.step(idx, episode)
+        # the one-call host step (lsm_step_host) takes indices or one-hot rows, pageable or page-locked
+        if t % 3 == 0:
+            o2 = host_env.step(idx, episode)
+        elif t % 3 == 1:
+            o2 = host_env.step(np.eye(25, dtype=np.float32)[idx], episode)
+        else:
+            pinned = torch.from_numpy(np.eye(25, dtype=np.float32)[idx]).pin_memory()
+            o2 = host_env.step(pinned.numpy(), episode)
         for k, (a, b) in enumerate(zip(o1[:6], o2[:6])):
             assert np.array_equal(a.cpu().numpy().view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), f"step {t} output {k}"
         st = dev_env.get_state()
@@ -376,8 +384,8 @@ def test_infos_on_an_auto_reset_step_are_the_terminal_steps():
 
 
 def test_pinned_host_actions_are_used_in_place():
-    """Host-facing path: a page-locked one-hot array is DMA'd straight from the caller's memory, a pageable one is
-    staged; both give the same step."""
+    """Host-facing path (lsm_step_host): a page-locked one-hot array is DMA'd straight from the caller's memory, a pageable
+    one goes through the library's staging buffer; both give the same step."""
     import torch
     from layered_safe_marl_b200 import B200GraphVecEnv
     args = G.default_args(num_agents=8, use_safety_filter=True, episode_length=25, world_size=4)
@@ -395,7 +403,6 @@ def test_pinned_host_actions_are_used_in_place():
             o = env.step(a, 6249)
             trace.append([np.array(x) for x in o[:6]])
         outs.append(trace)
-        assert (getattr(env, '_act_pinned', None) is None) == use_pinned     # no staging buffer on the pinned path
         env.close()
     for ta, tb in zip(*outs):
         for x, y in zip(ta, tb):
@@ -440,3 +447,44 @@ def test_oracle_batch_float32_interpolation(dyn, N):
                           interp_float32=True)
     _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=air, HJ_VALUE=(N == 6))), n=160, T=16, episode=6249, seed=41,
                          auto_reset=True)
+
+
+@pytest.mark.parametrize('shape', ['di8', 'air10'])
+def test_graph_replay_is_bit_identical(shape):
+    """lsm_tuning.use_graph: once the same parameter block repeats, a step's launches are replayed from a CUDA graph. The
+    replayed steps must be bit-identical to plain launches - across an episode-number change (in-place graph update),
+    re-pointed output buffers, a state edit (pair kernel in front of the next step) and auto-resets."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    kw = dict(di8=dict(num_agents=8, world_size=2, use_safety_filter=True),
+              air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6, use_safety_filter=True))[shape]
+    args = G.default_args(episode_length=9, **kw)
+    n, T = 192, 40
+    envs = [B200GraphVecEnv(args, num_envs=n, seed=5, tuning=dict(use_graph=g)) for g in (0, 1)]
+    rng = np.random.default_rng(8)
+    acts = [torch.zeros((n, args.num_agents), dtype=torch.int32, device=e.device) for e in envs]
+    alt = [(torch.empty_like(e.node_obs), torch.empty_like(e.adj)) for e in envs]
+    for e in envs:
+        e.reset(6249)
+    for t in range(T):
+        idx = torch.as_tensor(rng.integers(0, 25, (n, args.num_agents)).astype(np.int32))
+        episode = 6249 if t < 25 else 3000
+        outs = []
+        for e, a, (nb, ab) in zip(envs, acts, alt):
+            a.copy_(idx)
+            if t == 15:
+                e.set_output_buffers(node_obs=nb, adj=ab)
+            if t == 30:
+                st = e.get_state(); e.set_state(st)          # marks the pair values stale: pair kernel in front once
+            o = e.step(a, episode)
+            outs.append([x.cpu().numpy().copy() for x in o[:6]])
+        for k, (x, y) in enumerate(zip(*outs)):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"step {t} output {k}"
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k]), equal_nan=True), f"state {k}"
+    li0, li1 = envs[0].launch_info(), envs[1].launch_info()
+    assert li0['graph_replays'] == 0 and li0['graph_captures'] == 0
+    assert li1['graph_replays'] >= T - 12 and 1 <= li1['graph_captures'] <= 8, li1
+    for e in envs:
+        e.close()

@@ -96,7 +96,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for sym in declared:
         assert getattr(lib, sym) is not None
     lib.lsm_abi_version.restype = ctypes.c_int
-    assert lib.lsm_abi_version() == 3
+    assert lib.lsm_abi_version() == 4
     # struct sizes must agree with the header (checked via the oracle's identical layout of lsm_config)
     import oracle_env as O
     assert ctypes.sizeof(_lib.LsmConfig) == ctypes.sizeof(O.Params)
