@@ -157,8 +157,8 @@ def run_reference(a):
         return
     cores = os.cpu_count() or 1
     n_sample = 1024
-    _, dtp, _ = oracle_throughput(a.workload, n_sample, 5, 2, cores)
-    steps_run = int(max(a.steps, min(50000, 5.0 / max(dtp / 5, 1e-6))))
+    _, dtp, _ = oracle_throughput(a.workload, n_sample, 60, 10, cores)     # calibration (thread pool warm)
+    steps_run = int(max(a.steps, min(100000, 6.0 / max(dtp / 60, 1e-6))))
     val, dt, params = oracle_throughput(a.workload, n_sample, steps_run, a.warmup, cores)
     sample = (f"{n_sample} envs x {steps_run} steps ({dt:.1f} s; --steps asked for {a.steps}) of {a.workload} on {cores} host threads "
               f"(C oracle port of the reference's Python path)")
@@ -287,6 +287,8 @@ def run_ours(a):
     t_wall = time.perf_counter() - t_wall0
     step_ms = np.array([s.elapsed_time(e) for s, e in zip(starts, stops)])
     total_ms = float(step_ms.sum())
+    if os.environ.get('LSM_BENCH_DUMP'):
+        print(f"[rank {rank}] per-step us: " + ' '.join(f"{v * 1e3:.1f}" for v in step_ms), file=sys.stderr, flush=True)
     # back-to-back (no flush) timing for reference
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

@@ -209,6 +209,18 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
     SpecFns f;
     const void* fn = generic_ptr(kp.c.dynamics);
     if (spec) { if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue; fn = f.agent; }
+#ifdef LSM_EXPERIMENTS
+    if (spec) {
+        // LSM_AGENT_SMEM=<bytes>: pad the agent kernel's dynamic shared memory so that fewer blocks fit an SM and the
+        // rest of the SM stays free for emit / pair blocks of another env range (overlap experiment)
+        static const int pad = env_int("LSM_AGENT_SMEM", 0);
+        if (pad > smem_bytes) {
+            static thread_local const void* done = nullptr;
+            if (done != fn) { cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, pad); done = fn; }
+            smem_bytes = pad;
+        }
+    }
+#endif
     return launch_one(fn, kp, (unsigned)grid_blocks, block_threads, smem_bytes, stream, persist_ptr, persist_bytes, spec);
 }
 

@@ -14,7 +14,7 @@ for w in cfg1 cfg3 cfg4; do
   python bench.py --workload $w --steps 60 --warmup 5 --no-cpu-baseline --no-extra-workloads --e2e-steps 5 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err
 done
 python tools/edge_bench.py > $O/${TAG}_edge_bench.jsonl 2> $O/${TAG}_edge_bench.err
-python tools/e2e_probe.py cfg2 > $O/${TAG}_e2e_probe.log 2>&1
+python tools/e2e_probe.py cfg2 8,8 16,8 > $O/${TAG}_e2e_probe.log 2>&1
 CMD="python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-extra-workloads --e2e-steps 3"
 $CMD > $O/${TAG}_plain.log 2>&1 &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 120 --csv --log-file $O/${TAG}_launches_cfg2.csv $CMD > $O/${TAG}_ncu1.log 2>&1
