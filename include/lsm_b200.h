@@ -151,7 +151,8 @@ typedef struct lsm_tuning {
     int32_t chunks;               /* env ranges one step is split into on library-owned streams (1..16); 0 = automatic
                                      (4 from 0.4 GB of observations per step, else 1) */
     int32_t pair_placement;       /* where the next step's HJ pair values are computed: 0 behind the emit kernel,
-                                     2 in front of the agent kernel, 3 between agent and emit kernel; -1 = automatic
+                                     2 in front of the agent kernel, 3 between agent and emit kernel, 4 at the tail of the
+                                     agent kernel itself (no pair kernel); -1 = automatic
                                      (0 for the 4-D grid, 3 for the 5-D grid) */
     int32_t packed_grid;          /* 1 corner-packed value table (one aligned chunk per lookup), 0 scattered gathers;
                                      -1 = automatic (packed when the table fits 2 GiB) */

@@ -460,11 +460,11 @@ int lsm_set_ttr_grid(lsm_handle* h, const lsm_grid_desc* g) {
 int lsm_set_tuning(lsm_handle* h, const lsm_tuning* t) {
     if (h == nullptr || t == nullptr) return fail(1, "lsm_set_tuning: null argument");
     if (t->chunks < 0 || t->chunks > 16) return fail(2, "lsm_set_tuning: chunks must be 0 (automatic) or 1..16");
-    if (t->pair_placement != -1 && t->pair_placement != 0 && t->pair_placement != 2 && t->pair_placement != 3) {
+    if (t->pair_placement != -1 && t->pair_placement != 0 && t->pair_placement != 2 && t->pair_placement != 3 && t->pair_placement != 4) {
 #ifdef LSM_EXPERIMENTS
         if (t->pair_placement != 1)
 #endif
-        return fail(2, "lsm_set_tuning: pair_placement must be -1 (automatic), 0 (behind the emit kernel), 2 (in front of the agent kernel) or 3 (between them)");
+        return fail(2, "lsm_set_tuning: pair_placement must be -1 (automatic), 0 (behind the emit kernel), 2 (in front of the agent kernel), 3 (between them) or 4 (tail of the agent kernel)");
     }
     if (t->packed_grid < -1 || t->packed_grid > 1) return fail(2, "lsm_set_tuning: packed_grid must be -1, 0 or 1");
     if (t->use_graph < -1 || t->use_graph > 1) return fail(2, "lsm_set_tuning: use_graph must be -1, 0 or 1");
@@ -550,7 +550,7 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
         }
     }
     out->pair_regs_per_thread = h->pair_regs;
-    out->launches_per_step = h->spec ? ((pair_path_li && h->pair_placement != 1) ? 3 : 2) : 1;   // agent, emit [, pair]
+    out->launches_per_step = h->spec ? ((pair_path_li && h->pair_placement != 1 && h->pair_placement != 4) ? 3 : 2) : 1;   // agent, emit [, pair]
     out->emit_record_bytes = h->spec ? h->geo.rec_bytes : 0;
     {
         const int K = (h->spec && h->chunks > 1 && ngroups >= 4LL * h->chunks * h->warps_per_block) ? h->chunks : 1;
@@ -605,6 +605,13 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
         cudaError_t e;
         k.pairval = nullptr;
         k.pair_late = 0;
+        k.pair_tail = 0;
+        if (pair_path && placement == 4) {
+            // the agent kernel leaves the next step's pair values behind itself (all modes: a reset / observe launch makes
+            // them valid for the step that follows)
+            k.pairval = h->d_pairval;
+            k.pair_tail = 1;
+        }
         if (pair_path && mode == lsm::MODE_STEP) {
             // HJ values of every ordered agent pair for the states this step starts from: normally left behind by the
             // previous launch (emit kernel / late pair kernel); recomputed here when the state was edited in between
@@ -735,8 +742,8 @@ static int launch(lsm_handle* h, int mode, int flag, const int32_t* action_idx, 
     if (h->spec) {
         h->pairval_valid = false;
         if (pair_path && (placement == 0 || placement == 3)) h->pairval_valid = true;
-        // placement 1: a masked reset refreshes only the masked environments, the others keep what they had
-        if (pair_path && placement == 1 && !(kp.debug & 1))
+        // placements 1 and 4: a masked reset refreshes only the masked environments, the others keep what they had
+        if (pair_path && ((placement == 1 && !(kp.debug & 1)) || placement == 4))
             h->pairval_valid = env_mask == nullptr ? true : (was_valid && mode != lsm::MODE_STEP);
     }
     return 0;

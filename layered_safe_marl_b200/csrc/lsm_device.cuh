@@ -99,6 +99,7 @@ struct KParams {
     double* pairval;           // [num_envs][N][N] raw HJ value of (ego, other) from lsm_pair_kernel; NULL = compute in-kernel
     unsigned char* emit_rec;   // [num_envs][sizeof(EmitRec)] per-env record consumed by lsm_emit_kernel
     int pair_late;             // lsm_pair_kernel launched BEHIND the emit kernel of the same step (runs beside its drain)
+    int pair_tail;             // the agent kernel itself computes the NEXT step's pair values at its tail (placement 4)
     float* adj_base;           // compact adjacency (lsm_set_compact_adjacency): [num_envs][E][E], NULL = dense adj output
     unsigned* adj_keep;        //                                             [num_envs][N][W]
     // fused COO edge output (lsm_set_edge_output); edge_index == nullptr = off

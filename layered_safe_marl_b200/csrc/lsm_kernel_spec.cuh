@@ -403,6 +403,32 @@ __device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EmitRec<
     }
 }
 
+// placement 4 ("tail"): the agent kernel computes the NEXT step's pair values itself, right after it has left the state
+// and the emit records behind (safety_filter.py:192-201 evaluates V(x_i - x_j) at the start of a step, from exactly this
+// state). The per-agent chain is latency bound (~20 % issue utilisation), so these lookups ride on idle issue slots of
+// warps that are resident anyway - no pair kernel competing with the emit kernel for the SMs, one launch less. Same
+// conditions and arithmetic as lsm_pair_kernel (raw values; entries of done agents / filter-off envs are left alone).
+template <int DYN, int N, int L>
+__device__ __noinline__ void pair_tail_phase(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L>* Rw, double* __restrict__ pairval,
+                                            int env0, int nenv, unsigned on_mask, int lane) {
+    const GridDev g = *vg;
+    for (int t = lane; t < nenv * N * N; t += 32) {
+        const int el = t / (N * N), r = t - el * (N * N);
+        const int i = r / N, j = r - i * N;
+        const EmitRec<DYN, N, L>& R = Rw[el];
+        if (!((on_mask >> ((el * N) & 31)) & 1u) || !R.next_filter || i == j || R.done[1][i] || R.done[1][j]) continue;
+        const double2 pi = R.pos[i], pj = R.pos[j];
+        double i2, i3, j2, j3;
+        if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+            const double2 vi = R.vel[N + i], vj = R.vel[N + j];
+            i2 = vi.x; i3 = vi.y; j2 = vj.x; j3 = vj.y;
+        } else {
+            i2 = R.air.theta[i]; i3 = R.air.spd_post[i]; j2 = R.air.theta[j]; j3 = R.air.spd_post[j];
+        }
+        pairval[(size_t)(env0 + el) * (N * N) + r] = pair_value_raw<DYN>(g, pi.x, pi.y, i2, i3, pj.x, pj.y, j2, j3);
+    }
+}
+
 template <int DYN, int N, int L>
 __device__ __forceinline__ void emit_obs_row(const EmitRec<DYN, N, L>& R, const AgentScratch<DYN, N, L>& P, int ai,
                                              int g /* landmark index */, double x, double y, double s2, double s3, float* o) {
@@ -1151,6 +1177,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 int4* dst = reinterpret_cast<int4*>(kp.emit_rec + (size_t)(env0 + el) * sizeof(REC));
                 for (int k = lane; k < Q; k += 32) dst[k] = src[k];
             }
+            // placement 4: next step's HJ pair values from the records still in shared memory
+            if (kp.pair_tail) pair_tail_phase<DYN, N, L>(&kp.vg, Rw, kp.pairval, env0, nenv, on_mask, lane);
         }
         __syncwarp();
     }

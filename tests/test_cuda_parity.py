@@ -233,8 +233,8 @@ def test_onehot_actions_and_numpy_outputs():
 
 @pytest.mark.parametrize('shape', ['di8', 'air10', 'di32'])
 def test_pair_value_variants_agree(shape):
-    """The next step's HJ pair values may be produced at three places of the pipeline (behind the emit kernel, in front
-    of the agent kernel, between the two; lsm_tuning.pair_placement) and from two layouts of the value grid (corner-packed
+    """The next step's HJ pair values may be produced at four places of the pipeline (behind the emit kernel, in front
+    of the agent kernel, between the two, at the tail of the agent kernel itself; lsm_tuning.pair_placement) and from two layouts of the value grid (corner-packed
     table, scattered gathers; lsm_tuning.packed_grid). All of them must drive the filter identically: same deconflicting
     agent, same activation mask and bit-identical states."""
     import torch
@@ -243,7 +243,8 @@ def test_pair_value_variants_agree(shape):
               di32=dict(num_agents=32, world_size=4))[shape]
     args = G.default_args(use_safety_filter=True, episode_length=250, **kw)
     n, T, episode = (64, 12, 6249) if shape != 'di32' else (16, 6, 6249)
-    variants = [dict(pair_placement=0), dict(pair_placement=2), dict(pair_placement=3), dict(pair_placement=0, packed_grid=0)]
+    variants = [dict(pair_placement=0), dict(pair_placement=2), dict(pair_placement=3), dict(pair_placement=4),
+                dict(pair_placement=0, packed_grid=0)]
     results = []
     rng = np.random.default_rng(4)
     acts = rng.integers(0, 25, (T, n, args.num_agents)).astype(np.int32)
@@ -486,5 +487,44 @@ def test_graph_replay_is_bit_identical(shape):
     li0, li1 = envs[0].launch_info(), envs[1].launch_info()
     assert li0['graph_replays'] == 0 and li0['graph_captures'] == 0
     assert li1['graph_replays'] >= T - 12 and 1 <= li1['graph_captures'] <= 8, li1
+    for e in envs:
+        e.close()
+
+
+@pytest.mark.parametrize('shape', ['di8', 'air10', 'di4'])
+def test_pair_tail_placement_through_resets(shape):
+    """pair_placement=4 (the agent kernel leaves the next step's pair values behind itself) against the pair kernel behind
+    the emit kernel: bit-identical outputs and states through auto-resets, a curriculum episode where the filter is off
+    for part of the envs' life, a state edit (stale values -> pair kernel in front once) and a masked reset."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    kw = dict(di8=dict(num_agents=8, world_size=2), air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6),
+              di4=dict(num_agents=4, world_size=2))[shape]
+    args = G.default_args(use_safety_filter=True, episode_length=7, **kw)
+    n, T = 160, 36
+    envs = [B200GraphVecEnv(args, num_envs=n, seed=13, tuning=dict(pair_placement=p)) for p in (0, 4)]
+    assert [e.launch_info()['launches_per_step'] for e in envs] == [3, 2]
+    rng = np.random.default_rng(3)
+    for e in envs:
+        e.reset(6249)
+    for t in range(T):
+        idx = rng.integers(0, 25, (n, args.num_agents)).astype(np.int32)
+        episode = 6249 if t < 20 else 3500
+        outs = []
+        for e in envs:
+            if t == 12:
+                st = e.get_state(); e.set_state(st)
+            if t == 24:
+                mask = torch.zeros(n, dtype=torch.uint8, device=e.device); mask[::3] = 1
+                from layered_safe_marl_b200 import _lib
+                _lib.check(e.lib.lsm_reset(e._h, mask.data_ptr(), 3500, e.seed, 1, e._stream()), 'lsm_reset')
+            o = e.step(torch.as_tensor(idx, device=e.device), episode)
+            outs.append([x.cpu().numpy().copy() for x in o[:6]] + [e.safe_action.cpu().numpy().copy()])
+        for k, (x, y) in enumerate(zip(*outs)):
+            assert np.array_equal(x.view(np.uint8), y.view(np.uint8)), f"step {t} output {k}"
+    sa, sb = envs[0].get_state(), envs[1].get_state()
+    assert int(sa['safety_filtered'].sum()) >= 0
+    for k in sa:
+        assert np.array_equal(np.asarray(sa[k]), np.asarray(sb[k]), equal_nan=True), f"state {k}"
     for e in envs:
         e.close()

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Sweep the product's launch-shape knobs (lsm_tuning: pair placement x env ranges) for a workload.
-usage: tools/tuning_sweep.py <workload> [steps]"""
+usage: tools/tuning_sweep.py <workload> [steps] [placements, e.g. 0,4] [chunks, e.g. 1,4]"""
 import os, sys
 import numpy as np
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -12,8 +12,10 @@ wl = sys.argv[1]; K = int(sys.argv[2]) if len(sys.argv) > 2 else 60
 args, flags, n, episode = B.build_args(wl)
 flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device='cuda')
 acts = torch.randint(0, 25, (K + 8, n, args.num_agents), device='cuda', dtype=torch.int32)
-for placement in (0, 3, 2):
-    for chunks in (1, 2, 4, 8):
+PL = [int(v) for v in sys.argv[3].split(',')] if len(sys.argv) > 3 else [0, 3, 2, 4]
+CH = [int(v) for v in sys.argv[4].split(',')] if len(sys.argv) > 4 else [1, 2, 4, 8]
+for placement in PL:
+    for chunks in CH:
         env = B200GraphVecEnv(args, num_envs=n, seed=1234, binary_cfg=flags, tuning=dict(pair_placement=placement, chunks=chunks))
         env.reset(episode)
         for t in range(8):
