@@ -390,11 +390,12 @@ def run_ours(a):
     else:
         d2h = small + dense_adj_bytes
     e2e_host = {"adjacency": ("compact over PCIe (1 E x E matrix + N keep masks per env) in env ranges, each range expanded to the dense "
-                              f"(n,N,E,E) float32 array by {env_h.host_threads} host threads with non-temporal stores as it lands, while "
+                              f"(n,N,E,E) float32 array by {env_h.host_threads} host threads as it lands, while "
                               "the DMA engine moves the later ranges and node_obs; the whole step is one C-ABI call (lsm_step_host)")
                              if compact else "dense over PCIe",
                 "host_bytes_written_per_step": d2h + (dense_adj_bytes if compact else 0),
-                "host_threads": env_h.host_threads}
+                "host_threads": env_h.host_threads,
+                "host_stores": "ordinary" if env_h.host_cached_stores else "streaming"}
     env_h.close()
     del env_h
 

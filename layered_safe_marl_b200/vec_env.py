@@ -108,7 +108,8 @@ class B200GraphVecEnv:
                  value_grid: Optional[HjGrid] = None, ttr_grid: Optional[HjGrid] = None,
                  binary_cfg=RewardBinaryConfig, weight_cfg=RewardWeightConfig, env_id_base: int = 0,
                  numpy_outputs: bool = False, auto_reset: bool = True, tuning: Optional[dict] = None,
-                 host_threads: Optional[int] = None, numa_bind: bool = False, host_chunks: Optional[int] = None):
+                 host_threads: Optional[int] = None, numa_bind: bool = False, host_chunks: Optional[int] = None,
+                 host_cached_stores: Optional[bool] = None):
         if not torch.cuda.is_available():
             raise RuntimeError("B200GraphVecEnv needs a CUDA device; there is no CPU fallback")
         self.lib = _lib.load()   # raises if the sm_100a library is missing
@@ -121,12 +122,12 @@ class B200GraphVecEnv:
         self._dev_ctx.__enter__()      # lsm_create adopts the current device; restored at the end of __init__
         try:
             self._init(args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
-                       auto_reset, tuning, host_threads, host_chunks)
+                       auto_reset, tuning, host_threads, host_chunks, host_cached_stores)
         finally:
             self._dev_ctx.__exit__(None, None, None)
 
     def _init(self, args, num_envs, seed, value_grid, ttr_grid, binary_cfg, weight_cfg, env_id_base, numpy_outputs,
-              auto_reset, tuning, host_threads, host_chunks=None):
+              auto_reset, tuning, host_threads, host_chunks=None, host_cached_stores=None):
         self.params = scenario_params_from_args(args, binary_cfg=binary_cfg, weight_cfg=weight_cfg)
         p = self.params
         self.num_envs = int(num_envs if num_envs is not None else args.n_rollout_threads)
@@ -233,7 +234,9 @@ class B200GraphVecEnv:
         # host-facing path (numpy_outputs): the adjacency crosses PCIe as ONE thresholded E x E matrix per env + the
         # per-observer keep masks and is expanded on the host (lsm_set_compact_adjacency / lsm_expand_adjacency_host)
         self._compact = None
-        self.host_cached_stores = False
+        # streaming (non-temporal) stores by default for the host-side adjacency expansion; ordinary stores were within the
+        # run-to-run noise of the hosts measured (profiles/experiments/r02_e2e_probe_threads_chunks.txt)
+        self.host_cached_stores = bool(host_cached_stores) if host_cached_stores is not None else False
         self.host_profile = None      # set to {} to accumulate wall-clock seconds of the host-side phases of _outputs
         if host_threads is None:
             local_world = max(1, int(os.environ.get('LOCAL_WORLD_SIZE', '1')))

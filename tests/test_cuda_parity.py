@@ -315,7 +315,9 @@ def test_host_outputs_compact_adjacency_is_byte_identical(shape):
     n, T, episode = 300, 30, 6249
     dev_env = B200GraphVecEnv(args, num_envs=n, seed=3)
     # uneven env ranges and thread shares on purpose (300 envs in 7 ranges, 3 host threads)
-    host_env = B200GraphVecEnv(args, num_envs=n, seed=3, numpy_outputs=True, host_chunks=7, host_threads=3)
+    # (ordinary stores for one shape, streaming stores for the others: both expansion paths)
+    host_env = B200GraphVecEnv(args, num_envs=n, seed=3, numpy_outputs=True, host_chunks=7, host_threads=3,
+                               host_cached_stores=(shape == 'air10'))
     assert host_env._compact is not None
     o1, o2 = dev_env.reset(episode), host_env.reset(episode)
     for a, b in zip(o1[:4], o2[:4]):

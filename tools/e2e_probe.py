@@ -15,8 +15,8 @@ combos = [tuple(int(v) for v in a.split(',')) for a in sys.argv[2:]] or [(8, 4),
 print('cpus', len(os.sched_getaffinity(0)), flush=True)
 for threads, chunks in combos:
     for cached in (False, True):
-        env = B200GraphVecEnv(args, num_envs=n, seed=1, binary_cfg=flags, numpy_outputs=True, host_threads=threads, host_chunks=chunks)
-        env.host_cached_stores = cached
+        env = B200GraphVecEnv(args, num_envs=n, seed=1, binary_cfg=flags, numpy_outputs=True, host_threads=threads, host_chunks=chunks,
+                              host_cached_stores=cached)
         env.reset(episode)
         rng = np.random.default_rng(0)
         K = 30
