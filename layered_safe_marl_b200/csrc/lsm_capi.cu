@@ -438,7 +438,7 @@ int lsm_set_value_grid(lsm_handle* h, const lsm_grid_desc* g) {
     }
     if (h->d_grads8) { cudaFree(h->d_grads8); h->d_grads8 = nullptr; }
     h->kp.vg.grads8 = nullptr;
-    if (h->spec && g->ndim == 5 && want_packed) {
+    if (h->spec && g->ndim == 5) {     // always: stencil32_grad<5> has no scattered alternative (104 MB for 41x41x24x9x9)
         cudaError_t e = cudaMalloc(&h->d_grads8, cells * 8 * sizeof(float));
         if (e == cudaSuccess) e = lsm::pad_grads_launch(g->grads, h->d_grads8, (long long)cells);
         if (e == cudaSuccess) e = cudaDeviceSynchronize();

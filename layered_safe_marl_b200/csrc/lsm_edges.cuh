@@ -186,7 +186,11 @@ __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(co
             }
         }
         __syncwarp();
-        for (int i = 0; i < N; ++i) {
+        // no connectivity flag changed in this step: every observer sees the same graph, count it once
+        bool uniform = true;
+#pragma unroll
+        for (int w = 0; w < W; ++w) uniform = uniform && dpre[w] == dpost[w];
+        for (int i = 0; i < (uniform ? 1 : N); ++i) {
             int cn = 0;
             for (int a = lane; a < E; a += 32) {
                 if ((keep[i * W + (a >> 5)] >> (a & 31)) & 1u) {
@@ -196,7 +200,9 @@ __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(co
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) cn += __shfl_xor_sync(0xffffffffu, cn, o);
-            if (lane == 0) { kp.edge_counts[(size_t)ee * N + i] = cn; s_cnt[(ee - e0) * N + i] = cn; }
+            if (uniform) {
+                for (int q = lane; q < N; q += 32) { kp.edge_counts[(size_t)ee * N + q] = cn; s_cnt[(ee - e0) * N + q] = cn; }
+            } else if (lane == 0) { kp.edge_counts[(size_t)ee * N + i] = cn; s_cnt[(ee - e0) * N + i] = cn; }
         }
         __syncwarp();
     }

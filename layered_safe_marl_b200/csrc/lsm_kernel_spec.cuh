@@ -200,7 +200,9 @@ __device__ __forceinline__ void stencil32_grad(const GridDev& g, const Stencil32
             const float4 v = ldg_hint(reinterpret_cast<const float4*>(g.grads) + lin, keep);
             out[0] = out[0] + weight * (double)v.x; out[1] = out[1] + weight * (double)v.y;
             out[2] = out[2] + weight * (double)v.z; out[3] = out[3] + weight * (double)v.w;
-        } else if (ND == 5 && g.grads8 != nullptr) {
+        } else if (ND == 5) {
+            // the specialised pipeline always carries the padded rows (lsm_set_value_grid): no run-time alternative inside
+            // the 32 unrolled corners - the per-agent kernel is bound by instruction fetch
             const float4 a = ldg_hint(reinterpret_cast<const float4*>(g.grads8) + 2 * (size_t)lin, keep);
             const float4 b = ldg_hint(reinterpret_cast<const float4*>(g.grads8) + 2 * (size_t)lin + 1, keep);
             out[0] = out[0] + weight * (double)a.x; out[1] = out[1] + weight * (double)a.y;
@@ -1232,11 +1234,21 @@ struct __align__(16) EmitShared {
 // Fused COO edge output of one environment: kept OUT OF LINE so that its registers do not count against
 // the occupancy of the dense path (69 -> 91 registers per thread when inlined, one resident block per SM fewer).
 template <int DYN, int N, int L, int WPE>
-__device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KParams& kp, int ee, const float* dthr) {
+__device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KParams& kp, int ee, const float* dthr, bool uniform) {
     using GEO = EmitGeom<DYN, N, L>;
     constexpr int E = GEO::E, W = GEO::W;
     constexpr int T = 32 * WPE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // `uniform`: no connectivity flag changed in this step, so every observer sees the SAME graph (the keep masks of all
+    // observers are equal): row counts and row offsets are computed once (for observer 0) and shared.
+    // (e0) where this environment's N graphs start in the global list: independent loads, one thread per observer, issued
+    //      before anything else (lsm_edge_count_kernel left: prefix inside its block's env run + base of that block)
+    for (int i = tid; i < N; i += T) {
+        const long long gb = S.range_base + kp.edge_block_base[kp.edge_block_ofs + (ee - kp.env_begin) / kp.edge_envs_per_block] +
+                             kp.edge_local[(size_t)ee * N + i];
+        S.gbase[i] = gb;
+        kp.edge_offsets[(size_t)ee * N + i] = gb;
+    }
     // (e1) non-zero bit mask of every row (one ballot per 32 columns)
     for (int a = warp; a < E; a += WPE) {
 #pragma unroll
@@ -1248,7 +1260,8 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
     }
     __syncthreads();
     // (e2) edges of row a as observer i sees it, then the exclusive prefix over the rows of each observer
-    for (int k = tid; k < N * E; k += T) {
+    const int NO = uniform ? 1 : N;
+    for (int k = tid; k < NO * E; k += T) {
         const int i = k / E, a = k - i * E;
         int cnt = 0;
         if ((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u) {
@@ -1258,7 +1271,7 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
         S.rowoff[k] = (unsigned short)cnt;
     }
     __syncthreads();
-    for (int i = warp; i < N; i += WPE) {
+    for (int i = warp; i < NO; i += WPE) {
         int running = 0;
         for (int c0 = 0; c0 < E; c0 += 32) {
             const int a = c0 + lane;
@@ -1269,18 +1282,12 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
             if (a < E) S.rowoff[i * E + a] = (unsigned short)(running + incl - v);
             running += __shfl_sync(0xffffffffu, incl, 31);
         }
-        if (lane == 0) {
-            // lsm_edge_count_kernel left: prefix inside its block's env run + base of that block inside the range
-            const long long gb = S.range_base + kp.edge_block_base[kp.edge_block_ofs + (ee - kp.env_begin) / kp.edge_envs_per_block] +
-                                 kp.edge_local[(size_t)ee * N + i];
-            S.gbase[i] = gb;
-            kp.edge_offsets[(size_t)ee * N + i] = gb;
-        }
     }
     __syncthreads();
     // (e3) fill. Dense graphs (mean degree > 8): one warp per (observer, row), lane = column inside a 32-column word,
     //      rank by popcount - coalesced stores. Sparse graphs: one LANE per (observer, row) walking the few set bits
-    //      of its row (a warp per row would spend ~40 instructions on a row that holds two edges).
+    //      of its row (a warp per row would spend ~40 instructions on a row that holds two edges). A lane per ROW with an
+    //      inner loop over the observers of a shared graph was slower (cfg4 / world 40: 2.07 vs 1.5 ms per step).
     {
         long long* const src = kp.edge_index;
         long long* const dst = kp.edge_index + kp.edge_capacity;
@@ -1288,13 +1295,13 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
         const unsigned lt = (1u << lane) - 1u;
         // total edges of the env = last observer's end; mean degree decides the strategy (block-uniform)
         int env_edges = 0;
-        for (int i = 0; i < N; ++i) env_edges += S.rowoff[i * E + E - 1];          // lower bound is enough for the choice
+        for (int i = 0; i < N; ++i) env_edges += S.rowoff[(uniform ? 0 : i) * E + E - 1];          // lower bound is enough for the choice
         if (env_edges > 8 * N * E) {
             for (int r = warp; r < N * E; r += WPE) {
                 const int i = r / E, a = r - i * E;
                 if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
                 const long long node0 = ((long long)ee * N + i) * E;
-                long long p0 = S.gbase[i] + S.rowoff[r];
+                long long p0 = S.gbase[i] + S.rowoff[uniform ? a : r];
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
                     const unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
@@ -1313,7 +1320,7 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
                 const int i = r / E, a = r - i * E;
                 if (!((S.keepm[i * W + (a >> 5)] >> (a & 31)) & 1u)) continue;
                 const long long node0 = ((long long)ee * N + i) * E;
-                long long p = S.gbase[i] + S.rowoff[r];
+                long long p = S.gbase[i] + S.rowoff[uniform ? a : r];
 #pragma unroll
                 for (int w = 0; w < W; ++w) {
                     unsigned m = S.rowmask[a * W + w] & S.keepm[i * W + w];
@@ -1331,7 +1338,7 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
         }
     }
     __syncthreads();
-    }
+}
 
 // PIE ("pair in emit"): also compute the next step's HJ pair values per environment after its copies are issued - the
 // placement that wins for few agents (one launch less; the lookups of an 8-agent environment occupy half a block once).
@@ -1501,7 +1508,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             __syncthreads();
         }
-        if (edges) emit_edges<DYN, N, L, WPE>(S, kp, ee, dthr);
+        if (edges) emit_edges<DYN, N, L, WPE>(S, kp, ee, dthr, any_change == 0u);
         if (compact) {
             unsigned* kdst = kp.adj_keep + (size_t)ee * (N * W);
             for (int k = tid; k < N * W; k += T) kdst[k] = any_disc != 0u ? S.keepm[k] : 0xffffffffu;
