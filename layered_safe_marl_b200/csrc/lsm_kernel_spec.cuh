@@ -656,6 +656,42 @@ __device__ __noinline__ bool goal_reached_cold(double x, double y, double s2, do
 // ---------------------------------------------------------------------------------------------
 // K_b: per-agent physics. A warp owns EPW <= 32 / N consecutive environments, N lanes each.
 // ---------------------------------------------------------------------------------------------
+// Episode summary of a resetting environment (graphworker, env_wrappers.py:861-874 + Scenario.info_callback's episode
+// statistics): means over the env's N agents. Runs once per episode, so it lives OUT of the per-agent kernel's
+// instruction stream (whole warp calls it; lanes of envs that do not reset take part in the shuffles only).
+template <int N>
+__device__ __noinline__ void episode_summary(const KParams& kp, int le, int env, bool write, int ep_len, double ep_travel_dist,
+                                            int ep_done, int reached, int ep_conflict, int ep_multi, double ep_min_dist) {
+    const lsm_config& c = kp.c;
+    double s_len = 0, s_dist = 0, s_done = 0, s_reached = 0, s_conf = 0, s_min = 0, s_multi = 0, mn = INFINITY;
+    const double len_i = ep_len == 0 ? 1.0 : (double)ep_len;
+#pragma unroll 1
+    for (int k = 0; k < N; ++k) {
+        const int src = (le * N + k) & 31;
+        s_len += (double)__shfl_sync(0xffffffffu, ep_len, src);
+        s_dist += __shfl_sync(0xffffffffu, ep_travel_dist, src);
+        s_done += (double)__shfl_sync(0xffffffffu, ep_done, src);
+        s_reached += (double)__shfl_sync(0xffffffffu, reached, src);
+        s_conf += __shfl_sync(0xffffffffu, (double)ep_conflict / len_i, src);
+        s_multi += __shfl_sync(0xffffffffu, (double)ep_multi / len_i, src);
+        const double md = __shfl_sync(0xffffffffu, ep_min_dist, src);
+        s_min += md;
+        if (md < mn) mn = md;
+    }
+    if (write) {
+        double* out = kp.b.ep_info + (size_t)env * LSM_EP_COUNT;
+        out[LSM_EP_TRAVEL_TIME_MEAN] = c.dt * (s_len / N);
+        out[LSM_EP_TRAVEL_DISTANCE_MEAN] = s_dist / N;
+        out[LSM_EP_DONE_PERCENTAGE] = s_done / N;
+        out[LSM_EP_NUM_REACHED_GOAL_MEAN] = s_reached / N;
+        out[LSM_EP_CONFLICT_PERCENTAGE] = s_conf / N;
+        const double mm = s_min / N;
+        out[LSM_EP_MIN_DISTANCE_MEAN] = isinf(mm) ? c.coordination_range : mm;
+        out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
+        out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
+    }
+}
+
 template <int DYN, int N, int L, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_constant__ KParams kp) {
     using REC = EmitRec<DYN, N, L>;
@@ -1053,32 +1089,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
         const bool sample = (kp.mode == MODE_STEP) ? true : (kp.flag != 0);
         const unsigned reset_lanes = __ballot_sync(0xffffffffu, do_reset);
         if (reset_lanes != 0u) {
-            double s_len = 0, s_dist = 0, s_done = 0, s_reached = 0, s_conf = 0, s_min = 0, s_multi = 0, mn = INFINITY;
-            const double len_i = ep_len == 0 ? 1.0 : (double)ep_len;
-            for (int k = 0; k < N; ++k) {
-                const int src = (le * G + k) & 31;
-                s_len += (double)__shfl_sync(0xffffffffu, ep_len, src);
-                s_dist += __shfl_sync(0xffffffffu, ep_travel_dist, src);
-                s_done += (double)__shfl_sync(0xffffffffu, ep_done, src);
-                s_reached += (double)__shfl_sync(0xffffffffu, reached, src);
-                s_conf += __shfl_sync(0xffffffffu, (double)ep_conflict / len_i, src);
-                s_multi += __shfl_sync(0xffffffffu, (double)ep_multi / len_i, src);
-                const double md = __shfl_sync(0xffffffffu, ep_min_dist, src);
-                s_min += md;
-                if (md < mn) mn = md;
-            }
-            if (do_reset && ai == 0) {
-                double* out = kp.b.ep_info + (size_t)env * LSM_EP_COUNT;
-                out[LSM_EP_TRAVEL_TIME_MEAN] = c.dt * (s_len / N);
-                out[LSM_EP_TRAVEL_DISTANCE_MEAN] = s_dist / N;
-                out[LSM_EP_DONE_PERCENTAGE] = s_done / N;
-                out[LSM_EP_NUM_REACHED_GOAL_MEAN] = s_reached / N;
-                out[LSM_EP_CONFLICT_PERCENTAGE] = s_conf / N;
-                const double mm = s_min / N;
-                out[LSM_EP_MIN_DISTANCE_MEAN] = isinf(mm) ? c.coordination_range : mm;
-                out[LSM_EP_MIN_DISTANCE_MIN] = isinf(mn) ? c.coordination_range : mn;
-                out[LSM_EP_MULTIPLE_ENGAGEMENT_PERCENTAGE] = s_multi / N;
-            }
+            episode_summary<N>(kp, le, env, do_reset && ai == 0, ep_len, ep_travel_dist, ep_done, reached, ep_conflict, ep_multi,
+                               ep_min_dist);
             if (do_reset && kp.mode == MODE_STEP && kp.b.term_f64 != nullptr) {
                 // `parity` already names the slot this step's values go to; last step's are still in the other one
                 if (agent_on)
