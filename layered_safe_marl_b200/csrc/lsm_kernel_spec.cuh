@@ -119,11 +119,17 @@ __device__ __forceinline__ double div_exact(double a, double b, double y /* RN(1
     return fma(r, y, q0);
 }
 
-// periodic grid index: i mod n in [0, n). In-grid states land in [0, n) (an angle difference wrapped to one period), so
-// the integer division lives out of line - one shared copy instead of ~60 instructions per dimension of every unrolled
-// stencil (the per-agent kernel is bound by instruction fetch). Same result for every int.
+// periodic grid index: i mod n in [0, n). In-grid states land in [0, n) (an angle difference wrapped to one period), so the
+// integer division (~30 instructions) sits behind an "already in range" test. Measured on B200 (same-box A/B,
+// profiles/experiments/r02_wrap_index_ab.txt): for the 5-D airtaxi grid one shared out-of-line copy is faster (cfg3 352.7
+// -> 348.7 us; the unrolled 32-corner stencils are bound by instruction fetch), for the 4-D grids the call costs the
+// pair kernel six registers and a stack frame (cfg2 back-to-back 40.4 -> 43.2 us), so those keep it inline.
 __device__ __noinline__ int wrap_index_slow(int i, int n) { i %= n; if (i < 0) i += n; return i; }
-__device__ __forceinline__ int wrap_index(int i, int n) { return ((unsigned)i < (unsigned)n) ? i : wrap_index_slow(i, n); }
+template <bool OUT_OF_LINE>
+__device__ __forceinline__ int wrap_index(int i, int n) {
+    if constexpr (OUT_OF_LINE) return ((unsigned)i < (unsigned)n) ? i : wrap_index_slow(i, n);
+    else { if ((unsigned)i >= (unsigned)n) { i %= n; if (i < 0) i += n; } return i; }
+}
 
 template <int ND>
 struct Stencil32 {
@@ -147,7 +153,7 @@ __device__ __forceinline__ void stencil32_setup(const GridDev& g, const double (
         const int n = g.shape[d];
         int il = (int)fl, ih = il + 1;          // |fl| <= 1e9 fits in int32
         if (g.periodic[d]) {
-            il = wrap_index(il, n);
+            il = wrap_index<(ND == 5)>(il, n);
             ih = il + 1 == n ? 0 : il + 1;          // (il + 1) mod n
         } else {
             il = min(max(il, 0), n - 1);
@@ -285,7 +291,7 @@ __device__ __forceinline__ bool packed_value(const GridDev& g, const double (&x)
         wlo[d] = 1.0 - w; whi[d] = w;
         const int n = g.shape[d];
         if (g.periodic[d]) {
-            const int il = wrap_index((int)fl, n);
+            const int il = wrap_index<(ND == 5)>((int)fl, n);
             cell += il * mul; mul *= n;
         } else {
             const int c = min(max((int)fl, -1), n - 1) + 1;
@@ -1242,6 +1248,7 @@ struct __align__(16) EmitShared {
     alignas(16) float dthr[GEO::NBUF][GEO::EE];              // radius-thresholded distance matrix (float32, what adj stores)
     alignas(16) float nodes[GEO::NBUF][GEO::CR * GEO::F];    // node-row chunk
     unsigned disc[2][GEO::W], keepm[N * GEO::W];
+    unsigned sel[N * GEO::W];                                // KParams::sel_tab, read once per block (not once per environment)
     // fused COO edge output: non-zero bit mask of every row of the thresholded matrix, exclusive row offsets per observer
     unsigned rowmask[GEO::E * GEO::W];
     unsigned short rowoff[N * GEO::E];      // <= E * (E - 1) = 18 240 for the largest configuration
@@ -1437,6 +1444,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             kp.edge_offsets[(size_t)kp.b.num_envs * N] = b + kp.edge_range_totals[kp.edge_range];     // nnz of the step
     }
 
+    for (int k = tid; k < N * W; k += T) S.sel[k] = kp.sel_tab[k];     // visible after the first barrier of the loop below
     auto prefetch = [&](int env, int slot) {
         const int4* src = reinterpret_cast<const int4*>(kp.emit_rec + (size_t)env * sizeof(REC));
         int4* dst = reinterpret_cast<int4*>(&S.rec[slot]);
@@ -1521,7 +1529,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
         if (any_disc != 0u || edges) {
             for (int k = tid; k < N * W; k += T) {
                 const int w = k % W;
-                const unsigned sel = kp.sel_tab[k];
+                const unsigned sel = S.sel[k];
                 S.keepm[k] = ~((S.disc[1][w] & sel) | (S.disc[0][w] & ~sel));
             }
             __syncthreads();
