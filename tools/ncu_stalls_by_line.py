@@ -1,3 +1,8 @@
+#!/usr/bin/env python
+"""Per-source-line roll-up of an ncu source page: stall samples (by reason) and executed instructions.
+    ncu -i prof.ncu-rep --page source --csv --print-source cuda,sass -k regex:<kernel> --launch-count 1 > src.csv
+    python tools/ncu_stalls_by_line.py src.csv [top_n]
+(inlined frames are listed at every level, so a line's share includes the lines inlined into it)"""
 import csv, sys
 path = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 rows = list(csv.reader(open(path)))
