@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define LSM_ABI_VERSION 4
+#define LSM_ABI_VERSION 5
 
 enum { LSM_DYN_DOUBLE_INTEGRATOR = 0, LSM_DYN_AIRTAXI = 1 };
 
@@ -71,7 +71,7 @@ enum {
 enum {
     LSM_AI_REACHED = 0, LSM_AI_DONE, LSM_AI_SAFETY_FILTERED, LSM_AI_DECONFLICT_IDX,
     LSM_AI_NUM_COLLISIONS, LSM_AI_EP_TRAVEL_LEN, LSM_AI_EP_CONFLICT, LSM_AI_EP_MULTI,
-    LSM_AI_EP_DONE, LSM_AI_COUNT
+    LSM_AI_EP_DONE, LSM_AI_NUM_OBST_COLLISIONS /* world.num_obstacle_collisions (obstacle extension) */, LSM_AI_COUNT
 };
 enum { LSM_LF_X = 0, LSM_LF_Y, LSM_LF_HEADING, LSM_LF_SPEED, LSM_LF_SIN, LSM_LF_COS, LSM_LF_COUNT };
 enum { LSM_EF_CURRICULUM_RATIO = 0, LSM_EF_COUNT };
@@ -90,17 +90,23 @@ enum {
     LSM_TF_X = 0, LSM_TF_Y, LSM_TF_MIN_REL_DIST, LSM_TF_DIST_LEFT, LSM_TF_TIMES_REQ_NEW, LSM_TF_TIMES_REQ_OLD,
     LSM_TF_DISTS_GOAL_NEW, LSM_TF_DISTS_GOAL_OLD, LSM_TF_GOAL_MIN_TIME, LSM_TF_COUNT
 };
-enum { LSM_TI_NUM_COLLISIONS = 0, LSM_TI_SAFETY_FILTERED, LSM_TI_COUNT };
+enum { LSM_TI_NUM_COLLISIONS = 0, LSM_TI_SAFETY_FILTERED, LSM_TI_NUM_OBST_COLLISIONS, LSM_TI_COUNT };
 
 #define LSM_MAX_AGENTS 32
 #define LSM_MAX_LANDMARKS 128
+#define LSM_MAX_OBSTACLES 32
 #define LSM_NUM_ACTIONS 25
 
 typedef struct lsm_config {
     int32_t dynamics, num_agents, num_landmarks /* per agent */, episode_length;
     int32_t num_total_episode, num_internal_step;
     uint32_t flags;
-    int32_t _pad;
+    int32_t num_obstacles;        /* --num_obstacles. 0 in every shipped script; > 0 is a DECLARED EXTENSION (the reference raises,
+                                     navigation_graph_safe.py:1064-1065,1087 / :975-989): obstacles are placed, collide and enter the
+                                     distance matrix as the reference's own code does (:230-236,402-404,452-465,1204-1249,
+                                     core.py:489-543); an obstacle is never disconnected and its 'relative' node features are the
+                                     landmark builders' (utils.py:167-190,224-255) with heading 0, speed 0, entity type 2.
+                                     Runs the generic fused kernel */
     double world_size;
     double dt, coordination_range, dist_thresh, heading_thresh, speed_thresh;
     double goal_speed_min, goal_speed_max, separation_distance_target;
@@ -132,7 +138,7 @@ typedef struct lsm_buffers {
     int32_t *env_i32;             /* [LSM_EI_COUNT][num_envs] */
     /* outputs */
     float *obs;                   /* [num_envs][N][D]       D = 7 (DI) | 6 (airtaxi) */
-    float *node_obs;              /* [num_envs][N][E][F]    F = 10 (DI) | 11 (airtaxi) | 7 (global features), E = N(1+L) */
+    float *node_obs;              /* [num_envs][N][E][F]    F = 10 (DI) | 11 (airtaxi) | 7 (global features), E = N(1+L) + O */
     float *adj;                   /* [num_envs][N][E][E] */
     float *reward;                /* [num_envs][N] */
     uint8_t *done;                /* [num_envs][N] */
@@ -143,6 +149,7 @@ typedef struct lsm_buffers {
     double *term_f64;             /* [LSM_TF_COUNT][num_envs][N] */
     int32_t *term_i32;            /* [LSM_TI_COUNT][num_envs][N] */
     double *term_env_f64;         /* [num_envs] */
+    double *obstacles;            /* [2][num_envs][O] obstacle x / y; required when num_obstacles > 0, ignored otherwise */
 } lsm_buffers;
 
 /* Launch-shape choices a caller may override (lsm_set_tuning, right after lsm_create; 0 / -1 = automatic). These are

@@ -11,7 +11,7 @@ from . import _build
 class LsmConfig(C.Structure):
     _fields_ = [('dynamics', C.c_int32), ('num_agents', C.c_int32), ('num_landmarks', C.c_int32),
                 ('episode_length', C.c_int32), ('num_total_episode', C.c_int32),
-                ('num_internal_step', C.c_int32), ('flags', C.c_uint32), ('_pad', C.c_int32),
+                ('num_internal_step', C.c_int32), ('flags', C.c_uint32), ('num_obstacles', C.c_int32),
                 ('world_size', C.c_double), ('dt', C.c_double), ('coordination_range', C.c_double),
                 ('dist_thresh', C.c_double), ('heading_thresh', C.c_double), ('speed_thresh', C.c_double),
                 ('goal_speed_min', C.c_double), ('goal_speed_max', C.c_double),
@@ -38,7 +38,8 @@ class LsmBuffers(C.Structure):
                 ('obs', C.c_void_p), ('node_obs', C.c_void_p), ('adj', C.c_void_p),
                 ('reward', C.c_void_p), ('done', C.c_void_p), ('safe_action', C.c_void_p),
                 ('ep_info', C.c_void_p), ('reward_individual', C.c_void_p),
-                ('term_f64', C.c_void_p), ('term_i32', C.c_void_p), ('term_env_f64', C.c_void_p)]
+                ('term_f64', C.c_void_p), ('term_i32', C.c_void_p), ('term_env_f64', C.c_void_p),
+                ('obstacles', C.c_void_p)]
 
 
 class LsmTuning(C.Structure):

@@ -148,10 +148,13 @@ class ScenarioParams:
     diff_from_filtered_action_rew: float
     min_reward: float
     max_reward: float
+    # DECLARED EXTENSION (BASELINE config 3 '+ obstacles'): the reference raises for num_obstacles > 0, see
+    # scenario_params_from_args. Entities are agents, landmarks, obstacles (core.py:489-496).
+    num_obstacles: int = 0
 
     @property
     def num_entities(self) -> int:
-        return self.num_agents * (1 + self.num_landmarks)
+        return self.num_agents * (1 + self.num_landmarks) + self.num_obstacles
 
     @property
     def obs_dim(self) -> int:
@@ -203,9 +206,17 @@ def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
         agent_max_speed = AirTaxiConfig.V_MAX             # core.py:323
     else:
         raise NotImplementedError(f"dynamics_type {dyn_name!r}")
-    if int(getattr(args, 'num_obstacles', 0)) != 0:
-        # the reference itself raises for obstacles in this scenario
+    num_obstacles = int(getattr(args, 'num_obstacles', 0))
+    if num_obstacles != 0 and not bool(getattr(args, 'obstacle_extension', False)):
+        # the reference itself raises for obstacles in this scenario: 'relative' node features at
+        # navigation_graph_safe.py:1064-1065,1087, 'global' one statement later on the N(1+L)-entry disconnect mask (:975-989)
         raise ValueError("obstacle 0 not supported")
+    # args.obstacle_extension=True (not a reference argument) opts into the DECLARED extension of SURVEY.md 8c: obstacles are
+    # placed, collide (info 'Num_obst_collisions') and enter the distance matrix exactly as the reference's own code does
+    # (:230-236, 402-404, 452-465, 1204-1249, core.py:489-543); the two statements that raise are completed as: an obstacle is
+    # never disconnected, and its 'relative' node features are the landmark builders' with heading 0, speed 0, entity type 2.
+    if num_obstacles < 0 or num_obstacles > 32:
+        raise ValueError("num_obstacles must be in [0, 32]")
     if int(getattr(args, 'num_scripted_agents', 0)) != 0 or int(getattr(args, 'num_walls', 0)) != 0:
         raise NotImplementedError("scripted agents / walls are not part of the shipped scenario")
     graph_feat_type = getattr(args, 'graph_feat_type', 'relative')
@@ -257,4 +268,5 @@ def scenario_params_from_args(args, binary_cfg=RewardBinaryConfig,
         diff_from_filtered_action_rew=float(weight_cfg.DIFF_FROM_FILTERED_ACTION),
         min_reward=float(weight_cfg.MIN_REWARD),
         max_reward=float(weight_cfg.MAX_REWARD),
+        num_obstacles=num_obstacles,
     )

@@ -170,6 +170,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     if (cfg->num_internal_step < 1) return fail(2, "lsm_create: num_internal_step must be >= 1");
     if (cfg->num_total_episode < 1) return fail(2, "lsm_create: num_total_episode must be >= 1");
     if (cfg->episode_length < 1) return fail(2, "lsm_create: episode_length must be >= 1");
+    if (cfg->num_obstacles < 0 || cfg->num_obstacles > LSM_MAX_OBSTACLES) return fail(2, "lsm_create: num_obstacles must be in [0, 32]");
 
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -199,8 +200,9 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
 
     lsm::KParams& kp = h->kp;
     kp.c = *cfg;
-    const int M = N * L, E = N + M;
-    kp.N = N; kp.L = L; kp.M = M; kp.E = E;
+    const int O = cfg->num_obstacles;           // declared extension (lsm_b200.h): entities are agents, landmarks, obstacles
+    const int M = N * L, E = N + M + O;
+    kp.N = N; kp.L = L; kp.M = M; kp.E = E; kp.O = O;
     kp.D = cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 7 : 6;
     kp.F = (cfg->flags & LSM_FLAG_GRAPH_FEAT_GLOBAL) ? 7 : (cfg->dynamics == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11);
     kp.G = next_pow2(N);
@@ -257,6 +259,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     sl.rawx = take(dN, 8); sl.rawy = take(dN, 8);
     sl.lx = take(dM, 8); sl.ly = take(dM, 8); sl.lh = take(dM, 8); sl.lsp = take(dM, 8);
     sl.lsin = take(dM, 8); sl.lcos = take(dM, 8);
+    sl.ox = take(8 * O, 8); sl.oy = take(8 * O, 8);
     sl.daa = take(8 * N * N, 8);
     sl.dthr = take(4 * E * E, 16);
     sl.goal_pre = take(iN, 4); sl.goal_post = take(iN, 4); sl.reached_pre = take(iN, 4); sl.reached_post = take(iN, 4);
@@ -269,7 +272,8 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     // both node-feature types ('relative', which every shipped script uses, and 'global') run the specialised pipeline; the
     // float32 interpolation arithmetic (LSM_FLAG_INTERP_FLOAT32, a parity mode) lives in the generic kernel only, so that
     // the specialised kernels carry none of its code
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_INTERP_FLOAT32);
+    // so does the obstacle extension (E = N(1+L) + O is not a compile-time shape of the specialised kernels)
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_INTERP_FLOAT32) && O == 0;
 #ifdef LSM_EXPERIMENTS
     { const char* force_generic = std::getenv("LSM_FORCE_GENERIC"); if (force_generic != nullptr && force_generic[0] == '1') h->spec = false; }
 #endif
@@ -332,6 +336,7 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     kp.num_pairs = (int)(pairs.size() / 2);
     std::vector<uint32_t> sel((size_t)N * kp.W, 0u);
     for (int i = 0; i < N; ++i) for (int ent = 0; ent < E; ++ent) {
+        if (ent >= N + M) continue;                 // obstacles have no owner (their pre / post view is the same: never disconnected)
         const int owner = ent < N ? ent : (ent - N) % N;
         if (owner <= i) sel[(size_t)i * kp.W + (ent >> 5)] |= 1u << (ent & 31);
     }
@@ -480,6 +485,7 @@ int lsm_bind_buffers(lsm_handle* h, const lsm_buffers* b) {
     const void* ptrs[] = { b->agent_f64, b->agent_i32, b->landmarks, b->env_f64, b->env_i32, b->obs, b->node_obs,
                            b->adj, b->reward, b->done, b->safe_action, b->ep_info };
     for (const void* p : ptrs) if (p == nullptr) return fail(2, "lsm_bind_buffers: every buffer pointer must be non-null");
+    if (h->kp.O > 0 && b->obstacles == nullptr) return fail(2, "lsm_bind_buffers: obstacles must be non-null when num_obstacles > 0");
     if (((uintptr_t)b->adj & 15u) || ((uintptr_t)b->node_obs & 15u))
         return fail(2, "lsm_bind_buffers: adj and node_obs must be 16-byte aligned");
     if ((b->term_f64 != nullptr) != (b->term_i32 != nullptr) || (b->term_f64 != nullptr) != (b->term_env_f64 != nullptr))

@@ -52,6 +52,7 @@ struct SmemLayout {
     int spd_post, sth, cth;                // doubles [N]
     int rawx, rawy;                        // doubles [N] decoded raw controls
     int lx, ly, lh, lsp, lsin, lcos;       // doubles [M]
+    int ox, oy;                            // doubles [O] obstacle positions (obstacle extension)
     int daa;                               // doubles [N*N] agent-agent distances
     int dthr;                              // floats [E*E] radius-thresholded distances (16 B aligned)
     int goal_pre, goal_post, reached_pre, reached_post, done_pre, done_post;  // ints [N]
@@ -74,6 +75,7 @@ struct KParams {
     int mode;
     int flag;                  // STEP: auto_reset, RESET: sample
     int N, L, M, E, D, F;
+    int O;                     // obstacles (declared extension, lsm_config.num_obstacles); E = N + M + O
     int G;                     // lanes per env (power of two >= N)
     int EPW;                   // envs per warp = 32 / G
     int W;                     // 32-bit mask words per entity set

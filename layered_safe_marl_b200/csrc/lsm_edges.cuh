@@ -273,10 +273,14 @@ __global__ void __launch_bounds__(128) lsm_world_graph_kernel(const __grid_const
         if (e < N) {
             x = kp.b.agent_f64[LSM_AF_X * fs + env * N + e]; y = kp.b.agent_f64[LSM_AF_Y * fs + env * N + e];
             disc = kp.b.agent_i32[LSM_AI_DONE * fs + env * N + e] != 0;
-        } else {
+        } else if (e < N + M) {
             const int m = e - N, order = m / N, owner = m - order * N;
             x = kp.b.landmarks[LSM_LF_X * ls + env * M + m]; y = kp.b.landmarks[LSM_LF_Y * ls + env * M + m];
             disc = kp.b.agent_i32[LSM_AI_REACHED * fs + env * N + owner] > order;
+        } else {   // obstacle (extension): never disconnected
+            const int k = e - N - M;
+            x = kp.b.obstacles[((size_t)0 * n + env) * kp.O + k]; y = kp.b.obstacles[((size_t)1 * n + env) * kp.O + k];
+            disc = false;
         }
     };
     long long p = pass ? offsets[env] : 0;

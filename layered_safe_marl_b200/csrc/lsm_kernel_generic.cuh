@@ -8,6 +8,7 @@ namespace lsm {
 struct EnvSmem {
     double *ax, *ay, *as2, *as3, *vpre_x, *vpre_y, *vpost_x, *vpost_y, *spd_post, *sth, *cth, *rawx, *rawy;
     double *lx, *ly, *lh, *lsp, *lsin, *lcos, *daa;
+    double *ox, *oy;                    // obstacles (extension)
     float* dthr;
     int *goal_pre, *goal_post, *reached_pre, *reached_post, *done_pre, *done_post;
     unsigned *disc_pre, *disc_post, *keepm;
@@ -20,6 +21,7 @@ struct EnvSmem {
         lx = (double*)(base + sl.lx); ly = (double*)(base + sl.ly); lh = (double*)(base + sl.lh);
         lsp = (double*)(base + sl.lsp); lsin = (double*)(base + sl.lsin); lcos = (double*)(base + sl.lcos);
         daa = (double*)(base + sl.daa); dthr = (float*)(base + sl.dthr);
+        ox = (double*)(base + sl.ox); oy = (double*)(base + sl.oy);
         goal_pre = (int*)(base + sl.goal_pre); goal_post = (int*)(base + sl.goal_post);
         reached_pre = (int*)(base + sl.reached_pre); reached_post = (int*)(base + sl.reached_post);
         done_pre = (int*)(base + sl.done_pre); done_post = (int*)(base + sl.done_post);
@@ -27,6 +29,15 @@ struct EnvSmem {
         keepm = (unsigned*)(base + sl.keepm);
     }
 };
+
+// navigation_graph_safe.py:452-465 is_obstacle_collision (no walls): any obstacle closer than 1.05 * (size + size)
+__device__ __forceinline__ bool obstacle_collision(const double* ox, const double* oy, int O, double px, double py) {
+    for (int k = 0; k < O; ++k) {
+        const double dx = ox[k] - px, dy = oy[k] - py;
+        if (sqrt(dx * dx + dy * dy) < 1.05 * (0.050 + 0.050)) return true;
+    }
+    return false;
+}
 
 // World.apply_safety_filter for ONE ego agent (core.py:648-677; safety_filter.py:203-260, 378-433)
 template <int DYN>
@@ -69,7 +80,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
     const int lane = threadIdx.x & 31;
     const int warp_in_block = threadIdx.x >> 5;
     const int warps_per_block = blockDim.x >> 5;
-    const int N = kp.N, L = kp.L, M = kp.M, E = kp.E, G = kp.G, EPW = kp.EPW, W = kp.W;
+    const int N = kp.N, L = kp.L, M = kp.M, E = kp.E, G = kp.G, EPW = kp.EPW, W = kp.W, O = kp.O;
     const int Dobs = kp.D, F = kp.F;
     const long long n = kp.b.num_envs;
     const int le = lane / G;            // local env of this lane in the per-agent phases
@@ -94,7 +105,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
         double x = 0, y = 0, s2 = 0, s3 = 0, p_dist = 0, state_time = 0, min_rel = INFINITY, goal_min_time = INFINITY;
         double times_old = -1, dists_old = -1, dist_left = -1, ep_travel_dist = 0, ep_min_dist = INFINITY, action_diff = 0;
         int reached = 0, done = 0, safety_filtered = 0, deconflict = -1, ncoll = 0;
-        int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0;
+        int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0, nobst = 0;
         int current_step = 0, reset_count = 0, parity = 0;
         double ratio = 0.0;
         if (env_on) {
@@ -113,6 +124,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
             safety_filtered = *AIP(LSM_AI_SAFETY_FILTERED); deconflict = *AIP(LSM_AI_DECONFLICT_IDX);
             ncoll = *AIP(LSM_AI_NUM_COLLISIONS); ep_len = *AIP(LSM_AI_EP_TRAVEL_LEN);
             ep_conflict = *AIP(LSM_AI_EP_CONFLICT); ep_multi = *AIP(LSM_AI_EP_MULTI); ep_done = *AIP(LSM_AI_EP_DONE);
+            if (O > 0) nobst = *AIP(LSM_AI_NUM_OBST_COLLISIONS);
         }
         double times_req = times_old, dists_goal = dists_old;
         // landmarks of the warp's EPW environments: contiguous runs per field
@@ -131,6 +143,16 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     }
                     m += 32;
                     while (m >= M) { m -= M; ++el; }
+                }
+            }
+        }
+        if (O > 0) {   // obstacles of the warp's environments: [2][n][O]
+            for (int idx = lane; idx < EPW * O; idx += 32) {
+                const int el = idx / O, k = idx - el * O;
+                if (env0 + el < n) {
+                    unsigned char* eb = wbase + (size_t)el * kp.sl.bytes_per_env;
+                    ((double*)(eb + kp.sl.ox))[k] = kp.b.obstacles[((size_t)0 * (size_t)n + (size_t)(env0 + el)) * (size_t)O + k];
+                    ((double*)(eb + kp.sl.oy))[k] = kp.b.obstacles[((size_t)1 * (size_t)n + (size_t)(env0 + el)) * (size_t)O + k];
                 }
             }
         }
@@ -373,6 +395,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                     const bool r2 = goal_reached<DYN>(x, y, th2, sp2, gx, gy, S.lh[goal_post], S.lsp[goal_post], q);
                     if (r2 && times_req == -1.0) { times_req = (double)current_step * c.dt; dists_goal = p_dist; dist_left = dist; }
                     if (times_req == -1.0) { dists_goal = p_dist; dist_left = dist; }
+                    if (obstacle_collision(S.ox, S.oy, O, x, y)) nobst += 1;     // navigation_graph_safe.py:402-404
                     for (int a = 0; a < N; ++a) {
                         if (a == ai) continue;
                         if (S.daa[ai * N + a] < 1.05 * (0.050 + 0.050)) ncoll += 1;
@@ -448,6 +471,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 if (agent_on)
                     term_snapshot(kp.b, (size_t)env * N + ai, (size_t)kp.b.num_envs * N, x, y, min_rel, dist_left, times_req, times_old,
                                   dists_goal, dists_old, goal_min_time, ncoll, safety_filtered);
+                if (agent_on && O > 0) kp.b.term_i32[(size_t)LSM_TI_NUM_OBST_COLLISIONS * (size_t)kp.b.num_envs * N + (size_t)env * N + ai] = nobst;
                 if (ai == 0) kp.b.term_env_f64[env] = ratio;
             }
             if (do_reset) {
@@ -461,16 +485,28 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 const double ws = c.world_size;
                 double cra = ratio_sloped(ratio, 0.25, 0.75);
                 if (use_filter_arg) cra = 1.0;
+                // static obstacles first (:1204-1209): 0.8 * uniform(-ws/2, ws/2, 2)
+                for (int k = 0; k < O; ++k) {
+                    S.ox[k] = 0.8 * r.uniform(-ws / 2.0, ws / 2.0);
+                    S.oy[k] = 0.8 * r.uniform(-ws / 2.0, ws / 2.0);
+                }
                 for (int i = 0; i < N; ++i) {
-                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-                        S.ax[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.ay[i] = r.uniform(-0.8 * ws, 0.8 * ws);
-                        S.as2[i] = 0.0; S.as3[i] = 0.0;
-                    } else {
-                        const double xmin = -0.5 * ws;
-                        const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
-                        const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
-                        S.ax[i] = r.uniform(xmin, xmax); S.ay[i] = ry;
+                    // :1218-1249: redraw the position while it collides with an obstacle (bounded at 1000 tries); the airtaxi
+                    // speed / heading are drawn once the position is accepted
+                    for (int tries = 0; tries < 1000; ++tries) {
+                        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                            S.ax[i] = r.uniform(-0.8 * ws, 0.8 * ws);
+                            S.ay[i] = r.uniform(-0.8 * ws, 0.8 * ws);
+                        } else {
+                            const double xmin = -0.5 * ws;
+                            const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
+                            const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
+                            S.ax[i] = r.uniform(xmin, xmax); S.ay[i] = ry;
+                        }
+                        if (!obstacle_collision(S.ox, S.oy, O, S.ax[i], S.ay[i])) break;
+                    }
+                    if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { S.as2[i] = 0.0; S.as3[i] = 0.0; }
+                    else {
                         const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
                         S.as2[i] = r.uniform(0.0, 2.0 * kPi);
                         S.as3[i] = sp;
@@ -543,7 +579,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 done = 0; reached = 0;
                 p_dist = 0.0; state_time = 0.0;
                 goal_min_time = norm2(x - S.lx[ai], y - S.ly[ai]) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
-                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
+                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0; nobst = 0;
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
@@ -578,6 +614,10 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                                         : f == 4 ? kp.sl.lsin : kp.sl.lcos;
                         double* dst = kp.b.landmarks + ((size_t)f * (size_t)n + (size_t)(env0 + el)) * (size_t)M;
                         for (int m = lane; m < M; m += 32) dst[m] = ((const double*)(eb + off))[m];
+                    }
+                    for (int k = lane; k < O; k += 32) {
+                        kp.b.obstacles[((size_t)0 * (size_t)n + (size_t)(env0 + el)) * (size_t)O + k] = ((const double*)(eb + kp.sl.ox))[k];
+                        kp.b.obstacles[((size_t)1 * (size_t)n + (size_t)(env0 + el)) * (size_t)O + k] = ((const double*)(eb + kp.sl.oy))[k];
                     }
                 }
             }
@@ -620,6 +660,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 *AIP(LSM_AI_SAFETY_FILTERED) = safety_filtered; *AIP(LSM_AI_DECONFLICT_IDX) = deconflict;
                 *AIP(LSM_AI_NUM_COLLISIONS) = ncoll; *AIP(LSM_AI_EP_TRAVEL_LEN) = ep_len;
                 *AIP(LSM_AI_EP_CONFLICT) = ep_conflict; *AIP(LSM_AI_EP_MULTI) = ep_multi; *AIP(LSM_AI_EP_DONE) = ep_done;
+                if (O > 0) *AIP(LSM_AI_NUM_OBST_COLLISIONS) = nobst;
             }
         }
         __syncwarp();
@@ -636,8 +677,11 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
             for (int e = lane; e < E; e += 32) T.dthr[e * E + e] = 0.0f;
             for (int p = lane; p < kp.num_pairs; p += 32) {
                 const int a = kp.pair_tab[2 * p], b2 = kp.pair_tab[2 * p + 1];
-                const double pax = a < N ? T.ax[a] : T.lx[a - N], pay = a < N ? T.ay[a] : T.ly[a - N];
-                const double pbx = b2 < N ? T.ax[b2] : T.lx[b2 - N], pby = b2 < N ? T.ay[b2] : T.ly[b2 - N];
+                // entity order agents, landmarks, obstacles (core.py:489-496)
+                const double pax = a < N ? T.ax[a] : (a < N + M ? T.lx[a - N] : T.ox[a - N - M]);
+                const double pay = a < N ? T.ay[a] : (a < N + M ? T.ly[a - N] : T.oy[a - N - M]);
+                const double pbx = b2 < N ? T.ax[b2] : (b2 < N + M ? T.lx[b2 - N] : T.ox[b2 - N - M]);
+                const double pby = b2 < N ? T.ay[b2] : (b2 < N + M ? T.ly[b2 - N] : T.oy[b2 - N - M]);
                 const double dx = pax - pbx, dy = pay - pby;
                 const double d = sqrt(dx * dx + dy * dy);
                 const float v = (d < c.coordination_range && d > 0.0) ? (float)d : 0.0f;
@@ -649,7 +693,7 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                 const int e = w * 32 + lane;
                 bool dpre = false, dpost = false;
                 if (e < N) { dpre = T.done_pre[e] != 0; dpost = T.done_post[e] != 0; }
-                else if (e < E) {
+                else if (e < N + M) {   // obstacles (e >= N + M) are never disconnected
                     const int m = e - N, owner = m % N, order = m / N;
                     dpre = T.reached_pre[owner] > order; dpost = T.reached_post[owner] > order;
                 }
@@ -683,10 +727,14 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                             o[0] = (float)(post ? T.vpost_x[e] : T.vpre_x[e]); o[1] = (float)(post ? T.vpost_y[e] : T.vpre_y[e]);
                             o[2] = (float)T.ax[e]; o[3] = (float)T.ay[e];
                             o[4] = (float)T.lx[e]; o[5] = (float)T.ly[e]; o[6] = 0.0f;
-                        } else {
+                        } else if (e < N + M) {
                             const int m = e - N;
                             o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)T.lx[m]; o[3] = (float)T.ly[m];
                             o[4] = o[2]; o[5] = o[3]; o[6] = 1.0f;
+                        } else {   // obstacle: velocity 0, goal = own position, type 2 (:1030-1032)
+                            const int k = e - N - M;
+                            o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)T.ox[k]; o[3] = (float)T.oy[k];
+                            o[4] = o[2]; o[5] = o[3]; o[6] = 2.0f;
                         }
                     } else if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
                         float f0, f1, f2, f3, f4, f5, f6, f7, f8, f9;
@@ -698,11 +746,16 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                             f2 = (float)(vex - vix); f3 = (float)(vey - viy);
                             f4 = (float)(T.lx[g] - xi); f5 = (float)(T.ly[g] - yi);
                             f6 = (float)T.lsin[g]; f7 = (float)T.lcos[g]; f8 = (float)T.lsp[g]; f9 = 0.0f;
-                        } else {
+                        } else if (e < N + M) {
                             const int m = e - N;
                             f0 = (float)(T.lx[m] - xi); f1 = (float)(T.ly[m] - yi);
                             f2 = (float)(-vix); f3 = (float)(-viy); f4 = f0; f5 = f1;
                             f6 = (float)T.lsin[m]; f7 = (float)T.lcos[m]; f8 = (float)T.lsp[m]; f9 = 1.0f;
+                        } else {   // obstacle (extension): the landmark row with heading 0, speed 0; type 2
+                            const int k = e - N - M;
+                            f0 = (float)(T.ox[k] - xi); f1 = (float)(T.oy[k] - yi);
+                            f2 = (float)(-vix); f3 = (float)(-viy); f4 = f0; f5 = f1;
+                            f6 = 0.0f; f7 = 1.0f; f8 = 0.0f; f9 = 2.0f;
                         }
                         float2* o2 = reinterpret_cast<float2*>(o);   // rows are 40 B: 8 B aligned
                         o2[0] = make_float2(f0, f1); o2[1] = make_float2(f2, f3); o2[2] = make_float2(f4, f5);
@@ -724,13 +777,17 @@ __global__ void __launch_bounds__(256) lsm_generic_kernel(const __grid_constant_
                             o[7] = (float)(T.lsin[g] * ci - T.lcos[g] * si); o[8] = (float)(T.lcos[g] * ci + T.lsin[g] * si);
                             o[9] = (float)T.lsp[g]; o[10] = 0.0f;
                         } else {
+                            // landmark, or obstacle (extension): the landmark row with heading 0 (sin 0, cos 1), speed 0; type 2
                             const int m = e - N;
+                            const bool is_obst = e >= N + M;
+                            const double px = is_obst ? T.ox[m - M] : T.lx[m], py = is_obst ? T.oy[m - M] : T.ly[m];
+                            const double ls = is_obst ? 0.0 : T.lsin[m], lc = is_obst ? 1.0 : T.lcos[m];
                             double rx, ry;
-                            rotate_into(T.lx[m] - xi, T.ly[m] - yi, ci, si, rx, ry);
-                            const float sh = (float)(T.lsin[m] * ci - T.lcos[m] * si), ch = (float)(T.lcos[m] * ci + T.lsin[m] * si);
+                            rotate_into(px - xi, py - yi, ci, si, rx, ry);
+                            const float sh = (float)(ls * ci - lc * si), ch = (float)(lc * ci + ls * si);
                             o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)T.spd_post[i];
                             o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
-                            o[9] = (float)T.lsp[m]; o[10] = 1.0f;
+                            o[9] = is_obst ? 0.0f : (float)T.lsp[m]; o[10] = is_obst ? 2.0f : 1.0f;
                         }
                     }
                     e += 32;

@@ -55,7 +55,7 @@ def compute_agent_infos(agent_f64: np.ndarray, agent_i32: np.ndarray, env_i32: n
         'Dist_to_goal': f[LY.AF_DIST_LEFT],
         'Time_req_to_goal': times_new,
         'Num_agent_collisions': i[LY.AI_NUM_COLLISIONS].astype(np.float64),
-        'Num_obst_collisions': np.zeros((n, N)),
+        'Num_obst_collisions': i[LY.AI_NUM_OBST_COLLISIONS].astype(np.float64),   # 0 unless the obstacle extension is on
         'Distance_mean': d_mean,
         'Distance_variance': d_std,
         'Mean_by_variance': d_mean / (d_std + 0.0001),
@@ -92,6 +92,7 @@ def apply_terminal_snapshot(agent_f64, agent_i32, env_i32, ratio, term_f64, term
         f[slot_a][new_a] = term_f64[t_new][new_a]; f[slot_b][new_a] = term_f64[t_old][new_a]
     i[LY.AI_NUM_COLLISIONS][jr] = term_i32[LY.TI_NUM_COLLISIONS][jr]
     i[LY.AI_SAFETY_FILTERED][jr] = term_i32[LY.TI_SAFETY_FILTERED][jr]
+    i[LY.AI_NUM_OBST_COLLISIONS][jr] = term_i32[LY.TI_NUM_OBST_COLLISIONS][jr]
     ratio = np.array(ratio, dtype=np.float64, copy=True)
     ratio[jr] = term_ratio[jr]
     return ratio

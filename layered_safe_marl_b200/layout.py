@@ -6,6 +6,7 @@ environments reads each field as one contiguous, coalesced run of doubles.
     agent_f64 : (AF_COUNT, num_envs, N)      float64
     agent_i32 : (AI_COUNT, num_envs, N)      int32
     landmarks : (LF_COUNT, num_envs, N*L)    float64   landmark m = order * N + agent
+    obstacles : (2, num_envs, O)             float64   obstacle x / y (obstacle extension; O = 0 in every shipped script)
     env_f64   : (EF_COUNT, num_envs)         float64
     env_i32   : (EI_COUNT, num_envs)         int32
 
@@ -25,8 +26,8 @@ AF_COUNT = 16
 
 # per-agent int32 fields
 (AI_REACHED, AI_DONE, AI_SAFETY_FILTERED, AI_DECONFLICT_IDX, AI_NUM_COLLISIONS,
- AI_EP_TRAVEL_LEN, AI_EP_CONFLICT, AI_EP_MULTI, AI_EP_DONE) = range(9)
-AI_COUNT = 9
+ AI_EP_TRAVEL_LEN, AI_EP_CONFLICT, AI_EP_MULTI, AI_EP_DONE, AI_NUM_OBST_COLLISIONS) = range(10)
+AI_COUNT = 10
 
 # per-landmark float64 fields
 LF_X, LF_Y, LF_HEADING, LF_SPEED, LF_SIN, LF_COS = range(6)
@@ -42,8 +43,8 @@ EI_COUNT = 4
 (TF_X, TF_Y, TF_MIN_REL_DIST, TF_DIST_LEFT, TF_TIMES_REQ_NEW, TF_TIMES_REQ_OLD, TF_DISTS_GOAL_NEW, TF_DISTS_GOAL_OLD,
  TF_GOAL_MIN_TIME) = range(9)
 TF_COUNT = 9
-TI_NUM_COLLISIONS, TI_SAFETY_FILTERED = range(2)
-TI_COUNT = 2
+TI_NUM_COLLISIONS, TI_SAFETY_FILTERED, TI_NUM_OBST_COLLISIONS = range(3)
+TI_COUNT = 3
 
 # episode summary (environment.py:1065-1073), in this order
 EP_INFO_KEYS = ('travel_time_mean', 'travel_distance_mean', 'done_percentage', 'num_reached_goal_mean',
@@ -54,3 +55,4 @@ EP_COUNT = 8
 NUM_ACTIONS = 25
 MAX_AGENTS = 32
 MAX_LANDMARKS = 128   # np.int8 landmark index in the reference (Q8)
+MAX_OBSTACLES = 32

@@ -135,7 +135,8 @@ class B200GraphVecEnv:
         self.num_agents = self.N = p.num_agents
         self.L = p.num_landmarks
         self.M = self.N * self.L
-        self.E = self.N + self.M
+        self.O = p.num_obstacles          # declared extension (config.scenario_params_from_args); 0 in every shipped script
+        self.E = self.N + self.M + self.O
         self.D = p.obs_dim
         self.F = p.node_feat_dim
         self.seed = int(seed)
@@ -196,6 +197,7 @@ class B200GraphVecEnv:
         self.agent_i32 = torch.zeros((LY.AI_COUNT, n, N), dtype=i32, device=dev)
         self.agent_i32[LY.AI_DECONFLICT_IDX].fill_(-1)
         self.landmarks = torch.zeros((LY.LF_COUNT, n, M), dtype=f64, device=dev)
+        self.obstacles = torch.zeros((2, n, self.O), dtype=f64, device=dev)
         self.env_f64 = torch.zeros((LY.EF_COUNT, n), dtype=f64, device=dev)
         self.env_i32 = torch.zeros((LY.EI_COUNT, n), dtype=i32, device=dev)
         self.obs = torch.zeros((n, N, self.D), dtype=f32, device=dev)
@@ -222,6 +224,7 @@ class B200GraphVecEnv:
                      'reward', 'done', 'safe_action', 'ep_info', 'term_f64', 'term_i32', 'term_env_f64'):
             setattr(b, name, getattr(self, name).data_ptr())
         b.reward_individual = self.reward_individual.data_ptr() if self.reward_individual is not None else None
+        b.obstacles = self.obstacles.data_ptr() if self.O > 0 else None
         self._buffers = b
         _lib.check(self.lib.lsm_bind_buffers(self._h, C.byref(b)), 'lsm_bind_buffers')
         # pinned staging for host-side callers (the unmodified runner hands numpy one-hot actions)
@@ -610,6 +613,10 @@ class B200GraphVecEnv:
         lm[LY.LF_SIN].copy_(t(self.math_eval(0, lh_np), torch.float64)); lm[LY.LF_COS].copy_(t(self.math_eval(1, lh_np), torch.float64))
         self.env_f64[LY.EF_CURRICULUM_RATIO].copy_(t(s['curriculum_ratio'], torch.float64))
         self.env_i32[LY.EI_CURRENT_STEP].copy_(t(s['current_step'], torch.int32))
+        if self.O > 0:
+            op = t(s['obstacle_pos'], torch.float64)
+            self.obstacles[0].copy_(op[..., 0]); self.obstacles[1].copy_(op[..., 1])
+            i[LY.AI_NUM_OBST_COLLISIONS].copy_(t(s['num_obstacle_collisions'], torch.int32))
 
     def math_eval(self, op: int, a, b=None):
         """include/lsm_math.h on the host (op 0 sin, 1 cos, 2 atan2(a, b)): the kernels' own float64 trigonometry."""
@@ -648,6 +655,10 @@ class B200GraphVecEnv:
         s['landmark_pos'] = np.stack([lm[LY.LF_X], lm[LY.LF_Y]], axis=-1)
         s['landmark_heading'] = lm[LY.LF_HEADING]; s['landmark_speed'] = lm[LY.LF_SPEED]
         s['curriculum_ratio'] = ef[LY.EF_CURRICULUM_RATIO]; s['current_step'] = ei[LY.EI_CURRENT_STEP]
+        if self.O > 0:
+            ob = self.obstacles.cpu().numpy()
+            s['obstacle_pos'] = np.stack([ob[0], ob[1]], axis=-1)
+            s['num_obstacle_collisions'] = i[LY.AI_NUM_OBST_COLLISIONS].astype(np.float64)
         return s
 
     # ------------------------------------------------------------------------------------------

@@ -108,8 +108,9 @@ def observe_now(env):
 
 def run_case(name, args_kw, flags, episode, T, seed, greedy_agents=(), injections=(), post=None):
     interp_float32 = bool(args_kw.get('interp_float32', False))     # not a reference argument: selects the stub's arithmetic
-    args = H.make_args(**{k: v for k, v in args_kw.items() if k != 'interp_float32'})
-    env = H.make_env(args, seed=seed, interp_float32=interp_float32, **flags)
+    obstacle_extension = bool(args_kw.get('obstacle_extension', False))   # not a reference argument: ref_harness._obstacle_extension
+    args = H.make_args(**{k: v for k, v in args_kw.items() if k not in ('interp_float32', 'obstacle_extension')})
+    env = H.make_env(args, seed=seed, interp_float32=interp_float32, obstacle_extension=obstacle_extension, **flags)
     sc = H.scenario_of(env)
     N = args.num_agents
     env.reset(episode)
@@ -119,6 +120,10 @@ def run_case(name, args_kw, flags, episode, T, seed, greedy_agents=(), injection
             inject_near_goal(env, sc, *inj[1:])
         elif kind == 'pair':
             inject_pair_conflict(env, *inj[1:])
+        elif kind == 'obstacle_at_agent':      # obstacle k just ahead of agent i (drives Num_obst_collisions)
+            k, i, ahead = inj[1:]
+            a = env.world.agents[i]
+            env.world.obstacles[k].state.p_pos = a.state.p_pos + ahead * np.array([np.cos(a.state.theta), np.sin(a.state.theta)])
     for agent in env.world.agents:   # keep min_time consistent with injected positions (reset bookkeeping)
         sc.min_time(agent, env.world)
     s0 = H.snapshot(env)
@@ -226,6 +231,19 @@ CASES = [
          flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=36, seed=10, greedy_agents=(0, 1, 2, 3, 4),
          injections=(('near_goal', 0, 0.6, 1), ('near_goal', 1, 0.7, 0, 0.05), ('pair', 5, 6, 2.0, 0.08),
                      ('pair', 7, 8, 3.5, 0.06))),
+    # DECLARED obstacle extension (the reference raises for num_obstacles > 0; ref_harness._obstacle_extension completes the
+    # two raising statements, everything else is the reference's own obstacle code): 'relative' and 'global' features, both
+    # dynamics, BASELINE config 3's shape '+ obstacles' (airtaxi, 10 agents, POTENTIAL_CONFLICT, filter on, 4 obstacles)
+    dict(name='di3_obst2', args_kw=dict(DI, num_agents=3, num_obstacles=2, episode_length=50, obstacle_extension=True), flags={},
+         episode=3000, T=30, seed=21, greedy_agents=(0, 1), injections=(('near_goal', 0, 0.45, 1), ('obstacle_at_agent', 0, 2, 0.09),
+                                                                       ('obstacle_at_agent', 1, 0, 0.25))),
+    dict(name='di4_obst3_filter_global', args_kw=dict(DI, num_agents=4, num_obstacles=3, use_safety_filter=True, world_size=2,
+                                                       episode_length=250, graph_feat_type='global', obstacle_extension=True),
+         flags={}, episode=6249, T=20, seed=22, greedy_agents=(0,), injections=(('pair', 1, 2, 0.9, 0.4), ('obstacle_at_agent', 0, 3, 0.15))),
+    dict(name='at10_obst4_filter_pc', args_kw=dict(AT, num_agents=10, num_obstacles=4, use_safety_filter=True, episode_length=350,
+                                                   obstacle_extension=True),
+         flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=24, seed=23, greedy_agents=(0, 1, 2),
+         injections=(('near_goal', 0, 0.6, 1), ('pair', 5, 6, 2.0, 0.08), ('obstacle_at_agent', 0, 3, 0.2), ('obstacle_at_agent', 3, 7, 0.15))),
     dict(name='at6_allflags', args_kw=dict(AT, num_agents=6, use_safety_filter=True, world_size=3, episode_length=350),
          flags=ALL_FLAGS, episode=4000, T=30, seed=11, greedy_agents=(0, 1),
          injections=(('near_goal', 0, 0.5, 1), ('pair', 2, 3, 1.5, 0.085), ('pair', 4, 5, 2.5, 0.035))),

@@ -21,7 +21,8 @@
 
 #define MAXN 32
 #define MAXM 128
-#define MAXE (MAXN + MAXM)
+#define MAXO 32
+#define MAXE (MAXN + MAXM + MAXO)
 #define PI 3.141592653589793
 
 static inline double clipd(double v, double lo, double hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -234,7 +235,7 @@ double lsmo_magnetic_heading(double px, double py, double radius) {
 typedef struct {
     const lsmo_params *p;
     const lsmo_grid *vg, *tg;
-    int N, L, M, E, dyn;
+    int N, L, M, O, E, dyn;
     double cur[12];          /* curriculum scalars */
     double ratio;
     /* agents */
@@ -246,6 +247,9 @@ typedef struct {
     int ep_travel_len[MAXN], ep_conflict[MAXN], ep_multi[MAXN], ep_done[MAXN];
     /* landmarks */
     double lx[MAXM], ly[MAXM], lh[MAXM], ls[MAXM], lsin[MAXM], lcos[MAXM];
+    /* obstacles (declared extension, lsm_oracle.h: num_obstacles) */
+    double ox[MAXO], oy[MAXO];
+    int nobst[MAXN];         /* world.num_obstacle_collisions */
     int current_step, reset_count, parity;
     double *D;               /* E*E cached_dist_mag (masked in place like the reference) */
 } env_t;
@@ -522,9 +526,19 @@ static void integrate_airtaxi(env_t *w, int i, const double u[2], double dt) {
     w->state_time[i] += dt;
 }
 
-/* core.py:514-543 calculate_distances: entity order agents, landmarks (core.py:489-496) */
+/* core.py:514-543 calculate_distances: entity order agents, landmarks, obstacles (core.py:489-496) */
 static void entity_pos(const env_t *w, int e, double *px, double *py) {
-    if (e < w->N) { *px = w->x[e]; *py = w->y[e]; } else { *px = w->lx[e - w->N]; *py = w->ly[e - w->N]; }
+    if (e < w->N) { *px = w->x[e]; *py = w->y[e]; }
+    else if (e < w->N + w->M) { *px = w->lx[e - w->N]; *py = w->ly[e - w->N]; }
+    else { *px = w->ox[e - w->N - w->M]; *py = w->oy[e - w->N - w->M]; }
+}
+/* navigation_graph_safe.py:452-465 is_obstacle_collision (no walls): any obstacle closer than 1.05 * (size + size) */
+static int obstacle_collision(const env_t *w, double px, double py) {
+    for (int k = 0; k < w->O; ++k) {
+        double dx = w->ox[k] - px, dy = w->oy[k] - py;
+        if (sqrt(dx * dx + dy * dy) < 1.05 * (0.050 + 0.050)) return 1;
+    }
+    return 0;
 }
 static void calculate_distances(env_t *w) {
     int E = w->E;
@@ -613,10 +627,14 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 double ve[2]; a_vel(w, e, ve);
                 o[0] = (float)ve[0]; o[1] = (float)ve[1]; o[2] = (float)w->x[e]; o[3] = (float)w->y[e];
                 o[4] = (float)w->lx[e]; o[5] = (float)w->ly[e]; o[6] = 0.0f;
-            } else {
+            } else if (e < N + w->M) {
                 int m = e - N;
                 o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)w->lx[m]; o[3] = (float)w->ly[m];
                 o[4] = o[2]; o[5] = o[3]; o[6] = 1.0f;
+            } else {    /* obstacle: velocity 0 (state.stop()), goal = own position, type 2 (:1030-1032) */
+                int k = e - N - w->M;
+                o[0] = 0.0f; o[1] = 0.0f; o[2] = (float)w->ox[k]; o[3] = (float)w->oy[k];
+                o[4] = o[2]; o[5] = o[3]; o[6] = 2.0f;
             }
         }
         return;
@@ -631,13 +649,20 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 o[4] = (float)(w->lx[g] - w->x[i]); o[5] = (float)(w->ly[g] - w->y[i]);
                 o[6] = (float)lsm_sin(w->lh[g]); o[7] = (float)lsm_cos(w->lh[g]);
                 o[8] = (float)w->ls[g]; o[9] = 0.0f;
-            } else {
+            } else if (e < N + w->M) {
                 int m = e - N;
                 o[0] = (float)(w->lx[m] - w->x[i]); o[1] = (float)(w->ly[m] - w->y[i]);
                 o[2] = (float)(-vi[0]); o[3] = (float)(-vi[1]);
                 o[4] = o[0]; o[5] = o[1];
                 o[6] = (float)lsm_sin(w->lh[m]); o[7] = (float)lsm_cos(w->lh[m]);
                 o[8] = (float)w->ls[m]; o[9] = 1.0f;
+            } else {    /* obstacle (extension): the landmark builder with heading 0, speed 0; type 2 */
+                int k = e - N - w->M;
+                o[0] = (float)(w->ox[k] - w->x[i]); o[1] = (float)(w->oy[k] - w->y[i]);
+                o[2] = (float)(-vi[0]); o[3] = (float)(-vi[1]);
+                o[4] = o[0]; o[5] = o[1];
+                o[6] = (float)lsm_sin(0.0); o[7] = (float)lsm_cos(0.0);
+                o[8] = 0.0f; o[9] = 2.0f;
             }
         } else {
             float *o = out + (size_t)e * 11;
@@ -657,14 +682,16 @@ static void emit_node_obs(const env_t *w, int i, float *out) {
                 o[7] = (float)lsm_sin(rgh); o[8] = (float)lsm_cos(rgh);
                 o[9] = (float)w->ls[g]; o[10] = 0.0f;
             } else {
-                int m = e - N;
+                /* landmark, or obstacle (extension): the landmark builder with heading 0, speed 0; type 2 */
+                int m = e - N, is_obst = e >= N + w->M, k = e - N - w->M;
+                double px = is_obst ? w->ox[k] : w->lx[m], py = is_obst ? w->oy[k] : w->ly[m];
                 double rp[2];
-                rel_pos_from_reference(w->lx[m], w->ly[m], w->x[i], w->y[i], thi, rp);
-                double rh = w->lh[m] - thi;
+                rel_pos_from_reference(px, py, w->x[i], w->y[i], thi, rp);
+                double rh = (is_obst ? 0.0 : w->lh[m]) - thi;
                 o[0] = (float)rp[0]; o[1] = (float)rp[1]; o[2] = (float)w->s3[i];
                 o[3] = (float)lsm_sin(rh); o[4] = (float)lsm_cos(rh);
                 o[5] = o[0]; o[6] = o[1]; o[7] = o[3]; o[8] = o[4];
-                o[9] = (float)w->ls[m]; o[10] = 1.0f;
+                o[9] = is_obst ? 0.0f : (float)w->ls[m]; o[10] = is_obst ? 2.0f : 1.0f;
             }
         }
     }
@@ -675,7 +702,8 @@ static void emit_adj(env_t *w, float *out) {
     for (int e = 0; e < E; ++e) {
         int disc;
         if (e < N) disc = w->done[e];
-        else { int m = e - N; disc = w->reached[m % N] > (m / N); }
+        else if (e < N + w->M) { int m = e - N; disc = w->reached[m % N] > (m / N); }
+        else disc = 0;   /* obstacles are never disconnected (extension: the reference's mask has no entry for them) */
         if (disc) for (int k = 0; k < E; ++k) { w->D[e * E + k] = 0.0; w->D[k * E + e] = 0.0; }
     }
     double R = w->p->coordination_range;
@@ -818,7 +846,8 @@ static void env_load(env_t *w, const lsmo_params *p, const lsmo_grid *vg, const 
                      const lsmo_buffers *b, int64_t e) {
     w->p = p; w->vg = vg; w->tg = tg;
     int N = w->N = p->num_agents; w->L = p->num_landmarks; int M = w->M = N * p->num_landmarks;
-    w->E = N + M; w->dyn = p->dynamics;
+    int O = w->O = p->num_obstacles;
+    w->E = N + M + O; w->dyn = p->dynamics;
     w->current_step = EI(b, LSMO_EI_CURRENT_STEP, e);
     w->reset_count = EI(b, LSMO_EI_RESET_COUNT, e);
     w->parity = EI(b, LSMO_EI_PARITY, e);
@@ -841,6 +870,11 @@ static void env_load(env_t *w, const lsmo_params *p, const lsmo_grid *vg, const 
         w->ncoll[i] = AI(b, LSMO_AI_NUM_COLLISIONS, e, i, N); w->ep_travel_len[i] = AI(b, LSMO_AI_EP_TRAVEL_LEN, e, i, N);
         w->ep_conflict[i] = AI(b, LSMO_AI_EP_CONFLICT, e, i, N); w->ep_multi[i] = AI(b, LSMO_AI_EP_MULTI, e, i, N);
         w->ep_done[i] = AI(b, LSMO_AI_EP_DONE, e, i, N);
+        w->nobst[i] = AI(b, LSMO_AI_NUM_OBST_COLLISIONS, e, i, N);
+    }
+    for (int k = 0; k < O; ++k) {
+        w->ox[k] = b->obstacles[((size_t)0 * (size_t)b->num_envs + (size_t)e) * (size_t)O + k];
+        w->oy[k] = b->obstacles[((size_t)1 * (size_t)b->num_envs + (size_t)e) * (size_t)O + k];
     }
     for (int m = 0; m < M; ++m) {
         w->lx[m] = LF(b, LSMO_LF_X, e, m, M); w->ly[m] = LF(b, LSMO_LF_Y, e, m, M);
@@ -872,6 +906,11 @@ static void env_store(const env_t *w, const lsmo_buffers *b, int64_t e, int stor
         AI(b, LSMO_AI_NUM_COLLISIONS, e, i, N) = w->ncoll[i]; AI(b, LSMO_AI_EP_TRAVEL_LEN, e, i, N) = w->ep_travel_len[i];
         AI(b, LSMO_AI_EP_CONFLICT, e, i, N) = w->ep_conflict[i]; AI(b, LSMO_AI_EP_MULTI, e, i, N) = w->ep_multi[i];
         AI(b, LSMO_AI_EP_DONE, e, i, N) = w->ep_done[i];
+        AI(b, LSMO_AI_NUM_OBST_COLLISIONS, e, i, N) = w->nobst[i];
+    }
+    if (store_landmarks) for (int k = 0; k < w->O; ++k) {
+        b->obstacles[((size_t)0 * (size_t)b->num_envs + (size_t)e) * (size_t)w->O + k] = w->ox[k];
+        b->obstacles[((size_t)1 * (size_t)b->num_envs + (size_t)e) * (size_t)w->O + k] = w->oy[k];
     }
     if (store_landmarks) for (int m = 0; m < M; ++m) {
         LF(b, LSMO_LF_X, e, m, M) = w->lx[m]; LF(b, LSMO_LF_Y, e, m, M) = w->ly[m];
@@ -906,16 +945,28 @@ static void random_scenario(env_t *w, rng_t *r) {
     int use_filter_arg = (p->flags & LSMO_FLAG_USE_SAFETY_FILTER) != 0;
     double cra = ratio_sloped(w->ratio, 0.25, 0.75);
     if (use_filter_arg) cra = 1.0;
+    /* static obstacles first (:1204-1209): 0.8 * uniform(-ws/2, ws/2, 2) */
+    for (int k = 0; k < w->O; ++k) {
+        w->ox[k] = 0.8 * rng_uniform(r, -ws / 2.0, ws / 2.0);
+        w->oy[k] = 0.8 * rng_uniform(r, -ws / 2.0, ws / 2.0);
+    }
     for (int i = 0; i < N; ++i) {
-        if (w->dyn == LSMO_DYN_DI) {
-            w->x[i] = rng_uniform(r, -0.8 * ws, 0.8 * ws);
-            w->y[i] = rng_uniform(r, -0.8 * ws, 0.8 * ws);
-            w->s2[i] = 0.0; w->s3[i] = 0.0;
-        } else {
-            double xmin = -0.5 * ws;
-            double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
-            double ry = rng_uniform(r, -0.5 * ws, 0.5 * ws);
-            w->x[i] = rng_uniform(r, xmin, xmax); w->y[i] = ry;
+        /* :1218-1249: redraw the position while it collides with an obstacle (the reference loops without a bound; 1000
+         * tries here); the airtaxi speed / heading are drawn once the position is accepted */
+        for (int tries = 0; tries < 1000; ++tries) {
+            if (w->dyn == LSMO_DYN_DI) {
+                w->x[i] = rng_uniform(r, -0.8 * ws, 0.8 * ws);
+                w->y[i] = rng_uniform(r, -0.8 * ws, 0.8 * ws);
+            } else {
+                double xmin = -0.5 * ws;
+                double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
+                double ry = rng_uniform(r, -0.5 * ws, 0.5 * ws);
+                w->x[i] = rng_uniform(r, xmin, xmax); w->y[i] = ry;
+            }
+            if (!obstacle_collision(w, w->x[i], w->y[i])) break;
+        }
+        if (w->dyn == LSMO_DYN_DI) { w->s2[i] = 0.0; w->s3[i] = 0.0; }
+        else {
             double speed = rng_uniform(r, p->goal_speed_min, p->goal_speed_max);
             w->s2[i] = rng_uniform(r, 0.0, 2.0 * PI);
             w->s3[i] = speed;
@@ -1026,7 +1077,7 @@ static void env_reset(env_t *w, const lsmo_buffers *b, int64_t e, int64_t episod
         w->reached[i] = 0;
         w->times_req[i] = -1.0; w->times_req_old[i] = -1.0;
         w->dists_goal[i] = -1.0; w->dists_goal_old[i] = -1.0; w->dist_left[i] = -1.0;
-        w->ncoll[i] = 0;
+        w->ncoll[i] = 0; w->nobst[i] = 0;
         w->ep_travel_len[i] = 0; w->ep_travel_dist[i] = 0.0; w->ep_done[i] = 0;
         w->ep_conflict[i] = 0; w->ep_multi[i] = 0; w->ep_min_dist[i] = INFINITY;
     }
@@ -1090,6 +1141,7 @@ static void env_step(env_t *w, const lsmo_buffers *b, int64_t e, const int32_t *
                 w->dist_left[i] = dist;
             }
             if (w->times_req[i] == -1.0) { w->dists_goal[i] = w->p_dist[i]; w->dist_left[i] = dist; }
+            if (obstacle_collision(w, w->x[i], w->y[i])) w->nobst[i] += 1;     /* :402-404 */
             for (int a = 0; a < N; ++a) {
                 if (a == i) continue;
                 double d = norm2(w->x[i] - w->x[a], w->y[i] - w->y[a]);
@@ -1115,6 +1167,7 @@ static int check(const lsmo_params *p) {
     if (p->num_agents < 1 || p->num_agents > MAXN) return 1;
     if (p->num_landmarks < 2 || p->num_agents * p->num_landmarks > MAXM) return 1;
     if (p->dynamics != LSMO_DYN_DI && p->dynamics != LSMO_DYN_AIRTAXI) return 1;
+    if (p->num_obstacles < 0 || p->num_obstacles > MAXO) return 1;
     return 0;
 }
 
@@ -1129,7 +1182,7 @@ typedef struct {
 static void *job_run(void *arg) {
     job_t *j = (job_t *)arg;
     const lsmo_params *p = j->p; const lsmo_buffers *b = j->b;
-    int N = p->num_agents, E = N * (1 + p->num_landmarks);
+    int N = p->num_agents, E = N * (1 + p->num_landmarks) + p->num_obstacles;
     env_t *w = (env_t *)malloc(sizeof(env_t));
     w->D = (double *)malloc(sizeof(double) * (size_t)E * E);
     for (int64_t e = j->e0; e < j->e1; ++e) {

@@ -51,7 +51,7 @@ enum {
 enum {
     LSMO_AI_REACHED = 0, LSMO_AI_DONE, LSMO_AI_SAFETY_FILTERED, LSMO_AI_DECONFLICT_IDX,
     LSMO_AI_NUM_COLLISIONS, LSMO_AI_EP_TRAVEL_LEN, LSMO_AI_EP_CONFLICT, LSMO_AI_EP_MULTI,
-    LSMO_AI_EP_DONE, LSMO_AI_COUNT
+    LSMO_AI_EP_DONE, LSMO_AI_NUM_OBST_COLLISIONS /* world.num_obstacle_collisions (obstacle extension) */, LSMO_AI_COUNT
 };
 /* per-landmark float64 fields: landmarks[field][env][l*N + agent] */
 enum { LSMO_LF_X = 0, LSMO_LF_Y, LSMO_LF_HEADING, LSMO_LF_SPEED, LSMO_LF_SIN, LSMO_LF_COS, LSMO_LF_COUNT };
@@ -69,7 +69,9 @@ typedef struct lsmo_params {
     int32_t dynamics, num_agents, num_landmarks, episode_length;
     int32_t num_total_episode, num_internal_step;
     uint32_t flags;
-    int32_t _pad;
+    int32_t num_obstacles;   /* --num_obstacles. > 0 is the DECLARED EXTENSION of SURVEY 8c (the reference raises): entities are
+                                agents, landmarks, obstacles (core.py:489-496); obstacles are never disconnected; an obstacle's
+                                node features are the landmark builders' with heading 0, speed 0, entity type 2 */
     double world_size;
     double dt, coordination_range, dist_thresh, heading_thresh, speed_thresh;
     double goal_speed_min, goal_speed_max, separation_distance_target;
@@ -101,12 +103,13 @@ typedef struct lsmo_buffers {
     int32_t *env_i32;      /* [LSMO_EI_COUNT][num_envs] */
     /* outputs */
     float *obs;            /* [num_envs][N][D] */
-    float *node_obs;       /* [num_envs][N][E][F] */
+    float *node_obs;       /* [num_envs][N][E][F]   E = N(1+L) + O */
     float *adj;            /* [num_envs][N][E][E] */
     float *reward;         /* [num_envs][N] */
     uint8_t *done;         /* [num_envs][N] */
     double *safe_action;   /* [num_envs][N][2] applied (filtered) control of the last internal step */
     double *ep_info;       /* [num_envs][LSMO_EP_COUNT] */
+    double *obstacles;     /* [2][num_envs][O] obstacle x / y (NULL when num_obstacles == 0) */
 } lsmo_buffers;
 
 /* One env.step (+ graphworker auto-reset when `auto_reset`) for every env.

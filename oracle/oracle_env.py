@@ -20,8 +20,8 @@ AF = dict(X=0, Y=1, S2=2, S3=3, P_DIST=4, STATE_TIME=5, MIN_REL_DIST=6, GOAL_MIN
           EP_TRAVEL_DIST=13, EP_MIN_DIST=14, ACTION_DIFF=15)
 AF_COUNT = 16
 AI = dict(REACHED=0, DONE=1, SAFETY_FILTERED=2, DECONFLICT_IDX=3, NUM_COLLISIONS=4,
-          EP_TRAVEL_LEN=5, EP_CONFLICT=6, EP_MULTI=7, EP_DONE=8)
-AI_COUNT = 9
+          EP_TRAVEL_LEN=5, EP_CONFLICT=6, EP_MULTI=7, EP_DONE=8, NUM_OBST_COLLISIONS=9)
+AI_COUNT = 10
 LF = dict(X=0, Y=1, HEADING=2, SPEED=3, SIN=4, COS=5)
 LF_COUNT = 6
 EF_COUNT = 1
@@ -33,7 +33,7 @@ EP_COUNT = 8
 class Params(C.Structure):
     _fields_ = [('dynamics', C.c_int32), ('num_agents', C.c_int32), ('num_landmarks', C.c_int32),
                 ('episode_length', C.c_int32), ('num_total_episode', C.c_int32),
-                ('num_internal_step', C.c_int32), ('flags', C.c_uint32), ('_pad', C.c_int32),
+                ('num_internal_step', C.c_int32), ('flags', C.c_uint32), ('num_obstacles', C.c_int32),
                 ('world_size', C.c_double), ('dt', C.c_double), ('coordination_range', C.c_double),
                 ('dist_thresh', C.c_double), ('heading_thresh', C.c_double), ('speed_thresh', C.c_double),
                 ('goal_speed_min', C.c_double), ('goal_speed_max', C.c_double),
@@ -59,7 +59,7 @@ class Buffers(C.Structure):
                 ('env_f64', C.c_void_p), ('env_i32', C.c_void_p),
                 ('obs', C.c_void_p), ('node_obs', C.c_void_p), ('adj', C.c_void_p),
                 ('reward', C.c_void_p), ('done', C.c_void_p), ('safe_action', C.c_void_p),
-                ('ep_info', C.c_void_p)]
+                ('ep_info', C.c_void_p), ('obstacles', C.c_void_p)]
 
 
 def build(force=False):
@@ -126,7 +126,7 @@ def make_params(pd: dict) -> Params:
     for name, _ in Params._fields_:
         if name in ('_pad', 'act_tab0', 'act_tab1'):
             continue
-        setattr(p, name, pd[name])
+        setattr(p, name, pd.get(name, 0) if name == 'num_obstacles' else pd[name])
     t0, t1 = action_tables(int(pd['dynamics']))
     p.act_tab0 = (C.c_double * 5)(*[float(v) for v in t0])
     p.act_tab1 = (C.c_double * 5)(*[float(v) for v in t1])
@@ -169,7 +169,8 @@ class OracleEnv(object):
         self.N = int(self.pd['num_agents'])
         self.L = int(self.pd['num_landmarks'])
         self.M = self.N * self.L
-        self.E = self.N + self.M
+        self.O = int(self.pd.get('num_obstacles', 0))      # declared extension (lsm_oracle.h)
+        self.E = self.N + self.M + self.O
         self.dyn = int(self.pd['dynamics'])
         self.D = 7 if self.dyn == 0 else 6
         self.F = 7 if (int(params["flags"]) & (1 << 9)) else (10 if self.dyn == 0 else 11)   # 7: global node features
@@ -187,6 +188,7 @@ class OracleEnv(object):
         self.agent_i32 = np.zeros((AI_COUNT, n, N), dtype=np.int32)
         self.agent_i32[AI['DECONFLICT_IDX']] = -1
         self.landmarks = np.zeros((LF_COUNT, n, M), dtype=np.float64)
+        self.obstacles = np.zeros((2, n, self.O), dtype=np.float64)
         self.env_f64 = np.zeros((EF_COUNT, n), dtype=np.float64)
         self.env_i32 = np.zeros((EI_COUNT, n), dtype=np.int32)
         self.obs = np.zeros((n, N, self.D), dtype=np.float32)
@@ -202,6 +204,8 @@ class OracleEnv(object):
         for name in ('agent_f64', 'agent_i32', 'landmarks', 'env_f64', 'env_i32', 'obs', 'node_obs', 'adj',
                      'reward', 'done', 'safe_action', 'ep_info'):
             setattr(b, name, getattr(self, name).ctypes.data)
+        if self.O > 0:
+            b.obstacles = self.obstacles.ctypes.data
         self.b = b
 
     def _gp(self, g):
@@ -266,6 +270,10 @@ class OracleEnv(object):
         self.landmarks[LF['SIN']][sel] = math_eval(0, lh); self.landmarks[LF['COS']][sel] = math_eval(1, lh)
         self.env_f64[0][sel] = s['curriculum_ratio']
         self.env_i32[EI['CURRENT_STEP']][sel] = s['current_step']
+        if self.O > 0:
+            op = np.asarray(s['obstacle_pos'], dtype=np.float64)
+            self.obstacles[0][sel] = op[..., 0]; self.obstacles[1][sel] = op[..., 1]
+            i[AI['NUM_OBST_COLLISIONS']][sel] = np.asarray(s['num_obstacle_collisions']).astype(np.int32)
 
     def get_state(self):
         f, i = self.agent_f64, self.agent_i32
@@ -294,4 +302,7 @@ class OracleEnv(object):
         s['landmark_speed'] = self.landmarks[LF['SPEED']].copy()
         s['curriculum_ratio'] = self.env_f64[0].copy()
         s['current_step'] = self.env_i32[EI['CURRENT_STEP']].copy()
+        if self.O > 0:
+            s['obstacle_pos'] = np.stack([self.obstacles[0], self.obstacles[1]], axis=-1)
+            s['num_obstacle_collisions'] = i[AI['NUM_OBST_COLLISIONS']].astype(np.float64)
         return s

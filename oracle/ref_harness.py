@@ -83,18 +83,78 @@ BINARY_FLAGS = ('SAFETY_VIOLATION', 'HJ_VALUE', 'POTENTIAL_CONFLICT', 'SEPARATIO
                 'INITIAL_PHASE_USE_SAFETY_FILTER', 'DIFF_FROM_FILTERED_ACTION')
 
 
-def make_env(args, seed=0, interp_float32=False, **binary_flags):
+def _obstacle_extension(module):
+    """The DECLARED obstacle extension (BASELINE config 3 '+ obstacles'), applied to a freshly loaded scenario
+    module WITHOUT touching the reference's files. With num_obstacles > 0 the reference raises in exactly two statements:
+    `_get_entity_feat_relative` has no obstacle branch (navigation_graph_safe.py:1064-1065,1087) and `graph_observation`
+    indexes the E x E distance matrix with a mask of N(1+L) entries (:975-989). Everything else - obstacle creation,
+    placement, collision counting, distances, the 'global' features - is the reference's own code and runs unmodified.
+    The two statements are completed as declared: an obstacle's relative node features are the reference's landmark builders
+    (utils.py:167-190,224-255) called with heading 0 and speed 0, entity type 2; the disconnect mask is padded with False."""
+    import multiagent.custom_scenarios.utils as U
+    Sc = module.Scenario
+    orig_rel = Sc._get_entity_feat_relative
+
+    def _get_entity_feat_relative(self, agent, entity, world):
+        if 'obstacle' in entity.name:
+            if agent.dynamics_type == module.EntityDynamicsType.DoubleIntegratorXY:
+                f = U.get_landmark_node_observation_relative_without_heading(entity.state.p_pos, 0.0, 0.0, agent.state)
+            else:
+                f = U.get_landmark_node_observation_relative_with_heading(entity.state.p_pos, 0.0, 0.0, agent.state)
+            f = np.array(f, dtype=np.float64)
+            f[-1] = U.entity_mapping['obstacle']
+            return f
+        return orig_rel(self, agent, entity, world)
+
+    def graph_observation(self, agent, world):
+        # navigation_graph_safe.py:956-994 with the mask padded for the obstacles
+        node_obs = []
+        for entity in world.entities:
+            if world.graph_feat_type == 'global':
+                node_obs.append(self._get_entity_feat_global(entity, world))
+            elif world.graph_feat_type == 'relative':
+                node_obs.append(self._get_entity_feat_relative(agent, entity, world))
+        node_obs = np.array(node_obs)
+        adj = world.cached_dist_mag
+        disconnected_mask = [entity.done or not entity.departed for entity in world.agents]
+        for i_landmark, _ in enumerate(world.landmarks):
+            disconnected_mask.append(self.reached_goal[i_landmark % self.num_agents] > i_landmark // self.num_agents)
+        disconnected_mask += [False] * len(world.obstacles)
+        adj[disconnected_mask, :] = 0
+        adj[:, disconnected_mask] = 0
+        connect_mask = ((adj < self.max_edge_dist) & (adj > 0)).astype(np.float32)
+        return node_obs, adj * connect_mask
+
+    Sc._get_entity_feat_relative = _get_entity_feat_relative
+    Sc.graph_observation = graph_observation
+
+
+def make_env(args, seed=0, interp_float32=False, obstacle_extension=False, **binary_flags):
     """GraphMPEEnv(args) with the RewardBinaryConfig switches set the way the reference README says
-    to set them (edit the class attributes), then env.seed(seed) (scripts/train_mpe.py:38)."""
+    to set them (edit the class attributes), then env.seed(seed) (scripts/train_mpe.py:38).
+    obstacle_extension: see _obstacle_extension (not reference behaviour; the default leaves the reference untouched)."""
     setup_reference()
     import hj_reachability
     hj_reachability.FLOAT32_INTERPOLATION = bool(interp_float32)      # which declared Grid.interpolate arithmetic the stub runs
     import multiagent.config as C
     for k in BINARY_FLAGS:
         setattr(C.RewardBinaryConfig, k, bool(binary_flags.get(k, False)))
-    from multiagent.MPE_env import GraphMPEEnv
+    import multiagent.MPE_env as ME
     np.random.seed(seed)  # make_world itself draws (wall_length) and resets once
-    env = GraphMPEEnv(args)
+    if obstacle_extension:
+        orig_load = ME.load     # custom_scenarios.load executes a fresh copy of the scenario module on every call
+
+        def load(name):
+            module = orig_load(name)
+            _obstacle_extension(module)
+            return module
+        ME.load = load
+        try:
+            env = ME.GraphMPEEnv(args)
+        finally:
+            ME.load = orig_load
+    else:
+        env = ME.GraphMPEEnv(args)
     env.seed(seed)
     return env
 
@@ -138,6 +198,9 @@ def snapshot(env):
     s['ep_conflict'] = np.array(env.episode_agent_conflict_occurance_list, dtype=np.float64)
     s['ep_multi_engagement'] = np.array(env.episode_agent_in_multiple_engagement_list, dtype=np.float64)
     s['ep_min_distance'] = np.array(env.episode_agent_min_distance_list, dtype=np.float64)
+    if len(world.obstacles) > 0:      # obstacle extension only
+        s['obstacle_pos'] = np.array([o.state.p_pos for o in world.obstacles], dtype=np.float64)
+        s['num_obstacle_collisions'] = np.array(world.num_obstacle_collisions, dtype=np.float64)
     assert s['agent_values'].shape == (n, 4)
     return s
 

@@ -76,15 +76,22 @@ def value_grid_for(params):
     return vg, tg
 
 
+OBSTACLE_KEYS = ('obstacle_pos', 'num_obstacle_collisions')      # fixtures of the declared obstacle extension only
+
+
+def _state_keys(z, prefix):
+    return STATE_KEYS + tuple(k for k in OBSTACLE_KEYS if prefix + k in z.files)
+
+
 def state0(z, batch=True):
-    s = {k: np.array(z['s0_' + k]) for k in STATE_KEYS}
+    s = {k: np.array(z['s0_' + k]) for k in _state_keys(z, 's0_')}
     if batch:
         s = {k: v[None] for k, v in s.items()}
     return s
 
 
 def state_at(z, t, batch=True):
-    s = {k: np.array(z['st_' + k][t]) for k in STATE_KEYS}
+    s = {k: np.array(z['st_' + k][t]) for k in _state_keys(z, 'st_')}
     if batch:
         s = {k: v[None] for k, v in s.items()}
     return s

@@ -150,6 +150,9 @@ def _compare_with_oracle(args, flags, n, T, episode, seed, auto_reset):
             nonlocal state_equal
             so, sc = ora.get_state(), cu.get_state()
             bad = _report_divergence(tag, so, sc, ora, cu, state_equal, n)
+            if params.num_obstacles > 0:      # declared obstacle extension: positions bit for bit, collision counters exact
+                assert np.array_equal(so['obstacle_pos'], sc['obstacle_pos']), f"{tag}: obstacle positions differ"
+                assert np.array_equal(so['num_obstacle_collisions'], sc['num_obstacle_collisions']), f"{tag}: obstacle collision counters differ"
             assert not bad.any(), f"{tag}: {int(bad.sum())} of {n} envs diverged in a discrete output (see the report above)"
             eq = np.ones(n, dtype=bool)
             for k in EXACT_STATE_KEYS:
@@ -203,6 +206,40 @@ def test_oracle_batch_airtaxi_filter_pc():
     args = G.default_args(dynamics_type='airtaxi', num_agents=10, use_safety_filter=True, episode_length=350, world_size=6)
     _compare_with_oracle(args, G.BinaryFlags(dict(POTENTIAL_CONFLICT=True)), n=256, T=25, episode=6249, seed=2,
                          auto_reset=True)
+
+
+@pytest.mark.parametrize('shape', ['di', 'di_global', 'airtaxi_cfg3'])
+def test_oracle_batch_obstacle_extension(shape):
+    """The DECLARED obstacle extension (BASELINE config 3 '+ obstacles'; the reference raises, see config.scenario_params_from_args):
+    CUDA generic kernel == C oracle on seeded batches - Philox obstacle placement, agent positions redrawn while they collide
+    with an obstacle, obstacle nodes / edges, Num_obst_collisions, auto-reset. The oracle itself is pinned by the fixtures
+    di3_obst2 / di4_obst3_filter_global / at10_obst4_filter_pc (reference code + the two completed statements). Many
+    obstacles in a small world so that rejections and collisions are frequent."""
+    kw = dict(di=dict(num_agents=5, num_obstacles=12, world_size=1, episode_length=8, use_safety_filter=True),
+              di_global=dict(num_agents=3, num_obstacles=32, world_size=1, episode_length=6, graph_feat_type='global'),
+              airtaxi_cfg3=dict(dynamics_type='airtaxi', num_agents=10, num_obstacles=4, world_size=6, episode_length=350,
+                                use_safety_filter=True))[shape]
+    args = G.default_args(obstacle_extension=True, **kw)
+    flags = G.BinaryFlags(dict(POTENTIAL_CONFLICT=True) if shape == 'airtaxi_cfg3' else {})
+    n, T = (96, 12) if shape == 'airtaxi_cfg3' else (193, 20)
+    ora, cu = _compare_with_oracle(args, flags, n=n, T=T, episode=6249 if shape != 'di_global' else 0, seed=17, auto_reset=True)
+    assert cu.env.launch_info()['specialised'] == 0
+    s = cu.get_state()
+    if shape != 'airtaxi_cfg3':
+        assert s['num_obstacle_collisions'].sum() > 0, "the scenario was meant to produce obstacle collisions"
+    # COO edge list over E = N(1+L) + O entities in process_adj order (gnn.py:376-407): numpy nonzero of the dense tensor
+    adj = cu.adj.reshape(n * args.num_agents, cu.env.E, cu.env.E)
+    g, r, c = np.nonzero(adj)
+    ei, ea = cu.env.edge_list()
+    assert np.array_equal(ei.cpu().numpy(), np.stack([g * cu.env.E + r, g * cu.env.E + c]))
+    assert np.array_equal(ea.cpu().numpy()[:, 0], adj[g, r, c])
+    # the info dicts carry the counter (navigation_graph_safe.py:433)
+    infos = cu.env.step(cu.torch.zeros((n, args.num_agents), dtype=cu.torch.int32, device=cu.env.device), 0)[6]
+    st = cu.get_state()
+    just_reset = cu.env.env_i32[3].cpu().numpy() != 0
+    for e in range(0, n, 37):
+        if not just_reset[e]:
+            assert [infos[e][i]['Num_obst_collisions'] for i in range(args.num_agents)] == list(st['num_obstacle_collisions'][e])
 
 
 def test_oracle_batch_dense32():

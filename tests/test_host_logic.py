@@ -32,6 +32,11 @@ def test_config_mirrors_reference_constants():
 def test_invalid_configs_fail_like_the_reference():
     with pytest.raises(ValueError, match="obstacle 0 not supported"):
         cfg.scenario_params_from_args(G.default_args(num_obstacles=2))
+    # the declared extension is opt-in and changes the entity count only
+    p = cfg.scenario_params_from_args(G.default_args(num_obstacles=2, obstacle_extension=True))
+    assert p.num_obstacles == 2 and p.num_entities == 3 * 3 + 2
+    with pytest.raises(ValueError, match="num_obstacles"):
+        cfg.scenario_params_from_args(G.default_args(num_obstacles=33, obstacle_extension=True))
     with pytest.raises(AssertionError):
         cfg.scenario_params_from_args(G.default_args(num_landmarks=1))
     with pytest.raises(NotImplementedError):
@@ -96,7 +101,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     for sym in declared:
         assert getattr(lib, sym) is not None
     lib.lsm_abi_version.restype = ctypes.c_int
-    assert lib.lsm_abi_version() == 4
+    assert lib.lsm_abi_version() == 5
     # struct sizes must agree with the header (checked via the oracle's identical layout of lsm_config)
     import oracle_env as O
     assert ctypes.sizeof(_lib.LsmConfig) == ctypes.sizeof(O.Params)

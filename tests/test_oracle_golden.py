@@ -50,6 +50,8 @@ def check_step(env, z, t, name):
     G.assert_same_mask(s['safety_filtered'][0], z['st_safety_filtered'][t], f'{tag} safety_filtered')
     G.assert_same_mask(s['deconflicting_agent_index'][0], z['st_deconflicting_agent_index'][t], f'{tag} deconflict idx')
     G.assert_same_mask(s['num_agent_collisions'][0], z['st_num_agent_collisions'][t], f'{tag} collisions')
+    if 'st_num_obstacle_collisions' in z.files:      # declared obstacle extension
+        G.assert_same_mask(s['num_obstacle_collisions'][0], z['st_num_obstacle_collisions'][t], f'{tag} obstacle collisions')
     for k in ('ep_travel_length', 'ep_conflict', 'ep_multi_engagement', 'ep_done'):
         G.assert_same_mask(s[k][0], z['st_' + k][t], f'{tag} {k}')
     G.assert_close(s['agent_values'][0], z['st_agent_values'][t], f'{tag} state')

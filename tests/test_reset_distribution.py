@@ -23,8 +23,11 @@ REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(REPO, 'oracle'))
 from gen_reset_samples import features, N, L, NQ  # noqa: E402  (pure numpy; the generator's own feature definitions)
 
-FIX = np.load(os.path.join(REPO, 'tests', 'golden', 'aux', 'reset_samples.npz'))
-META = json.loads(str(FIX['meta']))
+FIX, META = {}, {}
+for _name in ('reset_samples.npz', 'reset_samples_obstacles.npz'):      # the second: declared obstacle extension
+    _z = np.load(os.path.join(REPO, 'tests', 'golden', 'aux', _name))
+    FIX.update({k: _z[k] for k in _z.files if k != 'meta'})
+    META.update(json.loads(str(_z['meta'])))
 N_RESETS = 5000
 
 
@@ -45,7 +48,10 @@ def _check(name, state):
     m = META[name]
     dyn = m['args']['dynamics_type']
     f, freq = features(np.asarray(state['agent_values']), np.asarray(state['landmark_pos']),
-                       np.asarray(state['landmark_heading']), np.asarray(state['landmark_speed']), dyn)
+                       np.asarray(state['landmark_heading']), np.asarray(state['landmark_speed']), dyn,
+                       np.asarray(state['obstacle_pos']) if 'obstacle_pos' in state else None)
+    if 'agent_nearest_obstacle' in f:
+        assert f['agent_nearest_obstacle'].min() >= 1.05 * (0.05 + 0.05), "an accepted agent position collides with an obstacle"
     report = []
     for k, v in f.items():
         ref = FIX[f'{name}__{k}']

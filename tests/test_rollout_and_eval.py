@@ -294,22 +294,25 @@ def test_edge_list_matches_process_adj(N, dyn):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize('tag', ['di4', 'at4', 'boundary'])
+@pytest.mark.parametrize('tag', ['di4', 'at4', 'boundary', 'di4_obst3'])
 def test_world_graph_matches_reference_update_graph(tag):
     """Row a16: lsm_world_graph against world.edge_list / world.edge_weight recorded from the unmodified reference's
     update_graph (navigation_graph_safe.py:996-1015; fixture + generator oracle/gen_world_graph_golden.py): every
     recorded step of a rollout is loaded as one environment of a batch. Integer indices and float64 weights bit-exact;
-    the inclusive radius (an entity exactly 4.0 away IS connected, one ulp farther is not) is part of the fixture."""
+    the inclusive radius (an entity exactly 4.0 away IS connected, one ulp farther is not) is part of the fixture.
+    'di4_obst3': the declared obstacle extension (obstacle nodes in the world graph; update_graph is reference code)."""
     import json
     from layered_safe_marl_b200 import B200GraphVecEnv
-    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux', 'world_graph.npz'))
+    obst = tag.endswith('obst3')
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden', 'aux', 'world_graph_obstacles.npz' if obst else 'world_graph.npz'))
     meta = json.loads(str(z['meta']))[tag]
     steps = meta['steps']
-    args = G.default_args(num_landmarks=2, use_safety_filter=False, **meta['args'])
+    args = G.default_args(num_landmarks=2, use_safety_filter=False, obstacle_extension=obst, **meta['args'])
     env = B200GraphVecEnv(args, num_envs=steps, seed=0)
     env.reset(0)
     s = env.get_state()
-    for k in ('agent_values', 'done', 'reached_goal', 'landmark_pos', 'landmark_heading', 'landmark_speed'):
+    for k in ('agent_values', 'done', 'reached_goal', 'landmark_pos', 'landmark_heading', 'landmark_speed') + \
+            (('obstacle_pos', 'num_obstacle_collisions') if obst else ()):
         s[k] = z[f'{tag}__{k}']
     env.set_state(s)
     ei, ew, off = env.world_graph()
