@@ -51,6 +51,9 @@ WORKLOADS = {
                   world_size=4, episode_length=250), {}, 8192, 6249),
     'cfg1': (dict(dynamics_type='double_integrator', num_agents=3, num_landmarks=2, use_safety_filter=False,
                   world_size=4, episode_length=25), {}, 4096, 0),
+    # BASELINE configs[2] WITH its obstacles: the declared obstacle extension (the reference raises; generic fused kernel)
+    'cfg3_obst4': (dict(dynamics_type='airtaxi', num_agents=10, num_landmarks=2, use_safety_filter=True, world_size=6,
+                        episode_length=350, num_obstacles=4, obstacle_extension=True), dict(POTENTIAL_CONFLICT=True), 16384, 6249),
 }
 WORKLOAD_DESC = {
     'cfg2': "BASELINE configs[1]: double integrator (crazyflie) 8 agents, HJ safety filter on (synthetic value grid "
@@ -58,12 +61,14 @@ WORKLOAD_DESC = {
     'cfg3': "BASELINE configs[2] (obstacle-free): airtaxi 10 agents, POTENTIAL_CONFLICT reward, filter on, 16384 envs per B200",
     'cfg4': "BASELINE configs[3]: dense 32 agents, 8192 envs per B200",
     'cfg1': "BASELINE configs[0] shape: double integrator 3 agents, filter off, 4096 envs per B200",
+    'cfg3_obst4': "BASELINE configs[2] with 4 obstacles (declared extension, not reference-pinned: the reference raises for "
+                  "obstacles; generic fused kernel): airtaxi 10 agents, POTENTIAL_CONFLICT, filter on, 16384 envs per B200",
 }
 
 
-def algorithmic_bytes_per_env_step(N, L, D, F):
-    """fp32 outputs + fp64 state read/write + flags + action index."""
-    E = N * (1 + L)
+def algorithmic_bytes_per_env_step(N, L, D, F, O=0):
+    """fp32 outputs + fp64 state read/write + flags + action index (O obstacles: extension only)."""
+    E = N * (1 + L) + O
     return 4 * N * (E * F + E * E + D + 2) + 77 * N
 
 
@@ -207,7 +212,7 @@ def measure_brief(workload, device, rank, world, steps, warmup, flush):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms, b2b_ms = float(tt[0]), float(tt[1])
     peak, _ = measured_peak()
-    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
+    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F, env.O) * n_envs
     li = env.launch_info()
     out = {"workload": WORKLOAD_DESC[workload], "envs_per_gpu": n_envs, "num_agents": N, "steps": steps,
            "value": n_envs * world * N * steps / (total_ms / 1000.0), "unit": UNIT, "ms_per_step": total_ms / steps,
@@ -405,7 +410,7 @@ def run_ours(a):
         extra = {}
         env.close()
         torch.cuda.empty_cache()
-        for w, ks in (('cfg3', 40), ('cfg4', 20)):
+        for w, ks in (('cfg3', 40), ('cfg3_obst4', 40), ('cfg4', 20)):
             extra[w] = measure_brief(w, device, rank, world, ks, 5, flush)
         extra['cfg5'] = measure_rollout(device, rank, world, 8192, 50, 25)
 
@@ -417,7 +422,7 @@ def run_ours(a):
     # ---- roofline: the WHOLE STEP on SURVEY 8d's algorithmic bytes; the dominant kernel as a sub-key ----------------
     li_spec = li0.get('specialised', 1)
     peak, peak_src = measured_peak()
-    bytes_per_step = algorithmic_bytes_per_env_step(N, L, D, F) * n_envs
+    bytes_per_step = algorithmic_bytes_per_env_step(N, L, D, F, int(getattr(args, 'num_obstacles', 0))) * n_envs
     step_s = float(step_ms.mean()) / 1000.0
     achieved = bytes_per_step / step_s / 1e9
     traffic = None
@@ -528,7 +533,7 @@ def measure_rollout(device, rank, world, n_envs, K, W):
     if world > 1:
         tt = torch.tensor([ms], dtype=torch.float64, device=device); dist.all_reduce(tt, op=dist.ReduceOp.MAX); ms = float(tt[0])
     peak, peak_src = measured_peak()
-    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F) * n_envs
+    bytes_per_step = algorithmic_bytes_per_env_step(N, env.L, env.D, env.F, env.O) * n_envs
     li = env.launch_info()
     out = {"workload": "BASELINE configs[4] shape: rollout collection (env.step + rollout-buffer insert, zero copy) "
                        "8 agents x 8192 envs per B200, HJ filter on; policy forward excluded (actions drawn on device)",

@@ -272,8 +272,8 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
     // both node-feature types ('relative', which every shipped script uses, and 'global') run the specialised pipeline; the
     // float32 interpolation arithmetic (LSM_FLAG_INTERP_FLOAT32, a parity mode) lives in the generic kernel only, so that
     // the specialised kernels carry none of its code
-    // so does the obstacle extension (E = N(1+L) + O is not a compile-time shape of the specialised kernels)
-    h->spec = lsm::spec_available(cfg->dynamics, N, L, &h->geo) && !(cfg->flags & LSM_FLAG_INTERP_FLOAT32) && O == 0;
+    // (the obstacle extension is specialised for the shapes LSM_SPEC_LIST names with O > 0; other obstacle counts: generic)
+    h->spec = lsm::spec_available(cfg->dynamics, N, L, O, &h->geo) && !(cfg->flags & LSM_FLAG_INTERP_FLOAT32);
 #ifdef LSM_EXPERIMENTS
     { const char* force_generic = std::getenv("LSM_FORCE_GENERIC"); if (force_generic != nullptr && force_generic[0] == '1') h->spec = false; }
 #endif
@@ -316,13 +316,13 @@ int lsm_create(const lsm_config* cfg, lsm_handle** out) {
         delete h;
         return fail(4, "lsm_create: one environment group does not fit in shared memory");
     }
-    e = lsm::kernel_prepare(cfg->dynamics, N, L, h->spec, h->smem_per_block, h->block_threads, &h->regs, &h->blocks_per_sm);
+    e = lsm::kernel_prepare(cfg->dynamics, N, L, O, h->spec, h->smem_per_block, h->block_threads, &h->regs, &h->blocks_per_sm);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "kernel_prepare"); }
     if (h->blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: kernel does not fit on an SM"); }
     h->grid_cap = h->sm_count * h->blocks_per_sm;
     if (h->spec) {
         if (h->geo.emit_smem > h->smem_optin) { delete h; return fail(4, "lsm_create: emit record does not fit in shared memory"); }
-        e = lsm::spec_prepare_aux(cfg->dynamics, N, L, &h->emit_regs, &h->emit_blocks_per_sm, &h->pair_regs);
+        e = lsm::spec_prepare_aux(cfg->dynamics, N, L, O, &h->emit_regs, &h->emit_blocks_per_sm, &h->pair_regs);
         if (e != cudaSuccess) { delete h; return cuda_fail(e, "spec_prepare_aux"); }
         if (h->emit_blocks_per_sm < 1) { delete h; return fail(4, "lsm_create: emit kernel does not fit on an SM"); }
     }
@@ -550,7 +550,7 @@ int lsm_get_launch_info(lsm_handle* h, lsm_launch_info* out) {
     const bool pair_path_li = h->spec && (h->kp.c.flags & LSM_FLAG_USE_SAFETY_FILTER) && h->kp.has_vg;
     if (h->spec) {   // the emit kernel / grid lsm_step launches (room left for the pair kernel with placement "late")
         int bps = 0, regs = 0;
-        if (lsm::spec_emit_blocks_per_sm(h->kp.c.dynamics, h->kp.N, h->kp.L, pair_path_li && h->pair_placement == 0,
+        if (lsm::spec_emit_blocks_per_sm(h->kp.c.dynamics, h->kp.N, h->kp.L, h->kp.O, pair_path_li && h->pair_placement == 0,
                                          pair_path_li && h->pair_placement == 1, &bps, &regs) == cudaSuccess) {
             out->emit_blocks_per_sm = bps; out->emit_regs_per_thread = regs;
         }

@@ -123,9 +123,9 @@ __device__ __forceinline__ long long edge_block_exscan(long long v, long long* s
     return base + incl - v;
 }
 
-template <int DYN, int N, int L>
+template <int DYN, int N, int L, int O>
 __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(const __grid_constant__ KParams kp) {
-    using REC = EmitRec<DYN, N, L>;
+    using REC = EmitRec<DYN, N, L, O>;
     constexpr int E = REC::E, W = REC::W;
     constexpr int T = 32 * kEdgeCountWarps;
     __shared__ unsigned s_rowmask[kEdgeCountWarps][E * W];
@@ -157,7 +157,7 @@ __global__ void __launch_bounds__(32 * kEdgeCountWarps) lsm_edge_count_kernel(co
             const int e = w * 32 + lane;
             bool pre = false, post = false;
             if (e < N) { pre = R.done[0][e] != 0; post = R.done[1][e] != 0; }
-            else if (e < E) {
+            else if (e < N + REC::M) {      // obstacles are never disconnected
                 const int m = e - N, order = m / N, owner = m - order * N;
                 pre = R.reached[0][owner] > order; post = R.reached[1][owner] > order;
             }

@@ -36,34 +36,37 @@
 namespace lsm {
 
 // airtaxi-only part of the emit record (rotations into the observer frame need float64 sin / cos)
-template <int DYN, int N, int L>
+template <int DYN, int N, int L, int O>
 struct AirExtra {
     double sth[N], cth[N], spd_post[N];           // sin/cos(theta), speed after the own update
     double theta[N];                              // heading (never changed by the goal update)
-    double lsin[N * L], lcos[N * L], lsp[N * L];   // landmark sin/cos(heading), speed
+    double lsin[N * L + O], lcos[N * L + O], lsp[N * L + O];   // landmark sin/cos(heading), speed; obstacles: (0, 1, 0)
     int goal[2][N];                                // landmark index of the goal before / after the own update
 };
-template <int N, int L>
-struct AirExtra<LSM_DYN_DOUBLE_INTEGRATOR, N, L> {};
+template <int N, int L, int O>
+struct AirExtra<LSM_DYN_DOUBLE_INTEGRATOR, N, L, O> {};
 
 // What the graph emission needs from the physics of one environment (written by lsm_agent_kernel, read by
 // lsm_emit_kernel). Unified per-entity tables for the branch-free node-feature rows:
 //   pos[e]                     position of entity e (agents after the dynamics, then landmarks)
 //   pos[E + s*N + a]           goal position of agent a before (s=0) / after (s=1) its own goal update
 //   vel[s*N + a], vel[2N] = 0  world-frame velocity of agent a before / after its update; landmarks use slot 2N
-//   cst[m], cst[M + s*N + a]   (sin heading, cos heading, speed, type) of landmark m / of agent a's goal
-template <int DYN, int N, int L>
+//   cst[m], cst[CA + s*N + a]  (sin heading, cos heading, speed, type) of landmark m / of agent a's goal
+// O > 0 (declared obstacle extension, lsm_b200.h num_obstacles): obstacle k is entity N + M + k - pos[N + M + k], and
+// cst[M + k] = (0, 1, 0, 2): the landmark row with heading 0, speed 0 and entity type 2; CA = M + O.
+template <int DYN, int N, int L, int O>
 struct __align__(16) EmitRec {
     static constexpr int M = N * L;
-    static constexpr int E = N + M;
+    static constexpr int E = N + M + O;
     static constexpr int W = (E + 31) / 32;
+    static constexpr int CA = M + O;      // first agent-goal entry of cst
     double2 pos[E + 2 * N];
     double2 vel[2 * N + 1];
-    float4 cst[M + 2 * N];
+    float4 cst[M + O + 2 * N];
     int reached[2][N], done[2][N];
     int next_filter;           // world.use_safety_filter this env will have at the NEXT step (curriculum after a reset)
     int _pad[3];
-    AirExtra<DYN, N, L> air;
+    AirExtra<DYN, N, L, O> air;
 };
 
 // physics-only shared-memory scratch of one environment inside lsm_agent_kernel
@@ -401,14 +404,14 @@ __global__ void __launch_bounds__(kPairThreads) lsm_pair_kernel(const __grid_con
 
 // in-kernel variant for internal steps after the first (states changed inside the launch): pair-parallel over
 // the warp's environments, shifted values into P.fval
-template <int DYN, int N, int L>
-__device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EmitRec<DYN, N, L>* Rw, AgentScratch<DYN, N, L>* Pw,
+template <int DYN, int N, int L, int O>
+__device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EmitRec<DYN, N, L, O>* Rw, AgentScratch<DYN, N, L>* Pw,
                                        int nenv, int lane) {
     const GridDev g = *vg;
     for (int t = lane; t < nenv * N * N; t += 32) {
         const int el = t / (N * N), r = t - el * (N * N);
         const int i = r / N, j = r - i * N;
-        const EmitRec<DYN, N, L>& R = Rw[el];
+        const EmitRec<DYN, N, L, O>& R = Rw[el];
         AgentScratch<DYN, N, L>& P = Pw[el];
         if (!P.cur_filter || i == j || R.done[0][i] || R.done[0][j]) continue;
         const double2 pi = R.pos[i], pj = R.pos[j];
@@ -422,14 +425,14 @@ __device__ __noinline__ void pair_phase(const GridDev* __restrict__ vg, EmitRec<
 // state). The per-agent chain is latency bound (~20 % issue utilisation), so these lookups ride on idle issue slots of
 // warps that are resident anyway - no pair kernel competing with the emit kernel for the SMs, one launch less. Same
 // conditions and arithmetic as lsm_pair_kernel (raw values; entries of done agents / filter-off envs are left alone).
-template <int DYN, int N, int L>
-__device__ __noinline__ void pair_tail_phase(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L>* Rw, double* __restrict__ pairval,
+template <int DYN, int N, int L, int O>
+__device__ __noinline__ void pair_tail_phase(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L, O>* Rw, double* __restrict__ pairval,
                                             int env0, int nenv, unsigned on_mask, int lane) {
     const GridDev g = *vg;
     for (int t = lane; t < nenv * N * N; t += 32) {
         const int el = t / (N * N), r = t - el * (N * N);
         const int i = r / N, j = r - i * N;
-        const EmitRec<DYN, N, L>& R = Rw[el];
+        const EmitRec<DYN, N, L, O>& R = Rw[el];
         if (!((on_mask >> ((el * N) & 31)) & 1u) || !R.next_filter || i == j || R.done[1][i] || R.done[1][j]) continue;
         const double2 pi = R.pos[i], pj = R.pos[j];
         double i2, i3, j2, j3;
@@ -443,8 +446,8 @@ __device__ __noinline__ void pair_tail_phase(const GridDev* __restrict__ vg, con
     }
 }
 
-template <int DYN, int N, int L>
-__device__ __forceinline__ void emit_obs_row(const EmitRec<DYN, N, L>& R, const AgentScratch<DYN, N, L>& P, int ai,
+template <int DYN, int N, int L, int O>
+__device__ __forceinline__ void emit_obs_row(const EmitRec<DYN, N, L, O>& R, const AgentScratch<DYN, N, L>& P, int ai,
                                              int g /* landmark index */, double x, double y, double s2, double s3, float* o) {
     // navigation_graph_safe.py:855-875, utils.py:114-137
     const double2 gp = R.pos[N + g];
@@ -481,8 +484,8 @@ __device__ __forceinline__ void bulk_store_wait_read() { asm volatile("cp.async.
 
 // Scenario.random_scenario for ONE environment, executed by the env's leader lane
 // (navigation_graph_safe.py:1199-1367, utils.py:39-68); Philox stream keyed by (seed, env, reset_count).
-template <int DYN, int N, int L>
-__device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, L>& R, AgentScratch<DYN, N, L>& P,
+template <int DYN, int N, int L, int O>
+__device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, L, O>& R, AgentScratch<DYN, N, L>& P,
                                             int env, int reset_count, double ratio) {
     constexpr int M = N * L;
     const lsm_config& c = kp.c;
@@ -491,18 +494,37 @@ __device__ __noinline__ void sample_scenario(const KParams& kp, EmitRec<DYN, N, 
     const double ws = c.world_size;
     double cra = ratio_sloped(ratio, 0.25, 0.75);
     if (use_filter_arg) cra = 1.0;
+    // static obstacles first (:1204-1209): 0.8 * uniform(-ws/2, ws/2, 2)
+    for (int k = 0; k < O; ++k) {
+        const double ox = 0.8 * r.uniform(-ws / 2.0, ws / 2.0);
+        const double oy = 0.8 * r.uniform(-ws / 2.0, ws / 2.0);
+        R.pos[N + M + k] = make_double2(ox, oy);
+    }
     for (int i = 0; i < N; ++i) {
-        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
-            const double px = r.uniform(-0.8 * ws, 0.8 * ws);
-            const double py = r.uniform(-0.8 * ws, 0.8 * ws);
-            R.pos[i] = make_double2(px, py);
-            P.as2[i] = 0.0; P.as3[i] = 0.0;
-        } else {
-            const double xmin = -0.5 * ws;
-            const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
-            const double ry = r.uniform(-0.5 * ws, 0.5 * ws);
-            const double rx = r.uniform(xmin, xmax);
-            R.pos[i] = make_double2(rx, ry);
+        // :1218-1249: with obstacles the position is redrawn while it collides with one (bounded at 1000 tries); the
+        // airtaxi speed / heading are drawn once the position is accepted
+        double px = 0.0, py = 0.0;
+        for (int tries = 0; tries < (O > 0 ? 1000 : 1); ++tries) {
+            if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
+                px = r.uniform(-0.8 * ws, 0.8 * ws);
+                py = r.uniform(-0.8 * ws, 0.8 * ws);
+            } else {
+                const double xmin = -0.5 * ws;
+                const double xmax = 0.25 * ws * cra + 0.0 * (1.0 - cra) * ws;
+                py = r.uniform(-0.5 * ws, 0.5 * ws);
+                px = r.uniform(xmin, xmax);
+            }
+            bool hit = false;
+            for (int k = 0; k < O; ++k) {      // navigation_graph_safe.py:452-465
+                const double2 po = R.pos[N + M + k];
+                const double dx = po.x - px, dy = po.y - py;
+                if (dx * dx + dy * dy < kp.col2_lt) { hit = true; break; }
+            }
+            if (!hit) break;
+        }
+        R.pos[i] = make_double2(px, py);
+        if (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { P.as2[i] = 0.0; P.as3[i] = 0.0; }
+        else {
             const double sp = r.uniform(c.goal_speed_min, c.goal_speed_max);
             P.as2[i] = r.uniform(0.0, 2.0 * kPi);
             P.as3[i] = sp;
@@ -608,8 +630,8 @@ __device__ __noinline__ double goal_reward_factor(double theta, double pdx, doub
 }
 
 // reward_multiple_engagement (navigation_graph_safe.py:800-823) over the agents flagged in `mask`
-template <int DYN, int N, int L>
-__device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, L>& R, unsigned mask, int ai, double x, double y,
+template <int DYN, int N, int L, int O>
+__device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, L, O>& R, unsigned mask, int ai, double x, double y,
                                                          double vpx, double vpy, double sep, double eng) {
     double pc_pen = 0.0;
     for (int a = 0; a < N; ++a) {
@@ -632,8 +654,8 @@ __device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, 
 }
 
 // reward_hj_value (navigation_graph_safe.py:830-837, core.py:459-468)
-template <int DYN, int N, int L>
-__device__ __noinline__ double hj_value_reward(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L>& R,
+template <int DYN, int N, int L, int O>
+__device__ __noinline__ double hj_value_reward(const GridDev* __restrict__ vg, const EmitRec<DYN, N, L, O>& R,
                                               const AgentScratch<DYN, N, L>& P, int ai, double x, double y, double sep, double cvalue_rew) {
     const GridDev g = *vg;
     double r = 0.0;
@@ -698,9 +720,9 @@ __device__ __noinline__ void episode_summary(const KParams& kp, int le, int env,
     }
 }
 
-template <int DYN, int N, int L, int BLOCK, int MINB>
+template <int DYN, int N, int L, int O, int BLOCK, int MINB>
 __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_constant__ KParams kp) {
-    using REC = EmitRec<DYN, N, L>;
+    using REC = EmitRec<DYN, N, L, O>;
     using SCR = AgentScratch<DYN, N, L>;
     constexpr int M = REC::M, E = REC::E;
     constexpr int G = N;                          // lanes per environment: 32 / N environments per warp, no padding lanes
@@ -778,6 +800,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
         double times_req = -1, dists_goal = -1, dist_left = -1, ep_travel_dist = 0, ep_min_dist = INFINITY, action_diff = 0;
         int reached = 0, done = 0, safety_filtered = 0, deconflict = -1, ncoll = 0;
         int ep_len = 0, ep_conflict = 0, ep_multi = 0, ep_done = 0;
+        int nobst = 0;                            // world.num_obstacle_collisions (O > 0 only)
         int current_step = 0, reset_count = 0, parity = 0;
         double ratio = 0.0;
         double* const af = kp.b.agent_f64 + ((size_t)env * N + ai);
@@ -808,6 +831,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             ncoll = aip[LSM_AI_NUM_COLLISIONS * fstride]; ep_len = aip[LSM_AI_EP_TRAVEL_LEN * fstride]; \
             ep_conflict = aip[LSM_AI_EP_CONFLICT * fstride]; ep_multi = aip[LSM_AI_EP_MULTI * fstride]; \
             ep_done = aip[LSM_AI_EP_DONE * fstride]; \
+            if constexpr (O > 0) nobst = aip[LSM_AI_NUM_OBST_COLLISIONS * fstride]; \
         }
         if (kp.mode != MODE_STEP) { LSM_LOAD_MOTION() LSM_LOAD_BOOKKEEPING(false) }
         // landmark tables of the group's environments: contiguous runs per field
@@ -824,6 +848,14 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 SCR& T = Pw[el];
                 T.lh[m] = lhv; T.lsp[m] = lsv; T.lsin[m] = sv; T.lcos[m] = cv;
                 Rw[el].cst[m] = make_float4((float)sv, (float)cv, (float)lsv, 1.0f);   // landmark rows: type 1
+            }
+        }
+        if constexpr (O > 0) {     // obstacle positions [2][n][O] of the group's environments; constant node columns
+            for (int idx = lane; idx < nenv * O; idx += 32) {
+                const int el = idx / O, k = idx - el * O;
+                const double ox = kp.b.obstacles[((size_t)0 * n + (env0 + el)) * O + k], oy = kp.b.obstacles[((size_t)1 * n + (env0 + el)) * O + k];
+                Rw[el].pos[N + M + k] = make_double2(ox, oy);
+                Rw[el].cst[M + k] = make_float4(0.0f, 1.0f, 0.0f, 2.0f);
             }
         }
         Curriculum q = curriculum(kp, ratio);
@@ -867,7 +899,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 // for later internal steps
                 const bool precomputed = it == 0 && kp.pairval != nullptr;
                 if (any_filter != 0u && !precomputed) {
-                    pair_phase<DYN, N, L>(&kp.vg, Rw, Pw, nenv, lane);
+                    pair_phase<DYN, N, L, O>(&kp.vg, Rw, Pw, nenv, lane);
                     __syncwarp();
                 }
                 if (agent_on && q.world_filter) {
@@ -931,7 +963,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 goal_pre = goal_index(reached, ai, N, M);
                 const double2 gp = R.pos[N + goal_pre];
                 const double gx = gp.x, gy = gp.y, gh = P.lh[goal_pre], gs = P.lsp[goal_pre];
-                emit_obs_row<DYN, N, L>(R, P, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+                emit_obs_row<DYN, N, L, O>(R, P, ai, goal_pre, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
                 // reward_reach_goal: navigation_graph_safe.py:691-791
                 const double he = 0.5 - 0.5 * lsm_cos_inl(theta - gh);     // direction_alignment_error, utils.py:79-81
                 const double hpr = 1.0 - clipd(he / q.heading_thresh, 0.0, 1.0);
@@ -976,8 +1008,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 goal_post = goal_index(reached_post, ai, N, M);
                 R.vel[ai] = make_double2(vpx, vpy); R.vel[N + ai] = make_double2(vqx, vqy);
                 R.pos[E + ai] = gp; R.pos[E + N + ai] = R.pos[N + goal_post];
-                { float4 t = R.cst[goal_pre]; t.w = 0.0f; R.cst[M + ai] = t; }
-                { float4 t = R.cst[goal_post]; t.w = 0.0f; R.cst[M + N + ai] = t; }
+                { float4 t = R.cst[goal_pre]; t.w = 0.0f; R.cst[REC::CA + ai] = t; }
+                { float4 t = R.cst[goal_post]; t.w = 0.0f; R.cst[REC::CA + N + ai] = t; }
                 if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
                     R.air.spd_post[ai] = s3q; R.air.goal[0][ai] = goal_pre; R.air.goal[1][ai] = goal_post;
                 }
@@ -1018,15 +1050,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                         if (d2 < stat_mind2) stat_mind2 = d2;
                     }
                 }
+                if constexpr (O > 0) {      // info_callback, navigation_graph_safe.py:402-404, 452-465: any obstacle within 1.05 * (size + size)
+                    bool hit = false;
+                    for (int k = 0; k < O; ++k) {
+                        const double2 po = R.pos[N + M + k];
+                        const double dx = po.x - x, dy = po.y - y;
+                        hit = hit || (dx * dx + dy * dy < kp.col2_lt);
+                    }
+                    if (hit) nobst += 1;
+                }
                 min_rel = sqrt(mind2);
                 if (want_sv) rew += r_sv;
                 if (pc_count > 1)
-                    rew += q.multi_rew * potential_conflict_penalty<DYN, N, L>(R, pc_mask, ai, x, y, vpx, vpy, q.sep, q.eng);
+                    rew += q.multi_rew * potential_conflict_penalty<DYN, N, L, O>(R, pc_mask, ai, x, y, vpx, vpy, q.sep, q.eng);
                 if ((c.flags & LSM_FLAG_DIFF_FROM_FILTERED_ACTION) && use_filter_arg) {   // :825-828
                     if (!done) rew += q.diff_rew * action_diff;
                 }
                 if (c.flags & LSM_FLAG_HJ_VALUE)
-                    rew += hj_value_reward<DYN, N, L>(&kp.vg, R, P, ai, x, y, q.sep, q.cvalue_rew);
+                    rew += hj_value_reward<DYN, N, L, O>(&kp.vg, R, P, ai, x, y, q.sep, q.cvalue_rew);
                 rew = clipd(rew, c.min_reward, c.max_reward);
                 if (!done_post) {
                     ep_len += 1;
@@ -1081,7 +1122,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 const double2 gp = R.pos[N + g];
                 R.pos[E + ai] = gp; R.pos[E + N + ai] = gp;
                 float4 cc = R.cst[g]; cc.w = 0.0f;
-                R.cst[M + ai] = cc; R.cst[M + N + ai] = cc;
+                R.cst[REC::CA + ai] = cc; R.cst[REC::CA + N + ai] = cc;
                 if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
                     R.air.spd_post[ai] = s3; R.air.goal[0][ai] = g; R.air.goal[1][ai] = g;
                 }
@@ -1104,6 +1145,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                                   af[(parity ? LSM_AF_TIMES_REQ_A : LSM_AF_TIMES_REQ_B) * fstride], dists_goal,
                                   af[(parity ? LSM_AF_DISTS_GOAL_A : LSM_AF_DISTS_GOAL_B) * fstride], goal_min_time, ncoll,
                                   safety_filtered);
+                if constexpr (O > 0) { if (agent_on) kp.b.term_i32[(size_t)LSM_TI_NUM_OBST_COLLISIONS * fstride + (size_t)env * N + ai] = nobst; }
                 if (ai == 0) kp.b.term_env_f64[env] = ratio;
             }
             if (do_reset) {
@@ -1111,7 +1153,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 ratio = clipd((double)kp.episode / (double)c.num_total_episode, 0.0, 1.0);
                 q = curriculum(kp, ratio);
             }
-            if (do_reset && sample && ai == 0) sample_scenario<DYN, N, L>(kp, R, P, env, reset_count, ratio);
+            if (do_reset && sample && ai == 0) sample_scenario<DYN, N, L, O>(kp, R, P, env, reset_count, ratio);
             __syncwarp();
             if (do_reset && agent_on) {
                 if (sample) { const double2 p = R.pos[ai]; x = p.x; y = p.y; s2 = P.as2[ai]; s3 = P.as3[ai]; }
@@ -1119,7 +1161,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 p_dist = 0.0; state_time = 0.0;
                 const double2 g0 = R.pos[N + ai];
                 goal_min_time = norm2(x - g0.x, y - g0.y) / c.agent_max_speed;   // navigation_graph_safe.py:525-535
-                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0;
+                times_req = -1.0; dists_goal = -1.0; dist_left = -1.0; ncoll = 0; nobst = 0;
                 ep_len = 0; ep_travel_dist = 0.0; ep_done = 0; ep_conflict = 0; ep_multi = 0; ep_min_dist = INFINITY;
                 double vx, vy;
                 if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) { vx = s2; vy = s3; }
@@ -1128,12 +1170,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 R.vel[ai] = make_double2(vx, vy); R.vel[N + ai] = make_double2(vx, vy);
                 R.pos[E + ai] = g0; R.pos[E + N + ai] = g0;
                 float4 cc = R.cst[ai]; cc.w = 0.0f;
-                R.cst[M + ai] = cc; R.cst[M + N + ai] = cc;
+                R.cst[REC::CA + ai] = cc; R.cst[REC::CA + N + ai] = cc;
                 if constexpr (DYN != LSM_DYN_DOUBLE_INTEGRATOR) {
                     R.air.spd_post[ai] = s3; R.air.goal[0][ai] = ai; R.air.goal[1][ai] = ai;
                 }
                 R.reached[0][ai] = 0; R.reached[1][ai] = 0; R.done[0][ai] = 0; R.done[1][ai] = 0;
-                emit_obs_row<DYN, N, L>(R, P, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+                emit_obs_row<DYN, N, L, O>(R, P, ai, ai, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
             }
             if (do_reset && sample) reset_count += 1;
             __syncwarp();
@@ -1150,10 +1192,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                         dst[LSM_LF_HEADING * lstride + m] = U.lh[m]; dst[LSM_LF_SPEED * lstride + m] = U.lsp[m];
                         dst[LSM_LF_SIN * lstride + m] = U.lsin[m]; dst[LSM_LF_COS * lstride + m] = U.lcos[m];
                     }
+                    if constexpr (O > 0) {
+                        for (int k = lane; k < O; k += 32) {
+                            const double2 p = T.pos[N + M + k];
+                            kp.b.obstacles[((size_t)0 * n + (env0 + el)) * O + k] = p.x;
+                            kp.b.obstacles[((size_t)1 * n + (env0 + el)) * O + k] = p.y;
+                        }
+                    }
                 }
             }
         } else if (kp.mode == MODE_OBSERVE && agent_on) {
-            emit_obs_row<DYN, N, L>(R, P, ai, goal_obs, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
+            emit_obs_row<DYN, N, L, O>(R, P, ai, goal_obs, x, y, s2, s3, kp.b.obs + ((size_t)env * N + ai) * Dobs);
         }
 
         // ---------------- state write-back ----------------
@@ -1182,6 +1231,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 aip[LSM_AI_NUM_COLLISIONS * fstride] = ncoll; aip[LSM_AI_EP_TRAVEL_LEN * fstride] = ep_len;
                 aip[LSM_AI_EP_CONFLICT * fstride] = ep_conflict; aip[LSM_AI_EP_MULTI * fstride] = ep_multi;
                 aip[LSM_AI_EP_DONE * fstride] = ep_done;
+                if constexpr (O > 0) aip[LSM_AI_NUM_OBST_COLLISIONS * fstride] = nobst;
             }
         }
         // ---------------- emit records -> global memory (consumed by lsm_emit_kernel; L2 resident) ----------------
@@ -1191,6 +1241,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
             for (int idx = lane; idx < nenv * M; idx += 32) {
                 const int el = idx / M, m = idx - el * M;
                 Rw[el].air.lsin[m] = Pw[el].lsin[m]; Rw[el].air.lcos[m] = Pw[el].lcos[m]; Rw[el].air.lsp[m] = Pw[el].lsp[m];
+            }
+            if constexpr (O > 0) {     // obstacles: heading 0, speed 0
+                for (int idx = lane; idx < nenv * O; idx += 32) {
+                    const int el = idx / O, k = idx - el * O;
+                    Rw[el].air.lsin[M + k] = 0.0; Rw[el].air.lcos[M + k] = 1.0; Rw[el].air.lsp[M + k] = 0.0;
+                }
             }
         }
         __syncwarp();
@@ -1204,7 +1260,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 for (int k = lane; k < Q; k += 32) dst[k] = src[k];
             }
             // placement 4: next step's HJ pair values from the records still in shared memory
-            if (kp.pair_tail) pair_tail_phase<DYN, N, L>(&kp.vg, Rw, kp.pairval, env0, nenv, on_mask, lane);
+            if (kp.pair_tail) pair_tail_phase<DYN, N, L, O>(&kp.vg, Rw, kp.pairval, env0, nenv, on_mask, lane);
         }
         __syncwarp();
     }
@@ -1224,9 +1280,9 @@ __device__ __forceinline__ void cp_async16(void* sdst, const void* gsrc) {
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int DYN, int N, int L>
+template <int DYN, int N, int L, int O>
 struct EmitGeom {
-    using REC = EmitRec<DYN, N, L>;
+    using REC = EmitRec<DYN, N, L, O>;
     static constexpr int E = REC::E, W = REC::W, EE = E * E;
     static constexpr int F = DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 10 : 11;
     static constexpr int ROWS = N * E;
@@ -1240,10 +1296,10 @@ struct EmitGeom {
     static constexpr int NBUF = (EE * 4 + CR * F * 4) <= 24 * 1024 ? 2 : 1;
 };
 
-template <int DYN, int N, int L, int WPE>
+template <int DYN, int N, int L, int O, int WPE>
 struct __align__(16) EmitShared {
-    using GEO = EmitGeom<DYN, N, L>;
-    using REC = EmitRec<DYN, N, L>;
+    using GEO = EmitGeom<DYN, N, L, O>;
+    using REC = EmitRec<DYN, N, L, O>;
     REC rec[2];                                              // current / prefetched record
     alignas(16) float dthr[GEO::NBUF][GEO::EE];              // radius-thresholded distance matrix (float32, what adj stores)
     alignas(16) float nodes[GEO::NBUF][GEO::CR * GEO::F];    // node-row chunk
@@ -1258,9 +1314,9 @@ struct __align__(16) EmitShared {
 
 // Fused COO edge output of one environment: kept OUT OF LINE so that its registers do not count against
 // the occupancy of the dense path (69 -> 91 registers per thread when inlined, one resident block per SM fewer).
-template <int DYN, int N, int L, int WPE>
-__device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KParams& kp, int ee, const float* dthr, bool uniform) {
-    using GEO = EmitGeom<DYN, N, L>;
+template <int DYN, int N, int L, int O, int WPE>
+__device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, O, WPE>& S, const KParams& kp, int ee, const float* dthr, bool uniform) {
+    using GEO = EmitGeom<DYN, N, L, O>;
     constexpr int E = GEO::E, W = GEO::W;
     constexpr int T = 32 * WPE;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -1368,11 +1424,11 @@ __device__ __noinline__ void emit_edges(EmitShared<DYN, N, L, WPE>& S, const KPa
 // PIE ("pair in emit"): also compute the next step's HJ pair values per environment after its copies are issued - the
 // placement that wins for few agents (one launch less; the lookups of an 8-agent environment occupy half a block once).
 // For many agents the per-block chain gets long and lsm_pair_kernel behind this kernel is faster (see lsm_capi.cu).
-template <int DYN, int N, int L, int WPE, int MINB, bool PIE = false>
+template <int DYN, int N, int L, int O, int WPE, int MINB, bool PIE = false>
 __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_constant__ KParams kp) {
-    using ES = EmitShared<DYN, N, L, WPE>;
-    using REC = EmitRec<DYN, N, L>;
-    using GEO = EmitGeom<DYN, N, L>;
+    using ES = EmitShared<DYN, N, L, O, WPE>;
+    using REC = EmitRec<DYN, N, L, O>;
+    using GEO = EmitGeom<DYN, N, L, O>;
     constexpr int M = REC::M, E = REC::E, W = REC::W, EE = E * E;
     constexpr int F = GEO::F, ROWS = GEO::ROWS, CR = GEO::CR, NCHUNK = GEO::NCHUNK, NBUF = GEO::NBUF;
     constexpr int T = 32 * WPE;
@@ -1517,7 +1573,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             const int e = w * 32 + lane;
             bool dpre = false, dpost = false;
             if (e < N) { dpre = R.done[0][e] != 0; dpost = R.done[1][e] != 0; }
-            else if (e < E) {
+            else if (e < N + M) {       // obstacles (e >= N + M) are never disconnected
                 const int m = e - N, order = m / N, owner = m - order * N;
                 dpre = R.reached[0][owner] > order; dpost = R.reached[1][owner] > order;
             }
@@ -1534,7 +1590,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             }
             __syncthreads();
         }
-        if (edges) emit_edges<DYN, N, L, WPE>(S, kp, ee, dthr, any_change == 0u);
+        if (edges) emit_edges<DYN, N, L, O, WPE>(S, kp, ee, dthr, any_change == 0u);
         if (compact) {
             unsigned* kdst = kp.adj_keep + (size_t)ee * (N * W);
             for (int k = tid; k < N * W; k += T) kdst[k] = any_disc != 0u ? S.keepm[k] : 0xffffffffu;
@@ -1598,13 +1654,13 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
             const int sel = (e <= i) ? N : 0;     // agents <= i are seen after their own update
             const int vidx = is_agent ? sel + e : 2 * N;
             const int gidx = is_agent ? E + sel + e : e;
-            const int cidx = is_agent ? M + sel + e : e - N;
+            const int cidx = is_agent ? REC::CA + sel + e : e - N;
             if (gfeat) {
                 // an agent's goal is its FIRST landmark (optimal_match_index = arange, navigation_graph_safe.py:179), a
                 // landmark's goal is itself; velocities are world-frame (landmarks: zero)
                 const double2 pe = R.pos[e], ve = R.vel[vidx], ge = is_agent ? R.pos[N + e] : pe;
                 o[0] = (float)ve.x; o[1] = (float)ve.y; o[2] = (float)pe.x; o[3] = (float)pe.y;
-                o[4] = (float)ge.x; o[5] = (float)ge.y; o[6] = is_agent ? 0.0f : 1.0f;
+                o[4] = (float)ge.x; o[5] = (float)ge.y; o[6] = is_agent ? 0.0f : ((O == 0 || e < N + M) ? 1.0f : 2.0f);
                 (void)gidx; (void)cidx; (void)pi; (void)vi;
             } else if constexpr (DYN == LSM_DYN_DOUBLE_INTEGRATOR) {
                 // utils.py:201-255: [p_e - p_i, v_e - v_i, goal_e - p_i, sin gh, cos gh, gspeed, type]
@@ -1638,7 +1694,7 @@ __global__ void __launch_bounds__(32 * WPE, MINB) lsm_emit_kernel(const __grid_c
                     const float sh = (float)(R.air.lsin[m] * ci - R.air.lcos[m] * si), ch = (float)(R.air.lcos[m] * ci + R.air.lsin[m] * si);
                     o[0] = (float)rx; o[1] = (float)ry; o[2] = (float)R.air.spd_post[i];
                     o[3] = sh; o[4] = ch; o[5] = (float)rx; o[6] = (float)ry; o[7] = sh; o[8] = ch;
-                    o[9] = (float)R.air.lsp[m]; o[10] = 1.0f;
+                    o[9] = (float)R.air.lsp[m]; o[10] = (O == 0 || e < N + M) ? 1.0f : 2.0f;
                 }
             }
         };

@@ -26,23 +26,28 @@ namespace lsm {
 // ---------------------------------------------------------------------------------------------
 // host-side launch helpers (used by lsm_capi.cu)
 // ---------------------------------------------------------------------------------------------
-// (dynamics, N, L, warps per env of the emit kernel, resident emit blocks per SM the register budget targets)
+// (dynamics, N, L, O, warps per env of the emit kernel, resident emit blocks per SM the register budget targets)
 #ifndef LSM_AIR_WPE
 #define LSM_AIR_WPE 2
 #endif
 // BASELINE.json's benchmark shapes (8 / 3 / 32 double-integrator agents, 10 airtaxi agents) and the shapes the
 // reference's own scripts ship with (train.sh: 4 agents, 2 landmarks, either dynamics; eval_airtaxi.sh: 8 and 16 agents;
 // eval_double_integrator.sh: 4 agents; the 16-agent dense golden rollout)
+// (dynamics, N, L, O obstacles, ...): O > 0 is the declared obstacle extension (lsm_b200.h num_obstacles) - BASELINE
+// configs[2] names "10 airtaxi agents + obstacles", so that shape (4 obstacles) and the bench shape of the double
+// integrator with 4 obstacles are specialised too; every other obstacle count runs the generic kernel
 #define LSM_SPEC_LIST(X)                               \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 4, 4)           \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2, 1, 16)          \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2, 4, 3)          \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 4, 2, 2, 8)           \
-    X(LSM_DYN_DOUBLE_INTEGRATOR, 16, 2, 4, 4)          \
-    X(LSM_DYN_AIRTAXI, 10, 2, LSM_AIR_WPE, 5)          \
-    X(LSM_DYN_AIRTAXI, 4, 2, 2, 8)                     \
-    X(LSM_DYN_AIRTAXI, 8, 2, 2, 5)                     \
-    X(LSM_DYN_AIRTAXI, 16, 2, 4, 4)
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 0, 4, 4)        \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 3, 2, 0, 1, 16)       \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 32, 2, 0, 4, 3)       \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 4, 2, 0, 2, 8)        \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 16, 2, 0, 4, 4)       \
+    X(LSM_DYN_AIRTAXI, 10, 2, 0, LSM_AIR_WPE, 5)       \
+    X(LSM_DYN_AIRTAXI, 4, 2, 0, 2, 8)                  \
+    X(LSM_DYN_AIRTAXI, 8, 2, 0, 2, 5)                  \
+    X(LSM_DYN_AIRTAXI, 16, 2, 0, 4, 4)                 \
+    X(LSM_DYN_AIRTAXI, 10, 2, 4, LSM_AIR_WPE, 5)       \
+    X(LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 4, 4, 4)
 
 constexpr int kAgentBlock = 128;
 constexpr int kAgentMinB = 2;
@@ -73,19 +78,19 @@ struct SpecFns {
 // LSM_WPE=2|4 selects an alternative emit-kernel shape for the cfg2 specialisation
 template <int WPE_, int EMINB_>
 static void cfg2_emit_variant(SpecFns* f) {
-    f->emit = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_>;
-    f->emit_pie = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_, EMINB_, true>;
-    f->emit_smem = (int)sizeof(EmitShared<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, WPE_>);
+    f->emit = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 0, WPE_, EMINB_>;
+    f->emit_pie = (const void*)lsm_emit_kernel<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 0, WPE_, EMINB_, true>;
+    f->emit_smem = (int)sizeof(EmitShared<LSM_DYN_DOUBLE_INTEGRATOR, 8, 2, 0, WPE_>);
     f->emit_threads = 32 * WPE_;
 }
 
 #endif
 
-static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f);
-static bool spec_fns(int dynamics, int N, int L, SpecFns* f) {
-    if (!spec_fns_base(dynamics, N, L, f)) return false;
+static bool spec_fns_base(int dynamics, int N, int L, int O, SpecFns* f);
+static bool spec_fns(int dynamics, int N, int L, int O, SpecFns* f) {
+    if (!spec_fns_base(dynamics, N, L, O, f)) return false;
 #ifdef LSM_EXPERIMENTS
-    if (dynamics == LSM_DYN_DOUBLE_INTEGRATOR && N == 8 && L == 2) {
+    if (dynamics == LSM_DYN_DOUBLE_INTEGRATOR && N == 8 && L == 2 && O == 0) {
         const int w = env_int("LSM_WPE", 0);
         if (w == 1) cfg2_emit_variant<1, 8>(f);
         if (w == 2) cfg2_emit_variant<2, 8>(f);
@@ -96,24 +101,24 @@ static bool spec_fns(int dynamics, int N, int L, SpecFns* f) {
 }
 
 #ifdef LSM_EXPERIMENTS
-#define LSM_AGENT_FN(DYN_, N_, L_) (agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, 3> \
-                                                      : (const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>)
-#define LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_) ((const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_, true>)
+#define LSM_AGENT_FN(DYN_, N_, L_, O_) (agent_minb() == 3 ? (const void*)lsm_agent_kernel<DYN_, N_, L_, O_, kAgentBlock, 3> \
+                                                          : (const void*)lsm_agent_kernel<DYN_, N_, L_, O_, kAgentBlock, kAgentMinB>)
+#define LSM_EMIT_PIE_FN(DYN_, N_, L_, O_, WPE_, EMINB_) ((const void*)lsm_emit_kernel<DYN_, N_, L_, O_, WPE_, EMINB_, true>)
 #else
-#define LSM_AGENT_FN(DYN_, N_, L_) ((const void*)lsm_agent_kernel<DYN_, N_, L_, kAgentBlock, kAgentMinB>)
-#define LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_) nullptr   /* "pair values inside the emit kernel": experiments only */
+#define LSM_AGENT_FN(DYN_, N_, L_, O_) ((const void*)lsm_agent_kernel<DYN_, N_, L_, O_, kAgentBlock, kAgentMinB>)
+#define LSM_EMIT_PIE_FN(DYN_, N_, L_, O_, WPE_, EMINB_) nullptr   /* "pair values inside the emit kernel": experiments only */
 #endif
-static bool spec_fns_base(int dynamics, int N, int L, SpecFns* f) {
-#define X(DYN_, N_, L_, WPE_, EMINB_)                                                             \
-    if (dynamics == DYN_ && N == N_ && L == L_) {                                                 \
+static bool spec_fns_base(int dynamics, int N, int L, int O, SpecFns* f) {
+#define X(DYN_, N_, L_, O_, WPE_, EMINB_)                                                         \
+    if (dynamics == DYN_ && N == N_ && L == L_ && O == O_) {                                      \
         f->pair = (const void*)lsm_pair_kernel<DYN_, N_>;                                         \
-        f->agent = LSM_AGENT_FN(DYN_, N_, L_);                                                    \
-        f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, WPE_, EMINB_>;                       \
-        f->emit_pie = LSM_EMIT_PIE_FN(DYN_, N_, L_, WPE_, EMINB_);                                \
-        f->edge_count = (const void*)lsm_edge_count_kernel<DYN_, N_, L_>;                         \
-        f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_>);                                        \
+        f->agent = LSM_AGENT_FN(DYN_, N_, L_, O_);                                                \
+        f->emit = (const void*)lsm_emit_kernel<DYN_, N_, L_, O_, WPE_, EMINB_>;                   \
+        f->emit_pie = LSM_EMIT_PIE_FN(DYN_, N_, L_, O_, WPE_, EMINB_);                            \
+        f->edge_count = (const void*)lsm_edge_count_kernel<DYN_, N_, L_, O_>;                     \
+        f->rec_bytes = (int)sizeof(EmitRec<DYN_, N_, L_, O_>);                                    \
         f->scratch_bytes = (int)sizeof(AgentScratch<DYN_, N_, L_>);                               \
-        f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, WPE_>);                               \
+        f->emit_smem = (int)sizeof(EmitShared<DYN_, N_, L_, O_, WPE_>);                           \
         f->emit_threads = 32 * WPE_;                                                              \
         return true;                                                                              \
     }
@@ -127,9 +132,9 @@ static const void* generic_ptr(int dynamics) {
                                                  : (const void*)lsm_generic_kernel<LSM_DYN_AIRTAXI>;
 }
 
-bool spec_available(int dynamics, int N, int L, SpecGeometry* g) {
+bool spec_available(int dynamics, int N, int L, int O, SpecGeometry* g) {
     SpecFns f;
-    if (!spec_fns(dynamics, N, L, &f)) return false;
+    if (!spec_fns(dynamics, N, L, O, &f)) return false;
     g->rec_bytes = f.rec_bytes; g->scratch_bytes = f.scratch_bytes; g->agent_block = kAgentBlock;
     g->emit_smem = f.emit_smem; g->emit_threads = f.emit_threads; g->pair_block = kPairBlock;
     return true;
@@ -145,17 +150,17 @@ static cudaError_t prepare_one(const void* fn, int block_threads, int smem_bytes
     return cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocks_per_sm, fn, block_threads, smem_bytes);
 }
 
-cudaError_t kernel_prepare(int dynamics, int N, int L, bool spec, int smem_bytes, int block_threads, int* regs,
+cudaError_t kernel_prepare(int dynamics, int N, int L, int O, bool spec, int smem_bytes, int block_threads, int* regs,
                            int* blocks_per_sm) {
     SpecFns f;
     const void* fn = generic_ptr(dynamics);
-    if (spec) { if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue; fn = f.agent; }
+    if (spec) { if (!spec_fns(dynamics, N, L, O, &f)) return cudaErrorInvalidValue; fn = f.agent; }
     return prepare_one(fn, block_threads, smem_bytes, regs, blocks_per_sm);
 }
 
-cudaError_t spec_prepare_aux(int dynamics, int N, int L, int* emit_regs, int* emit_blocks_per_sm, int* pair_regs) {
+cudaError_t spec_prepare_aux(int dynamics, int N, int L, int O, int* emit_regs, int* emit_blocks_per_sm, int* pair_regs) {
     SpecFns f;
-    if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
+    if (!spec_fns(dynamics, N, L, O, &f)) return cudaErrorInvalidValue;
     cudaError_t e = prepare_one(f.emit, f.emit_threads, f.emit_smem, emit_regs, emit_blocks_per_sm);
     if (e != cudaSuccess) return e;
     if (f.emit_pie != nullptr) { int r = 0, b = 0; e = prepare_one(f.emit_pie, f.emit_threads, f.emit_smem, &r, &b); if (e != cudaSuccess) return e; }
@@ -208,7 +213,7 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
                           cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
     SpecFns f;
     const void* fn = generic_ptr(kp.c.dynamics);
-    if (spec) { if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue; fn = f.agent; }
+    if (spec) { if (!spec_fns(kp.c.dynamics, kp.N, kp.L, kp.O, &f)) return cudaErrorInvalidValue; fn = f.agent; }
 #ifdef LSM_EXPERIMENTS
     if (spec) {
         // LSM_AGENT_SMEM=<bytes>: pad the agent kernel's dynamic shared memory so that fewer blocks fit an SM and the
@@ -226,7 +231,7 @@ cudaError_t kernel_launch(const KParams& kp, bool spec, int grid_blocks, int blo
 
 cudaError_t spec_launch_pair(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes) {
     SpecFns f;
-    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, kp.O, &f)) return cudaErrorInvalidValue;
     const long long tasks = (long long)(kp.env_end - kp.env_begin) * kp.N * kp.N;
     long long blocks = (tasks + kPairBlock - 1) / kPairBlock;
     if (blocks < 1) blocks = 1;
@@ -276,9 +281,9 @@ static cudaError_t emit_blocks_per_sm(const SpecFns& f, bool reserve_pair, bool 
     return cudaSuccess;
 }
 
-cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pair, bool pie, int* out, int* regs) {
+cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, int O, bool reserve_pair, bool pie, int* out, int* regs) {
     SpecFns f;
-    if (!spec_fns(dynamics, N, L, &f)) return cudaErrorInvalidValue;
+    if (!spec_fns(dynamics, N, L, O, &f)) return cudaErrorInvalidValue;
     if (regs != nullptr) {
         cudaFuncAttributes fa;
         cudaError_t e = cudaFuncGetAttributes(&fa, (pie && f.emit_pie != nullptr) ? f.emit_pie : f.emit);
@@ -290,7 +295,7 @@ cudaError_t spec_emit_blocks_per_sm(int dynamics, int N, int L, bool reserve_pai
 
 cudaError_t spec_launch_emit(const KParams& kp, cudaStream_t stream, const void* persist_ptr, size_t persist_bytes, bool reserve_pair, bool pie) {
     SpecFns f;
-    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, kp.O, &f)) return cudaErrorInvalidValue;
     // persistent blocks: as many as are resident at once, each loops over environments
     static int sm_count = 0;
     if (sm_count == 0) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev); }
@@ -317,7 +322,7 @@ int edge_count_envs_per_block(long long envs) {
 
 cudaError_t spec_launch_edge_count(const KParams& kp, cudaStream_t stream) {
     SpecFns f;
-    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, &f)) return cudaErrorInvalidValue;
+    if (!spec_fns(kp.c.dynamics, kp.N, kp.L, kp.O, &f)) return cudaErrorInvalidValue;
     const long long envs = kp.env_end - kp.env_begin;
     long long blocks = (envs + kp.edge_envs_per_block - 1) / kp.edge_envs_per_block;
     if (blocks < 1) blocks = 1;

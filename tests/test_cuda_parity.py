@@ -208,22 +208,26 @@ def test_oracle_batch_airtaxi_filter_pc():
                          auto_reset=True)
 
 
-@pytest.mark.parametrize('shape', ['di', 'di_global', 'airtaxi_cfg3'])
+@pytest.mark.parametrize('shape', ['di', 'di_global', 'airtaxi_cfg3', 'di8_spec', 'airtaxi_generic'])
 def test_oracle_batch_obstacle_extension(shape):
     """The DECLARED obstacle extension (BASELINE config 3 '+ obstacles'; the reference raises, see config.scenario_params_from_args):
-    CUDA generic kernel == C oracle on seeded batches - Philox obstacle placement, agent positions redrawn while they collide
+    CUDA == C oracle on seeded batches (the specialised pipeline for the two obstacle shapes LSM_SPEC_LIST names - BASELINE
+    config 3's 10 airtaxi agents + 4 obstacles and the 8-agent double integrator + 4 obstacles - the generic kernel otherwise) - Philox obstacle placement, agent positions redrawn while they collide
     with an obstacle, obstacle nodes / edges, Num_obst_collisions, auto-reset. The oracle itself is pinned by the fixtures
     di3_obst2 / di4_obst3_filter_global / at10_obst4_filter_pc (reference code + the two completed statements). Many
     obstacles in a small world so that rejections and collisions are frequent."""
     kw = dict(di=dict(num_agents=5, num_obstacles=12, world_size=1, episode_length=8, use_safety_filter=True),
               di_global=dict(num_agents=3, num_obstacles=32, world_size=1, episode_length=6, graph_feat_type='global'),
               airtaxi_cfg3=dict(dynamics_type='airtaxi', num_agents=10, num_obstacles=4, world_size=6, episode_length=350,
-                                use_safety_filter=True))[shape]
+                                use_safety_filter=True),
+              di8_spec=dict(num_agents=8, num_obstacles=4, world_size=1, episode_length=7, use_safety_filter=True),
+              airtaxi_generic=dict(dynamics_type='airtaxi', num_agents=6, num_obstacles=9, world_size=1, episode_length=5,
+                                   use_safety_filter=True))[shape]
     args = G.default_args(obstacle_extension=True, **kw)
-    flags = G.BinaryFlags(dict(POTENTIAL_CONFLICT=True) if shape == 'airtaxi_cfg3' else {})
-    n, T = (96, 12) if shape == 'airtaxi_cfg3' else (193, 20)
+    flags = G.BinaryFlags(dict(POTENTIAL_CONFLICT=True) if shape.startswith('airtaxi') else {})
+    n, T = (96, 12) if shape.startswith('airtaxi') else (193, 20)
     ora, cu = _compare_with_oracle(args, flags, n=n, T=T, episode=6249 if shape != 'di_global' else 0, seed=17, auto_reset=True)
-    assert cu.env.launch_info()['specialised'] == 0
+    assert cu.env.launch_info()['specialised'] == (1 if shape in ('airtaxi_cfg3', 'di8_spec') else 0)
     s = cu.get_state()
     if shape != 'airtaxi_cfg3':
         assert s['num_obstacle_collisions'].sum() > 0, "the scenario was meant to produce obstacle collisions"
@@ -337,7 +341,7 @@ def test_chunked_launches_identical(shape):
         assert np.array_equal(ep, outs[0][2], equal_nan=True)
 
 
-@pytest.mark.parametrize('shape', ['di8', 'air10', 'di3'])
+@pytest.mark.parametrize('shape', ['di8', 'air10', 'di3', 'air10_obst4'])
 def test_host_outputs_compact_adjacency_is_byte_identical(shape):
     """Host-facing path (numpy_outputs=True, what the unmodified runner consumes): the adjacency crosses PCIe as one
     thresholded E x E matrix per env + per-observer keep masks and is expanded on the host. Every returned array must be
@@ -347,7 +351,9 @@ def test_host_outputs_compact_adjacency_is_byte_identical(shape):
     from layered_safe_marl_b200 import B200GraphVecEnv
     kw = dict(di8=dict(num_agents=8, world_size=2, use_safety_filter=True),
               air10=dict(dynamics_type='airtaxi', num_agents=10, world_size=6, use_safety_filter=True),
-              di3=dict(num_agents=3, world_size=2, use_safety_filter=False))[shape]
+              di3=dict(num_agents=3, world_size=2, use_safety_filter=False),
+              air10_obst4=dict(dynamics_type='airtaxi', num_agents=10, world_size=6, use_safety_filter=True, num_obstacles=4,
+                               obstacle_extension=True))[shape]
     args = G.default_args(episode_length=12, **kw)
     n, T, episode = 300, 30, 6249
     dev_env = B200GraphVecEnv(args, num_envs=n, seed=3)
@@ -376,7 +382,7 @@ def test_host_outputs_compact_adjacency_is_byte_identical(shape):
             assert np.array_equal(a.cpu().numpy().view(np.uint8), np.ascontiguousarray(b).view(np.uint8)), f"step {t} output {k}"
         st = dev_env.get_state()
         saw_disconnected |= bool((st['reached_goal'] > 0).any())
-    assert saw_disconnected or shape == 'air10', "no goal was reached: the keep masks were never exercised"
+    assert saw_disconnected or shape.startswith('air10'), "no goal was reached: the keep masks were never exercised"
 
 
 def test_infos_on_an_auto_reset_step_are_the_terminal_steps():

@@ -16,6 +16,7 @@ pytestmark = pytest.mark.gpu
 
 FULL = {   # name: (workload key of bench.py, warm-up steps)
     'cfg2': 6, 'cfg3': 4, 'cfg4': 3,
+    'cfg3_obst4': 4,       # BASELINE configs[2] with its obstacles (declared extension)
 }
 
 
@@ -63,8 +64,10 @@ def test_full_size_graph_properties_and_sampled_oracle(workload):
     assert torch.equal(a, a.transpose(-1, -2)), "adjacency of every observer must be symmetric"
     assert bool((torch.diagonal(a, dim1=-2, dim2=-1) == 0).all()), "zero diagonal"
     assert bool(((a == 0) | ((a > 0) & (a < r))).all()), "entries are 0 or a distance strictly inside the radius"
-    # type flag: agents 0, landmarks 1 (last node feature)
-    assert bool((node_obs[:, :, :N, F - 1] == 0).all()) and bool((node_obs[:, :, N:, F - 1] == 1).all())
+    # type flag: agents 0, landmarks 1, obstacles 2 (last node feature)
+    NM = N + env.M
+    assert bool((node_obs[:, :, :N, F - 1] == 0).all()) and bool((node_obs[:, :, N:NM, F - 1] == 1).all())
+    assert bool((node_obs[:, :, NM:, F - 1] == 2).all())
     # observer i's own node: zero relative position; row i of its adjacency is the norm of the relative positions
     idx = torch.arange(N, device=env.device)
     own = node_obs[:, idx, idx, :2]

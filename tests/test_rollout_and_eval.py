@@ -224,15 +224,18 @@ def _process_adj(adj):
 @pytest.mark.gpu
 @pytest.mark.parametrize('N,dyn,world,chunks', [(8, 'double_integrator', 4, 1), (8, 'double_integrator', 10, 3), (3, 'double_integrator', 6, 1),
                                                  (10, 'airtaxi', 6, 1), (10, 'airtaxi', 14, 4), (32, 'double_integrator', 4, 1),
-                                                 (32, 'double_integrator', 16, 2)])
+                                                 (32, 'double_integrator', 16, 2), (-8, 'double_integrator', 3, 2), (-10, 'airtaxi', 6, 1)])
 def test_fused_edge_output_matches_process_adj(N, dyn, world, chunks):
     """N2, fused: the emission kernel writes (edge_index, edge_attr) itself (lsm_set_edge_output). Bit-exact against the
     reference's process_adj (gnn.py:376-407) applied to the dense adjacency of a twin env, at the cfg2 / cfg3 / cfg4
     shapes, dense and sparse worlds, chunked launches (per-range prefixes joined by events), goals reached and
     auto-resets; then with dense_adj=False (no dense tensor written at all) against the same twin."""
     from layered_safe_marl_b200 import B200GraphVecEnv
+    obst = 4 if N < 0 else 0          # negative N: the same shape with 4 obstacles (declared extension, specialised pipeline)
+    N = abs(N)
     n = 61 if N == 32 else 203
-    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=(N != 3), episode_length=9, world_size=world)
+    args = G.default_args(dynamics_type=dyn, num_agents=N, use_safety_filter=(N != 3), episode_length=9, world_size=world,
+                          num_obstacles=obst, obstacle_extension=obst > 0)
     twin = B200GraphVecEnv(args, num_envs=n, seed=5)
     env = B200GraphVecEnv(args, num_envs=n, seed=5, tuning=dict(chunks=chunks))
     assert env.launch_info()['chunks'] == chunks
