@@ -244,6 +244,15 @@ CASES = [
                                                    obstacle_extension=True),
          flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=24, seed=23, greedy_agents=(0, 1, 2),
          injections=(('near_goal', 0, 0.6, 1), ('pair', 5, 6, 2.0, 0.08), ('obstacle_at_agent', 0, 3, 0.2), ('obstacle_at_agent', 3, 7, 0.15))),
+    # edge shapes: a single agent (no "others": the filter, min distance and engagement terms see empty lists), and more than two
+    # landmarks per agent (goal chains of 3 / 4, run-time L on the generic kernel)
+    dict(name='di1_single_filter', args_kw=dict(DI, num_agents=1, use_safety_filter=True, episode_length=60), flags=ALL_FLAGS,
+         episode=6249, T=40, seed=31, greedy_agents=(0,), injections=(('near_goal', 0, 0.5, 0),)),
+    dict(name='di2_landmarks4', args_kw=dict(DI, num_agents=2, num_landmarks=4, use_safety_filter=True, episode_length=120, world_size=2),
+         flags={}, episode=6249, T=70, seed=32, greedy_agents=(0, 1), injections=(('near_goal', 0, 0.4, 0), ('near_goal', 1, 0.5, 2))),
+    dict(name='at3_landmarks3', args_kw=dict(AT, num_agents=3, num_landmarks=3, use_safety_filter=True, episode_length=200),
+         flags=dict(POTENTIAL_CONFLICT=True), episode=6249, T=40, seed=33, greedy_agents=(0, 1, 2),
+         injections=(('near_goal', 0, 0.5, 0), ('near_goal', 1, 0.6, 1), ('near_goal', 2, 0.4, 2))),
     dict(name='at6_allflags', args_kw=dict(AT, num_agents=6, use_safety_filter=True, world_size=3, episode_length=350),
          flags=ALL_FLAGS, episode=4000, T=30, seed=11, greedy_agents=(0, 1),
          injections=(('near_goal', 0, 0.5, 1), ('pair', 2, 3, 1.5, 0.085), ('pair', 4, 5, 2.5, 0.035))),

@@ -252,6 +252,25 @@ def test_oracle_batch_dense32():
     _compare_with_oracle(args, G.BinaryFlags({}), n=24, T=6, episode=6249, seed=9, auto_reset=True)
 
 
+@pytest.mark.parametrize('shape', ['n32_l4', 'n32_l2_o32', 'n1', 'n2_l5_airtaxi'])
+def test_oracle_batch_extreme_shapes(shape):
+    """Maximum and minimum sizes on the generic kernel: 32 agents x 4 landmarks (128 landmarks = LSM_MAX_LANDMARKS, the np.int8
+    index limit Q8; E = 160), 32 agents + 32 obstacles (E = 128), a single agent (empty "others" lists everywhere), and
+    5 landmarks per airtaxi agent - against the C oracle, whose behaviour at 1 agent and at 3 / 4 landmarks is pinned by the
+    fixtures di1_single_filter / at3_landmarks3 / di2_landmarks4."""
+    kw = dict(n32_l4=dict(num_agents=32, num_landmarks=4, use_safety_filter=True, episode_length=250, world_size=4),
+              n32_l2_o32=dict(num_agents=32, num_obstacles=32, obstacle_extension=True, use_safety_filter=True, episode_length=250,
+                              world_size=2),
+              n1=dict(num_agents=1, use_safety_filter=True, episode_length=5, world_size=1),
+              n2_l5_airtaxi=dict(dynamics_type='airtaxi', num_agents=2, num_landmarks=5, use_safety_filter=True, episode_length=6,
+                                 world_size=6))[shape]
+    args = G.default_args(**kw)
+    flags = G.BinaryFlags(dict(SAFETY_VIOLATION=True, POTENTIAL_CONFLICT=True, HJ_VALUE=True))
+    n, T = (7, 4) if shape.startswith('n32') else (130, 14)
+    ora, cu = _compare_with_oracle(args, flags, n=n, T=T, episode=6249, seed=23, auto_reset=True)
+    assert cu.env.launch_info()['specialised'] == 0
+
+
 def test_onehot_actions_and_numpy_outputs():
     import torch
     from layered_safe_marl_b200 import B200GraphVecEnv
