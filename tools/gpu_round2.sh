@@ -10,7 +10,7 @@ python -m pytest tests -m gpu -x -q > $O/${TAG}_pytest.log 2>&1; echo "pytest rc
 python __graft_entry__.py smoke > $O/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"
 python bench.py > $O/${TAG}_bench_cfg2.json 2> $O/${TAG}_bench_cfg2.err; echo "bench rc=$?"
 python bench.py --impl reference --steps 20 --warmup 3 > $O/${TAG}_bench_reference_arm.json 2>&1
-for w in cfg1 cfg3 cfg4; do
+for w in cfg1 cfg3 cfg3_obst4 cfg4; do
   python bench.py --workload $w --steps 60 --warmup 5 --no-cpu-baseline --no-extra-workloads --e2e-steps 5 > $O/${TAG}_bench_$w.json 2> $O/${TAG}_bench_$w.err
 done
 python tools/edge_bench.py > $O/${TAG}_edge_bench.jsonl 2> $O/${TAG}_edge_bench.err
@@ -23,7 +23,7 @@ ncu --set full --clock-control none --import-source on -k regex:lsm_ -s 12 -c 6 
 tail -3 $O/${TAG}_pytest.log; tail -2 $O/${TAG}_smoke.log
 python - <<PY
 import json
-for w in ('cfg2','cfg1','cfg3','cfg4'):
+for w in ("cfg2","cfg1","cfg3","cfg3_obst4","cfg4"):
     try:
         d=json.loads(open('$O/${TAG}_bench_%s.json'%w).read().strip().splitlines()[-1])
         r=d['roofline']; dk=r.get('dominant_kernel') or {}
