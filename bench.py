@@ -51,7 +51,7 @@ WORKLOADS = {
                   world_size=4, episode_length=250), {}, 8192, 6249),
     'cfg1': (dict(dynamics_type='double_integrator', num_agents=3, num_landmarks=2, use_safety_filter=False,
                   world_size=4, episode_length=25), {}, 4096, 0),
-    # BASELINE configs[2] WITH its obstacles: the declared obstacle extension (the reference raises; generic fused kernel)
+    # BASELINE configs[2] WITH its obstacles: the declared obstacle extension (the reference raises for obstacles)
     'cfg3_obst4': (dict(dynamics_type='airtaxi', num_agents=10, num_landmarks=2, use_safety_filter=True, world_size=6,
                         episode_length=350, num_obstacles=4, obstacle_extension=True), dict(POTENTIAL_CONFLICT=True), 16384, 6249),
 }
@@ -62,7 +62,7 @@ WORKLOAD_DESC = {
     'cfg4': "BASELINE configs[3]: dense 32 agents, 8192 envs per B200",
     'cfg1': "BASELINE configs[0] shape: double integrator 3 agents, filter off, 4096 envs per B200",
     'cfg3_obst4': "BASELINE configs[2] with 4 obstacles (declared extension, not reference-pinned: the reference raises for "
-                  "obstacles; generic fused kernel): airtaxi 10 agents, POTENTIAL_CONFLICT, filter on, 16384 envs per B200",
+                  "obstacles): airtaxi 10 agents + 4 obstacles, POTENTIAL_CONFLICT, filter on, 16384 envs per B200",
 }
 
 
