@@ -1293,7 +1293,9 @@ struct EmitGeom {
     static constexpr int NCHUNK = (ROWS + CR - 1) / CR;
     static constexpr bool ADJ_BULK = (EE % 4 == 0);             // 16-byte multiple per observer matrix
     // double-buffer the per-env tiles when they are small; one buffer (wait for the drain) when a tile is tens of KB
-    static constexpr int NBUF = (EE * 4 + CR * F * 4) <= 24 * 1024 ? 2 : 1;
+    // (airtaxi: 12 KB - measured at 10 agents, where one 17 KB tile and twice the resident blocks beat two tiles by 1-2 % of
+    // the step, profiles/experiments/r02_emit_ablation_cfg3.txt; the 8-agent double integrator's 10 KB tile stays double-buffered)
+    static constexpr int NBUF = (EE * 4 + CR * F * 4) <= (DYN == LSM_DYN_DOUBLE_INTEGRATOR ? 24 * 1024 : 12 * 1024) ? 2 : 1;
 };
 
 template <int DYN, int N, int L, int O, int WPE>

@@ -28,7 +28,7 @@ namespace lsm {
 // ---------------------------------------------------------------------------------------------
 // (dynamics, N, L, O, warps per env of the emit kernel, resident emit blocks per SM the register budget targets)
 #ifndef LSM_AIR_WPE
-#define LSM_AIR_WPE 2
+#define LSM_AIR_WPE 4
 #endif
 // BASELINE.json's benchmark shapes (8 / 3 / 32 double-integrator agents, 10 airtaxi agents) and the shapes the
 // reference's own scripts ship with (train.sh: 4 agents, 2 landmarks, either dynamics; eval_airtaxi.sh: 8 and 16 agents;
