@@ -634,17 +634,22 @@ template <int DYN, int N, int L, int O>
 __device__ __noinline__ double potential_conflict_penalty(const EmitRec<DYN, N, L, O>& R, unsigned mask, int ai, double x, double y,
                                                          double vpx, double vpy, double sep, double eng) {
     double pc_pen = 0.0;
+    // one float64 division per flagged neighbour instead of three (1 / (eng - sep) once per call, 1 / |r| once per neighbour):
+    // <= 1 ulp from the quotients, far inside the reward's 1e-5 tolerance; the function was 15 % of this kernel's stall
+    // samples in the airtaxi benchmark (profiles/r02_d_by_line_agent_cfg3.txt)
+    const double inv_span = 1.0 / (eng - sep);
     for (int a = 0; a < N; ++a) {
         if (!((mask >> a) & 1u)) continue;
         const double2 pa = R.pos[a];
         const double rx = pa.x - x, ry = pa.y - y;
         const double dx = x - pa.x, dy = y - pa.y;
         const double rd = sqrt(dx * dx + dy * dy);
-        const double closeness = 1.0 - clipd((rd - sep) / (eng - sep), 0.0, 1.0);
+        const double closeness = 1.0 - clipd((rd - sep) * inv_span, 0.0, 1.0);
         // unit vector towards the other agent: (cos, sin)(atan2(ry, rx)) == (rx, ry) / |r| to ~1e-16 (reward tolerance
         // 1e-5); atan2(0, 0) = 0 for coincident agents. Three libm calls per flagged neighbour were 31 % of this kernel's
         // instructions in the airtaxi benchmark (profiles/r01_v7_*).
-        const double cdir = rd > 0.0 ? rx / rd : 1.0, sdir = rd > 0.0 ? ry / rd : 0.0;
+        const double inv_rd = 1.0 / rd;
+        const double cdir = rd > 0.0 ? rx * inv_rd : 1.0, sdir = rd > 0.0 ? ry * inv_rd : 0.0;
         const double2 va = R.vel[(a < ai ? N : 0) + a];
         double change = cdir * (va.x - vpx) + sdir * (va.y - vpy);
         change = fabs(pymin(0.0, change));
