@@ -313,6 +313,12 @@ int lsm_world_graph(lsm_handle *h, int64_t *edge_index, double *edge_weight, int
 int lsm_rollout_insert(lsm_handle *h, const float *obs, const uint8_t *done, float *share_obs, float *masks,
                        float *active_masks, void *stream);
 
+/* Episode statistics of this shard for the runner's log line (MultiAgentGraphEnv.reset's summary dict, multiagent/environment.py:
+ * 1065-1073, averaged over the vectorised envs at onpolicy/runner/shared/graph_mpe_runner.py:155-158): out = DEVICE double
+ * [LSM_EP_COUNT + 1], the SUM over the bound environments of every column of ep_info followed by the environment count - the 9
+ * doubles a multi-GPU job all-reduces at log time (the only collective of the path). One launch, no host sync, fixed order. */
+int lsm_episode_stats(lsm_handle *h, double *out, void *stream);
+
 /* The float64 sin / cos / atan2 of include/lsm_math.h (what the kernels use instead of libdevice so that they agree bit
  * for bit with the CPU oracle), evaluated on the HOST (lsm_math_eval: a, b, out are host pointers; no GPU needed -
  * B200GraphVecEnv.set_state tabulates the landmark heading sin / cos with it, like the on-device reset does) or on the

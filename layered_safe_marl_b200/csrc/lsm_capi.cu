@@ -1066,6 +1066,15 @@ int lsm_rollout_insert(lsm_handle* h, const float* obs, const uint8_t* done, flo
     return 0;
 }
 
+int lsm_episode_stats(lsm_handle* h, double* out, void* stream) {
+    if (h == nullptr || out == nullptr) return fail(1, "lsm_episode_stats: null argument");
+    if (!h->have_buffers) return fail(5, "lsm_episode_stats: lsm_bind_buffers has not been called");
+    DeviceGuard guard(h->device);
+    cudaError_t e = lsm::episode_stats_launch(h->kp.b.ep_info, (long long)h->kp.b.num_envs, out, (cudaStream_t)stream);
+    if (e != cudaSuccess) return cuda_fail(e, "lsm_episode_stats");
+    return 0;
+}
+
 int lsm_math_eval(int op, const double* a, const double* b, double* out, int64_t n) {
     if (a == nullptr || out == nullptr || (op == 2 && b == nullptr)) return fail(1, "lsm_math_eval: null argument");
     if (op < 0 || op > 4) return fail(2, "lsm_math_eval: op must be 0 sin, 1 cos, 2 atan2, 3 sincos.sin, 4 sincos.cos");

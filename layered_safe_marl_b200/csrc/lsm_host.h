@@ -25,6 +25,7 @@ cudaError_t spec_launch_edge_count(const KParams& kp, cudaStream_t stream);
 cudaError_t world_graph_launch(const KParams& kp, int32_t* counts, long long* offsets, long long* edge_index, double* edge_weight,
                                long long capacity, cudaStream_t stream);
 cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells);
+cudaError_t episode_stats_launch(const double* ep_info, long long n, double* out, cudaStream_t stream);
 cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
                                   long long n, int N, int D, cudaStream_t stream);
 cudaError_t math_eval_launch(int op, const double* a, const double* b, double* out, long long n, cudaStream_t stream);

@@ -348,6 +348,11 @@ cudaError_t pack_grid_launch(const GridDev& g, float* packed, long long cells) {
     return cudaGetLastError();
 }
 
+cudaError_t episode_stats_launch(const double* ep_info, long long n, double* out, cudaStream_t stream) {
+    lsm_episode_stats_kernel<<<1, 256, 0, stream>>>(ep_info, n, LSM_EP_COUNT, out);
+    return cudaGetLastError();
+}
+
 cudaError_t rollout_insert_launch(const float* obs, const uint8_t* done, float* share_obs, float* masks, float* active_masks,
                                   long long n, int N, int D, cudaStream_t stream) {
     const long long total = n * (long long)N * N * D;

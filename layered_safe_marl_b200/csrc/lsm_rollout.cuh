@@ -33,4 +33,24 @@ __global__ void __launch_bounds__(256) lsm_rollout_insert_kernel(const float* __
     }
 }
 
+// Sums of the 8 episode-summary columns over the shard's environments + the environment count: the 9 doubles the
+// runner's log-time all-reduce exchanges. ONE block, fixed reduction order (deterministic).
+__global__ void __launch_bounds__(256) lsm_episode_stats_kernel(const double* __restrict__ ep_info, long long n, int cols, double* __restrict__ out) {
+    __shared__ double s_part[8][16];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int c = 0; c < cols; ++c) {
+        double acc = 0.0;
+        for (long long e = threadIdx.x; e < n; e += blockDim.x) acc += ep_info[e * cols + c];
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) s_part[warp][c] = acc;
+    }
+    __syncthreads();
+    if (threadIdx.x < cols) {
+        double t = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_part[w][threadIdx.x];
+        out[threadIdx.x] = t;
+    }
+    if (threadIdx.x == 0) out[cols] = (double)n;
+}
+
 }  // namespace lsm

@@ -17,11 +17,12 @@ def shard_range(num_envs_total: int, world_size: int, rank: int):
     return first, n
 
 
-def allreduce_episode_stats(ep_info: torch.Tensor, group=None) -> dict:
-    """ep_info: (n_local, 8) per-env episode summaries. Returns the mean over ALL shards."""
+def allreduce_episode_stats(ep_info: torch.Tensor, group=None, sums: torch.Tensor = None) -> dict:
+    """ep_info: (n_local, 8) per-env episode summaries. Returns the mean over ALL shards.
+    `sums`: the 9 doubles of lsm_episode_stats (column sums + env count) when the caller already has them on the device."""
     import torch.distributed as dist
-    s = torch.cat([ep_info.double().sum(dim=0),
-                   torch.tensor([float(ep_info.shape[0])], dtype=torch.float64, device=ep_info.device)])
+    s = sums if sums is not None else torch.cat([ep_info.double().sum(dim=0),
+                                                 torch.tensor([float(ep_info.shape[0])], dtype=torch.float64, device=ep_info.device)])
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(s, op=dist.ReduceOp.SUM, group=group)
     vals = (s[:-1] / s[-1]).cpu().numpy()

@@ -667,10 +667,14 @@ class B200GraphVecEnv:
         `reduce_group` (True = default group, or a torch.distributed group) the mean over all shards
         (one NCCL all_reduce of 9 doubles - the only collective of this path)."""
         from .sharding import allreduce_episode_stats
+        # column sums + env count in one launch of the library (lsm_episode_stats), then at most one all-reduce of 9 doubles
+        sums = torch.empty((LY.EP_COUNT + 1,), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.lsm_episode_stats(self._h, C.c_void_p(sums.data_ptr()), self._stream()), 'lsm_episode_stats')
         if reduce_group is None:
-            vals = self.ep_info.mean(dim=0).cpu().numpy()
+            vals = (sums[:-1] / sums[-1]).cpu().numpy()
             return {k: float(vals[j]) for j, k in enumerate(LY.EP_INFO_KEYS)}
-        return allreduce_episode_stats(self.ep_info, None if reduce_group is True else reduce_group)
+        return allreduce_episode_stats(self.ep_info, None if reduce_group is True else reduce_group, sums=sums)
 
 
 class B200GraphDummyVecEnv(B200GraphVecEnv):

@@ -271,6 +271,22 @@ def test_oracle_batch_extreme_shapes(shape):
     assert cu.env.launch_info()['specialised'] == 0
 
 
+def test_episode_stats_entry_point():
+    """lsm_episode_stats (column sums of the episode summaries + env count in one launch) against numpy on the same buffer."""
+    import torch
+    from layered_safe_marl_b200 import B200GraphVecEnv
+    args = G.default_args(num_agents=3, use_safety_filter=False, episode_length=4)
+    env = B200GraphVecEnv(args, num_envs=1037, seed=4)
+    env.reset(0)
+    rng = np.random.default_rng(0)
+    for _ in range(9):          # two auto-resets: the summaries are populated
+        env.step(torch.as_tensor(rng.integers(0, 25, (1037, 3)).astype(np.int32), device=env.device), 0)
+    want = env.ep_info.cpu().numpy().mean(axis=0)
+    got = env.episode_stats()
+    from layered_safe_marl_b200 import layout as LY
+    assert np.allclose([got[k] for k in LY.EP_INFO_KEYS], want, rtol=1e-12, atol=0) and want[0] > 0
+
+
 def test_onehot_actions_and_numpy_outputs():
     import torch
     from layered_safe_marl_b200 import B200GraphVecEnv
