@@ -359,13 +359,14 @@ def run_ours(a):
     value = total_envs * N * K / (total_ms / 1000.0)
 
     # ---- e2e: host one-hot actions in, every returned array back to pinned host memory --------------
-    Ke = max(3, min(K, a.e2e_steps))
+    Ke = max(3, a.e2e_steps)        # its own step count (reported as e2e.steps): 20 steps moved by +-15 % from run to run
+    We = 5
     env_h = B200GraphVecEnv(args, num_envs=n_envs, device=device, seed=4321, binary_cfg=flags,
                             env_id_base=rank * n_envs, numpy_outputs=True, numa_bind=a.numa_bind)
     env_h.reset(episode)
     rng = np.random.default_rng(99 + rank)
-    onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + 2, n_envs, N))]).pin_memory()
-    for t in range(2):
+    onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + We, n_envs, N))]).pin_memory()
+    for t in range(We):
         env_h.step(onehot_host[t].numpy(), episode)
     torch.cuda.synchronize()
     if world > 1:
@@ -374,7 +375,7 @@ def run_ours(a):
     s0.record()
     chk = 0.0
     for t in range(Ke):
-        out = env_h.step(onehot_host[2 + t].numpy(), episode)
+        out = env_h.step(onehot_host[We + t].numpy(), episode)
         chk += float(out[4][0, 0])            # touch the host result
     s1.record()
     torch.cuda.synchronize()
@@ -591,7 +592,7 @@ def main():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--workload', default='cfg2', choices=sorted(WORKLOADS) + ['cfg5'])
     ap.add_argument('--envs', type=int, default=0, help='envs per GPU (default: the workload’s)')
-    ap.add_argument('--e2e-steps', type=int, default=20)
+    ap.add_argument('--e2e-steps', type=int, default=60)
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--numa-bind', action='store_true', help='e2e: pin the process to the CPUs of the NUMA node of its GPU')
     ap.add_argument('--use-graph', type=int, default=-1, choices=[-1, 0, 1],
