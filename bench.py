@@ -365,9 +365,10 @@ def run_ours(a):
                             env_id_base=rank * n_envs, numpy_outputs=True, numa_bind=a.numa_bind)
     env_h.reset(episode)
     rng = np.random.default_rng(99 + rank)
-    onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (Ke + We, n_envs, N))]).pin_memory()
+    onehot_host = torch.from_numpy(np.eye(25, dtype=np.float32)[rng.integers(0, 25, (min(Ke + We, 16), n_envs, N))]).pin_memory()   # a pool of distinct action sets, cycled
+    pool = onehot_host.shape[0]
     for t in range(We):
-        env_h.step(onehot_host[t].numpy(), episode)
+        env_h.step(onehot_host[t % pool].numpy(), episode)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -375,7 +376,7 @@ def run_ours(a):
     s0.record()
     chk = 0.0
     for t in range(Ke):
-        out = env_h.step(onehot_host[We + t].numpy(), episode)
+        out = env_h.step(onehot_host[(We + t) % pool].numpy(), episode)
         chk += float(out[4][0, 0])            # touch the host result
     s1.record()
     torch.cuda.synchronize()
