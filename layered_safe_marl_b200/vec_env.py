@@ -613,10 +613,11 @@ class B200GraphVecEnv:
         lm[LY.LF_SIN].copy_(t(self.math_eval(0, lh_np), torch.float64)); lm[LY.LF_COS].copy_(t(self.math_eval(1, lh_np), torch.float64))
         self.env_f64[LY.EF_CURRICULUM_RATIO].copy_(t(s['curriculum_ratio'], torch.float64))
         self.env_i32[LY.EI_CURRENT_STEP].copy_(t(s['current_step'], torch.int32))
-        if self.O > 0:
+        if self.O > 0 and 'obstacle_pos' in s:      # a state without obstacle keys (e.g. eval_scenarios.build) keeps the current obstacles
             op = t(s['obstacle_pos'], torch.float64)
             self.obstacles[0].copy_(op[..., 0]); self.obstacles[1].copy_(op[..., 1])
-            i[LY.AI_NUM_OBST_COLLISIONS].copy_(t(s['num_obstacle_collisions'], torch.int32))
+            if 'num_obstacle_collisions' in s:
+                i[LY.AI_NUM_OBST_COLLISIONS].copy_(t(s['num_obstacle_collisions'], torch.int32))
 
     def math_eval(self, op: int, a, b=None):
         """include/lsm_math.h on the host (op 0 sin, 1 cos, 2 atan2(a, b)): the kernels' own float64 trigonometry."""
