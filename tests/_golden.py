@@ -18,9 +18,11 @@ STATE_KEYS = ('agent_values', 'p_dist', 'state_time', 'done', 'safety_filtered',
               'num_agent_collisions', 'current_step', 'curriculum_ratio', 'ep_travel_length',
               'ep_travel_distance', 'ep_done', 'ep_conflict', 'ep_multi_engagement', 'ep_min_distance')
 
-# relative tolerance of the north star for continuous values; fixtures store outputs as float32
+# relative tolerance of the north star for continuous values; fixtures store outputs as float32. The absolute term only
+# covers values that are zero up to roundoff (a difference of two nearly equal angles / positions): 1e-9, i.e. it adds
+# nothing to the relative bar for any value above 1e-4 (round 1 used 2e-6; every CPU and GPU parity test passes at 1e-9)
 RTOL = 1e-5
-ATOL = 2e-6
+ATOL = 1e-9
 
 
 def golden_names():
