@@ -1035,7 +1035,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) lsm_agent_kernel(const __grid_con
                 const bool want_sv = (c.flags & LSM_FLAG_SAFETY_VIOLATION) != 0;
                 const bool want_pc = (c.flags & LSM_FLAG_POTENTIAL_CONFLICT) != 0;
                 unsigned pc_mask = 0u;
-#pragma unroll
+                // airtaxi: the loop stays rolled (-5 % code in a kernel bound by instruction fetch: cfg3 0.3385 -> 0.3348 ms, same-box
+                // A/B); the double-integrator kernels measure the same either way and keep the unrolled loop
+#ifndef LSM_OTHERS_UNROLL
+#define LSM_OTHERS_UNROLL 0
+#endif
+                constexpr int kOthersUnroll = LSM_OTHERS_UNROLL > 0 ? LSM_OTHERS_UNROLL : (DYN == LSM_DYN_DOUBLE_INTEGRATOR ? N : 1);
+#pragma unroll kOthersUnroll
                 for (int a = 0; a < N; ++a) {
                     if (a == ai) continue;
                     // squared distance after the dynamics; (p_i - p_a)^2 == (p_a - p_i)^2 exactly, so both lanes of a
