@@ -28,7 +28,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_harness as H  # noqa: E402
 
-OUT_DIR = os.path.join(os.path.dirname(HERE), 'tests', 'golden')
+OUT_DIR = os.environ.get('LSM_GOLDEN_OUT') or os.path.join(os.path.dirname(HERE), 'tests', 'golden')   # override: reproducibility test
 
 
 def greedy_action(env, sc, i, rng):

@@ -135,6 +135,27 @@ def test_rollout_rotation_form(name):
         print(f"{name} (rotation form): roundoff ties at {ties}")
 
 
+@pytest.mark.skipif(not os.path.isdir('/root/reference/multiagent'), reason="the reference tree only exists in the build container")
+def test_golden_fixtures_are_reproducible_from_the_reference(tmp_path):
+    """Regenerate a few fixtures from /root/reference with the committed generator (pure reference code, filter on, the declared
+    obstacle extension, 3 landmarks per agent) and compare every array with the committed .npz, bit for bit."""
+    import subprocess
+    names = ['di3_nofilter_ep0', 'di8_filter', 'di3_obst2', 'at3_landmarks3']
+    env = dict(os.environ, LSM_GOLDEN_OUT=str(tmp_path))
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call([sys.executable, os.path.join(repo, 'oracle', 'gen_golden.py')] + names, env=env, cwd=str(tmp_path),
+                          stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for name in names:
+        new = np.load(os.path.join(str(tmp_path), name + '.npz'))
+        old = np.load(os.path.join(G.GOLDEN_DIR, name + '.npz'))
+        assert sorted(new.files) == sorted(old.files), name
+        for k in old.files:
+            if k == 'meta':
+                assert str(new[k]) == str(old[k]), f"{name} meta"
+            else:
+                assert np.array_equal(new[k], old[k], equal_nan=True), f"{name}: array '{k}' differs from the committed fixture"
+
+
 def test_relative_state_forms_agree_on_a_batch():
     """Literal vs rotation form on 256 seeded airtaxi environments x 25 steps (BASELINE config 3 shape): every
     divergence in a discrete output is counted and printed; the continuous states agree to 1e-9."""
