@@ -105,7 +105,7 @@ typedef struct lsm_config {
                                      navigation_graph_safe.py:1064-1065,1087 / :975-989): obstacles are placed, collide and enter the
                                      distance matrix as the reference's own code does (:230-236,402-404,452-465,1204-1249,
                                      core.py:489-543); an obstacle is never disconnected and its 'relative' node features are the
-                                     landmark builders' (utils.py:167-190,224-255) with heading 0, speed 0, entity type 2.
+                                     landmark builders' (utils.py:174-199,231-255) with heading 0, speed 0, entity type 2.
                                      Runs the generic fused kernel */
     double world_size;
     double dt, coordination_range, dist_thresh, heading_thresh, speed_thresh;

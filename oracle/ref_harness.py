@@ -90,7 +90,7 @@ def _obstacle_extension(module):
     indexes the E x E distance matrix with a mask of N(1+L) entries (:975-989). Everything else - obstacle creation,
     placement, collision counting, distances, the 'global' features - is the reference's own code and runs unmodified.
     The two statements are completed as declared: an obstacle's relative node features are the reference's landmark builders
-    (utils.py:167-190,224-255) called with heading 0 and speed 0, entity type 2; the disconnect mask is padded with False."""
+    (utils.py:174-199,231-255) called with heading 0 and speed 0, entity type 2; the disconnect mask is padded with False."""
     import multiagent.custom_scenarios.utils as U
     Sc = module.Scenario
     orig_rel = Sc._get_entity_feat_relative
