@@ -437,6 +437,12 @@ def run_ours(a):
                 traffic = json.load(f).get(a.workload)
         except Exception:
             traffic = None
+    step_traffic = None          # ncu dram bytes of all kernels of one step (profiles/traffic_r02.json "<workload>_step"), or null
+    try:
+        with open(tp) as f:
+            step_traffic = json.load(f).get(a.workload + '_step')
+    except Exception:
+        step_traffic = None
     dominant = None
     if emit_ms is not None:
         # lsm_emit_kernel alone on ITS 8d bytes: node_obs + adj written (the per-env record it reads is an implementation
@@ -450,7 +456,7 @@ def run_ours(a):
                             "output fits the 126 MB L2 (cfg2: 107 MB) about half of it is still dirty in L2 when the kernel "
                             "ends, so traffic / algorithmic ~ 0.5 there; at cfg3 / cfg4 (outputs >> L2) it is ~1.0"}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": step_traffic, "peak_source": peak_src,
                 "kernel": ("whole step = lsm_agent_kernel + lsm_emit_kernel + lsm_pair_kernel" if li_spec else "lsm_generic_kernel<dyn>"),
                 "algorithmic_bytes_per_launch": bytes_per_step, "mean_launch_ms": step_s * 1000.0,
                 "median_ms": float(np.median(step_ms)), "launches": li0.get('launches_per_step', 1),
