@@ -305,6 +305,34 @@ def test_expand_adjacency_host_matches_numpy(N, L):
         assert np.array_equal(out.view(np.uint32), want.view(np.uint32)), f"threads={threads} cached={cached}"
 
 
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors of include/lsm_b200.h (layered_safe_marl_b200/_lib.py) and of oracle/lsm_oracle.h (oracle/oracle_env.py)
+    have the C compiler's sizes and field offsets - a struct edited on one side only would otherwise corrupt memory silently."""
+    import subprocess
+    import oracle_env as O
+    from layered_safe_marl_b200 import _lib
+    checks = [('lsm_b200.h', os.path.join(REPO, 'include'), [('lsm_config', _lib.LsmConfig), ('lsm_grid_desc', _lib.LsmGridDesc),
+                                                            ('lsm_buffers', _lib.LsmBuffers), ('lsm_tuning', _lib.LsmTuning),
+                                                            ('lsm_launch_info', _lib.LsmLaunchInfo), ('lsm_host_io', _lib.LsmHostIo)]),
+              ('lsm_oracle.h', os.path.join(REPO, 'oracle'), [('lsmo_params', O.Params), ('lsmo_grid', O.Grid), ('lsmo_buffers', O.Buffers)])]
+    for header, inc, structs in checks:
+        lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{header}"', 'int main(void) {']
+        for cname, cls in structs:
+            lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+            for fname, _ in cls._fields_:
+                cfield = 'reserved' if fname == '_reserved' else fname
+                lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {cfield}));')
+        lines += ['  return 0;', '}']
+        src = tmp_path / (header + '.c'); exe = tmp_path / (header + '.exe')
+        src.write_text('\n'.join(lines))
+        subprocess.check_call(['gcc', '-I', inc, '-o', str(exe), str(src)])
+        got = dict(l.split() for l in subprocess.check_output([str(exe)], text=True).strip().splitlines())
+        for cname, cls in structs:
+            assert int(got[cname]) == ctypes.sizeof(cls), f"sizeof({cname}): C {got[cname]} vs ctypes {ctypes.sizeof(cls)}"
+            for fname, _ in cls._fields_:
+                assert int(got[f'{cname}.{fname}']) == getattr(cls, fname).offset, f"offsetof({cname}, {fname})"
+
+
 def test_edited_dynamics_limits_are_refused(monkeypatch):
     """The acceleration / speed / turn-rate limits are compile-time constants of the kernels; a config class edited
     without a rebuild must fail loudly instead of simulating something else than it says."""
